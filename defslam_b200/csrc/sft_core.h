@@ -1,0 +1,1124 @@
+/*
+ * sft_core.h -- the Shape-from-Template solve as ONE persistent CTA per frame.
+ *
+ * Replaces, for the graph Modules/Tracking/DefOptimizer.cc:251-578 builds:
+ *   sft_types.h edges (computeError / linearizeOplus)      -> eval_state(), build_system()
+ *   BaseMultiEdge/BinaryEdge/UnaryEdge::constructQuadraticForm
+ *   + RobustKernelHuber::robustify                          -> build_system()
+ *   BlockSolver::buildSystem/setLambda/solve + LinearSolverDense::solve
+ *                                                           -> factor_solve()
+ *   OptimizationAlgorithmLevenberg::solve + SparseOptimizer::optimize/update
+ *                                                           -> sft_solve_one()
+ *   outlier classing / repError / write-back (DefOptimizer.cc:515-577)
+ *                                                           -> finalize()
+ *
+ * Not a translation: the graph is never materialised.  Because the reference's
+ * node Jacobian of a reprojection edge is  b_k * A(node k)  with A depending
+ * only on the node and the pose (sft_types.h:176-205, quirk C1), the whole
+ * reprojection part of J^T W J collapses to per-facet sums of 48 scalars plus a
+ * 6x6 camera block; curvature and stretch terms are rank-1 per centre / edge.
+ * H is assembled by a deterministic gather (one thread per 3x3 block) into an
+ * arrowhead layout -- node band (half bandwidth bw) + 6 camera rows -- and
+ * (H + lambda I) dx = b is solved by a blocked banded Cholesky that slides an
+ * (NB+bw) x (bw+1) window through shared memory, with the camera border and the
+ * right-hand side carried as 8 extra rows of the same trailing update.
+ *
+ * Variable order inside the kernel: node 0 xyz, node 1 xyz, ..., camera
+ * (omega, upsilon) last.  Fixed nodes (outside OptLap) keep identity rows.
+ */
+#ifndef DS_SFT_CORE_H_
+#define DS_SFT_CORE_H_
+
+#include "ds_common.h"
+#include "ds_plan.h"
+#include "ds_se3.h"
+
+namespace ds {
+
+struct ResultScalars {
+  float Tcw[16];
+  float rep_error;
+  int n_inliers;
+  int lm_iterations;
+  int lm_trials;
+  double chi2_initial;
+  double chi2_final;
+  double lambda_final;
+  int status;
+  int n_viewed;
+  int n_optlap;
+  int pad;
+};
+
+enum { MODE_SOLVE = 0, MODE_NORMAL_EQ = 1 };
+
+struct ProbView {
+  const PlanView *plan;    /* resident with the template */
+  int mode;
+  int n_matches, n_kp, max_it, layers;
+  int trace_cap;
+  int e_in_smem;
+  double fx, fy, cx, cy;
+  double reg_lap, reg_inex, reg_temp;
+  float Tcw[16];
+  const double *node_xyz;  /* [3n] */
+  const int *match_nodes;  /* [3M] */
+  const double *match_bary;/* [3M] */
+  const float *match_uv;   /* [2M] */
+  const float *match_isig; /* [M]  */
+  double *out_nodes;       /* [3n] */
+  uint8_t *out_outlier;    /* [M]  */
+  uint8_t *out_role;       /* [n]  */
+  double *out_trace;       /* [4*trace_cap] */
+  ResultScalars *out_res;
+  double *out_H;           /* MODE_NORMAL_EQ: [D*D] */
+  double *out_b;           /* MODE_NORMAL_EQ: [D]   */
+};
+
+/* per-CTA scratch in global memory (L2 resident) */
+struct Workspace {
+  double *Hb;    /* [Dn_pad*ld]   band of H (lower, row i holds cols i-bw..i) */
+  double *Lb;    /* [Dn_pad*ld]   band of the Cholesky factor                 */
+  double *Dinv;  /* [nblk*64]     inverses of the diagonal blocks of L        */
+  double *Cg;    /* [8*Dn_pad]    rows 0-5 camera border, row 6 b_n, row 7 0  */
+  double *Eg;    /* [8*Dn_pad]    working copy when it does not fit in smem   */
+  double *F;     /* [NFACC*nf]    per-facet accumulators                      */
+  double *S;     /* [NMSCR*M]     per-match scratch                           */
+  int *mfac;     /* [M]  facet<<6 | slot0 | slot1<<2 | slot2<<4               */
+  int *mperm;    /* [M]  matches grouped by facet                             */
+  int *fptr;     /* [nf+1] */
+  int *fcnt;     /* [nf]   */
+};
+
+struct WorkspaceSizes {
+  size_t band, dinv, cg, F, S, M, nf; /* element counts (max over the batch) */
+};
+
+static inline
+#if DS_CUDA
+__host__ __device__
+#endif
+size_t workspace_bytes(const WorkspaceSizes &z) {
+  size_t b = sizeof(double) * (2 * z.band + z.dinv + 2 * z.cg + z.F + z.S) + sizeof(int) * (2 * z.M + 2 * z.nf + 2);
+  return (b + 255) & ~(size_t)255;
+}
+
+static inline
+#if DS_CUDA
+__host__ __device__
+#endif
+Workspace carve_workspace(uint8_t *base, const WorkspaceSizes &z) {
+  Workspace w;
+  double *d = (double *)base;
+  w.Hb = d; d += z.band;
+  w.Lb = d; d += z.band;
+  w.Dinv = d; d += z.dinv;
+  w.Cg = d; d += z.cg;
+  w.Eg = d; d += z.cg;
+  w.F = d; d += z.F;
+  w.S = d; d += z.S;
+  int *i = (int *)d;
+  w.mfac = i; i += z.M;
+  w.mperm = i; i += z.M;
+  w.fptr = i; i += z.nf + 1;
+  w.fcnt = i;
+  return w;
+}
+
+/* shared-memory carve-up (offsets in doubles) -- same function on host (size)
+ * and device (pointers) */
+struct SmemLayout {
+  int W, E, P, x, xb, dx, Lkk, invL, G, Hcc, red, pose, flags, total;
+};
+
+DS_FN int asm_scratch_doubles(int n, int ne) { return 11 * n + 5 * ne; }
+
+static inline
+#if DS_CUDA
+__host__ __device__
+#endif
+SmemLayout smem_layout(int n_nodes, int n_edges, int Dn_pad, int bwp, int ld, int Wr, bool e_in_smem) {
+  SmemLayout L;
+  int o = 0;
+  int wsz = Wr * ld;
+  const int asz = 11 * n_nodes + 5 * n_edges, bsz = 2 * (NB * ld + 64);
+  if (asz > wsz) wsz = asz;
+  if (bsz > wsz) wsz = bsz;
+  L.W = o;    o += wsz; o = (o + 1) & ~1;
+  L.E = o;    o += e_in_smem ? 8 * Dn_pad : 0;
+  L.P = o;    o += NB * (bwp + 8);
+  L.x = o;    o += Dn_pad;
+  L.xb = o;   o += Dn_pad;
+  L.dx = o;   o += Dn_pad + 8;
+  L.Lkk = o;  o += 64;
+  L.invL = o; o += 64;
+  L.G = o;    o += 64;
+  L.Hcc = o;  o += 48;   /* 36 Hcc + 6 bc + 6 dc(stale) */
+  L.red = o;  o += 40;
+  L.pose = o; o += 16;   /* pose (7) + backup (7) */
+  L.flags = o; o += (2 * n_nodes + 7) / 8 + 1;
+  L.total = o;
+  return L;
+}
+
+struct Ctx {
+  Team team;
+  PlanView pl;
+  ProbView pb;
+  Workspace ws;
+  SmemLayout sl;
+  double *sm;      /* shared memory base */
+  double *E;       /* working border rows (smem or global) */
+  uint8_t *viewed, *freev;
+  int n_optlap, n_viewed, n_str;
+  double info_ref, info_curv, info_str;
+  double hub_delta, hub_dsqr;
+  double inv_n;
+};
+
+/* ------------------------------------------------------------ prologue -- */
+
+/* returns 0 or an error code (uniform over the team) */
+DS_FN_NOINLINE int prologue(Ctx &c) {
+  const Team team = c.team;
+  const PlanView &pl = c.pl;
+  const ProbView &pb = c.pb;
+  const int n = pl.n_nodes, nf = pl.n_facets, M = pb.n_matches;
+  double *x = c.sm + c.sl.x;
+  double *red = c.sm + c.sl.red;
+
+  DS_FOR(i, pl.Dn_pad) x[i] = i < pl.Dn ? pb.node_xyz[i] : 0.0;
+  DS_FOR(i, pl.Dn_pad + 8) c.sm[c.sl.dx + i] = 0.0;
+  DS_FOR(i, 2 * n) c.viewed[i] = 0; /* viewed + freev are contiguous */
+  DS_FOR(f, nf) c.ws.fcnt[f] = 0;
+  if (team.tid == 0) {
+    Pose P;
+    pose_from_Tcw(pb.Tcw, P);
+    double *ps = c.sm + c.sl.pose;
+    for (int k = 0; k < 4; k++) ps[k] = P.q[k];
+    for (int k = 0; k < 3; k++) ps[4 + k] = P.t[k];
+  }
+  /* zero the band workspace; padding rows are identity */
+  {
+    const int tot = pl.Dn_pad * pl.ld;
+    DS_FOR(i, tot) c.ws.Hb[i] = 0.0;
+    DS_FOR(i, 8 * pl.Dn_pad) c.ws.Cg[i] = 0.0;
+  }
+  team.sync();
+  DS_FOR(i, pl.Dn_pad - pl.Dn) c.ws.Hb[(pl.Dn + i) * pl.ld + pl.bw] = 1.0;
+
+  /* facet of every match (DefMapPoint::getFacet) + viewed nodes
+   * (DefOptimizer.cc:326-335) */
+  int bad = 0;
+  DS_FOR(m, M) {
+    int v[3] = {pb.match_nodes[3 * m], pb.match_nodes[3 * m + 1], pb.match_nodes[3 * m + 2]};
+    int code = -1;
+    if (v[0] >= 0 && v[0] < n && v[1] >= 0 && v[1] < n && v[2] >= 0 && v[2] < n) {
+      for (int k = pl.nf_ptr[v[0]]; k < pl.nf_ptr[v[0] + 1] && code < 0; k++) {
+        const int f = pl.nf_ent[k] >> 2;
+        const int *fv = &pl.facets[3 * f];
+        int s[3];
+        bool ok = true;
+        for (int a = 0; a < 3; a++) {
+          s[a] = (v[a] == fv[0]) ? 0 : (v[a] == fv[1]) ? 1 : (v[a] == fv[2]) ? 2 : -1;
+          ok = ok && s[a] >= 0;
+        }
+        if (ok && s[0] != s[1] && s[1] != s[2] && s[0] != s[2]) code = (f << 6) | s[0] | (s[1] << 2) | (s[2] << 4);
+      }
+    }
+    c.ws.mfac[m] = code;
+    if (code < 0) bad++;
+    else {
+      atomic_inc_int(&c.ws.fcnt[code >> 6]);
+      c.viewed[v[0]] = 1; c.viewed[v[1]] = 1; c.viewed[v[2]] = 1;
+    }
+  }
+  bad = team_sum_int(team, bad, red);
+  if (bad > 0) return DEFSLAM_EBADARG;
+
+  /* OptLap = Viewed U ring1(Viewed)  (DefOptimizer.cc:384-406, quirk C3) */
+  DS_FOR(v, n) {
+    int fr = c.viewed[v];
+    if (!fr && pb.layers >= 1)
+      for (int k = pl.nbr_ptr[v]; k < pl.nbr_ptr[v + 1]; k++) fr |= c.viewed[pl.nbr_idx[k]];
+    c.freev[v] = (uint8_t)fr;
+  }
+  if (team.tid == 0) { /* exclusive scan of the facet histogram */
+    int s = 0;
+    for (int f = 0; f < nf; f++) { c.ws.fptr[f] = s; s += c.ws.fcnt[f]; }
+    c.ws.fptr[nf] = s;
+  }
+  team.sync();
+  int cnt_v = 0, cnt_o = 0, cnt_s = 0;
+  DS_FOR(v, n) { cnt_v += c.viewed[v]; cnt_o += c.freev[v]; }
+  DS_FOR(e, pl.n_edges) cnt_s += (c.freev[pl.edge_ab[2 * e]] | c.freev[pl.edge_ab[2 * e + 1]]);
+  DS_FOR(f, nf) c.ws.fcnt[f] = 0;
+  c.n_viewed = team_sum_int(team, cnt_v, red);
+  c.n_optlap = team_sum_int(team, cnt_o, red);
+  c.n_str = team_sum_int(team, cnt_s, red);
+  DS_FOR(m, M) {
+    const int f = c.ws.mfac[m] >> 6;
+    c.ws.mperm[c.ws.fptr[f] + atomic_inc_int(&c.ws.fcnt[f])] = m;
+  }
+  team.sync();
+  DS_FOR(f, nf) { /* fixed order inside a facet: ascending match index */
+    const int b = c.ws.fptr[f], e = c.ws.fptr[f + 1];
+    for (int i = b + 1; i < e; i++) {
+      const int key = c.ws.mperm[i];
+      int j = i - 1;
+      while (j >= b && c.ws.mperm[j] > key) { c.ws.mperm[j + 1] = c.ws.mperm[j]; j--; }
+      c.ws.mperm[j + 1] = key;
+    }
+  }
+  team.sync();
+
+  /* information matrices (DefOptimizer.cc:339-340,376-378,458,499) */
+  c.inv_n = 1.0; /* division by N is done per match as float/ int like the reference */
+  c.info_ref = pb.reg_temp / pow(pl.median_len, 2);
+  c.info_curv = c.n_optlap > 0 ? pb.reg_lap / (double)c.n_optlap : 0.0;
+  c.info_str = c.n_str > 0 ? pb.reg_inex / (double)c.n_str : 0.0;
+  const float deltaMono = (float)sqrt(5.991);
+  c.hub_delta = (double)deltaMono;
+  c.hub_dsqr = c.hub_delta * c.hub_delta;
+  return 0;
+}
+
+/* -------------------------------------------------- errors and chi2 ---- */
+
+DS_FN void load_pose(const double *ps, Pose &P) {
+  for (int k = 0; k < 4; k++) P.q[k] = ps[k];
+  for (int k = 0; k < 3; k++) P.t[k] = ps[4 + k];
+}
+
+/* reprojection error of one match at (x, P)  -- sft_types.h:102-133 */
+DS_FN void reproj_error(const Ctx &c, const double *x, const Pose &P, int m, double e[2], double Pc[3]) {
+  const ProbView &pb = c.pb;
+  const int v0 = pb.match_nodes[3 * m], v1 = pb.match_nodes[3 * m + 1], v2 = pb.match_nodes[3 * m + 2];
+  const double b0 = pb.match_bary[3 * m], b1 = pb.match_bary[3 * m + 1], b2 = pb.match_bary[3 * m + 2];
+  double Pw[3];
+  for (int k = 0; k < 3; k++) Pw[k] = b0 * x[3 * v0 + k] + b1 * x[3 * v1 + k] + b2 * x[3 * v2 + k];
+  pose_map(P, Pw, Pc);
+  const double u = Pc[0] / Pc[2] * pb.fx + pb.cx;
+  const double v = Pc[1] / Pc[2] * pb.fy + pb.cy;
+  e[0] = (double)pb.match_uv[2 * m] - u;
+  e[1] = (double)pb.match_uv[2 * m + 1] - v;
+}
+
+DS_FN double match_info(const Ctx &c, int m) { return (double)c.pb.match_isig[m] / (double)c.pb.n_kp; }
+
+/* curvature residual of centre i: delta = x_i - sum(w x_j)/W  (sft_types.h:257-291) */
+DS_FN double curv_residual(const Ctx &c, const double *x, int i, double d[3], double &nrm) {
+  const PlanView &pl = c.pl;
+  double a0 = 0, a1 = 0, a2 = 0;
+  for (int k = pl.nbr_ptr[i]; k < pl.nbr_ptr[i + 1]; k++) {
+    const int j = pl.nbr_idx[k];
+    const double w = pl.nbr_w[k];
+    a0 = a0 + w * x[3 * j]; a1 = a1 + w * x[3 * j + 1]; a2 = a2 + w * x[3 * j + 2];
+  }
+  const double W = pl.sum_w[i];
+  d[0] = x[3 * i] - a0 / W; d[1] = x[3 * i + 1] - a1 / W; d[2] = x[3 * i + 2] - a2 / W;
+  nrm = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+  return nrm - pl.kappa0[i];
+}
+
+/* SparseOptimizer::computeActiveErrors + activeRobustChi2 at state (x, pose).
+ * store=true additionally fills everything build_system() gathers from:
+ * per-match scratch S, per-node A / centre / edge quantities (overlaid on the
+ * window region of shared memory). */
+DS_FN_NOINLINE double eval_state(Ctx &c, const double *x, const double *ps, bool store) {
+  const Team team = c.team;
+  const PlanView &pl = c.pl;
+  const ProbView &pb = c.pb;
+  const int n = pl.n_nodes, ne = pl.n_edges, M = pb.n_matches;
+  Pose P;
+  load_pose(ps, P);
+  double *A = c.sm + c.sl.W;      /* [6n] */
+  double *cd = A + 6 * n;         /* [3n] unit Laplacian direction */
+  double *cg = cd + 3 * n;        /* [n]  info_curv * S_i (0 if inactive) */
+  double *cr = cg + n;            /* [n]  |delta| - kappa0 */
+  double *eu = cr + n;            /* [3ne] J_a of the stretch edge */
+  double *er = eu + 3 * ne;       /* [ne] stretch residual */
+  double *es = er + ne;           /* [ne] info_str if active else 0 */
+  double chi = 0.0;
+  double R[9];
+  if (store) quat_to_R(P.q, R);
+
+  /* reprojection edges, in facet-grouped order */
+  DS_FOR(s, M) {
+    const int m = c.ws.mperm[s];
+    double e[2], Pc[3];
+    reproj_error(c, x, P, m, e, Pc);
+    const double info = match_info(c, m);
+    const double c2 = e[0] * info * e[0] + e[1] * info * e[1];
+    double rho0, rho1; /* RobustKernelHuber::robustify robust_kernel_impl.cpp:78-91 */
+    if (c2 <= c.hub_dsqr) { rho0 = c2; rho1 = 1.0; }
+    else { const double sq = sqrt(c2); rho0 = 2 * sq * c.hub_delta - c.hub_dsqr; rho1 = c.hub_delta / sq; }
+    chi += rho0;
+    if (store) {
+      double *S = c.ws.S;
+      /* camera Jacobian at the interpolated point, from the node images like
+       * the reference (xyz = sum b_k (R x_k + t))  sft_types.h:151-174 */
+      const int v[3] = {pb.match_nodes[3 * m], pb.match_nodes[3 * m + 1], pb.match_nodes[3 * m + 2]};
+      const double b[3] = {pb.match_bary[3 * m], pb.match_bary[3 * m + 1], pb.match_bary[3 * m + 2]};
+      double xk[3][3];
+      for (int k = 0; k < 3; k++) pose_map(P, &x[3 * v[k]], xk[k]);
+      const double X = xk[0][0] * b[0] + xk[1][0] * b[1] + xk[2][0] * b[2];
+      const double Y = xk[0][1] * b[0] + xk[1][1] * b[1] + xk[2][1] * b[2];
+      const double Z = xk[0][2] * b[0] + xk[1][2] * b[1] + xk[2][2] * b[2];
+      const double Z2 = Z * Z, fx = pb.fx, fy = pb.fy;
+      S[0 * M + s] = e[0];
+      S[1 * M + s] = e[1];
+      S[2 * M + s] = rho1 * info;
+      S[3 * M + s] = X * Y / Z2 * fx;
+      S[4 * M + s] = -(1 + (X * X / Z2)) * fx;
+      S[5 * M + s] = Y / Z * fx;
+      S[6 * M + s] = -1. / Z * fx;
+      S[7 * M + s] = 0;
+      S[8 * M + s] = X / Z2 * fx;
+      S[9 * M + s] = (1 + Y * Y / Z2) * fy;
+      S[10 * M + s] = -X * Y / Z2 * fy;
+      S[11 * M + s] = -X / Z * fy;
+      S[12 * M + s] = 0;
+      S[13 * M + s] = -1. / Z * fy;
+      S[14 * M + s] = Y / Z2 * fy;
+      const int code = c.ws.mfac[m];
+      S[(15 + (code & 3)) * M + s] = b[0];
+      S[(15 + ((code >> 2) & 3)) * M + s] = b[1];
+      S[(15 + ((code >> 4) & 3)) * M + s] = b[2];
+    }
+  }
+  /* temporal (EdgesReference sft_types.h:403-408), curvature, per-node A */
+  DS_FOR(v, n) {
+    if (c.viewed[v]) {
+      const double e0 = x[3 * v] - pl.rest[3 * v], e1 = x[3 * v + 1] - pl.rest[3 * v + 1],
+                   e2 = x[3 * v + 2] - pl.rest[3 * v + 2];
+      chi += (e0 * e0 + e1 * e1 + e2 * e2) * c.info_ref;
+    }
+    const bool active = c.freev[v] && !pl.boundary[v] && (pl.nbr_ptr[v + 1] > pl.nbr_ptr[v]);
+    if (active) {
+      double d[3], nrm;
+      const double r = curv_residual(c, x, v, d, nrm);
+      const double g = c.info_curv * pl.inv_len2[v];
+      chi += r * r * g;
+      if (store) {
+        const double inv = nrm < 1E-15 ? 0.0 : 1.0 / nrm;
+        cd[3 * v] = d[0] * inv; cd[3 * v + 1] = d[1] * inv; cd[3 * v + 2] = d[2] * inv;
+        cg[v] = g; cr[v] = r;
+      }
+    } else if (store) {
+      cd[3 * v] = cd[3 * v + 1] = cd[3 * v + 2] = 0.0; cg[v] = 0.0; cr[v] = 0.0;
+    }
+    if (store) { /* A_v = -(1/z) [fx 0 -x/z fx; 0 fy -y/z fy] R   sft_types.h:176-190 */
+      double p[3];
+      pose_map(P, &x[3 * v], p);
+      const double t02 = -p[0] / p[2] * pb.fx, t12 = -p[1] / p[2] * pb.fy, mz = -1. / p[2];
+      for (int k = 0; k < 3; k++) {
+        A[6 * v + k] = mz * (pb.fx * R[k] + t02 * R[6 + k]);
+        A[6 * v + 3 + k] = mz * (pb.fy * R[3 + k] + t12 * R[6 + k]);
+      }
+    }
+  }
+  /* stretch (EdgesStreching sft_types.h:353-378) */
+  DS_FOR(e, ne) {
+    const int a = pl.edge_ab[2 * e], b = pl.edge_ab[2 * e + 1];
+    const bool active = c.freev[a] || c.freev[b];
+    if (active) {
+      const double d0 = x[3 * a] - x[3 * b], d1 = x[3 * a + 1] - x[3 * b + 1], d2 = x[3 * a + 2] - x[3 * b + 2];
+      const double nrm = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+      const double l0 = pl.edge_len0[e];
+      const double r = nrm * (1.0 / l0) - 1.0;
+      chi += r * c.info_str * r;
+      if (store) {
+        const double ddo = 1.0 / (nrm * l0);
+        eu[3 * e] = d0 * ddo; eu[3 * e + 1] = d1 * ddo; eu[3 * e + 2] = d2 * ddo;
+        er[e] = r; es[e] = c.info_str;
+      }
+    } else if (store) {
+      eu[3 * e] = eu[3 * e + 1] = eu[3 * e + 2] = 0.0; er[e] = 0.0; es[e] = 0.0;
+    }
+  }
+  return team_sum(team, chi, c.sm + c.sl.red);
+}
+
+/* ------------------------------------------------ normal equations ----- */
+
+/* BlockSolver::buildSystem for this graph.  Needs eval_state(store=true) at the
+ * same state.  Produces Hb (band), Cg rows 0-5 (camera border), Cg row 6 (b_n),
+ * Hcc/bc (shared).  Returns max |diag| over the free variables
+ * (computeLambdaInit, optimization_algorithm_levenberg.cpp:166-180). */
+DS_FN_NOINLINE double build_system(Ctx &c) {
+  const Team team = c.team;
+  const PlanView &pl = c.pl;
+  const int n = pl.n_nodes, ne = pl.n_edges, nf = pl.n_facets, M = c.pb.n_matches;
+  const int bw = pl.bw, ld = pl.ld, Dp = pl.Dn_pad;
+  const double *A = c.sm + c.sl.W;
+  const double *cd = A + 6 * n, *cg = cd + 3 * n, *cr = cg + n, *eu = cr + n, *er = eu + 3 * ne, *es = er + ne;
+  double *F = c.ws.F;
+  const double *S = c.ws.S;
+  double *Hcc = c.sm + c.sl.Hcc;
+  (void)M;
+  team.sync();
+
+  /* (1) per-facet sums.  item = (facet, group) */
+  DS_FOR(it, nf * 6) {
+    const int f = it / 6, g = it - 6 * f;
+    const int sb = c.ws.fptr[f], se = c.ws.fptr[f + 1];
+    const int Mm = c.pb.n_matches;
+    if (g == 0) {
+      double a[12];
+      for (int k = 0; k < 12; k++) a[k] = 0.0;
+      for (int s = sb; s < se; s++) {
+        const double w = S[2 * Mm + s], e0 = S[s], e1 = S[Mm + s];
+        const double b0 = S[15 * Mm + s], b1 = S[16 * Mm + s], b2 = S[17 * Mm + s];
+        a[0] += w * b0 * b0; a[1] += w * b0 * b1; a[2] += w * b0 * b2;
+        a[3] += w * b1 * b1; a[4] += w * b1 * b2; a[5] += w * b2 * b2;
+        a[6] += w * b0 * e0; a[7] += w * b0 * e1;
+        a[8] += w * b1 * e0; a[9] += w * b1 * e1;
+        a[10] += w * b2 * e0; a[11] += w * b2 * e1;
+      }
+      for (int k = 0; k < 12; k++) F[k * nf + f] = a[k];
+    } else if (g <= 3) {
+      double a[12];
+      for (int k = 0; k < 12; k++) a[k] = 0.0;
+      for (int s = sb; s < se; s++) {
+        const double wb = S[2 * Mm + s] * S[(14 + g) * Mm + s];
+        for (int k = 0; k < 12; k++) a[k] += wb * S[(3 + k) * Mm + s];
+      }
+      for (int k = 0; k < 12; k++) F[(12 * g + k) * nf + f] = a[k];
+    } else {
+      /* camera block: 21 upper entries of Jc^T w Jc, then 6 of Jc^T w e */
+      const int lo = g == 4 ? 0 : 14, hi = g == 4 ? 14 : 27;
+      double a[14];
+      for (int k = 0; k < 14; k++) a[k] = 0.0;
+      for (int s = sb; s < se; s++) {
+        const double w = S[2 * Mm + s], e0 = S[s], e1 = S[Mm + s];
+        double J[12];
+        for (int k = 0; k < 12; k++) J[k] = S[(3 + k) * Mm + s];
+        int idx = 0;
+        for (int r = 0; r < 6; r++)
+          for (int q = r; q < 6; q++, idx++)
+            if (idx >= lo && idx < hi) a[idx - lo] += w * (J[r] * J[q] + J[6 + r] * J[6 + q]);
+        for (int r = 0; r < 6; r++, idx++)
+          if (idx >= lo && idx < hi) a[idx - lo] += w * (J[r] * e0 + J[6 + r] * e1);
+      }
+      for (int k = lo; k < hi; k++) F[(48 + k) * nf + f] = a[k - lo];
+    }
+  }
+  team.sync();
+
+  /* (2) camera-camera block and b_c: reduction over facets in facet order */
+  DS_FOR(k, 27) {
+    double s = 0.0;
+    const double *Fk = &F[(48 + k) * nf];
+    for (int f = 0; f < nf; f++) s += Fk[f];
+    if (k < 21) {
+      int r = 0, rem = k;
+      while (rem >= 6 - r) { rem -= 6 - r; r++; }
+      const int q = r + rem;
+      Hcc[r * 6 + q] = s; Hcc[q * 6 + r] = s;
+    } else {
+      Hcc[36 + (k - 21)] = -s;
+    }
+  }
+
+  /* (3) node-node blocks: gather */
+  double maxd = 0.0;
+  DS_FOR(bi, pl.n_blk) {
+    const int p = pl.blk_pq[2 * bi], q = pl.blk_pq[2 * bi + 1];
+    double h[9];
+    for (int k = 0; k < 9; k++) h[k] = 0.0;
+    const bool fp = c.freev[p], fq = c.freev[q];
+    if (fp && fq) {
+      /* reprojection: (sum over shared facets of sum_m w b_p b_q) * A_p^T A_q */
+      double beta = 0.0;
+      for (int k = pl.blk_fac_ptr[bi]; k < pl.blk_fac_ptr[bi + 1]; k++) {
+        const int ent = pl.blk_fac[k], f = ent >> 4, sp = (ent >> 2) & 3, sq = ent & 3;
+        const int lo = sp < sq ? sp : sq, hi = sp < sq ? sq : sp;
+        const int idx = lo == 0 ? hi : (lo == 1 ? 2 + hi : 5); /* (0,0)0 (0,1)1 (0,2)2 (1,1)3 (1,2)4 (2,2)5 */
+        beta += F[idx * nf + f];
+      }
+      const double *Ap = &A[6 * p], *Aq = &A[6 * q];
+      for (int r = 0; r < 3; r++)
+        for (int s = 0; s < 3; s++) h[3 * r + s] = beta * (Ap[r] * Aq[s] + Ap[3 + r] * Aq[3 + s]);
+      /* curvature: g_i c_ip c_iq d_i d_i^T */
+      for (int k = pl.blk_ctr_ptr[bi]; k < pl.blk_ctr_ptr[bi + 1]; k++) {
+        const int i = pl.blk_ctr[3 * k], ip = pl.blk_ctr[3 * k + 1], iq = pl.blk_ctr[3 * k + 2];
+        const double g = cg[i];
+        if (g == 0.0) continue;
+        const double cp = ip < 0 ? 1.0 : -pl.nbr_c[ip], cq = iq < 0 ? 1.0 : -pl.nbr_c[iq];
+        const double gc = g * cp * cq;
+        const double *d = &cd[3 * i];
+        for (int r = 0; r < 3; r++)
+          for (int s = 0; s < 3; s++) h[3 * r + s] += gc * d[r] * d[s];
+      }
+      /* stretch */
+      if (p == q) {
+        for (int k = pl.ne_ptr[p]; k < pl.ne_ptr[p + 1]; k++) {
+          const int e = pl.ne_ent[k] >> 1;
+          const double w = es[e];
+          const double *u = &eu[3 * e];
+          for (int r = 0; r < 3; r++)
+            for (int s = 0; s < 3; s++) h[3 * r + s] += w * u[r] * u[s];
+        }
+        if (c.viewed[p]) { h[0] += c.info_ref; h[4] += c.info_ref; h[8] += c.info_ref; }
+      } else if (pl.blk_edge[bi] >= 0) {
+        const int e = pl.blk_edge[bi];
+        const double w = es[e];
+        const double *u = &eu[3 * e];
+        for (int r = 0; r < 3; r++)
+          for (int s = 0; s < 3; s++) h[3 * r + s] -= w * u[r] * u[s];
+      }
+    } else if (p == q) {
+      h[0] = h[4] = h[8] = 1.0; /* fixed vertex: identity rows */
+    }
+    /* rows of p (i), cols of q (j <= i) */
+    for (int r = 0; r < 3; r++) {
+      const int i = 3 * p + r;
+      for (int s = 0; s < 3; s++) {
+        const int j = 3 * q + s;
+        if (j > i) continue;
+        c.ws.Hb[i * ld + (j - i + bw)] = h[3 * r + s];
+      }
+      if (p == q && fp) maxd = fmax(maxd, fabs(h[4 * r]));
+    }
+  }
+
+  /* (4) per-node gradient b_n and camera border C */
+  DS_FOR(p, n) {
+    double b[3] = {0, 0, 0}, C[18];
+    for (int k = 0; k < 18; k++) C[k] = 0.0;
+    if (c.freev[p]) {
+      const double *Ap = &A[6 * p];
+      double be0 = 0, be1 = 0, bj[12];
+      for (int k = 0; k < 12; k++) bj[k] = 0.0;
+      for (int k = pl.nf_ptr[p]; k < pl.nf_ptr[p + 1]; k++) {
+        const int f = pl.nf_ent[k] >> 2, sl = pl.nf_ent[k] & 3;
+        be0 += F[(6 + 2 * sl) * nf + f];
+        be1 += F[(7 + 2 * sl) * nf + f];
+        for (int t = 0; t < 12; t++) bj[t] += F[(12 * (sl + 1) + t) * nf + f];
+      }
+      for (int r = 0; r < 3; r++) b[r] = -(Ap[r] * be0 + Ap[3 + r] * be1);
+      /* C[a][r] = sum_rows bj[row][a] * Ap[row][r] */
+      for (int a = 0; a < 6; a++)
+        for (int r = 0; r < 3; r++) C[3 * a + r] = bj[a] * Ap[r] + bj[6 + a] * Ap[3 + r];
+      if (c.viewed[p])
+        for (int r = 0; r < 3; r++) b[r] -= c.info_ref * ((c.sm + c.sl.x)[3 * p + r] - pl.rest[3 * p + r]);
+      for (int k = pl.nc_ptr[p]; k < pl.nc_ptr[p + 1]; k++) {
+        const int i = pl.nc_ent[2 * k], ip = pl.nc_ent[2 * k + 1];
+        const double g = cg[i];
+        if (g == 0.0) continue;
+        const double cp = ip < 0 ? 1.0 : -pl.nbr_c[ip];
+        const double s = g * cp * cr[i];
+        for (int r = 0; r < 3; r++) b[r] -= s * cd[3 * i + r];
+      }
+      for (int k = pl.ne_ptr[p]; k < pl.ne_ptr[p + 1]; k++) {
+        const int ent = pl.ne_ent[k], e = ent >> 1;
+        const double s = (ent & 1) ? es[e] * er[e] : -es[e] * er[e];
+        for (int r = 0; r < 3; r++) b[r] += s * eu[3 * e + r];
+      }
+    }
+    for (int r = 0; r < 3; r++) {
+      c.ws.Cg[6 * Dp + 3 * p + r] = b[r];
+      for (int a = 0; a < 6; a++) c.ws.Cg[a * Dp + 3 * p + r] = C[3 * a + r];
+    }
+  }
+  maxd = team_max(team, maxd, c.sm + c.sl.red); /* also a barrier: Hcc complete */
+  for (int k = 0; k < 6; k++) maxd = fmax(maxd, fabs(Hcc[7 * k]));
+  return maxd;
+}
+
+/* ------------------------------------------- banded Cholesky + solve --- */
+
+/* Solve (H + lambda I) dx = b.  dx -> sm[sl.dx] (nodes, then camera at Dn_pad).
+ * Returns false if a pivot is not positive (LinearSolverDense::solve returning
+ * false, linear_solver_dense.h:107-112); dx is then left untouched (stale), as
+ * in the reference. */
+DS_FN_NOINLINE bool factor_solve(Ctx &c, double lambda) {
+  const Team team = c.team;
+  const PlanView &pl = c.pl;
+  const int bw = pl.bw, ld = pl.ld, Dp = pl.Dn_pad, Wr = pl.Wr, bwp = pl.bwp, nblk = pl.nblk;
+  const int PS = bwp + 8;
+  double *W = c.sm + c.sl.W, *P = c.sm + c.sl.P, *Lkk = c.sm + c.sl.Lkk, *invL = c.sm + c.sl.invL;
+  double *G = c.sm + c.sl.G, *Hcc = c.sm + c.sl.Hcc, *dx = c.sm + c.sl.dx;
+  double *E = c.E;
+  int *flag = (int *)(c.sm + c.sl.red + 36);
+  const int nt = bwp / TILE;
+
+  team.sync();
+  /* window <- first Wr rows of H; border/rhs working copy; corner */
+  {
+    const int rows = Wr < Dp ? Wr : Dp;
+    DS_FOR(i, rows * ld) W[i] = c.ws.Hb[i];
+    DS_FOR(i, 8 * Dp) E[i] = c.ws.Cg[i];
+    DS_FOR(i, 64) {
+      const int a = i >> 3, b = i & 7;
+      double v = 0.0;
+      if (a < 6 && b < 6) v = Hcc[a * 6 + b] + (a == b ? lambda : 0.0);
+      else if (a == 6 && b < 6) v = Hcc[36 + b];
+      G[i] = v;
+    }
+    if (team.tid == 0) *flag = 0;
+  }
+  team.sync();
+
+  for (int kb = 0; kb < nblk; kb++) {
+    const int k = kb * NB;
+    /* S1: factor the diagonal block (warp 0) */
+    if (team.warp0()) {
+      DS_WARP_FOR(l, 64) {
+        const int a = l >> 3, b = l & 7;
+        double v = 0.0;
+        if (b <= a) {
+          const int i = k + a, j = k + b;
+          v = W[(i % Wr) * ld + (j - i + bw)];
+          if (a == b) v += lambda;
+        }
+        Lkk[l] = v;
+        invL[l] = 0.0;
+      }
+      team.warp_sync();
+      for (int cc = 0; cc < NB; cc++) {
+        const double d = Lkk[cc * 8 + cc];
+        const bool pos = d > 0.0;
+#if DS_CUDA
+        const double inv = rsqrt(d);
+#else
+        const double inv = 1.0 / sqrt(d);
+#endif
+        team.warp_sync();
+        DS_WARP_FOR(a, NB) {
+          if (a == cc) { Lkk[cc * 8 + cc] = d * inv; P[a] = inv; if (!pos) *flag = 1; }
+          else if (a > cc) Lkk[a * 8 + cc] *= inv;
+        }
+        team.warp_sync();
+        DS_WARP_FOR(l, 64) {
+          const int a = l >> 3, b = l & 7;
+          if (b > cc && a >= b) Lkk[a * 8 + b] -= Lkk[a * 8 + cc] * Lkk[b * 8 + cc];
+        }
+        team.warp_sync();
+      }
+      /* inverse of the lower-triangular block, one column per lane; P[0..7] = 1/diag */
+      DS_WARP_FOR(j, NB) {
+        double X[NB];
+        for (int a = 0; a < NB; a++) {
+          double s = (a == j) ? 1.0 : 0.0;
+          for (int m = j; m < a; m++) s -= Lkk[a * 8 + m] * X[m];
+          X[a] = (a >= j) ? s * P[a] : 0.0;
+          invL[a * 8 + j] = X[a];
+        }
+      }
+      team.warp_sync();
+      DS_WARP_FOR(l, 64) {
+        const int a = l >> 3, b = l & 7;
+        if (b <= a) {
+          const int i = k + a, j = k + b;
+          W[(i % Wr) * ld + (j - i + bw)] = Lkk[l];
+        }
+        c.ws.Dinv[kb * 64 + l] = invL[l];
+      }
+    }
+    team.sync();
+
+    /* S2: panel = rows below (and the 8 border rows) times L_kk^-T */
+    const int n_trail = (Dp - (k + NB)) < bwp ? (Dp - (k + NB)) : bwp;
+    DS_FOR(r, bwp + 8) {
+      double a[NB], xr[NB];
+      int slot = -1, i = 0;
+      if (r < bwp) {
+        i = k + NB + r;
+        if (r < n_trail) {
+          slot = (i % Wr) * ld;
+          for (int cc = 0; cc < NB; cc++) {
+            const int off = k + cc - i + bw;
+            a[cc] = off >= 0 ? W[slot + off] : 0.0;
+          }
+        } else {
+          for (int cc = 0; cc < NB; cc++) a[cc] = 0.0;
+        }
+      } else {
+        const int e = r - bwp;
+        for (int cc = 0; cc < NB; cc++) a[cc] = E[e * Dp + k + cc];
+      }
+      for (int cc = 0; cc < NB; cc++) {
+        double s = 0.0;
+        for (int m = 0; m <= cc; m++) s += a[m] * invL[cc * 8 + m];
+        xr[cc] = s;
+        P[cc * PS + r] = s;
+      }
+      if (r < bwp) {
+        if (slot >= 0)
+          for (int cc = 0; cc < NB; cc++) {
+            const int off = k + cc - i + bw;
+            if (off >= 0) W[slot + off] = xr[cc];
+          }
+      } else {
+        const int e = r - bwp;
+        for (int cc = 0; cc < NB; cc++) E[e * Dp + k + cc] = xr[cc];
+      }
+    }
+    team.sync();
+
+    /* S3: trailing update (window, border rows, corner) with 4x4 register tiles */
+    {
+      const int ntr = nt + 2;
+      const int ntiles = ntr * (ntr + 1) / 2;
+      DS_FOR(t, ntiles) {
+        int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+        while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
+        while (ti * (ti + 1) / 2 > t) ti--;
+        const int tj = t - ti * (ti + 1) / 2;
+        const bool erow = ti >= nt, ecol = tj >= nt;
+        if (!erow && TILE * ti >= n_trail) continue;
+        if (!ecol && TILE * tj >= n_trail) continue;
+        const int r0 = erow ? bwp + TILE * (ti - nt) : TILE * ti;
+        const int c0 = ecol ? bwp + TILE * (tj - nt) : TILE * tj;
+        double acc[TILE][TILE];
+        for (int a = 0; a < TILE; a++)
+          for (int b = 0; b < TILE; b++) acc[a][b] = 0.0;
+        for (int cc = 0; cc < NB; cc++) {
+          double pa[TILE], pb[TILE];
+          for (int a = 0; a < TILE; a++) { pa[a] = P[cc * PS + r0 + a]; pb[a] = P[cc * PS + c0 + a]; }
+          for (int a = 0; a < TILE; a++)
+            for (int b = 0; b < TILE; b++) acc[a][b] += pa[a] * pb[b];
+        }
+        if (!erow) {
+          for (int a = 0; a < TILE; a++) {
+            const int i = k + NB + r0 + a;
+            const int slot = (i % Wr) * ld;
+            for (int b = 0; b < TILE; b++) {
+              const int j = k + NB + c0 + b;
+              const int off = j - i + bw;
+              if (j <= i && off >= 0) W[slot + off] -= acc[a][b];
+            }
+          }
+        } else if (!ecol) {
+          for (int a = 0; a < TILE; a++) {
+            const int e = r0 - bwp + a;
+            for (int b = 0; b < TILE; b++) E[e * Dp + k + NB + c0 + b] -= acc[a][b];
+          }
+        } else {
+          for (int a = 0; a < TILE; a++)
+            for (int b = 0; b < TILE; b++) {
+              const int e = r0 - bwp + a, e2 = c0 - bwp + b;
+              if (e2 <= e) G[e * 8 + e2] -= acc[a][b];
+            }
+        }
+      }
+      /* finished rows k..k+7 -> L (global); refill their slots with rows k+Wr.. */
+      {
+        const int slot = (k % Wr) * ld;
+        const bool refill = k + Wr < Dp;
+        DS_FOR(i, NB * ld) {
+          c.ws.Lb[k * ld + i] = W[slot + i];
+          if (refill) W[slot + i] = c.ws.Hb[(k + Wr) * ld + i];
+        }
+      }
+    }
+    team.sync();
+  }
+
+  /* Schur complement system of the camera: S dc = rhs  (6x6 Cholesky) */
+  if (team.tid == 0) {
+    double Sx[36], rhs[6];
+    for (int a = 0; a < 6; a++) {
+      for (int b = 0; b <= a; b++) Sx[a * 6 + b] = G[a * 8 + b];
+      rhs[a] = G[6 * 8 + a];
+    }
+    bool ok = true;
+    for (int j = 0; j < 6; j++) {
+      double d = Sx[j * 6 + j];
+      for (int m = 0; m < j; m++) d -= Sx[j * 6 + m] * Sx[j * 6 + m];
+      if (!(d > 0.0)) ok = false;
+      const double l = sqrt(d);
+      Sx[j * 6 + j] = l;
+      for (int i = j + 1; i < 6; i++) {
+        double s = Sx[i * 6 + j];
+        for (int m = 0; m < j; m++) s -= Sx[i * 6 + m] * Sx[j * 6 + m];
+        Sx[i * 6 + j] = s / l;
+      }
+    }
+    if (!ok) *flag = 1;
+    if (*flag == 0) {
+      double y[6];
+      for (int i = 0; i < 6; i++) {
+        double s = rhs[i];
+        for (int m = 0; m < i; m++) s -= Sx[i * 6 + m] * y[m];
+        y[i] = s / Sx[i * 6 + i];
+      }
+      for (int i = 5; i >= 0; i--) {
+        double s = y[i];
+        for (int m = i + 1; m < 6; m++) s -= Sx[m * 6 + i] * y[m];
+        y[i] = s / Sx[i * 6 + i];
+      }
+      for (int i = 0; i < 6; i++) dx[Dp + i] = y[i];
+    }
+  }
+  team.sync();
+  if (*flag != 0) { team.sync(); return false; }
+
+  /* v = z - Y^T dc */
+  DS_FOR(i, Dp) {
+    double s = E[6 * Dp + i];
+    for (int e = 0; e < 6; e++) s -= E[e * Dp + i] * dx[Dp + e];
+    dx[i] = s;
+  }
+  /* backward sweep  L^T dn = v, one block of NB rows per step, rows of L
+   * streamed back from global through two buffers in the (now free) window */
+  double *LR0 = W, *LR1 = W + NB * ld + 64;
+  {
+    const int k = (nblk - 1) * NB;
+    DS_FOR(i, NB * ld) LR0[i] = c.ws.Lb[k * ld + i];
+    DS_FOR(i, 64) LR0[NB * ld + i] = c.ws.Dinv[(nblk - 1) * 64 + i];
+  }
+  team.sync();
+  for (int kb = nblk - 1; kb >= 0; kb--) {
+    const int k = kb * NB;
+    double *LR = ((nblk - 1 - kb) & 1) ? LR1 : LR0;
+    double *LRn = ((nblk - 1 - kb) & 1) ? LR0 : LR1;
+    const double *Di = LR + NB * ld;
+    /* prefetch the next block while this one is processed */
+    if (kb > 0) {
+      const int kn = (kb - 1) * NB;
+      DS_FOR(i, NB * ld) LRn[i] = c.ws.Lb[kn * ld + i];
+      DS_FOR(i, 64) LRn[NB * ld + i] = c.ws.Dinv[(kb - 1) * 64 + i];
+    }
+    /* d = invL^T y  (8 values; every thread that needs them recomputes from smem) */
+    DS_FOR(cc, NB) {
+      double s = 0.0;
+      for (int a = cc; a < NB; a++) s += Di[a * 8 + cc] * dx[k + a];
+      P[cc] = s;
+    }
+    team.sync();
+    DS_FOR(cc, NB) dx[k + cc] = P[cc];
+    {
+      const int j0 = k - bw > 0 ? k - bw : 0;
+      DS_FOR(jj, k - j0) {
+        const int j = j0 + jj;
+        double s = dx[j];
+        for (int a = 0; a < NB; a++) {
+          const int off = j - (k + a) + bw;
+          if (off >= 0) s -= LR[a * ld + off] * P[a];
+        }
+        dx[j] = s;
+      }
+    }
+    team.sync();
+  }
+  return true;
+}
+
+/* ------------------------------------------------------------- LM ------ */
+
+DS_FN void apply_update(Ctx &c) {
+  const Team team = c.team;
+  const PlanView &pl = c.pl;
+  double *x = c.sm + c.sl.x, *dx = c.sm + c.sl.dx;
+  /* VertexSBAPointXYZ::oplusImpl (types_sba.h:52-56); fixed nodes have dx = 0 */
+  DS_FOR(i, pl.Dn) x[i] += dx[i];
+  if (team.tid == 0) { /* VertexSE3Expmap::oplusImpl */
+    Pose P;
+    load_pose(c.sm + c.sl.pose, P);
+    pose_oplus(P, &dx[pl.Dn_pad]);
+    double *ps = c.sm + c.sl.pose;
+    for (int k = 0; k < 4; k++) ps[k] = P.q[k];
+    for (int k = 0; k < 3; k++) ps[4 + k] = P.t[k];
+  }
+  team.sync();
+}
+
+DS_FN void expand_dense(Ctx &c, double chi) {
+  const Team team = c.team;
+  const PlanView &pl = c.pl;
+  const int Dn = pl.Dn, D = Dn + 6, bw = pl.bw, ld = pl.ld, Dp = pl.Dn_pad;
+  const double *Hcc = c.sm + c.sl.Hcc;
+  team.sync();
+  if (c.pb.out_H) {
+    DS_FOR(idx, D * D) {
+      const int i = idx / D, j = idx - i * D;
+      const int hi = i > j ? i : j, lo = i > j ? j : i;
+      double v = 0.0;
+      if (hi < Dn) { if (hi - lo <= bw) v = c.ws.Hb[hi * ld + (lo - hi + bw)]; }
+      else if (lo < Dn) v = c.ws.Cg[(hi - Dn) * Dp + lo];
+      else v = Hcc[(hi - Dn) * 6 + (lo - Dn)];
+      c.pb.out_H[idx] = v;
+    }
+  }
+  if (c.pb.out_b) {
+    DS_FOR(i, D) {
+      double v = i < Dn ? c.ws.Cg[6 * Dp + i] : Hcc[36 + (i - Dn)];
+      if (i < Dn && !c.freev[i / 3]) v = 0.0;
+      c.pb.out_b[i] = v;
+    }
+  }
+  if (team.tid == 0) {
+    c.pb.out_res->chi2_initial = chi;
+    c.pb.out_res->chi2_final = chi;
+    c.pb.out_res->status = 0;
+    c.pb.out_res->n_viewed = c.n_viewed;
+    c.pb.out_res->n_optlap = c.n_optlap;
+  }
+}
+
+/* DefOptimizer.cc:515-577 */
+DS_FN_NOINLINE void finalize(Ctx &c, bool last_rejected, int iterations, int trials, double chi_ini, double chi_fin,
+                             double lambda) {
+  const Team team = c.team;
+  const PlanView &pl = c.pl;
+  const ProbView &pb = c.pb;
+  const int M = pb.n_matches, n = pl.n_nodes;
+  const double *x = c.sm + c.sl.x, *xb = c.sm + c.sl.xb;
+  Pose P, Pb;
+  load_pose(c.sm + c.sl.pose, P);
+  load_pose(c.sm + c.sl.pose + 8, Pb);
+  /* e->chi2() is the error of the LAST computeActiveErrors, i.e. of the last LM
+   * trial whether it was accepted or not (the state was popped, the edges were
+   * not re-evaluated). */
+  const double *xl = last_rejected ? xb : x;
+  const Pose &Pl = last_rejected ? Pb : P;
+  int nbad = 0, cnt = 0;
+  double sum = 0.0;
+  DS_FOR(m, M) {
+    double e[2], Pc[3];
+    reproj_error(c, xl, Pl, m, e, Pc);
+    const double info = match_info(c, m);
+    const float chi2 = (float)(e[0] * info * e[0] + e[1] * info * e[1]);
+    const bool out = chi2 > 5.991;
+    if (pb.out_outlier) pb.out_outlier[m] = out ? 1 : 0;
+    if (out) nbad++;
+    else {
+      reproj_error(c, x, P, m, e, Pc);
+      sum += sqrt(pow(e[0], 2) + pow(e[1], 2));
+      cnt++;
+    }
+  }
+  nbad = team_sum_int(team, nbad, c.sm + c.sl.red);
+  cnt = team_sum_int(team, cnt, c.sm + c.sl.red);
+  sum = team_sum(team, sum, c.sm + c.sl.red);
+  if (pb.out_nodes) DS_FOR(i, pl.Dn) pb.out_nodes[i] = x[i];
+  if (pb.out_role) DS_FOR(v, n) pb.out_role[v] = (uint8_t)(c.viewed[v] | (c.freev[v] << 1));
+  if (team.tid == 0) {
+    ResultScalars *r = pb.out_res;
+    pose_to_Tcw(P, r->Tcw);
+    r->rep_error = (float)(sum / (double)(unsigned)cnt);
+    r->n_inliers = M - nbad;
+    r->lm_iterations = iterations;
+    r->lm_trials = trials;
+    r->chi2_initial = chi_ini;
+    r->chi2_final = chi_fin;
+    r->lambda_final = lambda;
+    r->status = 0;
+    r->n_viewed = c.n_viewed;
+    r->n_optlap = c.n_optlap;
+  }
+}
+
+/* One frame, start to finish.  All threads of the team call this. */
+DS_FN_NOINLINE void sft_solve_one(Ctx &c) {
+  const Team team = c.team;
+  const PlanView &pl = c.pl;
+  const ProbView &pb = c.pb;
+  double *x = c.sm + c.sl.x, *xb = c.sm + c.sl.xb, *dx = c.sm + c.sl.dx;
+  double *ps = c.sm + c.sl.pose, *psb = ps + 8;
+  double *red = c.sm + c.sl.red;
+  const int Dp = pl.Dn_pad;
+
+  const int rc = prologue(c);
+  if (rc != 0) {
+    if (team.tid == 0) pb.out_res->status = rc;
+    return;
+  }
+  if (pb.mode == MODE_NORMAL_EQ) {
+    const double chi = eval_state(c, x, ps, true);
+    build_system(c);
+    expand_dense(c, chi);
+    return;
+  }
+
+  /* OptimizationAlgorithmLevenberg::solve, optimization_algorithm_levenberg.cpp:61-164,
+   * driven by SparseOptimizer::optimize, sparse_optimizer.cpp:403-475 */
+  const int max_it = pb.max_it > 0 ? pb.max_it : 50;
+  const double tau = 1e-5, goodUpper = 2. / 3., goodLower = 1. / 3.;
+  const int maxTrials = 10;
+  double lambda = -1., ni = 2., chi_ini0 = 0., chi_fin = 0.;
+  int nBad = 0, iterations = 0, trials = 0;
+  bool last_rejected = false;
+  for (int it = 0; it < max_it; it++) {
+    double currentChi = eval_state(c, x, ps, true);
+    double tempChi = currentChi;
+    const double iniChi = currentChi;
+    if (it == 0) chi_ini0 = currentChi;
+    const double maxDiag = build_system(c);
+    if (it == 0) { lambda = tau * maxDiag; ni = 2; nBad = 0; }
+    const double lambda_start = lambda;
+    double rho = 0;
+    int qmax = 0;
+    do {
+      /* push */
+      team.sync();
+      DS_FOR(i, pl.Dn) xb[i] = x[i];
+      if (team.tid == 0) for (int k = 0; k < 7; k++) psb[k] = ps[k];
+      const bool ok2 = factor_solve(c, lambda);
+      apply_update(c);
+      tempChi = eval_state(c, x, ps, false);
+      if (!ok2) tempChi = DBL_MAX;
+      rho = currentChi - tempChi;
+      double scale = 0.; /* computeScale :182-189 */
+      DS_FOR(j, pl.Dn) scale += dx[j] * (lambda * dx[j] + c.ws.Cg[6 * Dp + j]);
+      scale = team_sum(team, scale, red);
+      for (int j = 0; j < 6; j++) scale += dx[Dp + j] * (lambda * dx[Dp + j] + (c.sm + c.sl.Hcc)[36 + j]);
+      scale += 1e-3;
+      rho /= scale;
+      if (rho > 0 && isfinite(tempChi)) {
+        double alpha = 1. - pow((2 * rho - 1), 3);
+        alpha = fmin(alpha, goodUpper);
+        const double scaleFactor = fmax(goodLower, alpha);
+        lambda *= scaleFactor;
+        ni = 2;
+        currentChi = tempChi;
+        last_rejected = false;
+      } else {
+        lambda *= ni;
+        ni *= 2;
+        /* pop: restore; the backup buffers keep the rejected trial state */
+        team.sync();
+        DS_FOR(i, pl.Dn) { const double t = x[i]; x[i] = xb[i]; xb[i] = t; }
+        if (team.tid == 0) for (int k = 0; k < 7; k++) { const double t = ps[k]; ps[k] = psb[k]; psb[k] = t; }
+        team.sync();
+        last_rejected = true;
+      }
+      qmax++;
+      trials++;
+    } while (rho < 0 && qmax < maxTrials);
+    if (pb.out_trace && it < pb.trace_cap && team.tid == 0) {
+      pb.out_trace[4 * it + 0] = iniChi; pb.out_trace[4 * it + 1] = lambda_start;
+      pb.out_trace[4 * it + 2] = (double)qmax; pb.out_trace[4 * it + 3] = currentChi;
+    }
+    chi_fin = currentChi;
+    iterations = it + 1;
+    if (qmax == maxTrials || rho == 0) break;
+    if ((iniChi - currentChi) * 1e3 < iniChi) nBad++; else nBad = 0;
+    if (nBad >= 3) break;
+  }
+  team.sync();
+  finalize(c, last_rejected, iterations, trials, chi_ini0, chi_fin, lambda);
+}
+
+/* Entry shared by the CUDA kernel and the emulation: bind a problem to a team,
+ * its shared memory and its global workspace, then solve it. */
+DS_FN void sft_run_problem(const Team &team, const ProbView &pv, double *smem, uint8_t *ws_base,
+                           const WorkspaceSizes &z) {
+  Ctx c;
+  c.team = team;
+  c.pb = pv;
+  c.pl = *pv.plan;
+  c.ws = carve_workspace(ws_base, z);
+  c.sl = smem_layout(c.pl.n_nodes, c.pl.n_edges, c.pl.Dn_pad, c.pl.bwp, c.pl.ld, c.pl.Wr, pv.e_in_smem != 0);
+  c.sm = smem;
+  c.E = pv.e_in_smem ? smem + c.sl.E : c.ws.Eg;
+  c.viewed = (uint8_t *)(smem + c.sl.flags);
+  c.freev = c.viewed + c.pl.n_nodes;
+  sft_solve_one(c);
+}
+
+}  // namespace ds
+#endif

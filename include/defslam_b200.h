@@ -1,0 +1,315 @@
+/*
+ * defslam_b200.h -- C ABI of the B200-native DefSLAM deformable hot path.
+ *
+ * This is the drop-in boundary.  The reference has no
+ * FFI of its own: the path sits behind C++ free functions / classes.  Every
+ * entry point below names the reference interface it replaces (file:line under
+ * the DefSLAM tree).  All arrays are caller-owned, row-major, plain pointers
+ * and sizes; no C++ / torch types cross this boundary.
+ *
+ * Return codes (all entry points):
+ *    0  DEFSLAM_OK
+ *   -1  DEFSLAM_EBADARG   null pointer / inconsistent sizes / match references
+ *                         a node triple that is not coupled in the template
+ *   -2  DEFSLAM_ECUDA     CUDA runtime error or no CUDA device (there is NO
+ *                         CPU fallback: the call fails)
+ *   -3  DEFSLAM_ENUMERIC  non-finite input/outcome; outputs untouched, which
+ *                         mirrors the reference's silent "keep the previous
+ *                         estimate" behaviour
+ *   -4  DEFSLAM_ETOOLARGE problem does not fit the on-chip working set
+ */
+#ifndef DEFSLAM_B200_H_
+#define DEFSLAM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DEFSLAM_OK 0
+#define DEFSLAM_EBADARG (-1)
+#define DEFSLAM_ECUDA (-2)
+#define DEFSLAM_ENUMERIC (-3)
+#define DEFSLAM_ETOOLARGE (-4)
+
+/* ------------------------------------------------------------------------- *
+ *  Template (mesh) description
+ *  replaces the data the SfT solve reads out of defSLAM::Template / Node /
+ *  Edge / Facet / LaplacianMesh:
+ *    Modules/Template/Node.cc:114-129,193-204  (1-ring, rest pose, boundary)
+ *    Modules/Template/Edge.cc:29-59,72         (edge list, rest length)
+ *    Modules/Template/Facet.cc:32-62,77-80     (facet node triples)
+ *    Modules/Template/LaplacianMesh.cc:53-162  (mean-value weights, kappa0)
+ *    Modules/Template/Template.cc:158-175      (median edge length)
+ *  Node order is the caller's (grid order for the regular mesh); the
+ *  reference's std::set<Node*> address order is not reproducible.
+ * ------------------------------------------------------------------------- */
+typedef struct defslam_template_desc {
+  int32_t n_nodes;
+  int32_t n_edges;
+  int32_t n_facets;
+  const double *node_rest_xyz;  /* [n_nodes*3]  Node::xO,yO,zO                   */
+  const uint8_t *node_boundary; /* [n_nodes]    Node::isBoundary()               */
+  const int32_t *nbr_ptr;       /* [n_nodes+1]  CSR of Node::GetNeighbours()     */
+  const int32_t *nbr_idx;       /* [nbr_ptr[n]]                                  */
+  const double *nbr_w;          /* [nbr_ptr[n]] Node::weights (mean-value w_ij)  */
+  const double *node_kappa0;    /* [n_nodes]    |LaplacianCoords| (0 on boundary)*/
+  const int32_t *edge_ab;       /* [n_edges*2]                                   */
+  const double *edge_len0;      /* [n_edges]    Edge::getDist()                  */
+  const int32_t *facets;        /* [n_facets*3] Facet::getNodesArray()           */
+  double edge_median_len;       /* Template::getEdgeMeanSize() (the median)      */
+} defslam_template_desc;
+
+/* Opaque device-resident plan of a template (topology + Laplacian constants +
+ * the normal-matrix sparsity plan).  Lifetime mirrors defSLAM::Template as owned
+ * by DefMap (Modules/Common/DefMap.cc:55-82): create when the template is
+ * (re)built, destroy when it is replaced. */
+typedef struct defslam_template defslam_template;
+
+/* replaces: TemplateGenerator::LaplacianMeshCreate (TemplateGenerator.h:49-50)
+ * as far as the solver-visible state goes.  device < 0: current device. */
+int defslam_template_create(const defslam_template_desc *desc, int device,
+                            defslam_template **out);
+void defslam_template_destroy(defslam_template *t);
+
+/* ------------------------------------------------------------------------- *
+ *  Mesh Laplacian set-up (runs on the GPU)
+ *  replaces: LaplacianMesh::ExtractMeanCurvatures  LaplacianMesh.cc:53-148
+ *            Edge ctor rest lengths                Edge.cc:52
+ *            Template::getEdgeMeanSize             Template.cc:158-175
+ *  in : node xyz, facets.   out: everything a defslam_template_desc needs.
+ *  nbr_* use a fixed stride of max_ring entries per node (nbr_cnt[n] valid).
+ * ------------------------------------------------------------------------- */
+int defslam_mesh_laplacian(int32_t n_nodes, const double *node_xyz,
+                           int32_t n_facets, const int32_t *facets,
+                           int32_t max_ring,
+                           int32_t *nbr_cnt,       /* [n_nodes]              */
+                           int32_t *nbr_idx,       /* [n_nodes*max_ring]     */
+                           double *nbr_w,          /* [n_nodes*max_ring]     */
+                           uint8_t *node_boundary, /* [n_nodes]              */
+                           double *node_kappa0,    /* [n_nodes]              */
+                           int32_t *n_edges_out,
+                           int32_t *edge_ab,  /* [cap_edges*2], cap = 3*n_facets */
+                           double *edge_len0, /* [cap_edges]                 */
+                           double *edge_median_len);
+
+/* ------------------------------------------------------------------------- *
+ *  Shape-from-Template solve
+ *  replaces: defSLAM::Optimizer::DefPoseOptimization(Frame*,Map*,RegLap,
+ *            RegInex,RegTemp,NeighboursLayers)
+ *            Modules/Tracking/DefOptimizer.cc:251-578  (DefOptimizer.h:51-53)
+ *  and everything below it: sft_types.h edges, g2o LM + BlockSolverX +
+ *  LinearSolverDense.
+ * ------------------------------------------------------------------------- */
+typedef struct defslam_sft_problem {
+  /* template: either a plan handle, or (tmpl == NULL) an inline description
+   * from which a temporary plan is built for this call */
+  const defslam_template *tmpl;
+  const defslam_template_desc *tmpl_desc;
+
+  const double *node_xyz;         /* [n_nodes*3] current Node::x,y,z            */
+  int32_t n_matches;              /* matched map points that have a facet       */
+  int32_t n_frame_keypoints;      /* Frame::N -- the 1/N in Omega (:340)        */
+  const int32_t *match_nodes;     /* [n_matches*3] Facet::getNodes() order      */
+  const double *match_bary;       /* [n_matches*3] DefMapPoint::b1,b2,b3        */
+  const float *match_uv;          /* [n_matches*2] Frame::mvKeysUn[i].pt        */
+  const float *match_inv_sigma2;  /* [n_matches]   mvInvLevelSigma2[octave]     */
+  double fx, fy, cx, cy;          /* Frame::fx,fy,cx,cy                         */
+  float T_cw[16];                 /* Frame::mTcw, row-major 4x4 f32 (cv::Mat)   */
+  double reg_lap;                 /* RegLap                                     */
+  double reg_inex;                /* RegInex                                    */
+  double reg_temp;                /* RegTemp                                    */
+  int32_t neighbour_layers;       /* NeighboursLayers (>=1 behaves as 1, C3)    */
+  int32_t max_iterations;         /* optimizer.optimize(50) (:513); <=0 -> 50   */
+} defslam_sft_problem;
+
+typedef struct defslam_sft_result {
+  double *node_xyz_out;  /* [n_nodes*3]   Node::setXYZ values        (:570)    */
+  uint8_t *outlier_out;  /* [n_matches]   Frame::mvbOutlier[idx]     (:515-537)*/
+  uint8_t *node_role_out;/* [n_nodes] optional: bit0 viewed, bit1 in OptLap    */
+  float T_cw_out[16];    /* Frame::SetPose(Converter::toCvMat(SE3)) (:562-566) */
+  float rep_error;       /* Frame::repError                          (:559)    */
+  int32_t n_inliers;     /* return value nInitialCorrespondences-nBad (:577)   */
+  int32_t lm_iterations; /* outer iterations executed (optimize() return)      */
+  int32_t lm_trials;     /* total inner trials (linear solves)                 */
+  double chi2_initial;   /* activeRobustChi2 before the first iteration        */
+  double chi2_final;     /* currentChi after the last accepted step            */
+  double lambda_final;
+  /* optional LM trace for parity tests: one row per outer iteration
+   * {chi2 at start, lambda at start, trials, chi2 at end}; NULL to skip */
+  double *trace;         /* [trace_capacity*4]                                 */
+  int32_t trace_capacity;
+  int32_t status;        /* per-problem return code (batched call)             */
+} defslam_sft_result;
+
+int defslam_sft_solve(const defslam_sft_problem *p, defslam_sft_result *r);
+
+/* Batched-frames mode: nprob independent solves in one launch.  device = -1:
+ * current device.  Multi-GPU sharding is one process per GPU above this call
+ * (SURVEY.md section 8(e)). */
+int defslam_sft_solve_batched(int32_t nprob, const defslam_sft_problem *p,
+                              defslam_sft_result *r, int device);
+
+/* Normal equations at the current state (one LM linearisation, no step).
+ * replaces: SparseOptimizer::computeActiveErrors + activeRobustChi2
+ *           (sparse_optimizer.cpp:104-120) and BlockSolver::buildSystem
+ *           (block_solver.hpp:502-560) for the graph DefOptimizer.cc builds.
+ * Variable order: node 0 xyz, node 1 xyz, ..., then the 6 camera dofs
+ * (omega, upsilon).  Rows/cols of nodes outside OptLap are identity/zero.
+ * H_dense: [D*D] full symmetric, b: [D], D = 3*n_nodes + 6. */
+int defslam_sft_normal_equations(const defslam_sft_problem *p, double *H_dense,
+                                 double *b, double *chi2);
+
+/* Map-point write-back: x = sum_k b_k * node_k, stored fp32.
+ * replaces: DefMapPoint::RecalculatePosition  Modules/Common/DefMapPoint.cc:129-147 */
+int defslam_mappoints_recalculate(int32_t n_nodes, const double *node_xyz,
+                                  int32_t n_points, const int32_t *point_nodes,
+                                  const double *point_bary, float *point_xyz_out);
+
+/* ------------------------------------------------------------------------- *
+ *  Template construction helpers
+ * ------------------------------------------------------------------------- */
+/* Barycentric embedding of map points (fp32 arithmetic as in the reference).
+ * replaces: TriangularMesh::calculateFeaturesCoordinates / pointInTriangle
+ *           Modules/Template/TriangularMesh.cc:133-236
+ * out_facet[i] = facet index or -1; out_bary in the facet's ascending-node order */
+int defslam_embed_points(int32_t n_nodes, const double *node_xyz,
+                         int32_t n_facets, const int32_t *facets,
+                         int32_t n_points, const float *point_xyz,
+                         int32_t *out_facet, int32_t *out_nodes /*[n*3]*/,
+                         float *out_bary /*[n*3]*/);
+
+/* ------------------------------------------------------------------------- *
+ *  Bicubic B-spline (BBS) evaluation
+ *  replaces: BBS::EvalEigen   Thirdparty/BBS/bbs_coloc.cc:610-653
+ *            BBS::eval        Thirdparty/BBS/bbs.cc:155-195
+ * ------------------------------------------------------------------------- */
+typedef struct defslam_bbs {
+  double umin, umax;
+  int32_t nptsu;
+  double vmin, vmax;
+  int32_t nptsv;
+  int32_t valdim;
+} defslam_bbs;
+
+/* ctrl: [valdim * nptsu * nptsv], index valdim*((iu)*nptsv + iv) + d
+ * val : [nsites * valdim]  (site-major, like bbs.cc eval)                    */
+int defslam_bbs_eval(const defslam_bbs *bbs, const double *ctrl, int32_t nsites,
+                     const double *u, const double *v, int32_t du, int32_t dv,
+                     double *val);
+
+/* All six derivative orders (0,0),(1,0),(0,1),(2,0),(1,1),(0,2) in one pass.
+ * replaces: the 6x Warp::getEstimates calls  SchwarpDatabase.cc:243-264
+ * val6: [6 * nsites * valdim] */
+int defslam_bbs_eval6(const defslam_bbs *bbs, const double *ctrl, int32_t nsites,
+                      const double *u, const double *v, double *val6);
+
+/* Dense collocation matrix rows, 16 non-zeros per site.
+ * replaces: BBS::colocEigen / coloc_derivEigen  bbs_coloc.cc:76-207
+ * C: [nsites * nptsu*nptsv] row-major dense */
+int defslam_bbs_coloc(const defslam_bbs *bbs, int32_t nsites, const double *u,
+                      const double *v, int32_t du, int32_t dv, double *C);
+
+/* Dense bending-energy matrix (lambda = 1).
+ * replaces: BBS::BendingEigen  bbs_coloc.cc:406-507 / bending_ur bbs.cc:563-640
+ * B: [NC*NC], NC = nptsu*nptsv */
+int defslam_bbs_bending(const defslam_bbs *bbs, double *B);
+
+/* ------------------------------------------------------------------------- *
+ *  NRSfM stages
+ * ------------------------------------------------------------------------- */
+/* Schwarp fit between two keyframes.
+ * replaces: SchwarpDatabase::calculateSchwarps  Modules/Mapping/SchwarpDatabase.cc:145-349
+ *           Warps::Warp / Warps::Schwarzian     Modules/Mapping/Schwarp.cc
+ *           DefORBmatcher::CalculateInitialSchwarp (init only) DefORBmatcher.cc:111-187
+ */
+typedef struct defslam_schwarp_problem {
+  defslam_bbs bbs;            /* domain of KF1 (DefKeyFrame umin..vmax), valdim=2 */
+  int32_t n_matches;
+  const float *kp1;           /* [n*2] normalised keypoints in KF1               */
+  const float *kp2;           /* [n*2] normalised keypoints in KF2               */
+  const float *inv_sigma;     /* [n]   invSigma per match                        */
+  double lambda;              /* LocalMapping.Schwarp.Regularizer                */
+  double fx, fy;              /* as passed by the reference (fy,fx swap is the
+                                 caller's business, quirk C6)                   */
+  int32_t max_iterations;     /* 3 in the reference                              */
+  int32_t init_from_affine;   /* 1: x0 = (C'C + lambda*B)^-1 C' q2 (Warp::initialize) */
+  double *x;                  /* in/out [2*NC] control points, [all x; all y]    */
+} defslam_schwarp_problem;
+
+typedef struct defslam_diffprop {
+  /* per match, fp32 like Modules/Mapping/diffProp.h:52-88 */
+  float *warp_uv;   /* [n*2] warped position of kp1                             */
+  float *J12;       /* [n*4] a,b,c,d                                            */
+  float *J21;       /* [n*4] inverse                                            */
+  float *H12;       /* [n*6] uux,uuy,uvx,uvy,vvx,vvy                            */
+  uint8_t *keep;    /* [n]   0 if reprojection > 10 px (unlinked)               */
+  double cost_initial, cost_final;
+  int32_t iterations;
+} defslam_diffprop;
+
+int defslam_schwarp_fit(const defslam_schwarp_problem *p, defslam_diffprop *out);
+
+/* Residuals/Jacobian of the Schwarp cost at x (parity hook).
+ * replaces: Warp::Evaluate Schwarp.cc:235-303 + Schwarzian::Evaluate :368-543
+ * r: [2n + 4NC]; J: [(2n+4NC) * 2NC] row-major dense or NULL                 */
+int defslam_schwarp_evaluate(const defslam_schwarp_problem *p, double *r, double *J);
+
+/* Batched isometric-NRSfM normal estimation: one 2-unknown LM per map point.
+ * replaces: NormalEstimator::ObtainK1K2  Modules/Mapping/NormalEstimator.cc:38-229
+ *           PolySolver::getCoefficients/Evaluate Modules/Mapping/PolySolver.cc
+ * pair data is CSR by point. */
+typedef struct defslam_normals_problem {
+  int32_t n_points;
+  const int32_t *pair_ptr; /* [n_points+1]                                      */
+  const float *J12;        /* [npairs*4] a,b,c,d                                */
+  const float *H12;        /* [npairs*6] uux,uuy,uvx,uvy,vvx,vvy                */
+  const float *I1;         /* [npairs*2] point in KF1 (u,v)                     */
+  const float *I2;         /* [npairs*2] point in KF2 (u,v)                     */
+  const double *k_init;    /* [n_points*2] initial (k1,k2)                      */
+  int32_t max_iterations;  /* 200                                               */
+} defslam_normals_problem;
+
+int defslam_normals_batched(const defslam_normals_problem *p,
+                            double *k_out /*[n*2]*/, double *cov_out /*[n*4]*/,
+                            float *normal_out /*[n*3]*/, int32_t *iters_out);
+
+/* Shape-from-normals depth-spline solve.
+ * replaces: ShapeFromNormals::{obtainM,estimate}  Modules/Mapping/ShapeFromNormals.cc:81-260 */
+typedef struct defslam_sfn_problem {
+  defslam_bbs bbs;          /* valdim = 1                                       */
+  int32_t n_normals;
+  const float *uv;          /* [n*2] normalised keypoint                        */
+  const float *normals;     /* [n*3]                                            */
+  double bending;           /* LocalMapping.Bending                             */
+  double mean_depth;        /* DefKeyFrame::accMean (=1)                        */
+  int32_t n_eval;           /* sites where depth is evaluated afterwards        */
+  const float *eval_uv;     /* [n_eval*2]                                       */
+} defslam_sfn_problem;
+
+int defslam_sfn_solve(const defslam_sfn_problem *p, double *ctrl_out /*[NC]*/,
+                      float *xyz_out /*[n_eval*3] (u d, v d, d)*/);
+
+/* Surface -> template nodes.
+ * replaces: Surface::getVertex  Modules/Mapping/Surface.cc:125-161
+ * nodes_out: [xs*ys*3] fp32 (u d, v d, d), x-major outer loop */
+int defslam_surface_vertices(const defslam_bbs *bbs, const double *ctrl_depth,
+                             int32_t xs, int32_t ys, float *nodes_out);
+
+/* ------------------------------------------------------------------------- *
+ *  Library information
+ * ------------------------------------------------------------------------- */
+const char *defslam_version(void);
+/* number of kernel launches issued by this process through the library */
+int64_t defslam_kernel_launch_count(void);
+int defslam_device_count(void);
+/* device time (ms) of the kernels of the last batched solve on this thread,
+ * measured with CUDA events on the library's stream */
+double defslam_last_kernel_ms(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEFSLAM_B200_H_ */

@@ -1,0 +1,33 @@
+/* Oracle entry points.  TEST INFRASTRUCTURE ONLY -- see sft_oracle.c header. */
+#ifndef DEFSLAM_ORACLE_H_
+#define DEFSLAM_ORACLE_H_
+#include "../include/defslam_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- SfT (sft_oracle.c) ---- */
+int oracle_sft_solve(const defslam_sft_problem *p, defslam_sft_result *r);
+int oracle_sft_normal_equations(const defslam_sft_problem *p, double *H_dense, double *b, double *chi2);
+int oracle_sft_residuals(const defslam_sft_problem *p, double *res, double *J, int max_rows);
+int oracle_sft_residuals_pose(const defslam_sft_problem *p, const double *q, const double *t,
+                              const double *node_xyz, double *res, int max_rows);
+int oracle_sft_apply_update(const defslam_sft_problem *p, const double *d, double *node_xyz_out,
+                            float *T_cw_out, double *q_out, double *t_out);
+int oracle_mappoints_recalculate(int32_t n_nodes, const double *node_xyz, int32_t n_points,
+                                 const int32_t *point_nodes, const double *point_bary, float *out);
+
+/* ---- template (template_oracle.c) ---- */
+int oracle_regular_triangulation(int nodes_ver, int nodes_hor, int32_t *facets /*[2*(v-1)*(h-1)*3]*/);
+int oracle_mesh_laplacian(int32_t n_nodes, const double *node_xyz, int32_t n_facets, const int32_t *facets,
+                          int32_t max_ring, int32_t *nbr_cnt, int32_t *nbr_idx, double *nbr_w,
+                          uint8_t *node_boundary, double *node_kappa0, int32_t *n_edges_out,
+                          int32_t *edge_ab, double *edge_len0, double *edge_median_len);
+int oracle_embed_points(int32_t n_nodes, const double *node_xyz, int32_t n_facets, const int32_t *facets,
+                        int32_t n_points, const float *point_xyz, int32_t *out_facet, int32_t *out_nodes,
+                        float *out_bary);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
