@@ -15,7 +15,8 @@ c_float_p = C.POINTER(C.c_float)
 c_int32_p = C.POINTER(C.c_int32)
 c_uint8_p = C.POINTER(C.c_uint8)
 
-OK, EBADARG, ECUDA, ENUMERIC, ETOOLARGE = 0, -1, -2, -3, -4
+OK, EBADARG, ECUDA, ENUMERIC, ETOOLARGE, ENOTIMPL = 0, -1, -2, -3, -4, -5
+c_int64_p = C.POINTER(C.c_int64)
 
 
 class TemplateDesc(C.Structure):
@@ -151,6 +152,13 @@ class SfnProblem(C.Structure):
 PROTOTYPES = {
     "defslam_template_create": (C.c_int, [C.POINTER(TemplateDesc), C.c_int, C.POINTER(C.c_void_p)]),
     "defslam_template_destroy": (None, [C.c_void_p]),
+    "defslam_template_info": (C.c_int, [C.c_void_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p]),
+    "defslam_sft_batch_create": (C.c_int, [C.c_int32, C.POINTER(SftProblem), C.c_int, C.POINTER(C.c_void_p)]),
+    "defslam_sft_batch_run": (C.c_int, [C.c_void_p]),
+    "defslam_sft_batch_fetch": (C.c_int, [C.c_void_p, C.POINTER(SftResult)]),
+    "defslam_sft_batch_info": (
+        C.c_int, [C.c_void_p, c_int32_p, c_int32_p, c_int32_p, c_int64_p, c_int64_p, c_double_p]),
+    "defslam_sft_batch_destroy": (None, [C.c_void_p]),
     "defslam_mesh_laplacian": (
         C.c_int,
         [C.c_int32, c_double_p, C.c_int32, c_int32_p, C.c_int32, c_int32_p, c_int32_p, c_double_p,

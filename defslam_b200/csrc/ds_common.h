@@ -121,7 +121,10 @@ DS_FN int atomic_inc_int(int *p) {
 #endif
 }
 
-DS_FN int round_up(int a, int m) { return ((a + m - 1) / m) * m; }
+#if DS_CUDA
+__host__ __device__
+#endif
+static inline int round_up(int a, int m) { return ((a + m - 1) / m) * m; }
 
 }  // namespace ds
 #endif

@@ -1,0 +1,321 @@
+/*
+ * sft_cuda.cu -- CUDA kernel wrapper + C ABI of the Shape-from-Template solve.
+ *
+ * One persistent CTA per frame runs the whole Levenberg-Marquardt solve
+ * (sft_core.h); a batch of frames is one launch.  Entry points replace
+ * defSLAM::Optimizer::DefPoseOptimization (Modules/Tracking/DefOptimizer.cc:251-578)
+ * and everything below it; see include/defslam_b200.h.
+ */
+#include <stdio.h>
+
+#include <vector>
+
+#include "ds_batch.h"
+#include "ds_runtime.h"
+
+using namespace ds;
+
+namespace {
+
+constexpr int SFT_THREADS = 256;
+
+__global__ void __launch_bounds__(SFT_THREADS, 2)
+sft_lm_kernel(const ProbView *__restrict__ probs, int nprob, uint8_t *ws_base, size_t ws_stride, WorkspaceSizes z) {
+  extern __shared__ __align__(16) double smem[];
+  Team team;
+  team.tid = threadIdx.x;
+  team.nthr = blockDim.x;
+  uint8_t *ws = ws_base + (size_t)blockIdx.x * ws_stride;
+  for (int pi = blockIdx.x; pi < nprob; pi += gridDim.x) {
+    sft_run_problem(team, probs[pi], smem, ws, z);
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+/* ------------------------------------------------------------ templates -- */
+
+struct defslam_template {
+  PlanHost host;
+  PlanView hview;       /* host-addressable */
+  PlanView dview_host;  /* device pointers, host copy */
+  int device = -1;
+  double *d_dbl = nullptr;
+  int *d_i32 = nullptr;
+  uint8_t *d_u8 = nullptr;
+  PlanView *d_view = nullptr;
+};
+
+static void template_free(defslam_template *t) {
+  if (!t) return;
+  if (t->d_dbl || t->d_i32 || t->d_u8 || t->d_view) {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (t->device >= 0) cudaSetDevice(t->device);
+    cudaFree(t->d_dbl); cudaFree(t->d_i32); cudaFree(t->d_u8); cudaFree(t->d_view);
+    cudaSetDevice(cur);
+  }
+  delete t;
+}
+
+static int template_make(const defslam_template_desc *desc, DevCtx *ctx, defslam_template **out) {
+  std::unique_ptr<defslam_template> t(new defslam_template);
+  const int rc = t->host.build(desc);
+  if (rc) return rc;
+  t->hview = t->host.host_view();
+  t->device = ctx->device;
+  defslam_template *raw = t.release();
+  auto fail = [&](int code) { template_free(raw); return code; };
+  const size_t nd = raw->host.dbl.size() * sizeof(double), ni = raw->host.i32.size() * sizeof(int),
+               nu = raw->host.u8.size();
+  if (cudaMalloc(&raw->d_dbl, nd + 8) != cudaSuccess || cudaMalloc(&raw->d_i32, ni + 8) != cudaSuccess ||
+      cudaMalloc(&raw->d_u8, nu + 8) != cudaSuccess || cudaMalloc(&raw->d_view, sizeof(PlanView)) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(DEFSLAM_ECUDA);
+  }
+  raw->dview_host = raw->host.bind(raw->d_dbl, raw->d_i32, raw->d_u8);
+  if (cudaMemcpyAsync(raw->d_dbl, raw->host.dbl.data(), nd, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+      cudaMemcpyAsync(raw->d_i32, raw->host.i32.data(), ni, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+      cudaMemcpyAsync(raw->d_u8, raw->host.u8.data(), nu, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+      cudaMemcpyAsync(raw->d_view, &raw->dview_host, sizeof(PlanView), cudaMemcpyHostToDevice, ctx->stream) !=
+          cudaSuccess ||
+      cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(DEFSLAM_ECUDA);
+  }
+  *out = raw;
+  return DEFSLAM_OK;
+}
+
+/* --------------------------------------------------------------- batches -- */
+
+struct defslam_sft_batch {
+  DevCtx *ctx = nullptr;
+  BatchMarshal bm;
+  DevBuf h_in, h_out, d_in, d_out, d_views, d_ws;
+  std::vector<defslam_template *> temps;
+  int nprob = 0, grid = 0, smem_bytes = 0, mode = MODE_SOLVE;
+  size_t ws_stride = 0;
+  float last_ms = 0.f;
+  defslam_sft_batch() { h_in.pinned = true; h_out.pinned = true; }
+  void drop_temps() {
+    for (auto *t : temps) template_free(t);
+    temps.clear();
+  }
+  ~defslam_sft_batch() {
+    drop_temps();
+    h_in.release(); h_out.release(); d_in.release(); d_out.release(); d_views.release(); d_ws.release();
+  }
+};
+
+/* marshal + upload; after this the batch is resident on the device */
+static int batch_load(defslam_sft_batch *B, int nprob, const defslam_sft_problem *p, int mode) {
+  DevCtx *ctx = B->ctx;
+  B->drop_temps();
+  B->nprob = nprob;
+  B->mode = mode;
+  std::map<const defslam_template_desc *, defslam_template *> by_desc;
+  auto resolve = [&](const defslam_sft_problem &q, const PlanView **hv, const PlanView **dv) -> int {
+    const defslam_template *t = q.tmpl;
+    if (!t) {
+      if (!q.tmpl_desc) return DEFSLAM_EBADARG;
+      auto it = by_desc.find(q.tmpl_desc);
+      if (it == by_desc.end()) {
+        defslam_template *nt = nullptr;
+        const int rc = template_make(q.tmpl_desc, ctx, &nt);
+        if (rc) return rc;
+        B->temps.push_back(nt);
+        it = by_desc.emplace(q.tmpl_desc, nt).first;
+      }
+      t = it->second;
+    } else if (t->device != ctx->device) {
+      return DEFSLAM_EBADARG;
+    }
+    *hv = &t->hview;
+    *dv = t->d_view;
+    return 0;
+  };
+  const int smem_limit = (ctx->smem_optin - 1024) / (int)sizeof(double);
+  int rc = B->bm.plan(nprob, p, mode, smem_limit, resolve);
+  if (rc) return rc;
+  if ((rc = B->h_in.ensure(B->bm.in_bytes)) || (rc = B->h_out.ensure(B->bm.out_bytes)) ||
+      (rc = B->d_in.ensure(B->bm.in_bytes)) || (rc = B->d_out.ensure(B->bm.out_bytes)) ||
+      (rc = B->d_views.ensure(sizeof(ProbView) * (size_t)nprob)))
+    return rc;
+  B->bm.pack_inputs(p, (uint8_t *)B->h_in.p);
+  B->bm.bind((uint8_t *)B->d_in.p, (uint8_t *)B->d_out.p);
+
+  B->smem_bytes = B->bm.smem_doubles * (int)sizeof(double);
+  DS_CUDA_TRY(cudaFuncSetAttribute(sft_lm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B->smem_bytes));
+  int occ = 0;
+  DS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sft_lm_kernel, SFT_THREADS, B->smem_bytes));
+  if (occ < 1) return DEFSLAM_ETOOLARGE;
+  B->grid = ctx->sm_count * occ;
+  if (B->grid > nprob) B->grid = nprob;
+  const WorkspaceSizes z = B->bm.ws_sizes();
+  B->ws_stride = workspace_bytes(z);
+  if ((rc = B->d_ws.ensure(B->ws_stride * (size_t)B->grid))) return rc;
+
+  DS_CUDA_TRY(cudaMemcpyAsync(B->d_in.p, B->h_in.p, B->bm.in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  DS_CUDA_TRY(cudaMemcpyAsync(B->d_views.p, B->bm.views.data(), sizeof(ProbView) * (size_t)nprob,
+                              cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+
+static int batch_launch(defslam_sft_batch *B) {
+  DevCtx *ctx = B->ctx;
+  const WorkspaceSizes z = B->bm.ws_sizes();
+  DS_CUDA_TRY(cudaEventRecord(ctx->e0, ctx->stream));
+  sft_lm_kernel<<<B->grid, SFT_THREADS, B->smem_bytes, ctx->stream>>>((const ProbView *)B->d_views.p, B->nprob,
+                                                                      (uint8_t *)B->d_ws.p, B->ws_stride, z);
+  DS_CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  DS_CUDA_TRY(cudaEventRecord(ctx->e1, ctx->stream));
+  return 0;
+}
+
+static int batch_wait_kernel(defslam_sft_batch *B) {
+  DevCtx *ctx = B->ctx;
+  DS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  float ms = 0.f;
+  DS_CUDA_TRY(cudaEventElapsedTime(&ms, ctx->e0, ctx->e1));
+  B->last_ms = ms;
+  g_last_kernel_ms = ms;
+  return 0;
+}
+
+static int batch_download(defslam_sft_batch *B) {
+  DevCtx *ctx = B->ctx;
+  DS_CUDA_TRY(cudaMemcpyAsync(B->h_out.p, B->d_out.p, B->bm.out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  DS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+static defslam_sft_batch *tl_batch(DevCtx *ctx) {
+  static thread_local std::map<int, std::unique_ptr<defslam_sft_batch>> tl;
+  auto &b = tl[ctx->device];
+  if (!b) { b.reset(new defslam_sft_batch); b->ctx = ctx; }
+  return b.get();
+}
+
+/* ------------------------------------------------------------------ ABI -- */
+
+extern "C" {
+
+int defslam_template_create(const defslam_template_desc *desc, int device, defslam_template **out) {
+  if (!desc || !out) return DEFSLAM_EBADARG;
+  *out = nullptr;
+  DevCtx *ctx = get_ctx(device);
+  if (!ctx) return DEFSLAM_ECUDA;
+  return template_make(desc, ctx, out);
+}
+
+void defslam_template_destroy(defslam_template *t) { template_free(t); }
+
+int defslam_template_info(const defslam_template *t, int32_t *bandwidth, int32_t *band_ld, int32_t *dn_pad,
+                          int32_t *n_blocks, int32_t *smem_bytes) {
+  if (!t) return DEFSLAM_EBADARG;
+  const PlanView &v = t->hview;
+  if (bandwidth) *bandwidth = v.bw;
+  if (band_ld) *band_ld = v.ld;
+  if (dn_pad) *dn_pad = v.Dn_pad;
+  if (n_blocks) *n_blocks = v.n_blk;
+  if (smem_bytes)
+    *smem_bytes = (int32_t)sizeof(double) * smem_layout(v.n_nodes, v.n_edges, v.Dn_pad, v.bwp, v.ld, v.Wr, true).total;
+  return DEFSLAM_OK;
+}
+
+int defslam_sft_solve_batched(int32_t nprob, const defslam_sft_problem *p, defslam_sft_result *r, int device) {
+  if (nprob < 0 || (nprob > 0 && (!p || !r))) return DEFSLAM_EBADARG;
+  DevCtx *ctx = get_ctx(device);
+  if (!ctx) return DEFSLAM_ECUDA;
+  if (nprob == 0) return DEFSLAM_OK;
+  defslam_sft_batch *B = tl_batch(ctx);
+  int rc;
+  if ((rc = batch_load(B, nprob, p, MODE_SOLVE))) return rc;
+  if ((rc = batch_launch(B))) return rc;
+  if ((rc = batch_download(B))) return rc;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, ctx->e0, ctx->e1) == cudaSuccess) { B->last_ms = ms; g_last_kernel_ms = ms; }
+  rc = B->bm.unpack((const uint8_t *)B->h_out.p, r);
+  B->drop_temps();
+  return rc;
+}
+
+int defslam_sft_solve(const defslam_sft_problem *p, defslam_sft_result *r) {
+  if (!p || !r) return DEFSLAM_EBADARG;
+  return defslam_sft_solve_batched(1, p, r, -1);
+}
+
+int defslam_sft_normal_equations(const defslam_sft_problem *p, double *H_dense, double *b, double *chi2) {
+  if (!p) return DEFSLAM_EBADARG;
+  DevCtx *ctx = get_ctx(-1);
+  if (!ctx) return DEFSLAM_ECUDA;
+  defslam_sft_batch *B = tl_batch(ctx);
+  int rc;
+  if ((rc = batch_load(B, 1, p, MODE_NORMAL_EQ))) return rc;
+  if ((rc = batch_launch(B))) return rc;
+  if ((rc = batch_download(B))) return rc;
+  const ProbSlot &s = B->bm.slots[0];
+  const uint8_t *o = (const uint8_t *)B->h_out.p + s.out_off;
+  const ResultScalars *rs = (const ResultScalars *)(o + s.o_res);
+  B->drop_temps();
+  if (rs->status) return rs->status;
+  const size_t D = 3 * (size_t)s.n_nodes + 6;
+  if (H_dense) memcpy(H_dense, o + s.o_H, D * D * sizeof(double));
+  if (b) memcpy(b, o + s.o_b, D * sizeof(double));
+  if (chi2) *chi2 = rs->chi2_initial;
+  return DEFSLAM_OK;
+}
+
+/* resident batch: inputs uploaded once, solve re-runnable, results fetched on demand */
+int defslam_sft_batch_create(int32_t nprob, const defslam_sft_problem *p, int device, defslam_sft_batch **out) {
+  if (!out || nprob <= 0 || !p) return DEFSLAM_EBADARG;
+  *out = nullptr;
+  DevCtx *ctx = get_ctx(device);
+  if (!ctx) return DEFSLAM_ECUDA;
+  std::unique_ptr<defslam_sft_batch> B(new defslam_sft_batch);
+  B->ctx = ctx;
+  int rc = batch_load(B.get(), nprob, p, MODE_SOLVE);
+  if (rc) return rc;
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cudaGetLastError(); return DEFSLAM_ECUDA; }
+  *out = B.release();
+  return DEFSLAM_OK;
+}
+
+int defslam_sft_batch_run(defslam_sft_batch *B) {
+  if (!B) return DEFSLAM_EBADARG;
+  if (cudaSetDevice(B->ctx->device) != cudaSuccess) { cudaGetLastError(); return DEFSLAM_ECUDA; }
+  int rc = batch_launch(B);
+  if (rc) return rc;
+  return batch_wait_kernel(B);
+}
+
+int defslam_sft_batch_fetch(defslam_sft_batch *B, defslam_sft_result *r) {
+  if (!B || !r) return DEFSLAM_EBADARG;
+  if (cudaSetDevice(B->ctx->device) != cudaSuccess) { cudaGetLastError(); return DEFSLAM_ECUDA; }
+  int rc = batch_download(B);
+  if (rc) return rc;
+  return B->bm.unpack((const uint8_t *)B->h_out.p, r);
+}
+
+int defslam_sft_batch_info(const defslam_sft_batch *B, int32_t *grid, int32_t *threads, int32_t *smem_bytes,
+                           int64_t *h2d_bytes, int64_t *d2h_bytes, double *last_kernel_ms) {
+  if (!B) return DEFSLAM_EBADARG;
+  if (grid) *grid = B->grid;
+  if (threads) *threads = SFT_THREADS;
+  if (smem_bytes) *smem_bytes = B->smem_bytes;
+  if (h2d_bytes) *h2d_bytes = (int64_t)(B->bm.in_bytes + sizeof(ProbView) * (size_t)B->nprob);
+  if (d2h_bytes) *d2h_bytes = (int64_t)B->bm.out_bytes;
+  if (last_kernel_ms) *last_kernel_ms = B->last_ms;
+  return DEFSLAM_OK;
+}
+
+void defslam_sft_batch_destroy(defslam_sft_batch *B) {
+  if (!B) return;
+  cudaSetDevice(B->ctx->device);
+  delete B;
+}
+
+}  // extern "C"

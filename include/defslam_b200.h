@@ -17,6 +17,7 @@
  *                         mirrors the reference's silent "keep the previous
  *                         estimate" behaviour
  *   -4  DEFSLAM_ETOOLARGE problem does not fit the on-chip working set
+ *   -5  DEFSLAM_ENOTIMPL  entry point declared but not built yet in this round
  */
 #ifndef DEFSLAM_B200_H_
 #define DEFSLAM_B200_H_
@@ -33,6 +34,7 @@ extern "C" {
 #define DEFSLAM_ECUDA (-2)
 #define DEFSLAM_ENUMERIC (-3)
 #define DEFSLAM_ETOOLARGE (-4)
+#define DEFSLAM_ENOTIMPL (-5)
 
 /* ------------------------------------------------------------------------- *
  *  Template (mesh) description
@@ -73,6 +75,13 @@ typedef struct defslam_template defslam_template;
 int defslam_template_create(const defslam_template_desc *desc, int device,
                             defslam_template **out);
 void defslam_template_destroy(defslam_template *t);
+
+/* Solver-side facts of a plan (any pointer may be NULL): scalar half-bandwidth of
+ * the node part of the normal matrix in the caller's node order, band row
+ * length, padded node dimension, number of coupled 3x3 blocks, and the dynamic
+ * shared memory one solve needs. */
+int defslam_template_info(const defslam_template *t, int32_t *bandwidth, int32_t *band_ld,
+                          int32_t *dn_pad, int32_t *n_blocks, int32_t *smem_bytes);
 
 /* ------------------------------------------------------------------------- *
  *  Mesh Laplacian set-up (runs on the GPU)
@@ -151,6 +160,22 @@ int defslam_sft_solve(const defslam_sft_problem *p, defslam_sft_result *r);
  * (SURVEY.md section 8(e)). */
 int defslam_sft_solve_batched(int32_t nprob, const defslam_sft_problem *p,
                               defslam_sft_result *r, int device);
+
+/* Resident batch: the frames of a batch are marshalled and uploaded once
+ * (create), solved by one kernel launch per run() with inputs already in HBM,
+ * and results are copied back on demand (fetch).  This is what a tracking loop
+ * that keeps its template and match tables on the device uses; it is also how
+ * bench.py separates kernel time from host<->device traffic.  No reference
+ * counterpart: the reference solves one frame at a time on the host. */
+typedef struct defslam_sft_batch defslam_sft_batch;
+int defslam_sft_batch_create(int32_t nprob, const defslam_sft_problem *p, int device,
+                             defslam_sft_batch **out);
+int defslam_sft_batch_run(defslam_sft_batch *b);   /* launch + wait; sets defslam_last_kernel_ms */
+int defslam_sft_batch_fetch(defslam_sft_batch *b, defslam_sft_result *r);
+int defslam_sft_batch_info(const defslam_sft_batch *b, int32_t *grid, int32_t *threads,
+                           int32_t *smem_bytes, int64_t *h2d_bytes, int64_t *d2h_bytes,
+                           double *last_kernel_ms);
+void defslam_sft_batch_destroy(defslam_sft_batch *b);
 
 /* Normal equations at the current state (one LM linearisation, no step).
  * replaces: SparseOptimizer::computeActiveErrors + activeRobustChi2
