@@ -92,13 +92,13 @@ struct BatchMarshal {
 
       SmemLayout L = smem_layout(hv->n_nodes, hv->n_edges, hv->Dn_pad, hv->bwp, hv->ld, hv->Wr, true);
       v.e_in_smem = 1;
-      if (L.total > smem_limit_doubles) {
+      if (L.total + CTX_DOUBLES > smem_limit_doubles) {
         L = smem_layout(hv->n_nodes, hv->n_edges, hv->Dn_pad, hv->bwp, hv->ld, hv->Wr, false);
         v.e_in_smem = 0;
         any_e_global = true;
-        if (L.total > smem_limit_doubles) return DEFSLAM_ETOOLARGE;
+        if (L.total + CTX_DOUBLES > smem_limit_doubles) return DEFSLAM_ETOOLARGE;
       }
-      if (L.total > smem_doubles) smem_doubles = L.total;
+      if (L.total + CTX_DOUBLES > smem_doubles) smem_doubles = L.total + CTX_DOUBLES;
       ws_band = std::max(ws_band, (size_t)hv->Dn_pad * hv->ld);
       ws_dinv = std::max(ws_dinv, (size_t)hv->nblk * 64);
       ws_cg = std::max(ws_cg, (size_t)8 * hv->Dn_pad);

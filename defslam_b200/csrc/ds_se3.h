@@ -19,6 +19,8 @@ struct Pose {
   double t[3];
 };
 
+/* Eigen::Quaterniond(Matrix3d); written without run-time array indexing so that
+ * everything stays in registers */
 DS_FN void quat_from_R(const double R[9], double q[4]) {
   double t = R[0] + R[4] + R[8];
   if (t > 0.0) {
@@ -31,16 +33,26 @@ DS_FN void quat_from_R(const double R[9], double q[4]) {
   } else {
     int i = 0;
     if (R[4] > R[0]) i = 1;
-    if (R[8] > R[i * 3 + i]) i = 2;
-    const int j = (i + 1) % 3, k = (j + 1) % 3;
-    t = sqrt(R[i * 3 + i] - R[j * 3 + j] - R[k * 3 + k] + 1.0);
-    double qq[4];
-    qq[i] = 0.5 * t;
-    t = 0.5 / t;
-    qq[3] = (R[k * 3 + j] - R[j * 3 + k]) * t;
-    qq[j] = (R[j * 3 + i] + R[i * 3 + j]) * t;
-    qq[k] = (R[k * 3 + i] + R[i * 3 + k]) * t;
-    q[0] = qq[0]; q[1] = qq[1]; q[2] = qq[2]; q[3] = qq[3];
+    if (R[8] > (i == 0 ? R[0] : R[4])) i = 2;
+    if (i == 0) {        /* j = 1, k = 2 */
+      t = sqrt(R[0] - R[4] - R[8] + 1.0);
+      q[0] = 0.5 * t; t = 0.5 / t;
+      q[3] = (R[7] - R[5]) * t;
+      q[1] = (R[3] + R[1]) * t;
+      q[2] = (R[6] + R[2]) * t;
+    } else if (i == 1) { /* j = 2, k = 0 */
+      t = sqrt(R[4] - R[8] - R[0] + 1.0);
+      q[1] = 0.5 * t; t = 0.5 / t;
+      q[3] = (R[2] - R[6]) * t;
+      q[2] = (R[7] + R[5]) * t;
+      q[0] = (R[1] + R[3]) * t;
+    } else {             /* j = 0, k = 1 */
+      t = sqrt(R[8] - R[0] - R[4] + 1.0);
+      q[2] = 0.5 * t; t = 0.5 / t;
+      q[3] = (R[3] - R[1]) * t;
+      q[0] = (R[2] + R[6]) * t;
+      q[1] = (R[5] + R[7]) * t;
+    }
   }
 }
 
@@ -85,7 +97,9 @@ DS_FN void pose_map(const Pose &P, const double v[3], double o[3]) {
 }
 
 DS_FN void mat3_mul(const double A[9], const double B[9], double C[9]) {
+#pragma unroll
   for (int i = 0; i < 3; i++)
+#pragma unroll
     for (int j = 0; j < 3; j++)
       C[i * 3 + j] = A[i * 3] * B[j] + A[i * 3 + 1] * B[3 + j] + A[i * 3 + 2] * B[6 + j];
 }
@@ -98,6 +112,7 @@ DS_FN void se3_exp(const double u[6], double q[4], double t[3]) {
   double Om2[9], R[9], V[9];
   mat3_mul(Om, Om, Om2);
   if (theta < 0.00001) {
+#pragma unroll
     for (int i = 0; i < 9; i++) {
       R[i] = ((i % 4) == 0 ? 1.0 : 0.0) + Om[i] + Om2[i];
       V[i] = R[i];
@@ -105,6 +120,7 @@ DS_FN void se3_exp(const double u[6], double q[4], double t[3]) {
   } else {
     const double a = sin(theta) / theta, b = (1 - cos(theta)) / (theta * theta),
                  c = (theta - sin(theta)) / pow(theta, 3);
+#pragma unroll
     for (int i = 0; i < 9; i++) {
       const double I = (i % 4) == 0 ? 1.0 : 0.0;
       R[i] = I + a * Om[i] + b * Om2[i];
@@ -112,6 +128,7 @@ DS_FN void se3_exp(const double u[6], double q[4], double t[3]) {
     }
   }
   quat_from_R(R, q);
+#pragma unroll
   for (int i = 0; i < 3; i++) t[i] = V[i * 3] * u[3] + V[i * 3 + 1] * u[4] + V[i * 3 + 2] * u[5];
   quat_normalize(q);
 }

@@ -146,7 +146,7 @@ SmemLayout smem_layout(int n_nodes, int n_edges, int Dn_pad, int bwp, int ld, in
   if (bsz > wsz) wsz = bsz;
   L.W = o;    o += wsz; o = (o + 1) & ~1;
   L.E = o;    o += e_in_smem ? 8 * Dn_pad : 0;
-  L.P = o;    o += NB * (bwp + 8);
+  L.P = o;    o += (NB * (bwp + 8) > 216 ? NB * (bwp + 8) : 216);
   L.x = o;    o += Dn_pad;
   L.xb = o;   o += Dn_pad;
   L.dx = o;   o += Dn_pad + 8;
@@ -162,7 +162,6 @@ SmemLayout smem_layout(int n_nodes, int n_edges, int Dn_pad, int bwp, int ld, in
 }
 
 struct Ctx {
-  Team team;
   PlanView pl;
   ProbView pb;
   Workspace ws;
@@ -176,11 +175,21 @@ struct Ctx {
   double inv_n;
 };
 
+/* Band row layout: a row holds the band-relative offsets off = j - i + bw in
+ * [0, bw], de-interleaved by 4 (offsets congruent mod 4 are contiguous).  The
+ * trailing update walks a row in steps of one 4-wide tile per lane, so this
+ * makes its shared-memory accesses conflict-free; global H/L bands use the same
+ * layout so that rows move between HBM and the window as plain block copies. */
+DS_FN int boff(int off, int Q) { return (off & 3) * Q + (off >> 2); }
+/* same idea for the 8 border rows (camera border, rhs): column de-interleave */
+DS_FN int eidx(int e, int col, int Dp) { return e * Dp + (col & 3) * (Dp >> 2) + (col >> 2); }
+/* panel buffer: P[cc][r] with r de-interleaved by 4 */
+DS_FN int pidx(int cc, int r, int PS) { return cc * PS + (r & 3) * (PS >> 2) + (r >> 2); }
+
 /* ------------------------------------------------------------ prologue -- */
 
 /* returns 0 or an error code (uniform over the team) */
-DS_FN_NOINLINE int prologue(Ctx &c) {
-  const Team team = c.team;
+DS_FN_NOINLINE int prologue(const Team team, Ctx &c) {
   const PlanView &pl = c.pl;
   const ProbView &pb = c.pb;
   const int n = pl.n_nodes, nf = pl.n_facets, M = pb.n_matches;
@@ -205,7 +214,7 @@ DS_FN_NOINLINE int prologue(Ctx &c) {
     DS_FOR(i, 8 * pl.Dn_pad) c.ws.Cg[i] = 0.0;
   }
   team.sync();
-  DS_FOR(i, pl.Dn_pad - pl.Dn) c.ws.Hb[(pl.Dn + i) * pl.ld + pl.bw] = 1.0;
+  DS_FOR(i, pl.Dn_pad - pl.Dn) c.ws.Hb[(pl.Dn + i) * pl.ld + boff(pl.bw, pl.Q)] = 1.0;
 
   /* facet of every match (DefMapPoint::getFacet) + viewed nodes
    * (DefOptimizer.cc:326-335) */
@@ -253,9 +262,9 @@ DS_FN_NOINLINE int prologue(Ctx &c) {
   DS_FOR(v, n) { cnt_v += c.viewed[v]; cnt_o += c.freev[v]; }
   DS_FOR(e, pl.n_edges) cnt_s += (c.freev[pl.edge_ab[2 * e]] | c.freev[pl.edge_ab[2 * e + 1]]);
   DS_FOR(f, nf) c.ws.fcnt[f] = 0;
-  c.n_viewed = team_sum_int(team, cnt_v, red);
-  c.n_optlap = team_sum_int(team, cnt_o, red);
-  c.n_str = team_sum_int(team, cnt_s, red);
+  const int n_viewed = team_sum_int(team, cnt_v, red);
+  const int n_optlap = team_sum_int(team, cnt_o, red);
+  const int n_str = team_sum_int(team, cnt_s, red);
   DS_FOR(m, M) {
     const int f = c.ws.mfac[m] >> 6;
     c.ws.mperm[c.ws.fptr[f] + atomic_inc_int(&c.ws.fcnt[f])] = m;
@@ -272,14 +281,19 @@ DS_FN_NOINLINE int prologue(Ctx &c) {
   }
   team.sync();
 
-  /* information matrices (DefOptimizer.cc:339-340,376-378,458,499) */
-  c.inv_n = 1.0; /* division by N is done per match as float/ int like the reference */
-  c.info_ref = pb.reg_temp / pow(pl.median_len, 2);
-  c.info_curv = c.n_optlap > 0 ? pb.reg_lap / (double)c.n_optlap : 0.0;
-  c.info_str = c.n_str > 0 ? pb.reg_inex / (double)c.n_str : 0.0;
-  const float deltaMono = (float)sqrt(5.991);
-  c.hub_delta = (double)deltaMono;
-  c.hub_dsqr = c.hub_delta * c.hub_delta;
+  /* information matrices (DefOptimizer.cc:339-340,376-378,458,499); the context
+   * is shared by the CTA: one writer */
+  if (team.tid == 0) {
+    c.n_viewed = n_viewed; c.n_optlap = n_optlap; c.n_str = n_str;
+    c.inv_n = 1.0; /* division by N is done per match as float / int like the reference */
+    c.info_ref = pb.reg_temp / pow(pl.median_len, 2);
+    c.info_curv = n_optlap > 0 ? pb.reg_lap / (double)n_optlap : 0.0;
+    c.info_str = n_str > 0 ? pb.reg_inex / (double)n_str : 0.0;
+    const float deltaMono = (float)sqrt(5.991);
+    c.hub_delta = (double)deltaMono;
+    c.hub_dsqr = c.hub_delta * c.hub_delta;
+  }
+  team.sync();
   return 0;
 }
 
@@ -325,8 +339,7 @@ DS_FN double curv_residual(const Ctx &c, const double *x, int i, double d[3], do
  * store=true additionally fills everything build_system() gathers from:
  * per-match scratch S, per-node A / centre / edge quantities (overlaid on the
  * window region of shared memory). */
-DS_FN_NOINLINE double eval_state(Ctx &c, const double *x, const double *ps, bool store) {
-  const Team team = c.team;
+DS_FN_NOINLINE double eval_state(const Team team, Ctx &c, const double *x, const double *ps, bool store) {
   const PlanView &pl = c.pl;
   const ProbView &pb = c.pb;
   const int n = pl.n_nodes, ne = pl.n_edges, M = pb.n_matches;
@@ -446,78 +459,115 @@ DS_FN_NOINLINE double eval_state(Ctx &c, const double *x, const double *ps, bool
  * same state.  Produces Hb (band), Cg rows 0-5 (camera border), Cg row 6 (b_n),
  * Hcc/bc (shared).  Returns max |diag| over the free variables
  * (computeLambdaInit, optimization_algorithm_levenberg.cpp:166-180). */
-DS_FN_NOINLINE double build_system(Ctx &c) {
-  const Team team = c.team;
+DS_FN_NOINLINE double build_system(const Team team, Ctx &c) {
   const PlanView &pl = c.pl;
   const int n = pl.n_nodes, ne = pl.n_edges, nf = pl.n_facets, M = c.pb.n_matches;
-  const int bw = pl.bw, ld = pl.ld, Dp = pl.Dn_pad;
+  const int bw = pl.bw, ld = pl.ld, Dp = pl.Dn_pad, Q = pl.Q;
   const double *A = c.sm + c.sl.W;
   const double *cd = A + 6 * n, *cg = cd + 3 * n, *cr = cg + n, *eu = cr + n, *er = eu + 3 * ne, *es = er + ne;
   double *F = c.ws.F;
   const double *S = c.ws.S;
   double *Hcc = c.sm + c.sl.Hcc;
-  (void)M;
   team.sync();
 
   /* (1) per-facet sums.  item = (facet, group) */
   DS_FOR(it, nf * 6) {
     const int f = it / 6, g = it - 6 * f;
     const int sb = c.ws.fptr[f], se = c.ws.fptr[f + 1];
-    const int Mm = c.pb.n_matches;
     if (g == 0) {
-      double a[12];
-      for (int k = 0; k < 12; k++) a[k] = 0.0;
+      double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0, a9 = 0, a10 = 0, a11 = 0;
       for (int s = sb; s < se; s++) {
-        const double w = S[2 * Mm + s], e0 = S[s], e1 = S[Mm + s];
-        const double b0 = S[15 * Mm + s], b1 = S[16 * Mm + s], b2 = S[17 * Mm + s];
-        a[0] += w * b0 * b0; a[1] += w * b0 * b1; a[2] += w * b0 * b2;
-        a[3] += w * b1 * b1; a[4] += w * b1 * b2; a[5] += w * b2 * b2;
-        a[6] += w * b0 * e0; a[7] += w * b0 * e1;
-        a[8] += w * b1 * e0; a[9] += w * b1 * e1;
-        a[10] += w * b2 * e0; a[11] += w * b2 * e1;
+        const double w = S[2 * M + s], e0 = S[s], e1 = S[M + s];
+        const double b0 = S[15 * M + s], b1 = S[16 * M + s], b2 = S[17 * M + s];
+        a0 += w * b0 * b0; a1 += w * b0 * b1; a2 += w * b0 * b2;
+        a3 += w * b1 * b1; a4 += w * b1 * b2; a5 += w * b2 * b2;
+        a6 += w * b0 * e0; a7 += w * b0 * e1;
+        a8 += w * b1 * e0; a9 += w * b1 * e1;
+        a10 += w * b2 * e0; a11 += w * b2 * e1;
       }
-      for (int k = 0; k < 12; k++) F[k * nf + f] = a[k];
+      F[0 * nf + f] = a0; F[1 * nf + f] = a1; F[2 * nf + f] = a2; F[3 * nf + f] = a3;
+      F[4 * nf + f] = a4; F[5 * nf + f] = a5; F[6 * nf + f] = a6; F[7 * nf + f] = a7;
+      F[8 * nf + f] = a8; F[9 * nf + f] = a9; F[10 * nf + f] = a10; F[11 * nf + f] = a11;
     } else if (g <= 3) {
       double a[12];
+#pragma unroll
       for (int k = 0; k < 12; k++) a[k] = 0.0;
       for (int s = sb; s < se; s++) {
-        const double wb = S[2 * Mm + s] * S[(14 + g) * Mm + s];
-        for (int k = 0; k < 12; k++) a[k] += wb * S[(3 + k) * Mm + s];
+        const double wb = S[2 * M + s] * S[(14 + g) * M + s];
+#pragma unroll
+        for (int k = 0; k < 12; k++) a[k] += wb * S[(3 + k) * M + s];
       }
+#pragma unroll
       for (int k = 0; k < 12; k++) F[(12 * g + k) * nf + f] = a[k];
-    } else {
-      /* camera block: 21 upper entries of Jc^T w Jc, then 6 of Jc^T w e */
-      const int lo = g == 4 ? 0 : 14, hi = g == 4 ? 14 : 27;
-      double a[14];
-      for (int k = 0; k < 14; k++) a[k] = 0.0;
+    } else if (g == 4) {
+      /* camera block, rows 0-1 of the upper triangle of Jc^T w Jc (11 entries) */
+      double a[11];
+#pragma unroll
+      for (int k = 0; k < 11; k++) a[k] = 0.0;
       for (int s = sb; s < se; s++) {
-        const double w = S[2 * Mm + s], e0 = S[s], e1 = S[Mm + s];
+        const double w = S[2 * M + s];
         double J[12];
-        for (int k = 0; k < 12; k++) J[k] = S[(3 + k) * Mm + s];
-        int idx = 0;
-        for (int r = 0; r < 6; r++)
-          for (int q = r; q < 6; q++, idx++)
-            if (idx >= lo && idx < hi) a[idx - lo] += w * (J[r] * J[q] + J[6 + r] * J[6 + q]);
-        for (int r = 0; r < 6; r++, idx++)
-          if (idx >= lo && idx < hi) a[idx - lo] += w * (J[r] * e0 + J[6 + r] * e1);
+#pragma unroll
+        for (int k = 0; k < 12; k++) J[k] = S[(3 + k) * M + s];
+#pragma unroll
+        for (int q = 0; q < 6; q++) a[q] += w * (J[0] * J[q] + J[6] * J[6 + q]);
+#pragma unroll
+        for (int q = 1; q < 6; q++) a[5 + q] += w * (J[1] * J[q] + J[7] * J[6 + q]);
       }
-      for (int k = lo; k < hi; k++) F[(48 + k) * nf + f] = a[k - lo];
+#pragma unroll
+      for (int k = 0; k < 11; k++) F[(48 + k) * nf + f] = a[k];
+    } else {
+      /* rows 2-5 (10 entries), then the 6 entries of Jc^T w e */
+      double a[16];
+#pragma unroll
+      for (int k = 0; k < 16; k++) a[k] = 0.0;
+      for (int s = sb; s < se; s++) {
+        const double w = S[2 * M + s], e0 = S[s], e1 = S[M + s];
+        double J[12];
+#pragma unroll
+        for (int k = 0; k < 12; k++) J[k] = S[(3 + k) * M + s];
+#pragma unroll
+        for (int q = 2; q < 6; q++) a[q - 2] += w * (J[2] * J[q] + J[8] * J[6 + q]);
+#pragma unroll
+        for (int q = 3; q < 6; q++) a[4 + q - 3] += w * (J[3] * J[q] + J[9] * J[6 + q]);
+#pragma unroll
+        for (int q = 4; q < 6; q++) a[7 + q - 4] += w * (J[4] * J[q] + J[10] * J[6 + q]);
+        a[9] += w * (J[5] * J[5] + J[11] * J[11]);
+#pragma unroll
+        for (int r = 0; r < 6; r++) a[10 + r] += w * (J[r] * e0 + J[6 + r] * e1);
+      }
+#pragma unroll
+      for (int k = 0; k < 16; k++) F[(59 + k) * nf + f] = a[k];
     }
   }
   team.sync();
 
-  /* (2) camera-camera block and b_c: reduction over facets in facet order */
-  DS_FOR(k, 27) {
-    double s = 0.0;
-    const double *Fk = &F[(48 + k) * nf];
-    for (int f = 0; f < nf; f++) s += Fk[f];
-    if (k < 21) {
-      int r = 0, rem = k;
-      while (rem >= 6 - r) { rem -= 6 - r; r++; }
-      const int q = r + rem;
-      Hcc[r * 6 + q] = s; Hcc[q * 6 + r] = s;
-    } else {
-      Hcc[36 + (k - 21)] = -s;
+  /* (2) camera-camera block and b_c: fixed two-level reduction over facets.
+   * 27 sums x NPART partial ranges, then the partials in order. */
+  {
+    constexpr int NPART = 8;
+    double *part = c.sm + c.sl.P; /* 27*NPART doubles, free outside factor_solve */
+    const int chunk = (nf + NPART - 1) / NPART;
+    DS_FOR(it, 27 * NPART) {
+      const int k = it % 27, pt = it / 27;
+      const int f0 = pt * chunk, f1 = (f0 + chunk) < nf ? (f0 + chunk) : nf;
+      double s = 0.0;
+      const double *Fk = &F[(48 + k) * nf];
+      for (int f = f0; f < f1; f++) s += Fk[f];
+      part[it] = s;
+    }
+    team.sync();
+    DS_FOR(k, 27) {
+      double s = 0.0;
+      for (int pt = 0; pt < NPART; pt++) s += part[pt * 27 + k];
+      if (k < 21) {
+        int r = 0, rem = k;
+        while (rem >= 6 - r) { rem -= 6 - r; r++; }
+        const int q = r + rem;
+        Hcc[r * 6 + q] = s; Hcc[q * 6 + r] = s;
+      } else {
+        Hcc[36 + (k - 21)] = -s;
+      }
     }
   }
 
@@ -577,7 +627,7 @@ DS_FN_NOINLINE double build_system(Ctx &c) {
       for (int s = 0; s < 3; s++) {
         const int j = 3 * q + s;
         if (j > i) continue;
-        c.ws.Hb[i * ld + (j - i + bw)] = h[3 * r + s];
+        c.ws.Hb[i * ld + boff(j - i + bw, Q)] = h[3 * r + s];
       }
       if (p == q && fp) maxd = fmax(maxd, fabs(h[4 * r]));
     }
@@ -618,8 +668,8 @@ DS_FN_NOINLINE double build_system(Ctx &c) {
       }
     }
     for (int r = 0; r < 3; r++) {
-      c.ws.Cg[6 * Dp + 3 * p + r] = b[r];
-      for (int a = 0; a < 6; a++) c.ws.Cg[a * Dp + 3 * p + r] = C[3 * a + r];
+      c.ws.Cg[eidx(6, 3 * p + r, Dp)] = b[r];
+      for (int a = 0; a < 6; a++) c.ws.Cg[eidx(a, 3 * p + r, Dp)] = C[3 * a + r];
     }
   }
   maxd = team_max(team, maxd, c.sm + c.sl.red); /* also a barrier: Hcc complete */
@@ -629,27 +679,122 @@ DS_FN_NOINLINE double build_system(Ctx &c) {
 
 /* ------------------------------------------- banded Cholesky + solve --- */
 
+/* Cholesky of one NB x NB diagonal block + inverse of its factor, by warp 0.
+ * in : the block's lower triangle in the window (lambda added to the diagonal)
+ * out: L_kk written back to the window, inv(L_kk) -> invL (shared) and Dinv
+ *      (global, for the backward sweep); *flag set when a pivot is not > 0. */
+DS_FN void diag_factor(const Team team, double *W, int kslot, int Wr, int ld, int bw, int Q, double lambda,
+                       double *invL, double *Dinv_kb, int *flag) {
+#if DS_CUDA
+  /* lane a (< 8) owns row a of the block in registers; columns are eliminated
+   * with warp shuffles, no shared-memory round trips on the critical path */
+  const int lane = team.tid & 31, a = lane & 7;
+  const unsigned full = 0xffffffffu;
+  int slot = kslot + a;
+  if (slot >= Wr) slot -= Wr;
+  double *row = W + slot * ld;
+  double r[NB];
+#pragma unroll
+  for (int b = 0; b < NB; b++) r[b] = (b <= a) ? row[boff(b - a + bw, Q)] : 0.0;
+#pragma unroll
+  for (int b = 0; b < NB; b++)
+    if (b == a) r[b] += lambda;
+  double dinv[NB];
+  bool bad = false;
+#pragma unroll
+  for (int cc = 0; cc < NB; cc++) {
+    const double d = __shfl_sync(full, r[cc], cc);
+    bad = bad || !(d > 0.0);
+    const double inv = rsqrt(d);
+    dinv[cc] = inv;
+    double l = r[cc] * inv;
+    if (a == cc) l = d * inv;
+    r[cc] = l;
+#pragma unroll
+    for (int b = cc + 1; b < NB; b++) {
+      const double lb = __shfl_sync(full, l, b);
+      r[b] -= l * lb; /* meaningful for b <= a; other entries are never read */
+    }
+  }
+  /* column `a` of inv(L): X[i] = (delta_ia - sum_{m<i} L[i][m] X[m]) / L[i][i] */
+  double X[NB];
+#pragma unroll
+  for (int i = 0; i < NB; i++) {
+    double s = (i == a) ? 1.0 : 0.0;
+#pragma unroll
+    for (int m = 0; m < i; m++) {
+      const double Lim = __shfl_sync(full, r[m], i);
+      s -= Lim * X[m];
+    }
+    X[i] = (i >= a) ? s * dinv[i] : 0.0;
+  }
+  if (lane < NB) {
+#pragma unroll
+    for (int b = 0; b < NB; b++)
+      if (b <= a) row[boff(b - a + bw, Q)] = r[b];
+#pragma unroll
+    for (int i = 0; i < NB; i++) {
+      invL[i * NB + a] = X[i];
+      Dinv_kb[i * NB + a] = X[i];
+    }
+    if (bad) *flag = 1;
+  }
+#else
+  (void)team;
+  double L[NB][NB], X[NB][NB], dinv[NB];
+  for (int a = 0; a < NB; a++) {
+    int slot = kslot + a;
+    if (slot >= Wr) slot -= Wr;
+    for (int b = 0; b < NB; b++) L[a][b] = (b <= a) ? W[slot * ld + boff(b - a + bw, Q)] : 0.0;
+    L[a][a] += lambda;
+  }
+  for (int cc = 0; cc < NB; cc++) {
+    const double d = L[cc][cc];
+    if (!(d > 0.0)) *flag = 1;
+    const double inv = 1.0 / sqrt(d);
+    dinv[cc] = inv;
+    for (int a = cc; a < NB; a++) L[a][cc] = (a == cc) ? d * inv : L[a][cc] * inv;
+    for (int a = cc + 1; a < NB; a++)
+      for (int b = cc + 1; b <= a; b++) L[a][b] -= L[a][cc] * L[b][cc];
+  }
+  for (int j = 0; j < NB; j++)
+    for (int i = 0; i < NB; i++) {
+      double s = (i == j) ? 1.0 : 0.0;
+      for (int m = 0; m < i; m++) s -= L[i][m] * X[m][j];
+      X[i][j] = (i >= j) ? s * dinv[i] : 0.0;
+    }
+  for (int a = 0; a < NB; a++) {
+    int slot = kslot + a;
+    if (slot >= Wr) slot -= Wr;
+    for (int b = 0; b <= a; b++) W[slot * ld + boff(b - a + bw, Q)] = L[a][b];
+    for (int j = 0; j < NB; j++) { invL[a * NB + j] = X[a][j]; Dinv_kb[a * NB + j] = X[a][j]; }
+  }
+#endif
+}
+
 /* Solve (H + lambda I) dx = b.  dx -> sm[sl.dx] (nodes, then camera at Dn_pad).
  * Returns false if a pivot is not positive (LinearSolverDense::solve returning
  * false, linear_solver_dense.h:107-112); dx is then left untouched (stale), as
  * in the reference. */
-DS_FN_NOINLINE bool factor_solve(Ctx &c, double lambda) {
-  const Team team = c.team;
-  const PlanView &pl = c.pl;
-  const int bw = pl.bw, ld = pl.ld, Dp = pl.Dn_pad, Wr = pl.Wr, bwp = pl.bwp, nblk = pl.nblk;
+DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &c, double lambda) {
+  const int bw = c.pl.bw, ld = c.pl.ld, Dp = c.pl.Dn_pad, Wr = c.pl.Wr, bwp = c.pl.bwp, nblk = c.pl.nblk, Q = c.pl.Q;
   const int PS = bwp + 8;
-  double *W = c.sm + c.sl.W, *P = c.sm + c.sl.P, *Lkk = c.sm + c.sl.Lkk, *invL = c.sm + c.sl.invL;
-  double *G = c.sm + c.sl.G, *Hcc = c.sm + c.sl.Hcc, *dx = c.sm + c.sl.dx;
+  double *const sm = c.sm;
+  double *W = sm + c.sl.W, *P = sm + c.sl.P, *invL = sm + c.sl.invL;
+  double *G = sm + c.sl.G, *Hcc = sm + c.sl.Hcc, *dx = sm + c.sl.dx;
   double *E = c.E;
-  int *flag = (int *)(c.sm + c.sl.red + 36);
+  const double *Hb = c.ws.Hb;
+  double *Lb = c.ws.Lb, *Dinv = c.ws.Dinv;
+  int *flag = (int *)(sm + c.sl.red + 36);
   const int nt = bwp / TILE;
 
   team.sync();
   /* window <- first Wr rows of H; border/rhs working copy; corner */
   {
     const int rows = Wr < Dp ? Wr : Dp;
-    DS_FOR(i, rows * ld) W[i] = c.ws.Hb[i];
-    DS_FOR(i, 8 * Dp) E[i] = c.ws.Cg[i];
+    DS_FOR(i, rows * ld) W[i] = Hb[i];
+    const double *Cg = c.ws.Cg;
+    DS_FOR(i, 8 * Dp) E[i] = Cg[i];
     DS_FOR(i, 64) {
       const int a = i >> 3, b = i & 7;
       double v = 0.0;
@@ -661,99 +806,54 @@ DS_FN_NOINLINE bool factor_solve(Ctx &c, double lambda) {
   }
   team.sync();
 
+  int kslot = 0; /* k mod Wr */
   for (int kb = 0; kb < nblk; kb++) {
     const int k = kb * NB;
     /* S1: factor the diagonal block (warp 0) */
-    if (team.warp0()) {
-      DS_WARP_FOR(l, 64) {
-        const int a = l >> 3, b = l & 7;
-        double v = 0.0;
-        if (b <= a) {
-          const int i = k + a, j = k + b;
-          v = W[(i % Wr) * ld + (j - i + bw)];
-          if (a == b) v += lambda;
-        }
-        Lkk[l] = v;
-        invL[l] = 0.0;
-      }
-      team.warp_sync();
-      for (int cc = 0; cc < NB; cc++) {
-        const double d = Lkk[cc * 8 + cc];
-        const bool pos = d > 0.0;
-#if DS_CUDA
-        const double inv = rsqrt(d);
-#else
-        const double inv = 1.0 / sqrt(d);
-#endif
-        team.warp_sync();
-        DS_WARP_FOR(a, NB) {
-          if (a == cc) { Lkk[cc * 8 + cc] = d * inv; P[a] = inv; if (!pos) *flag = 1; }
-          else if (a > cc) Lkk[a * 8 + cc] *= inv;
-        }
-        team.warp_sync();
-        DS_WARP_FOR(l, 64) {
-          const int a = l >> 3, b = l & 7;
-          if (b > cc && a >= b) Lkk[a * 8 + b] -= Lkk[a * 8 + cc] * Lkk[b * 8 + cc];
-        }
-        team.warp_sync();
-      }
-      /* inverse of the lower-triangular block, one column per lane; P[0..7] = 1/diag */
-      DS_WARP_FOR(j, NB) {
-        double X[NB];
-        for (int a = 0; a < NB; a++) {
-          double s = (a == j) ? 1.0 : 0.0;
-          for (int m = j; m < a; m++) s -= Lkk[a * 8 + m] * X[m];
-          X[a] = (a >= j) ? s * P[a] : 0.0;
-          invL[a * 8 + j] = X[a];
-        }
-      }
-      team.warp_sync();
-      DS_WARP_FOR(l, 64) {
-        const int a = l >> 3, b = l & 7;
-        if (b <= a) {
-          const int i = k + a, j = k + b;
-          W[(i % Wr) * ld + (j - i + bw)] = Lkk[l];
-        }
-        c.ws.Dinv[kb * 64 + l] = invL[l];
-      }
-    }
+    if (team.warp0()) diag_factor(team, W, kslot, Wr, ld, bw, Q, lambda, invL, Dinv + kb * 64, flag);
     team.sync();
 
     /* S2: panel = rows below (and the 8 border rows) times L_kk^-T */
     const int n_trail = (Dp - (k + NB)) < bwp ? (Dp - (k + NB)) : bwp;
     DS_FOR(r, bwp + 8) {
       double a[NB], xr[NB];
-      int slot = -1, i = 0;
+      double *rowp = nullptr;
+      int o0 = 0; /* band offset of column k in this row */
       if (r < bwp) {
-        i = k + NB + r;
         if (r < n_trail) {
-          slot = (i % Wr) * ld;
-          for (int cc = 0; cc < NB; cc++) {
-            const int off = k + cc - i + bw;
-            a[cc] = off >= 0 ? W[slot + off] : 0.0;
-          }
+          int slot = kslot + NB + r;
+          if (slot >= Wr) slot -= Wr;
+          rowp = W + slot * ld;
+          o0 = bw - NB - r;
+#pragma unroll
+          for (int cc = 0; cc < NB; cc++) a[cc] = (o0 + cc >= 0) ? rowp[boff(o0 + cc, Q)] : 0.0;
         } else {
+#pragma unroll
           for (int cc = 0; cc < NB; cc++) a[cc] = 0.0;
         }
       } else {
         const int e = r - bwp;
-        for (int cc = 0; cc < NB; cc++) a[cc] = E[e * Dp + k + cc];
+#pragma unroll
+        for (int cc = 0; cc < NB; cc++) a[cc] = E[eidx(e, k + cc, Dp)];
       }
+#pragma unroll
       for (int cc = 0; cc < NB; cc++) {
         double s = 0.0;
-        for (int m = 0; m <= cc; m++) s += a[m] * invL[cc * 8 + m];
+#pragma unroll
+        for (int m = 0; m <= cc; m++) s += a[m] * invL[cc * NB + m];
         xr[cc] = s;
-        P[cc * PS + r] = s;
+        P[pidx(cc, r, PS)] = s;
       }
       if (r < bwp) {
-        if (slot >= 0)
-          for (int cc = 0; cc < NB; cc++) {
-            const int off = k + cc - i + bw;
-            if (off >= 0) W[slot + off] = xr[cc];
-          }
+        if (rowp) {
+#pragma unroll
+          for (int cc = 0; cc < NB; cc++)
+            if (o0 + cc >= 0) rowp[boff(o0 + cc, Q)] = xr[cc];
+        }
       } else {
         const int e = r - bwp;
-        for (int cc = 0; cc < NB; cc++) E[e * Dp + k + cc] = xr[cc];
+#pragma unroll
+        for (int cc = 0; cc < NB; cc++) E[eidx(e, k + cc, Dp)] = xr[cc];
       }
     }
     team.sync();
@@ -762,6 +862,7 @@ DS_FN_NOINLINE bool factor_solve(Ctx &c, double lambda) {
     {
       const int ntr = nt + 2;
       const int ntiles = ntr * (ntr + 1) / 2;
+      const int PQ = PS >> 2;
       DS_FOR(t, ntiles) {
         int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
         while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
@@ -770,85 +871,110 @@ DS_FN_NOINLINE bool factor_solve(Ctx &c, double lambda) {
         const bool erow = ti >= nt, ecol = tj >= nt;
         if (!erow && TILE * ti >= n_trail) continue;
         if (!ecol && TILE * tj >= n_trail) continue;
-        const int r0 = erow ? bwp + TILE * (ti - nt) : TILE * ti;
-        const int c0 = ecol ? bwp + TILE * (tj - nt) : TILE * tj;
+        /* tile index inside the (de-interleaved) panel buffer */
+        const int pr = erow ? (bwp >> 2) + (ti - nt) : ti;
+        const int pc = ecol ? (bwp >> 2) + (tj - nt) : tj;
         double acc[TILE][TILE];
+#pragma unroll
         for (int a = 0; a < TILE; a++)
+#pragma unroll
           for (int b = 0; b < TILE; b++) acc[a][b] = 0.0;
+#pragma unroll
         for (int cc = 0; cc < NB; cc++) {
           double pa[TILE], pb[TILE];
-          for (int a = 0; a < TILE; a++) { pa[a] = P[cc * PS + r0 + a]; pb[a] = P[cc * PS + c0 + a]; }
+#pragma unroll
+          for (int a = 0; a < TILE; a++) { pa[a] = P[cc * PS + a * PQ + pr]; pb[a] = P[cc * PS + a * PQ + pc]; }
+#pragma unroll
           for (int a = 0; a < TILE; a++)
+#pragma unroll
             for (int b = 0; b < TILE; b++) acc[a][b] += pa[a] * pb[b];
         }
         if (!erow) {
-          for (int a = 0; a < TILE; a++) {
-            const int i = k + NB + r0 + a;
-            const int slot = (i % Wr) * ld;
-            for (int b = 0; b < TILE; b++) {
-              const int j = k + NB + c0 + b;
-              const int off = j - i + bw;
-              if (j <= i && off >= 0) W[slot + off] -= acc[a][b];
+          const int r0 = TILE * ti, c0 = TILE * tj;
+          const int d0 = c0 - r0 + bw; /* band offset of (row r0, col c0) */
+          int slot0 = kslot + NB + r0;
+          if (slot0 >= Wr) slot0 -= Wr;
+          const bool interior = (ti > tj) && (r0 - c0 + 3 <= bw);
+          if (interior) {
+#pragma unroll
+            for (int a = 0; a < TILE; a++) {
+              int slot = slot0 + a;
+              if (slot >= Wr) slot -= Wr;
+              double *rowp = W + slot * ld;
+#pragma unroll
+              for (int b = 0; b < TILE; b++) rowp[boff(d0 + b - a, Q)] -= acc[a][b];
+            }
+          } else {
+#pragma unroll
+            for (int a = 0; a < TILE; a++) {
+              int slot = slot0 + a;
+              if (slot >= Wr) slot -= Wr;
+              double *rowp = W + slot * ld;
+#pragma unroll
+              for (int b = 0; b < TILE; b++) {
+                const int off = d0 + b - a;
+                if (off <= bw && off >= 0) rowp[boff(off, Q)] -= acc[a][b];
+              }
             }
           }
         } else if (!ecol) {
-          for (int a = 0; a < TILE; a++) {
-            const int e = r0 - bwp + a;
-            for (int b = 0; b < TILE; b++) E[e * Dp + k + NB + c0 + b] -= acc[a][b];
-          }
-        } else {
+          const int e0 = TILE * (ti - nt), col0 = k + NB + TILE * tj;
+#pragma unroll
           for (int a = 0; a < TILE; a++)
-            for (int b = 0; b < TILE; b++) {
-              const int e = r0 - bwp + a, e2 = c0 - bwp + b;
-              if (e2 <= e) G[e * 8 + e2] -= acc[a][b];
-            }
+#pragma unroll
+            for (int b = 0; b < TILE; b++) E[eidx(e0 + a, col0 + b, Dp)] -= acc[a][b];
+        } else {
+          const int e0 = TILE * (ti - nt), f0 = TILE * (tj - nt);
+#pragma unroll
+          for (int a = 0; a < TILE; a++)
+#pragma unroll
+            for (int b = 0; b < TILE; b++)
+              if (f0 + b <= e0 + a) G[(e0 + a) * 8 + f0 + b] -= acc[a][b];
         }
       }
       /* finished rows k..k+7 -> L (global); refill their slots with rows k+Wr.. */
       {
-        const int slot = (k % Wr) * ld;
+        const int slot = kslot * ld;
         const bool refill = k + Wr < Dp;
         DS_FOR(i, NB * ld) {
-          c.ws.Lb[k * ld + i] = W[slot + i];
-          if (refill) W[slot + i] = c.ws.Hb[(k + Wr) * ld + i];
+          Lb[k * ld + i] = W[slot + i];
+          if (refill) W[slot + i] = Hb[(k + Wr) * ld + i];
         }
       }
     }
     team.sync();
+    kslot += NB;
+    if (kslot >= Wr) kslot -= Wr;
   }
 
-  /* Schur complement system of the camera: S dc = rhs  (6x6 Cholesky) */
+  /* Schur complement system of the camera: S dc = rhs  (6x6 Cholesky, in place
+   * in the shared corner block; row 6 of G is the right-hand side) */
   if (team.tid == 0) {
-    double Sx[36], rhs[6];
-    for (int a = 0; a < 6; a++) {
-      for (int b = 0; b <= a; b++) Sx[a * 6 + b] = G[a * 8 + b];
-      rhs[a] = G[6 * 8 + a];
-    }
     bool ok = true;
     for (int j = 0; j < 6; j++) {
-      double d = Sx[j * 6 + j];
-      for (int m = 0; m < j; m++) d -= Sx[j * 6 + m] * Sx[j * 6 + m];
+      double d = G[j * 8 + j];
+      for (int m = 0; m < j; m++) d -= G[j * 8 + m] * G[j * 8 + m];
       if (!(d > 0.0)) ok = false;
       const double l = sqrt(d);
-      Sx[j * 6 + j] = l;
+      G[j * 8 + j] = l;
       for (int i = j + 1; i < 6; i++) {
-        double s = Sx[i * 6 + j];
-        for (int m = 0; m < j; m++) s -= Sx[i * 6 + m] * Sx[j * 6 + m];
-        Sx[i * 6 + j] = s / l;
+        double s = G[i * 8 + j];
+        for (int m = 0; m < j; m++) s -= G[i * 8 + m] * G[j * 8 + m];
+        G[i * 8 + j] = s / l;
       }
     }
     if (!ok) *flag = 1;
     if (*flag == 0) {
-      double y[6];
+      double *y = G + 56; /* row 7 of the corner is unused */
       for (int i = 0; i < 6; i++) {
-        double s = rhs[i];
-        for (int m = 0; m < i; m++) s -= Sx[i * 6 + m] * y[m];
-        y[i] = s / Sx[i * 6 + i];
+        double s = G[48 + i];
+        for (int m = 0; m < i; m++) s -= G[i * 8 + m] * y[m];
+        y[i] = s / G[i * 8 + i];
       }
       for (int i = 5; i >= 0; i--) {
         double s = y[i];
-        for (int m = i + 1; m < 6; m++) s -= Sx[m * 6 + i] * y[m];
-        y[i] = s / Sx[i * 6 + i];
+        for (int m = i + 1; m < 6; m++) s -= G[m * 8 + i] * y[m];
+        y[i] = s / G[i * 8 + i];
       }
       for (int i = 0; i < 6; i++) dx[Dp + i] = y[i];
     }
@@ -858,8 +984,9 @@ DS_FN_NOINLINE bool factor_solve(Ctx &c, double lambda) {
 
   /* v = z - Y^T dc */
   DS_FOR(i, Dp) {
-    double s = E[6 * Dp + i];
-    for (int e = 0; e < 6; e++) s -= E[e * Dp + i] * dx[Dp + e];
+    double s = E[eidx(6, i, Dp)];
+#pragma unroll
+    for (int e = 0; e < 6; e++) s -= E[eidx(e, i, Dp)] * dx[Dp + e];
     dx[i] = s;
   }
   /* backward sweep  L^T dn = v, one block of NB rows per step, rows of L
@@ -867,8 +994,8 @@ DS_FN_NOINLINE bool factor_solve(Ctx &c, double lambda) {
   double *LR0 = W, *LR1 = W + NB * ld + 64;
   {
     const int k = (nblk - 1) * NB;
-    DS_FOR(i, NB * ld) LR0[i] = c.ws.Lb[k * ld + i];
-    DS_FOR(i, 64) LR0[NB * ld + i] = c.ws.Dinv[(nblk - 1) * 64 + i];
+    DS_FOR(i, NB * ld) LR0[i] = Lb[k * ld + i];
+    DS_FOR(i, 64) LR0[NB * ld + i] = Dinv[(nblk - 1) * 64 + i];
   }
   team.sync();
   for (int kb = nblk - 1; kb >= 0; kb--) {
@@ -879,13 +1006,13 @@ DS_FN_NOINLINE bool factor_solve(Ctx &c, double lambda) {
     /* prefetch the next block while this one is processed */
     if (kb > 0) {
       const int kn = (kb - 1) * NB;
-      DS_FOR(i, NB * ld) LRn[i] = c.ws.Lb[kn * ld + i];
-      DS_FOR(i, 64) LRn[NB * ld + i] = c.ws.Dinv[(kb - 1) * 64 + i];
+      DS_FOR(i, NB * ld) LRn[i] = Lb[kn * ld + i];
+      DS_FOR(i, 64) LRn[NB * ld + i] = Dinv[(kb - 1) * 64 + i];
     }
-    /* d = invL^T y  (8 values; every thread that needs them recomputes from smem) */
+    /* d = invL^T y */
     DS_FOR(cc, NB) {
       double s = 0.0;
-      for (int a = cc; a < NB; a++) s += Di[a * 8 + cc] * dx[k + a];
+      for (int a = cc; a < NB; a++) s += Di[a * NB + cc] * dx[k + a];
       P[cc] = s;
     }
     team.sync();
@@ -895,9 +1022,10 @@ DS_FN_NOINLINE bool factor_solve(Ctx &c, double lambda) {
       DS_FOR(jj, k - j0) {
         const int j = j0 + jj;
         double s = dx[j];
+#pragma unroll
         for (int a = 0; a < NB; a++) {
           const int off = j - (k + a) + bw;
-          if (off >= 0) s -= LR[a * ld + off] * P[a];
+          if (off >= 0) s -= LR[a * ld + boff(off, Q)] * P[a];
         }
         dx[j] = s;
       }
@@ -909,8 +1037,7 @@ DS_FN_NOINLINE bool factor_solve(Ctx &c, double lambda) {
 
 /* ------------------------------------------------------------- LM ------ */
 
-DS_FN void apply_update(Ctx &c) {
-  const Team team = c.team;
+DS_FN void apply_update(const Team team, Ctx &c) {
   const PlanView &pl = c.pl;
   double *x = c.sm + c.sl.x, *dx = c.sm + c.sl.dx;
   /* VertexSBAPointXYZ::oplusImpl (types_sba.h:52-56); fixed nodes have dx = 0 */
@@ -926,10 +1053,9 @@ DS_FN void apply_update(Ctx &c) {
   team.sync();
 }
 
-DS_FN void expand_dense(Ctx &c, double chi) {
-  const Team team = c.team;
+DS_FN void expand_dense(const Team team, Ctx &c, double chi) {
   const PlanView &pl = c.pl;
-  const int Dn = pl.Dn, D = Dn + 6, bw = pl.bw, ld = pl.ld, Dp = pl.Dn_pad;
+  const int Dn = pl.Dn, D = Dn + 6, bw = pl.bw, ld = pl.ld, Dp = pl.Dn_pad, Q = pl.Q;
   const double *Hcc = c.sm + c.sl.Hcc;
   team.sync();
   if (c.pb.out_H) {
@@ -937,15 +1063,15 @@ DS_FN void expand_dense(Ctx &c, double chi) {
       const int i = idx / D, j = idx - i * D;
       const int hi = i > j ? i : j, lo = i > j ? j : i;
       double v = 0.0;
-      if (hi < Dn) { if (hi - lo <= bw) v = c.ws.Hb[hi * ld + (lo - hi + bw)]; }
-      else if (lo < Dn) v = c.ws.Cg[(hi - Dn) * Dp + lo];
+      if (hi < Dn) { if (hi - lo <= bw) v = c.ws.Hb[hi * ld + boff(lo - hi + bw, Q)]; }
+      else if (lo < Dn) v = c.ws.Cg[eidx(hi - Dn, lo, Dp)];
       else v = Hcc[(hi - Dn) * 6 + (lo - Dn)];
       c.pb.out_H[idx] = v;
     }
   }
   if (c.pb.out_b) {
     DS_FOR(i, D) {
-      double v = i < Dn ? c.ws.Cg[6 * Dp + i] : Hcc[36 + (i - Dn)];
+      double v = i < Dn ? c.ws.Cg[eidx(6, i, Dp)] : Hcc[36 + (i - Dn)];
       if (i < Dn && !c.freev[i / 3]) v = 0.0;
       c.pb.out_b[i] = v;
     }
@@ -960,9 +1086,8 @@ DS_FN void expand_dense(Ctx &c, double chi) {
 }
 
 /* DefOptimizer.cc:515-577 */
-DS_FN_NOINLINE void finalize(Ctx &c, bool last_rejected, int iterations, int trials, double chi_ini, double chi_fin,
-                             double lambda) {
-  const Team team = c.team;
+DS_FN_NOINLINE void finalize(const Team team, Ctx &c, bool last_rejected, int iterations, int trials, double chi_ini,
+                             double chi_fin, double lambda) {
   const PlanView &pl = c.pl;
   const ProbView &pb = c.pb;
   const int M = pb.n_matches, n = pl.n_nodes;
@@ -1013,8 +1138,7 @@ DS_FN_NOINLINE void finalize(Ctx &c, bool last_rejected, int iterations, int tri
 }
 
 /* One frame, start to finish.  All threads of the team call this. */
-DS_FN_NOINLINE void sft_solve_one(Ctx &c) {
-  const Team team = c.team;
+DS_FN_NOINLINE void sft_solve_one(const Team team, Ctx &c) {
   const PlanView &pl = c.pl;
   const ProbView &pb = c.pb;
   double *x = c.sm + c.sl.x, *xb = c.sm + c.sl.xb, *dx = c.sm + c.sl.dx;
@@ -1022,15 +1146,15 @@ DS_FN_NOINLINE void sft_solve_one(Ctx &c) {
   double *red = c.sm + c.sl.red;
   const int Dp = pl.Dn_pad;
 
-  const int rc = prologue(c);
+  const int rc = prologue(team, c);
   if (rc != 0) {
     if (team.tid == 0) pb.out_res->status = rc;
     return;
   }
   if (pb.mode == MODE_NORMAL_EQ) {
-    const double chi = eval_state(c, x, ps, true);
-    build_system(c);
-    expand_dense(c, chi);
+    const double chi = eval_state(team, c, x, ps, true);
+    build_system(team, c);
+    expand_dense(team, c, chi);
     return;
   }
 
@@ -1043,11 +1167,11 @@ DS_FN_NOINLINE void sft_solve_one(Ctx &c) {
   int nBad = 0, iterations = 0, trials = 0;
   bool last_rejected = false;
   for (int it = 0; it < max_it; it++) {
-    double currentChi = eval_state(c, x, ps, true);
+    double currentChi = eval_state(team, c, x, ps, true);
     double tempChi = currentChi;
     const double iniChi = currentChi;
     if (it == 0) chi_ini0 = currentChi;
-    const double maxDiag = build_system(c);
+    const double maxDiag = build_system(team, c);
     if (it == 0) { lambda = tau * maxDiag; ni = 2; nBad = 0; }
     const double lambda_start = lambda;
     double rho = 0;
@@ -1057,13 +1181,13 @@ DS_FN_NOINLINE void sft_solve_one(Ctx &c) {
       team.sync();
       DS_FOR(i, pl.Dn) xb[i] = x[i];
       if (team.tid == 0) for (int k = 0; k < 7; k++) psb[k] = ps[k];
-      const bool ok2 = factor_solve(c, lambda);
-      apply_update(c);
-      tempChi = eval_state(c, x, ps, false);
+      const bool ok2 = factor_solve(team, c, lambda);
+      apply_update(team, c);
+      tempChi = eval_state(team, c, x, ps, false);
       if (!ok2) tempChi = DBL_MAX;
       rho = currentChi - tempChi;
       double scale = 0.; /* computeScale :182-189 */
-      DS_FOR(j, pl.Dn) scale += dx[j] * (lambda * dx[j] + c.ws.Cg[6 * Dp + j]);
+      DS_FOR(j, pl.Dn) scale += dx[j] * (lambda * dx[j] + c.ws.Cg[eidx(6, j, Dp)]);
       scale = team_sum(team, scale, red);
       for (int j = 0; j < 6; j++) scale += dx[Dp + j] * (lambda * dx[Dp + j] + (c.sm + c.sl.Hcc)[36 + j]);
       scale += 1e-3;
@@ -1100,24 +1224,33 @@ DS_FN_NOINLINE void sft_solve_one(Ctx &c) {
     if (nBad >= 3) break;
   }
   team.sync();
-  finalize(c, last_rejected, iterations, trials, chi_ini0, chi_fin, lambda);
+  finalize(team, c, last_rejected, iterations, trials, chi_ini0, chi_fin, lambda);
 }
 
+/* doubles reserved at the head of shared memory for the CTA-wide context */
+constexpr int CTX_DOUBLES = (int)((sizeof(Ctx) + 15) / 16) * 2;
+
 /* Entry shared by the CUDA kernel and the emulation: bind a problem to a team,
- * its shared memory and its global workspace, then solve it. */
+ * its shared memory and its global workspace, then solve it.  The context is
+ * kept in shared memory (one copy per CTA): with the shared-memory carve-out
+ * this kernel uses there is almost no L1 left for a per-thread stack copy. */
 DS_FN void sft_run_problem(const Team &team, const ProbView &pv, double *smem, uint8_t *ws_base,
                            const WorkspaceSizes &z) {
-  Ctx c;
-  c.team = team;
-  c.pb = pv;
-  c.pl = *pv.plan;
-  c.ws = carve_workspace(ws_base, z);
-  c.sl = smem_layout(c.pl.n_nodes, c.pl.n_edges, c.pl.Dn_pad, c.pl.bwp, c.pl.ld, c.pl.Wr, pv.e_in_smem != 0);
-  c.sm = smem;
-  c.E = pv.e_in_smem ? smem + c.sl.E : c.ws.Eg;
-  c.viewed = (uint8_t *)(smem + c.sl.flags);
-  c.freev = c.viewed + c.pl.n_nodes;
-  sft_solve_one(c);
+  Ctx &c = *(Ctx *)smem;
+  double *sm = smem + CTX_DOUBLES;
+  team.sync();
+  if (team.tid == 0) {
+    c.pb = pv;
+    c.pl = *pv.plan;
+    c.ws = carve_workspace(ws_base, z);
+    c.sl = smem_layout(c.pl.n_nodes, c.pl.n_edges, c.pl.Dn_pad, c.pl.bwp, c.pl.ld, c.pl.Wr, pv.e_in_smem != 0);
+    c.sm = sm;
+    c.E = pv.e_in_smem ? sm + c.sl.E : c.ws.Eg;
+    c.viewed = (uint8_t *)(sm + c.sl.flags);
+    c.freev = c.viewed + c.pl.n_nodes;
+  }
+  team.sync();
+  sft_solve_one(team, c);
 }
 
 }  // namespace ds

@@ -222,7 +222,8 @@ int defslam_template_info(const defslam_template *t, int32_t *bandwidth, int32_t
   if (dn_pad) *dn_pad = v.Dn_pad;
   if (n_blocks) *n_blocks = v.n_blk;
   if (smem_bytes)
-    *smem_bytes = (int32_t)sizeof(double) * smem_layout(v.n_nodes, v.n_edges, v.Dn_pad, v.bwp, v.ld, v.Wr, true).total;
+    *smem_bytes = (int32_t)sizeof(double) *
+                  (CTX_DOUBLES + smem_layout(v.n_nodes, v.n_edges, v.Dn_pad, v.bwp, v.ld, v.Wr, true).total);
   return DEFSLAM_OK;
 }
 

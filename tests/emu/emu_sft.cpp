@@ -102,7 +102,7 @@ void emu_template_destroy(void *t) { delete (EmuTemplate *)t; }
 int emu_plan_info(void *t, int32_t *out /* bw, ld, Dn_pad, Wr, n_blk, smem_doubles */) {
   const EmuTemplate *e = (const EmuTemplate *)t;
   out[0] = e->view.bw; out[1] = e->view.ld; out[2] = e->view.Dn_pad; out[3] = e->view.Wr; out[4] = e->view.n_blk;
-  out[5] = smem_layout(e->view.n_nodes, e->view.n_edges, e->view.Dn_pad, e->view.bwp, e->view.ld, e->view.Wr, true).total;
+  out[5] = CTX_DOUBLES + smem_layout(e->view.n_nodes, e->view.n_edges, e->view.Dn_pad, e->view.bwp, e->view.ld, e->view.Wr, true).total;
   return 0;
 }
 }
