@@ -90,10 +90,10 @@ struct BatchMarshal {
       v.reg_lap = p[i].reg_lap; v.reg_inex = p[i].reg_inex; v.reg_temp = p[i].reg_temp;
       for (int k = 0; k < 16; k++) v.Tcw[k] = p[i].T_cw[k];
 
-      SmemLayout L = smem_layout(hv->n_nodes, hv->n_edges, hv->Dn_pad, hv->bwp, hv->ld, hv->Wr, true);
+      SmemLayout L = smem_layout(hv->n_nodes, hv->n_edges, hv->Dn_pad, hv->bwp, hv->ld, hv->Wr, hv->ES, true);
       v.e_in_smem = 1;
       if (L.total + CTX_DOUBLES > smem_limit_doubles) {
-        L = smem_layout(hv->n_nodes, hv->n_edges, hv->Dn_pad, hv->bwp, hv->ld, hv->Wr, false);
+        L = smem_layout(hv->n_nodes, hv->n_edges, hv->Dn_pad, hv->bwp, hv->ld, hv->Wr, hv->ES, false);
         v.e_in_smem = 0;
         any_e_global = true;
         if (L.total + CTX_DOUBLES > smem_limit_doubles) return DEFSLAM_ETOOLARGE;
@@ -101,7 +101,7 @@ struct BatchMarshal {
       if (L.total + CTX_DOUBLES > smem_doubles) smem_doubles = L.total + CTX_DOUBLES;
       ws_band = std::max(ws_band, (size_t)hv->Dn_pad * hv->ld);
       ws_dinv = std::max(ws_dinv, (size_t)hv->nblk * 64);
-      ws_cg = std::max(ws_cg, (size_t)8 * hv->Dn_pad);
+      ws_cg = std::max(ws_cg, (size_t)8 * hv->ES);
       ws_F = std::max(ws_F, (size_t)NFACC * hv->n_facets);
       ws_S = std::max(ws_S, (size_t)NMSCR * M);
       ws_M = std::max(ws_M, M);

@@ -32,8 +32,9 @@ struct PlanView {
   int Dn;      /* 3*n_nodes                                              */
   int Dn_pad;  /* Dn rounded up to NB (padding rows are identity)        */
   int bw;      /* scalar half bandwidth                                   */
-  int ld;      /* band row length: 4*Q (+1 so that ld-Q is odd)           */
-  int Q;       /* ceil((bw+1)/4): length of one de-interleaved quarter    */
+  int bwE;     /* bw rounded up to even: column of the diagonal in a band row */
+  int ld;      /* band row length: >= bwE+1 and == 9 (mod 16), see sft_core.h */
+  int ES;      /* row stride of the 8 border rows: >= Dn_pad, == 8 (mod 16)   */
   int bwp;     /* bw rounded up to TILE: extent of the trailing update    */
   int Wr;      /* rows of the sliding window (multiple of NB, >= NB+bwp)  */
   int nblk;    /* Dn_pad / NB                                             */
@@ -204,8 +205,10 @@ struct PlanHost {
     v.Dn_pad = round_up(v.Dn, NB);
     v.bw = std::min(3 * bwn + 2, v.Dn - 1);
     if (v.bw < 2) v.bw = 2;
-    v.Q = (v.bw + 1 + 3) / 4;
-    v.ld = 4 * v.Q + (((3 * v.Q) & 1) ? 0 : 1);
+    v.bwE = round_up(v.bw, 2);
+    v.ld = v.bwE + 1;
+    while ((v.ld & 15) != 9) v.ld++;
+    v.ES = (v.Dn_pad & 15) == 8 ? v.Dn_pad : v.Dn_pad + 8;
     v.bwp = round_up(v.bw, TILE);
     v.Wr = round_up(NB + v.bwp, NB);
     v.nblk = v.Dn_pad / NB;

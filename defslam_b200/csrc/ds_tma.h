@@ -1,0 +1,60 @@
+/*
+ * ds_tma.h -- bulk asynchronous copies (TMA, cp.async.bulk) + mbarrier helpers.
+ *
+ * The banded factorisation streams 8-row blocks of the H / L bands between HBM
+ * and the shared-memory window.  Rows of a block are contiguous in both places,
+ * so the non-tensor bulk form of TMA is enough: one elected thread issues
+ * cp.async.bulk global->shared with an mbarrier that counts the bytes, the CTA
+ * waits on the barrier's phase parity where it needs the rows.
+ * Under emulation (g++) the copy is a memcpy and the waits are no-ops.
+ */
+#ifndef DS_TMA_H_
+#define DS_TMA_H_
+#include "ds_common.h"
+
+namespace ds {
+
+#if DS_CUDA
+DS_FN uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+DS_FN void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+DS_FN void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+/* order generic-proxy accesses (plain ld/st) before later async-proxy (TMA) accesses */
+DS_FN void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+DS_FN void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+/* bytes: multiple of 16; dst/src 16-byte aligned */
+DS_FN void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(__cvta_generic_to_global(src_gmem)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+DS_FN void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LAB_DONE%=;\n"
+      "bra LAB_WAIT%=;\n"
+      "LAB_DONE%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+#else
+DS_FN void mbar_init(uint64_t *, int) {}
+DS_FN void fence_mbar_init() {}
+DS_FN void fence_proxy_async() {}
+DS_FN void mbar_expect_tx(uint64_t *, uint32_t) {}
+DS_FN void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *) { memcpy(dst, src, bytes); }
+DS_FN void mbar_wait(uint64_t *, uint32_t) {}
+#endif
+
+}  // namespace ds
+#endif

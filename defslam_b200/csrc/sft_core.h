@@ -32,6 +32,7 @@
 #include "ds_common.h"
 #include "ds_plan.h"
 #include "ds_se3.h"
+#include "ds_tma.h"
 
 namespace ds {
 
@@ -137,21 +138,21 @@ static inline
 #if DS_CUDA
 __host__ __device__
 #endif
-SmemLayout smem_layout(int n_nodes, int n_edges, int Dn_pad, int bwp, int ld, int Wr, bool e_in_smem) {
+SmemLayout smem_layout(int n_nodes, int n_edges, int Dn_pad, int bwp, int ld, int Wr, int ES, bool e_in_smem) {
   SmemLayout L;
   int o = 0;
   int wsz = Wr * ld;
-  const int asz = 11 * n_nodes + 5 * n_edges, bsz = 2 * (NB * ld + 64);
+  const int asz = 11 * n_nodes + 5 * n_edges, bsz = 4 * (NB * ld);
   if (asz > wsz) wsz = asz;
   if (bsz > wsz) wsz = bsz;
   L.W = o;    o += wsz; o = (o + 1) & ~1;
-  L.E = o;    o += e_in_smem ? 8 * Dn_pad : 0;
-  L.P = o;    o += (NB * (bwp + 8) > 216 ? NB * (bwp + 8) : 216);
+  L.E = o;    o += e_in_smem ? 8 * ES : 0;
+  L.P = o;    o += (NB * (bwp + 8) > 216 ? NB * (bwp + 8) : 216); o = (o + 1) & ~1;
   L.x = o;    o += Dn_pad;
   L.xb = o;   o += Dn_pad;
   L.dx = o;   o += Dn_pad + 8;
   L.Lkk = o;  o += 64;
-  L.invL = o; o += 64;
+  L.invL = o; o += 96;   /* inv(L_kk), row stride 12 */
   L.G = o;    o += 64;
   L.Hcc = o;  o += 48;   /* 36 Hcc + 6 bc + 6 dc(stale) */
   L.red = o;  o += 40;
@@ -173,18 +174,36 @@ struct Ctx {
   double info_ref, info_curv, info_str;
   double hub_delta, hub_dsqr;
   double inv_n;
+  long long *prof;  /* optional per-phase cycle counters (global), CTA 0 only */
+  long long prof_last;
+  uint32_t ph[8];  /* phase parity of each mbarrier */
+  uint64_t mbar[8]; /* 0: forward window, 1..4: backward ring (fixed address for the whole launch) */
 };
 
-/* Band row layout: a row holds the band-relative offsets off = j - i + bw in
- * [0, bw], de-interleaved by 4 (offsets congruent mod 4 are contiguous).  The
- * trailing update walks a row in steps of one 4-wide tile per lane, so this
- * makes its shared-memory accesses conflict-free; global H/L bands use the same
- * layout so that rows move between HBM and the window as plain block copies. */
-DS_FN int boff(int off, int Q) { return (off & 3) * Q + (off >> 2); }
-/* same idea for the 8 border rows (camera border, rhs): column de-interleave */
-DS_FN int eidx(int e, int col, int Dp) { return e * Dp + (col & 3) * (Dp >> 2) + (col >> 2); }
-/* panel buffer: P[cc][r] with r de-interleaved by 4 */
-DS_FN int pidx(int cc, int r, int PS) { return cc * PS + (r & 3) * (PS >> 2) + (r >> 2); }
+/* phase-cycle accounting (diagnostics; enabled by DEFSLAM_PROFILE=1 on the host side) */
+enum { PF_PROLOGUE = 0, PF_EVAL_STORE, PF_BUILD, PF_FS_INIT, PF_S1, PF_S1_WAIT, PF_S2, PF_S3, PF_SCHUR, PF_BWD_INIT,
+       PF_BWD, PF_UPDATE, PF_EVAL_TRIAL, PF_LM_SCALAR, PF_FINALIZE, PF_COUNT };
+DS_FN void prof_mark(const Team team, Ctx &c, int idx) {
+#if DS_CUDA
+  if (c.prof != nullptr && team.tid == 0) {
+    const long long now = clock64();
+    c.prof[idx] += now - c.prof_last;
+    c.prof_last = now;
+  }
+#else
+  (void)team; (void)c; (void)idx;
+#endif
+}
+
+/* Layouts (chosen for the FP64 tensor-core tiles of the factorisation):
+ *  - band row i holds H[i][j] at column j - i + bwE (bwE even), row stride ld
+ *    odd with ld == 9 (mod 16): the two adjacent columns a DMMA accumulator
+ *    lane owns are 16-byte aligned in every row, and the 8 rows of a tile fall
+ *    on distinct bank groups;
+ *  - the 8 border rows (camera border 0-5, rhs 6, unused 7) are E[e*ES + col];
+ *  - the panel buffer is P[h][r][4]: column cc = 4h + c4 of panel row r, so that
+ *    one DMMA operand fragment (row T/4, k = T%4) is 32 consecutive doubles. */
+DS_FN int pidx(int cc, int r, int HS) { return (cc >> 2) * HS + r * 4 + (cc & 3); }
 
 /* ------------------------------------------------------------ prologue -- */
 
@@ -211,10 +230,10 @@ DS_FN_NOINLINE int prologue(const Team team, Ctx &c) {
   {
     const int tot = pl.Dn_pad * pl.ld;
     DS_FOR(i, tot) c.ws.Hb[i] = 0.0;
-    DS_FOR(i, 8 * pl.Dn_pad) c.ws.Cg[i] = 0.0;
+    DS_FOR(i, 8 * pl.ES) c.ws.Cg[i] = 0.0;
   }
   team.sync();
-  DS_FOR(i, pl.Dn_pad - pl.Dn) c.ws.Hb[(pl.Dn + i) * pl.ld + boff(pl.bw, pl.Q)] = 1.0;
+  DS_FOR(i, pl.Dn_pad - pl.Dn) c.ws.Hb[(pl.Dn + i) * pl.ld + pl.bwE] = 1.0;
 
   /* facet of every match (DefMapPoint::getFacet) + viewed nodes
    * (DefOptimizer.cc:326-335) */
@@ -462,7 +481,7 @@ DS_FN_NOINLINE double eval_state(const Team team, Ctx &c, const double *x, const
 DS_FN_NOINLINE double build_system(const Team team, Ctx &c) {
   const PlanView &pl = c.pl;
   const int n = pl.n_nodes, ne = pl.n_edges, nf = pl.n_facets, M = c.pb.n_matches;
-  const int bw = pl.bw, ld = pl.ld, Dp = pl.Dn_pad, Q = pl.Q;
+  const int bwE = pl.bwE, ld = pl.ld, ES = pl.ES;
   const double *A = c.sm + c.sl.W;
   const double *cd = A + 6 * n, *cg = cd + 3 * n, *cr = cg + n, *eu = cr + n, *er = eu + 3 * ne, *es = er + ne;
   double *F = c.ws.F;
@@ -627,7 +646,7 @@ DS_FN_NOINLINE double build_system(const Team team, Ctx &c) {
       for (int s = 0; s < 3; s++) {
         const int j = 3 * q + s;
         if (j > i) continue;
-        c.ws.Hb[i * ld + boff(j - i + bw, Q)] = h[3 * r + s];
+        c.ws.Hb[i * ld + (j - i + bwE)] = h[3 * r + s];
       }
       if (p == q && fp) maxd = fmax(maxd, fabs(h[4 * r]));
     }
@@ -668,8 +687,8 @@ DS_FN_NOINLINE double build_system(const Team team, Ctx &c) {
       }
     }
     for (int r = 0; r < 3; r++) {
-      c.ws.Cg[eidx(6, 3 * p + r, Dp)] = b[r];
-      for (int a = 0; a < 6; a++) c.ws.Cg[eidx(a, 3 * p + r, Dp)] = C[3 * a + r];
+      c.ws.Cg[6 * ES + 3 * p + r] = b[r];
+      for (int a = 0; a < 6; a++) c.ws.Cg[a * ES + 3 * p + r] = C[3 * a + r];
     }
   }
   maxd = team_max(team, maxd, c.sm + c.sl.red); /* also a barrier: Hcc complete */
@@ -679,96 +698,172 @@ DS_FN_NOINLINE double build_system(const Team team, Ctx &c) {
 
 /* ------------------------------------------- banded Cholesky + solve --- */
 
-/* Cholesky of one NB x NB diagonal block + inverse of its factor, by warp 0.
- * in : the block's lower triangle in the window (lambda added to the diagonal)
- * out: L_kk written back to the window, inv(L_kk) -> invL (shared) and Dinv
- *      (global, for the backward sweep); *flag set when a pivot is not > 0. */
-DS_FN void diag_factor(const Team team, double *W, int kslot, int Wr, int ld, int bw, int Q, double lambda,
-                       double *invL, double *Dinv_kb, int *flag) {
+/* Cholesky of one NB x NB diagonal block, by warp 0.
+ * in : the block's lower triangle in the window (lambda is added to the diagonal)
+ * out: L_kk written back to the window with the RECIPROCAL of each diagonal
+ *      entry on the diagonal (only 1/L_ii is ever needed afterwards), and a
+ *      dense copy in Lkk[8][8] (shared) for the panel solve; *flag set when a
+ *      pivot is not > 0.
+ * Every lane holds the whole block in registers and runs the same elimination:
+ * the critical path is 8 x (rsqrt + mul + fma) with no shuffle or shared-memory
+ * round trip on it; lanes only split the stores. */
+DS_FN double ds_rsqrt(double d) {
 #if DS_CUDA
-  /* lane a (< 8) owns row a of the block in registers; columns are eliminated
-   * with warp shuffles, no shared-memory round trips on the critical path */
-  const int lane = team.tid & 31, a = lane & 7;
-  const unsigned full = 0xffffffffu;
-  int slot = kslot + a;
-  if (slot >= Wr) slot -= Wr;
-  double *row = W + slot * ld;
-  double r[NB];
-#pragma unroll
-  for (int b = 0; b < NB; b++) r[b] = (b <= a) ? row[boff(b - a + bw, Q)] : 0.0;
-#pragma unroll
-  for (int b = 0; b < NB; b++)
-    if (b == a) r[b] += lambda;
-  double dinv[NB];
-  bool bad = false;
-#pragma unroll
-  for (int cc = 0; cc < NB; cc++) {
-    const double d = __shfl_sync(full, r[cc], cc);
-    bad = bad || !(d > 0.0);
-    const double inv = rsqrt(d);
-    dinv[cc] = inv;
-    double l = r[cc] * inv;
-    if (a == cc) l = d * inv;
-    r[cc] = l;
-#pragma unroll
-    for (int b = cc + 1; b < NB; b++) {
-      const double lb = __shfl_sync(full, l, b);
-      r[b] -= l * lb; /* meaningful for b <= a; other entries are never read */
-    }
-  }
-  /* column `a` of inv(L): X[i] = (delta_ia - sum_{m<i} L[i][m] X[m]) / L[i][i] */
-  double X[NB];
-#pragma unroll
-  for (int i = 0; i < NB; i++) {
-    double s = (i == a) ? 1.0 : 0.0;
-#pragma unroll
-    for (int m = 0; m < i; m++) {
-      const double Lim = __shfl_sync(full, r[m], i);
-      s -= Lim * X[m];
-    }
-    X[i] = (i >= a) ? s * dinv[i] : 0.0;
-  }
-  if (lane < NB) {
-#pragma unroll
-    for (int b = 0; b < NB; b++)
-      if (b <= a) row[boff(b - a + bw, Q)] = r[b];
-#pragma unroll
-    for (int i = 0; i < NB; i++) {
-      invL[i * NB + a] = X[i];
-      Dinv_kb[i * NB + a] = X[i];
-    }
-    if (bad) *flag = 1;
-  }
+  return rsqrt(d);
 #else
-  (void)team;
-  double L[NB][NB], X[NB][NB], dinv[NB];
+  return 1.0 / sqrt(d);
+#endif
+}
+
+/* in-register Cholesky of a 4x4 lower triangle (10 entries, row-major packed:
+ * 00 10 11 20 21 22 30 31 32 33); diagonal entries are replaced by 1/L_ii */
+DS_FN bool chol4(double t[10]) {
+  bool bad = false;
+  double inv;
+  bad = bad || !(t[0] > 0.0); inv = ds_rsqrt(t[0]); t[0] = inv;
+  t[1] *= inv; t[3] *= inv; t[6] *= inv;
+  t[2] -= t[1] * t[1]; t[4] -= t[3] * t[1]; t[7] -= t[6] * t[1];
+  t[5] -= t[3] * t[3]; t[8] -= t[6] * t[3]; t[9] -= t[6] * t[6];
+  bad = bad || !(t[2] > 0.0); inv = ds_rsqrt(t[2]); t[2] = inv;
+  t[4] *= inv; t[7] *= inv;
+  t[5] -= t[4] * t[4]; t[8] -= t[7] * t[4]; t[9] -= t[7] * t[7];
+  bad = bad || !(t[5] > 0.0); inv = ds_rsqrt(t[5]); t[5] = inv;
+  t[8] *= inv;
+  t[9] -= t[8] * t[8];
+  bad = bad || !(t[9] > 0.0); inv = ds_rsqrt(t[9]); t[9] = inv;
+  return bad;
+}
+
+constexpr int ILS = 12; /* row stride of inv(L_kk) in shared memory */
+
+/* Cholesky of one NB x NB diagonal block + inverse of its factor, by warp 0.
+ * in : the block's lower triangle in the window (lambda is added to the diagonal)
+ * out: L_kk written back to the window and to Lkk[8][8] (shared), with the
+ *      RECIPROCAL of each diagonal entry on the diagonal (only 1/L_ii is ever
+ *      needed afterwards); inv(L_kk) -> invL (shared, row stride ILS);
+ *      *flag set when a pivot is not > 0.
+ * Phase 1: two-level [A11 0; A21 A22] with 4x4 blocks; every lane runs the same
+ * arithmetic on registers, so the dependent chain (8 x rsqrt-mul-fma) has no
+ * shuffle or shared-memory hop on it.  Phase 2: lane j builds column j of the
+ * inverse by forward substitution from the shared copy. */
+DS_FN void diag_factor(const Team team, double *W, int kslot, int Wr, int ld, int bwE, double lambda, double *Lkk,
+                       double *invL, int *flag) {
+  const int lane = team.lane();
+  double *rowp[NB]; /* rowp[a][t] = entry (a, a - (bwE - t)); diagonal at rowp[a][bwE] */
+#pragma unroll
   for (int a = 0; a < NB; a++) {
     int slot = kslot + a;
     if (slot >= Wr) slot -= Wr;
-    for (int b = 0; b < NB; b++) L[a][b] = (b <= a) ? W[slot * ld + boff(b - a + bw, Q)] : 0.0;
-    L[a][a] += lambda;
+    rowp[a] = W + slot * ld + bwE - a; /* rowp[a][b] = entry (row a, col b) of the block */
   }
-  for (int cc = 0; cc < NB; cc++) {
-    const double d = L[cc][cc];
-    if (!(d > 0.0)) *flag = 1;
-    const double inv = 1.0 / sqrt(d);
-    dinv[cc] = inv;
-    for (int a = cc; a < NB; a++) L[a][cc] = (a == cc) ? d * inv : L[a][cc] * inv;
-    for (int a = cc + 1; a < NB; a++)
-      for (int b = cc + 1; b <= a; b++) L[a][b] -= L[a][cc] * L[b][cc];
+  double A11[10], L21[16], A22[10];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b <= a; b++) A11[a * (a + 1) / 2 + b] = rowp[a][b] + (a == b ? lambda : 0.0);
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) L21[a * 4 + b] = rowp[4 + a][b];
+  bool bad = chol4(A11);
+  /* L21 = A21 L11^-T, the four rows are independent chains */
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    double *x = &L21[a * 4];
+    x[0] *= A11[0];
+    x[1] = (x[1] - x[0] * A11[1]) * A11[2];
+    x[2] = (x[2] - x[0] * A11[3] - x[1] * A11[4]) * A11[5];
+    x[3] = (x[3] - x[0] * A11[6] - x[1] * A11[7] - x[2] * A11[8]) * A11[9];
   }
-  for (int j = 0; j < NB; j++)
-    for (int i = 0; i < NB; i++) {
-      double s = (i == j) ? 1.0 : 0.0;
-      for (int m = 0; m < i; m++) s -= L[i][m] * X[m][j];
-      X[i][j] = (i >= j) ? s * dinv[i] : 0.0;
+  /* rows 0-3: every lane stores the same values (benign, one wavefront each) */
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+      const double v = b <= a ? A11[a * (a + 1) / 2 + b] : 0.0;
+      Lkk[a * NB + b] = v;
+      if (b <= a) rowp[a][b] = v;
     }
-  for (int a = 0; a < NB; a++) {
-    int slot = kslot + a;
-    if (slot >= Wr) slot -= Wr;
-    for (int b = 0; b <= a; b++) W[slot * ld + boff(b - a + bw, Q)] = L[a][b];
-    for (int j = 0; j < NB; j++) { invL[a * NB + j] = X[a][j]; Dinv_kb[a * NB + j] = X[a][j]; }
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b <= a; b++) {
+      double v = rowp[4 + a][4 + b] + (a == b ? lambda : 0.0);
+#pragma unroll
+      for (int m = 0; m < 4; m++) v -= L21[a * 4 + m] * L21[b * 4 + m];
+      A22[a * (a + 1) / 2 + b] = v;
+    }
+  bad = chol4(A22) || bad;
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+      const double v = b < 4 ? L21[a * 4 + b] : (b - 4 <= a ? A22[a * (a + 1) / 2 + (b - 4)] : 0.0);
+      Lkk[(4 + a) * NB + b] = v;
+      if (b <= 4 + a) rowp[4 + a][b] = v;
+    }
+  if (bad && lane == 0) *flag = 1;
+  team.warp_sync();
+  /* column j of X = inv(L): s_i = delta_ij - sum_{m<i} L[i][m] X[m];  X[i] = s_i / L_ii */
+  DS_WARP_FOR(j, NB) {
+    double sacc[NB];
+#pragma unroll
+    for (int i = 0; i < NB; i++) sacc[i] = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+    for (int m = 0; m < NB; m++) {
+      const double xm = sacc[m] * Lkk[m * NB + m];
+      invL[m * ILS + j] = xm;
+#pragma unroll
+      for (int i = m + 1; i < NB; i++) sacc[i] -= Lkk[i * NB + m] * xm;
+    }
   }
+}
+
+#if DS_CUDA
+/* D(8x8) += A(8x4) B(4x8) on the FP64 tensor cores.  Lane T holds a = A[T/4][T%4],
+ * b = B[T%4][T/4], and d0,d1 = D[T/4][2*(T%4)], D[T/4][2*(T%4)+1]. */
+DS_FN void dmma884(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+#endif
+
+/* X (8x8) = R (8x8) * C^T (8x8), R[g][m] = ra[g*sa + m], C[c][m] = cb[c*sb + m]; lane
+ * (g = T/4, q = T%4) receives X[g][2q], X[g][2q+1].  Used for the panel solve
+ * (C = inv(L_kk)) and, through P, for the trailing update. */
+DS_FN void tile_mul_nt(int lane, const double *ra, int sa, const double *cb, int sb, double &d0, double &d1) {
+  const int g = lane >> 2, q = lane & 3;
+#if DS_CUDA
+  d0 = 0.0; d1 = 0.0;
+  dmma884(d0, d1, ra[g * sa + q], cb[g * sb + q]);
+  dmma884(d0, d1, ra[g * sa + 4 + q], cb[g * sb + 4 + q]);
+#else
+  double s0 = 0.0, s1 = 0.0;
+  for (int m = 0; m < NB; m++) {
+    s0 += ra[g * sa + m] * cb[(2 * q) * sb + m];
+    s1 += ra[g * sa + m] * cb[(2 * q + 1) * sb + m];
+  }
+  d0 = s0; d1 = s1;
+#endif
+}
+
+/* same product with both operands taken from the panel buffer P[h][r][4]:
+ * X[g][c] = sum_cc P(rA+g, cc) P(rB+c, cc) */
+DS_FN void tile_mul_pp(int lane, const double *P, int HS, int rA, int rB, double &d0, double &d1) {
+  const int g = lane >> 2, q = lane & 3;
+#if DS_CUDA
+  d0 = 0.0; d1 = 0.0;
+  dmma884(d0, d1, P[(rA + g) * 4 + q], P[(rB + g) * 4 + q]);
+  dmma884(d0, d1, P[HS + (rA + g) * 4 + q], P[HS + (rB + g) * 4 + q]);
+#else
+  double s0 = 0.0, s1 = 0.0;
+  for (int cc = 0; cc < NB; cc++) {
+    const double a = P[pidx(cc, rA + g, HS)];
+    s0 += a * P[pidx(cc, rB + 2 * q, HS)];
+    s1 += a * P[pidx(cc, rB + 2 * q + 1, HS)];
+  }
+  d0 = s0; d1 = s1;
 #endif
 }
 
@@ -777,24 +872,45 @@ DS_FN void diag_factor(const Team team, double *W, int kslot, int Wr, int ld, in
  * false, linear_solver_dense.h:107-112); dx is then left untouched (stale), as
  * in the reference. */
 DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &c, double lambda) {
-  const int bw = c.pl.bw, ld = c.pl.ld, Dp = c.pl.Dn_pad, Wr = c.pl.Wr, bwp = c.pl.bwp, nblk = c.pl.nblk, Q = c.pl.Q;
-  const int PS = bwp + 8;
+  const int bw = c.pl.bw, bwE = c.pl.bwE, ld = c.pl.ld, Dp = c.pl.Dn_pad, Wr = c.pl.Wr, bwp = c.pl.bwp,
+            nblk = c.pl.nblk, ES = c.pl.ES;
+  const int PR = bwp + 8, HS = 4 * PR; /* panel rows: trailing rows, then the 8 border rows */
   double *const sm = c.sm;
-  double *W = sm + c.sl.W, *P = sm + c.sl.P, *invL = sm + c.sl.invL;
+  double *W = sm + c.sl.W, *P = sm + c.sl.P, *Lkk = sm + c.sl.Lkk, *invL = sm + c.sl.invL;
   double *G = sm + c.sl.G, *Hcc = sm + c.sl.Hcc, *dx = sm + c.sl.dx;
   double *E = c.E;
   const double *Hb = c.ws.Hb;
-  double *Lb = c.ws.Lb, *Dinv = c.ws.Dinv;
+  double *Lb = c.ws.Lb;
   int *flag = (int *)(sm + c.sl.red + 36);
-  const int nt = bwp / TILE;
+  const int nt8 = bwp / NB;
+#if DS_CUDA
+  const int warp = team.tid >> 5, nwarp = team.nthr >> 5, lane = team.tid & 31;
+#else
+  const int warp = 0, nwarp = 1;
+#endif
+  (void)Lkk;
 
+  /* Everything H/border related in global memory was written with plain stores
+   * (build_system); order them before the TMA reads. */
+  fence_proxy_async();
   team.sync();
-  /* window <- first Wr rows of H; border/rhs working copy; corner */
+  uint64_t *bar0 = &c.mbar[0];
+  uint32_t ph0 = c.ph[0];
+  /* window <- first Wr rows of H; border/rhs working copy (bulk async); corner */
   {
     const int rows = Wr < Dp ? Wr : Dp;
-    DS_FOR(i, rows * ld) W[i] = Hb[i];
-    const double *Cg = c.ws.Cg;
-    DS_FOR(i, 8 * Dp) E[i] = Cg[i];
+    const bool e_smem = c.pb.e_in_smem != 0;
+    if (team.tid == 0) {
+      const uint32_t bw_bytes = (uint32_t)(rows * ld * sizeof(double));
+      const uint32_t e_bytes = e_smem ? (uint32_t)(8 * ES * sizeof(double)) : 0u;
+      mbar_expect_tx(bar0, bw_bytes + e_bytes);
+      tma_load_1d(W, Hb, bw_bytes, bar0);
+      if (e_smem) tma_load_1d(E, c.ws.Cg, e_bytes, bar0);
+    }
+    if (!e_smem) {
+      const double *Cg = c.ws.Cg;
+      DS_FOR(i, 8 * ES) E[i] = Cg[i];
+    }
     DS_FOR(i, 64) {
       const int a = i >> 3, b = i & 7;
       double v = 0.0;
@@ -803,146 +919,141 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &c, double lambda) {
       G[i] = v;
     }
     if (team.tid == 0) *flag = 0;
+    mbar_wait(bar0, ph0);
+    ph0 ^= 1u;
   }
   team.sync();
+  prof_mark(team, c, PF_FS_INIT);
 
   int kslot = 0; /* k mod Wr */
   for (int kb = 0; kb < nblk; kb++) {
     const int k = kb * NB;
     /* S1: factor the diagonal block (warp 0) */
-    if (team.warp0()) diag_factor(team, W, kslot, Wr, ld, bw, Q, lambda, invL, Dinv + kb * 64, flag);
+    if (team.warp0()) diag_factor(team, W, kslot, Wr, ld, bwE, lambda, Lkk, invL, flag);
     team.sync();
+    prof_mark(team, c, PF_S1);
+    /* rows requested during the previous step (they enter this step's panel) */
+    if (kb > 0 && (k - NB) + Wr < Dp) { mbar_wait(bar0, ph0); ph0 ^= 1u; }
+    prof_mark(team, c, PF_S1_WAIT);
 
-    /* S2: panel = rows below (and the 8 border rows) times L_kk^-T */
+    /* S2: panel = (rows below, then the 8 border rows) times L_kk^-T, one 8-row
+     * tile per warp: X = A inv(L_kk)^T on the tensor cores */
     const int n_trail = (Dp - (k + NB)) < bwp ? (Dp - (k + NB)) : bwp;
-    DS_FOR(r, bwp + 8) {
-      double a[NB], xr[NB];
-      double *rowp = nullptr;
-      int o0 = 0; /* band offset of column k in this row */
-      if (r < bwp) {
-        if (r < n_trail) {
-          int slot = kslot + NB + r;
-          if (slot >= Wr) slot -= Wr;
-          rowp = W + slot * ld;
-          o0 = bw - NB - r;
-#pragma unroll
-          for (int cc = 0; cc < NB; cc++) a[cc] = (o0 + cc >= 0) ? rowp[boff(o0 + cc, Q)] : 0.0;
-        } else {
-#pragma unroll
-          for (int cc = 0; cc < NB; cc++) a[cc] = 0.0;
+    const int nrt = n_trail / NB; /* trailing row tiles that exist */
+    for (int rt = warp; rt <= nt8; rt += nwarp) {
+      const bool erow = rt == nt8;
+      if (!erow && rt >= nrt) continue; /* rows beyond the matrix: never read by S3 */
+      const int r0 = erow ? bwp : rt * NB; /* first panel row of this tile */
+      /* trailing rows i = k+8+r0+g: column k+cc sits at band offset o0+cc with
+       * o0 = bwE-8-r0-g; offsets below lo = bwE-bw are outside the band (zero).
+       * The 8 rows of a tile never wrap inside the ring (Wr, r0 multiples of 8). */
+      int s0 = kslot + NB + r0;
+      if (s0 >= Wr) s0 -= Wr;
+      double *base = erow ? (E + k) : (W + s0 * ld + (bwE - NB - r0));
+      const int rs = erow ? ES : (ld - 1); /* stride between the tile's rows at a fixed column */
+      const int lo = bwE - bw;
+#if DS_CUDA
+      {
+        const int g = lane >> 2, q = lane & 3;
+        const int o0 = erow ? bwE : (bwE - NB - r0 - g);
+        const double a0 = (o0 + q >= lo) ? base[g * rs + q] : 0.0;
+        const double a1 = (o0 + 4 + q >= lo) ? base[g * rs + 4 + q] : 0.0;
+        double d0 = 0.0, d1 = 0.0;
+        dmma884(d0, d1, a0, invL[g * ILS + q]);
+        dmma884(d0, d1, a1, invL[g * ILS + 4 + q]);
+        /* mma.sync is warp-synchronous: every lane has read its operands */
+        if (o0 + 2 * q >= lo) base[g * rs + 2 * q] = d0;
+        if (o0 + 2 * q + 1 >= lo) base[g * rs + 2 * q + 1] = d1;
+        *(dbl2 *)&P[pidx(2 * q, r0 + g, HS)] = dbl2{d0, d1};
+      }
+#else
+      {
+        double X[NB][NB];
+        for (int g = 0; g < NB; g++) {
+          const int o0 = erow ? bwE : (bwE - NB - r0 - g);
+          for (int cc = 0; cc < NB; cc++) {
+            double sx = 0.0;
+            for (int m = 0; m < NB; m++) {
+              const double a = (o0 + m >= lo) ? base[g * rs + m] : 0.0;
+              sx += a * invL[cc * ILS + m];
+            }
+            X[g][cc] = sx;
+          }
         }
-      } else {
-        const int e = r - bwp;
-#pragma unroll
-        for (int cc = 0; cc < NB; cc++) a[cc] = E[eidx(e, k + cc, Dp)];
-      }
-#pragma unroll
-      for (int cc = 0; cc < NB; cc++) {
-        double s = 0.0;
-#pragma unroll
-        for (int m = 0; m <= cc; m++) s += a[m] * invL[cc * NB + m];
-        xr[cc] = s;
-        P[pidx(cc, r, PS)] = s;
-      }
-      if (r < bwp) {
-        if (rowp) {
-#pragma unroll
-          for (int cc = 0; cc < NB; cc++)
-            if (o0 + cc >= 0) rowp[boff(o0 + cc, Q)] = xr[cc];
+        for (int g = 0; g < NB; g++) {
+          const int o0 = erow ? bwE : (bwE - NB - r0 - g);
+          for (int cc = 0; cc < NB; cc++) {
+            if (o0 + cc >= lo) base[g * rs + cc] = X[g][cc];
+            P[pidx(cc, r0 + g, HS)] = X[g][cc];
+          }
         }
-      } else {
-        const int e = r - bwp;
-#pragma unroll
-        for (int cc = 0; cc < NB; cc++) E[eidx(e, k + cc, Dp)] = xr[cc];
       }
+#endif
+    }
+    /* finished rows k..k+7 (final after S1) -> L band in global memory */
+    {
+      const double *src = W + kslot * ld;
+      double *dst = Lb + k * ld;
+      DS_FOR(i, NB * ld) dst[i] = src[i];
     }
     team.sync();
+    prof_mark(team, c, PF_S2);
+    /* refill the freed slot with rows k+Wr.. (needed by the next step's panel).
+     * All reads of the slot happened before the barrier above. */
+    if (team.tid == 0 && k + Wr < Dp) {
+      const uint32_t bytes = (uint32_t)(NB * ld * sizeof(double));
+      mbar_expect_tx(bar0, bytes);
+      tma_load_1d(W + kslot * ld, Hb + (k + Wr) * ld, bytes, bar0);
+    }
 
-    /* S3: trailing update (window, border rows, corner) with 4x4 register tiles */
+    /* S3: trailing update, one 8x8 tile per warp iteration: C -= P_I P_J^T */
     {
-      const int ntr = nt + 2;
-      const int ntiles = ntr * (ntr + 1) / 2;
-      const int PQ = PS >> 2;
-      DS_FOR(t, ntiles) {
+      const int nrow = nt8 + 1; /* tile rows: trailing tiles, then the border tile row */
+      const int ntiles = nrow * (nrow + 1) / 2;
+      for (int t = warp; t < ntiles; t += nwarp) {
         int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
         while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
         while (ti * (ti + 1) / 2 > t) ti--;
         const int tj = t - ti * (ti + 1) / 2;
-        const bool erow = ti >= nt, ecol = tj >= nt;
-        if (!erow && TILE * ti >= n_trail) continue;
-        if (!ecol && TILE * tj >= n_trail) continue;
-        /* tile index inside the (de-interleaved) panel buffer */
-        const int pr = erow ? (bwp >> 2) + (ti - nt) : ti;
-        const int pc = ecol ? (bwp >> 2) + (tj - nt) : tj;
-        double acc[TILE][TILE];
-#pragma unroll
-        for (int a = 0; a < TILE; a++)
-#pragma unroll
-          for (int b = 0; b < TILE; b++) acc[a][b] = 0.0;
-#pragma unroll
-        for (int cc = 0; cc < NB; cc++) {
-          double pa[TILE], pb[TILE];
-#pragma unroll
-          for (int a = 0; a < TILE; a++) { pa[a] = P[cc * PS + a * PQ + pr]; pb[a] = P[cc * PS + a * PQ + pc]; }
-#pragma unroll
-          for (int a = 0; a < TILE; a++)
-#pragma unroll
-            for (int b = 0; b < TILE; b++) acc[a][b] += pa[a] * pb[b];
-        }
-        if (!erow) {
-          const int r0 = TILE * ti, c0 = TILE * tj;
-          const int d0 = c0 - r0 + bw; /* band offset of (row r0, col c0) */
-          int slot0 = kslot + NB + r0;
-          if (slot0 >= Wr) slot0 -= Wr;
-          const bool interior = (ti > tj) && (r0 - c0 + 3 <= bw);
-          if (interior) {
-#pragma unroll
-            for (int a = 0; a < TILE; a++) {
-              int slot = slot0 + a;
-              if (slot >= Wr) slot -= Wr;
-              double *rowp = W + slot * ld;
-#pragma unroll
-              for (int b = 0; b < TILE; b++) rowp[boff(d0 + b - a, Q)] -= acc[a][b];
+        const bool erow = ti == nt8, ecol = tj == nt8;
+        if (!erow && ti >= nrt) continue;
+        if (!ecol && tj >= nrt) continue;
+        const int rA = erow ? bwp : ti * NB, rB = ecol ? bwp : tj * NB;
+        DS_WARP_FOR(T, 32) {
+          const int g = T >> 2, q = T & 3;
+          double d0, d1;
+          tile_mul_pp(T, P, HS, rA, rB, d0, d1);
+          if (!erow) {
+            /* entry (i, j): i = k+8+rA+g, j = k+8+rB+2q(+1); band offset j-i+bwE */
+            int s0 = kslot + NB + rA;
+            if (s0 >= Wr) s0 -= Wr;
+            const int off = rB + 2 * q - rA - g + bwE;
+            double *dst = W + (s0 + g) * ld + off;
+            const int lo = bwE - bw;
+            const bool v0 = off <= bwE && off >= lo, v1 = off + 1 <= bwE && off + 1 >= lo;
+            if (v0 && v1) {
+              dbl2 *p2 = (dbl2 *)dst;
+              dbl2 cv = *p2;
+              cv.x -= d0; cv.y -= d1;
+              *p2 = cv;
+            } else {
+              if (v0) dst[0] -= d0;
+              if (v1) dst[1] -= d1;
             }
+          } else if (!ecol) {
+            dbl2 *p2 = (dbl2 *)(E + g * ES + k + NB + rB + 2 * q);
+            dbl2 cv = *p2;
+            cv.x -= d0; cv.y -= d1;
+            *p2 = cv;
           } else {
-#pragma unroll
-            for (int a = 0; a < TILE; a++) {
-              int slot = slot0 + a;
-              if (slot >= Wr) slot -= Wr;
-              double *rowp = W + slot * ld;
-#pragma unroll
-              for (int b = 0; b < TILE; b++) {
-                const int off = d0 + b - a;
-                if (off <= bw && off >= 0) rowp[boff(off, Q)] -= acc[a][b];
-              }
-            }
+            if (2 * q <= g) G[g * 8 + 2 * q] -= d0;
+            if (2 * q + 1 <= g) G[g * 8 + 2 * q + 1] -= d1;
           }
-        } else if (!ecol) {
-          const int e0 = TILE * (ti - nt), col0 = k + NB + TILE * tj;
-#pragma unroll
-          for (int a = 0; a < TILE; a++)
-#pragma unroll
-            for (int b = 0; b < TILE; b++) E[eidx(e0 + a, col0 + b, Dp)] -= acc[a][b];
-        } else {
-          const int e0 = TILE * (ti - nt), f0 = TILE * (tj - nt);
-#pragma unroll
-          for (int a = 0; a < TILE; a++)
-#pragma unroll
-            for (int b = 0; b < TILE; b++)
-              if (f0 + b <= e0 + a) G[(e0 + a) * 8 + f0 + b] -= acc[a][b];
-        }
-      }
-      /* finished rows k..k+7 -> L (global); refill their slots with rows k+Wr.. */
-      {
-        const int slot = kslot * ld;
-        const bool refill = k + Wr < Dp;
-        DS_FOR(i, NB * ld) {
-          Lb[k * ld + i] = W[slot + i];
-          if (refill) W[slot + i] = Hb[(k + Wr) * ld + i];
         }
       }
     }
     team.sync();
+    prof_mark(team, c, PF_S3);
     kslot += NB;
     if (kslot >= Wr) kslot -= Wr;
   }
@@ -979,59 +1090,96 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &c, double lambda) {
       for (int i = 0; i < 6; i++) dx[Dp + i] = y[i];
     }
   }
+  /* every thread wrote part of L with plain stores: order them before the TMA
+   * reads of the backward sweep */
+  fence_proxy_async();
   team.sync();
+  if (team.tid == 0) c.ph[0] = ph0;
+  prof_mark(team, c, PF_SCHUR);
   if (*flag != 0) { team.sync(); return false; }
 
   /* v = z - Y^T dc */
   DS_FOR(i, Dp) {
-    double s = E[eidx(6, i, Dp)];
+    double s = E[6 * ES + i];
 #pragma unroll
-    for (int e = 0; e < 6; e++) s -= E[eidx(e, i, Dp)] * dx[Dp + e];
+    for (int e = 0; e < 6; e++) s -= E[e * ES + i] * dx[Dp + e];
     dx[i] = s;
   }
-  /* backward sweep  L^T dn = v, one block of NB rows per step, rows of L
-   * streamed back from global through two buffers in the (now free) window */
-  double *LR0 = W, *LR1 = W + NB * ld + 64;
-  {
-    const int k = (nblk - 1) * NB;
-    DS_FOR(i, NB * ld) LR0[i] = Lb[k * ld + i];
-    DS_FOR(i, 64) LR0[NB * ld + i] = Dinv[(nblk - 1) * 64 + i];
+  /* backward sweep  L^T dn = v, one block of NB rows per step.  Rows of L stream
+   * back from global memory through a ring of NBUF buffers in the (now free)
+   * window, NBUF-1 steps ahead. */
+  constexpr int NBUF = 4;
+  const int bufsz = NB * ld;
+  const uint32_t row_bytes = (uint32_t)(NB * ld * sizeof(double));
+  uint32_t phb[NBUF];
+#pragma unroll
+  for (int b = 0; b < NBUF; b++) phb[b] = c.ph[1 + b];
+  team.sync(); /* all reads of the window / E done before the ring overwrites it */
+  if (team.tid == 0) {
+    for (int j = 0; j < NBUF - 1 && j < nblk; j++) {
+      const int kbj = nblk - 1 - j;
+      mbar_expect_tx(&c.mbar[1 + (j % NBUF)], row_bytes);
+      tma_load_1d(W + (j % NBUF) * bufsz, Lb + kbj * NB * ld, row_bytes, &c.mbar[1 + (j % NBUF)]);
+    }
   }
-  team.sync();
+  prof_mark(team, c, PF_BWD_INIT);
   for (int kb = nblk - 1; kb >= 0; kb--) {
     const int k = kb * NB;
-    double *LR = ((nblk - 1 - kb) & 1) ? LR1 : LR0;
-    double *LRn = ((nblk - 1 - kb) & 1) ? LR0 : LR1;
-    const double *Di = LR + NB * ld;
-    /* prefetch the next block while this one is processed */
-    if (kb > 0) {
-      const int kn = (kb - 1) * NB;
-      DS_FOR(i, NB * ld) LRn[i] = Lb[kn * ld + i];
-      DS_FOR(i, 64) LRn[NB * ld + i] = Dinv[(kb - 1) * 64 + i];
+    const int j = nblk - 1 - kb, buf = j % NBUF;
+    /* request block j+NBUF-1: its buffer was last read at step j-1, before the
+     * barrier that ended that step */
+    if (team.tid == 0) {
+      const int jn = j + NBUF - 1;
+      if (jn < nblk) {
+        const int kbn = nblk - 1 - jn, bn = jn % NBUF;
+        mbar_expect_tx(&c.mbar[1 + bn], row_bytes);
+        tma_load_1d(W + bn * bufsz, Lb + kbn * NB * ld, row_bytes, &c.mbar[1 + bn]);
+      }
     }
-    /* d = invL^T y */
-    DS_FOR(cc, NB) {
-      double s = 0.0;
-      for (int a = cc; a < NB; a++) s += Di[a * NB + cc] * dx[k + a];
-      P[cc] = s;
+    const double *LR = W + buf * bufsz;
+#pragma unroll
+    for (int b = 0; b < NBUF; b++)
+      if (b == buf) { mbar_wait(&c.mbar[1 + b], phb[b]); phb[b] ^= 1u; }
+    /* d = L_kk^-T y by backward substitution (1/L_ii on the diagonal); every
+     * thread that needs d computes it redundantly from shared memory */
+    double d[NB];
+#pragma unroll
+    for (int a = 0; a < NB; a++) d[a] = dx[k + a];
+#pragma unroll
+    for (int a = NB - 1; a >= 0; a--) {
+      d[a] *= LR[a * ld + bwE];
+#pragma unroll
+      for (int m = 0; m < a; m++) d[m] -= d[a] * LR[a * ld + bwE - a + m];
     }
-    team.sync();
-    DS_FOR(cc, NB) dx[k + cc] = P[cc];
+    team.sync(); /* everybody has read dx[k..k+7] */
+#pragma unroll
+    for (int a = 0; a < NB; a++) {
+#if DS_CUDA
+      if (team.tid == a) dx[k + a] = d[a];
+#else
+      dx[k + a] = d[a];
+#endif
+    }
     {
       const int j0 = k - bw > 0 ? k - bw : 0;
       DS_FOR(jj, k - j0) {
-        const int j = j0 + jj;
-        double s = dx[j];
+        const int jc = j0 + jj;
+        double s = dx[jc];
 #pragma unroll
         for (int a = 0; a < NB; a++) {
-          const int off = j - (k + a) + bw;
-          if (off >= 0) s -= LR[a * ld + boff(off, Q)] * P[a];
+          const int off = jc - (k + a) + bwE;
+          if (off >= bwE - bw) s -= LR[a * ld + off] * d[a];
         }
-        dx[j] = s;
+        dx[jc] = s;
       }
     }
     team.sync();
   }
+  if (team.tid == 0) {
+#pragma unroll
+    for (int b = 0; b < NBUF; b++) c.ph[1 + b] = phb[b];
+  }
+  prof_mark(team, c, PF_BWD);
   return true;
 }
 
@@ -1055,7 +1203,7 @@ DS_FN void apply_update(const Team team, Ctx &c) {
 
 DS_FN void expand_dense(const Team team, Ctx &c, double chi) {
   const PlanView &pl = c.pl;
-  const int Dn = pl.Dn, D = Dn + 6, bw = pl.bw, ld = pl.ld, Dp = pl.Dn_pad, Q = pl.Q;
+  const int Dn = pl.Dn, D = Dn + 6, bw = pl.bw, bwE = pl.bwE, ld = pl.ld, ES = pl.ES;
   const double *Hcc = c.sm + c.sl.Hcc;
   team.sync();
   if (c.pb.out_H) {
@@ -1063,15 +1211,15 @@ DS_FN void expand_dense(const Team team, Ctx &c, double chi) {
       const int i = idx / D, j = idx - i * D;
       const int hi = i > j ? i : j, lo = i > j ? j : i;
       double v = 0.0;
-      if (hi < Dn) { if (hi - lo <= bw) v = c.ws.Hb[hi * ld + boff(lo - hi + bw, Q)]; }
-      else if (lo < Dn) v = c.ws.Cg[eidx(hi - Dn, lo, Dp)];
+      if (hi < Dn) { if (hi - lo <= bw) v = c.ws.Hb[hi * ld + (lo - hi + bwE)]; }
+      else if (lo < Dn) v = c.ws.Cg[(hi - Dn) * ES + lo];
       else v = Hcc[(hi - Dn) * 6 + (lo - Dn)];
       c.pb.out_H[idx] = v;
     }
   }
   if (c.pb.out_b) {
     DS_FOR(i, D) {
-      double v = i < Dn ? c.ws.Cg[eidx(6, i, Dp)] : Hcc[36 + (i - Dn)];
+      double v = i < Dn ? c.ws.Cg[6 * ES + i] : Hcc[36 + (i - Dn)];
       if (i < Dn && !c.freev[i / 3]) v = 0.0;
       c.pb.out_b[i] = v;
     }
@@ -1147,6 +1295,7 @@ DS_FN_NOINLINE void sft_solve_one(const Team team, Ctx &c) {
   const int Dp = pl.Dn_pad;
 
   const int rc = prologue(team, c);
+  prof_mark(team, c, PF_PROLOGUE);
   if (rc != 0) {
     if (team.tid == 0) pb.out_res->status = rc;
     return;
@@ -1168,10 +1317,12 @@ DS_FN_NOINLINE void sft_solve_one(const Team team, Ctx &c) {
   bool last_rejected = false;
   for (int it = 0; it < max_it; it++) {
     double currentChi = eval_state(team, c, x, ps, true);
+    prof_mark(team, c, PF_EVAL_STORE);
     double tempChi = currentChi;
     const double iniChi = currentChi;
     if (it == 0) chi_ini0 = currentChi;
     const double maxDiag = build_system(team, c);
+    prof_mark(team, c, PF_BUILD);
     if (it == 0) { lambda = tau * maxDiag; ni = 2; nBad = 0; }
     const double lambda_start = lambda;
     double rho = 0;
@@ -1181,13 +1332,16 @@ DS_FN_NOINLINE void sft_solve_one(const Team team, Ctx &c) {
       team.sync();
       DS_FOR(i, pl.Dn) xb[i] = x[i];
       if (team.tid == 0) for (int k = 0; k < 7; k++) psb[k] = ps[k];
+      prof_mark(team, c, PF_LM_SCALAR);
       const bool ok2 = factor_solve(team, c, lambda);
       apply_update(team, c);
+      prof_mark(team, c, PF_UPDATE);
       tempChi = eval_state(team, c, x, ps, false);
+      prof_mark(team, c, PF_EVAL_TRIAL);
       if (!ok2) tempChi = DBL_MAX;
       rho = currentChi - tempChi;
       double scale = 0.; /* computeScale :182-189 */
-      DS_FOR(j, pl.Dn) scale += dx[j] * (lambda * dx[j] + c.ws.Cg[eidx(6, j, Dp)]);
+      DS_FOR(j, pl.Dn) scale += dx[j] * (lambda * dx[j] + c.ws.Cg[6 * pl.ES + j]);
       scale = team_sum(team, scale, red);
       for (int j = 0; j < 6; j++) scale += dx[Dp + j] * (lambda * dx[Dp + j] + (c.sm + c.sl.Hcc)[36 + j]);
       scale += 1e-3;
@@ -1224,7 +1378,9 @@ DS_FN_NOINLINE void sft_solve_one(const Team team, Ctx &c) {
     if (nBad >= 3) break;
   }
   team.sync();
+  prof_mark(team, c, PF_LM_SCALAR);
   finalize(team, c, last_rejected, iterations, trials, chi_ini0, chi_fin, lambda);
+  prof_mark(team, c, PF_FINALIZE);
 }
 
 /* doubles reserved at the head of shared memory for the CTA-wide context */
@@ -1235,15 +1391,23 @@ constexpr int CTX_DOUBLES = (int)((sizeof(Ctx) + 15) / 16) * 2;
  * kept in shared memory (one copy per CTA): with the shared-memory carve-out
  * this kernel uses there is almost no L1 left for a per-thread stack copy. */
 DS_FN void sft_run_problem(const Team &team, const ProbView &pv, double *smem, uint8_t *ws_base,
-                           const WorkspaceSizes &z) {
+                           const WorkspaceSizes &z, bool first_of_launch, long long *prof) {
   Ctx &c = *(Ctx *)smem;
   double *sm = smem + CTX_DOUBLES;
   team.sync();
   if (team.tid == 0) {
+    if (first_of_launch) {
+      for (int i = 0; i < 8; i++) { mbar_init(&c.mbar[i], 1); c.ph[i] = 0; }
+      fence_mbar_init();
+    }
+    c.prof = prof;
+#if DS_CUDA
+    c.prof_last = clock64();
+#endif
     c.pb = pv;
     c.pl = *pv.plan;
     c.ws = carve_workspace(ws_base, z);
-    c.sl = smem_layout(c.pl.n_nodes, c.pl.n_edges, c.pl.Dn_pad, c.pl.bwp, c.pl.ld, c.pl.Wr, pv.e_in_smem != 0);
+    c.sl = smem_layout(c.pl.n_nodes, c.pl.n_edges, c.pl.Dn_pad, c.pl.bwp, c.pl.ld, c.pl.Wr, c.pl.ES, pv.e_in_smem != 0);
     c.sm = sm;
     c.E = pv.e_in_smem ? sm + c.sl.E : c.ws.Eg;
     c.viewed = (uint8_t *)(sm + c.sl.flags);

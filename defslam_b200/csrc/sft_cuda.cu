@@ -7,6 +7,7 @@
  * and everything below it; see include/defslam_b200.h.
  */
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -20,14 +21,17 @@ namespace {
 constexpr int SFT_THREADS = 256;
 
 __global__ void __launch_bounds__(SFT_THREADS, 2)
-sft_lm_kernel(const ProbView *__restrict__ probs, int nprob, uint8_t *ws_base, size_t ws_stride, WorkspaceSizes z) {
+sft_lm_kernel(const ProbView *__restrict__ probs, int nprob, uint8_t *ws_base, size_t ws_stride, WorkspaceSizes z,
+              long long *prof) {
   extern __shared__ __align__(16) double smem[];
   Team team;
   team.tid = threadIdx.x;
   team.nthr = blockDim.x;
   uint8_t *ws = ws_base + (size_t)blockIdx.x * ws_stride;
+  bool first = true;
   for (int pi = blockIdx.x; pi < nprob; pi += gridDim.x) {
-    sft_run_problem(team, probs[pi], smem, ws, z);
+    sft_run_problem(team, probs[pi], smem, ws, z, first, blockIdx.x == 0 ? prof : nullptr);
+    first = false;
     __syncthreads();
   }
 }
@@ -93,7 +97,7 @@ static int template_make(const defslam_template_desc *desc, DevCtx *ctx, defslam
 struct defslam_sft_batch {
   DevCtx *ctx = nullptr;
   BatchMarshal bm;
-  DevBuf h_in, h_out, d_in, d_out, d_views, d_ws;
+  DevBuf h_in, h_out, d_in, d_out, d_views, d_ws, d_prof;
   std::vector<defslam_template *> temps;
   int nprob = 0, grid = 0, smem_bytes = 0, mode = MODE_SOLVE;
   size_t ws_stride = 0;
@@ -106,6 +110,7 @@ struct defslam_sft_batch {
   ~defslam_sft_batch() {
     drop_temps();
     h_in.release(); h_out.release(); d_in.release(); d_out.release(); d_views.release(); d_ws.release();
+    d_prof.release();
   }
 };
 
@@ -166,9 +171,16 @@ static int batch_load(defslam_sft_batch *B, int nprob, const defslam_sft_problem
 static int batch_launch(defslam_sft_batch *B) {
   DevCtx *ctx = B->ctx;
   const WorkspaceSizes z = B->bm.ws_sizes();
+  long long *prof = nullptr;
+  if (getenv("DEFSLAM_PROFILE")) { /* diagnostics: per-phase cycles of CTA 0 */
+    int rc = B->d_prof.ensure(sizeof(long long) * PF_COUNT);
+    if (rc) return rc;
+    prof = (long long *)B->d_prof.p;
+    DS_CUDA_TRY(cudaMemsetAsync(prof, 0, sizeof(long long) * PF_COUNT, ctx->stream));
+  }
   DS_CUDA_TRY(cudaEventRecord(ctx->e0, ctx->stream));
   sft_lm_kernel<<<B->grid, SFT_THREADS, B->smem_bytes, ctx->stream>>>((const ProbView *)B->d_views.p, B->nprob,
-                                                                      (uint8_t *)B->d_ws.p, B->ws_stride, z);
+                                                                      (uint8_t *)B->d_ws.p, B->ws_stride, z, prof);
   DS_CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1);
   DS_CUDA_TRY(cudaEventRecord(ctx->e1, ctx->stream));
@@ -182,6 +194,17 @@ static int batch_wait_kernel(defslam_sft_batch *B) {
   DS_CUDA_TRY(cudaEventElapsedTime(&ms, ctx->e0, ctx->e1));
   B->last_ms = ms;
   g_last_kernel_ms = ms;
+  if (getenv("DEFSLAM_PROFILE") && B->d_prof.p) {
+    long long h[PF_COUNT];
+    DS_CUDA_TRY(cudaMemcpy(h, B->d_prof.p, sizeof(h), cudaMemcpyDeviceToHost));
+    static const char *names[PF_COUNT] = {"prologue", "eval_store", "build", "fs_init", "S1", "S1_wait", "S2", "S3",
+                                          "schur", "bwd_init", "bwd", "update", "eval_trial", "lm_scalar", "finalize"};
+    long long tot = 0;
+    for (int i = 0; i < PF_COUNT; i++) tot += h[i];
+    fprintf(stderr, "[defslam profile] CTA0 cycles total %lld:", tot);
+    for (int i = 0; i < PF_COUNT; i++) fprintf(stderr, " %s=%.1f%%", names[i], 100.0 * (double)h[i] / (double)(tot ? tot : 1));
+    fprintf(stderr, "\n");
+  }
   return 0;
 }
 
@@ -223,7 +246,7 @@ int defslam_template_info(const defslam_template *t, int32_t *bandwidth, int32_t
   if (n_blocks) *n_blocks = v.n_blk;
   if (smem_bytes)
     *smem_bytes = (int32_t)sizeof(double) *
-                  (CTX_DOUBLES + smem_layout(v.n_nodes, v.n_edges, v.Dn_pad, v.bwp, v.ld, v.Wr, true).total);
+                  (CTX_DOUBLES + smem_layout(v.n_nodes, v.n_edges, v.Dn_pad, v.bwp, v.ld, v.Wr, v.ES, true).total);
   return DEFSLAM_OK;
 }
 

@@ -60,7 +60,7 @@ int run(int nprob, const defslam_sft_problem *p, defslam_sft_result *r, int mode
   for (int i = 0; i < nprob; i++) {
     /* poison the scratch so that stale-state bugs between problems show up */
     for (auto &v : smem) v = 1e300;
-    sft_run_problem(team, bm.views[i], smem.data(), ws.data(), z);
+    sft_run_problem(team, bm.views[i], smem.data(), ws.data(), z, true, nullptr);
   }
   if (mode == MODE_NORMAL_EQ) {
     const ProbSlot &s = bm.slots[0];
@@ -102,7 +102,7 @@ void emu_template_destroy(void *t) { delete (EmuTemplate *)t; }
 int emu_plan_info(void *t, int32_t *out /* bw, ld, Dn_pad, Wr, n_blk, smem_doubles */) {
   const EmuTemplate *e = (const EmuTemplate *)t;
   out[0] = e->view.bw; out[1] = e->view.ld; out[2] = e->view.Dn_pad; out[3] = e->view.Wr; out[4] = e->view.n_blk;
-  out[5] = CTX_DOUBLES + smem_layout(e->view.n_nodes, e->view.n_edges, e->view.Dn_pad, e->view.bwp, e->view.ld, e->view.Wr, true).total;
+  out[5] = CTX_DOUBLES + smem_layout(e->view.n_nodes, e->view.n_edges, e->view.Dn_pad, e->view.bwp, e->view.ld, e->view.Wr, e->view.ES, true).total;
   return 0;
 }
 }
