@@ -28,13 +28,13 @@ struct BatchMarshal {
   std::vector<ProbView> views;
   size_t in_bytes = 0, out_bytes = 0;
   /* workspace / launch sizing (max over the batch) */
-  size_t ws_band = 0, ws_dinv = 0, ws_cg = 0, ws_F = 0, ws_S = 0, ws_M = 0, ws_nf = 0;
+  size_t ws_band = 0, ws_dinv = 0, ws_cg = 0, ws_F = 0, ws_S = 0, ws_M = 0, ws_nf = 0, ws_dp = 0;
   int smem_doubles = 0;
   bool any_e_global = false;
 
   WorkspaceSizes ws_sizes() const {
     WorkspaceSizes z;
-    z.band = ws_band; z.dinv = ws_dinv; z.cg = ws_cg; z.F = ws_F; z.S = ws_S; z.M = ws_M; z.nf = ws_nf;
+    z.band = ws_band; z.dinv = ws_dinv; z.cg = ws_cg; z.F = ws_F; z.S = ws_S; z.M = ws_M; z.nf = ws_nf; z.dp = ws_dp;
     return z;
   }
 
@@ -46,7 +46,7 @@ struct BatchMarshal {
     slots.assign(nprob, ProbSlot());
     views.assign(nprob, ProbView());
     in_bytes = out_bytes = 0;
-    ws_band = ws_dinv = ws_cg = ws_F = ws_S = ws_M = ws_nf = 0;
+    ws_band = ws_dinv = ws_cg = ws_F = ws_S = ws_M = ws_nf = ws_dp = 0;
     smem_doubles = 0;
     any_e_global = false;
     for (int i = 0; i < nprob; i++) {
@@ -106,6 +106,7 @@ struct BatchMarshal {
       ws_S = std::max(ws_S, (size_t)NMSCR * M);
       ws_M = std::max(ws_M, M);
       ws_nf = std::max(ws_nf, (size_t)hv->n_facets + 1);
+      ws_dp = std::max(ws_dp, (size_t)hv->Dn_pad);
     }
     return 0;
   }

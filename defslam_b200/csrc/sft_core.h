@@ -85,6 +85,7 @@ struct Workspace {
   double *Eg;    /* [8*Dn_pad]    working copy when it does not fit in smem   */
   double *F;     /* [NFACC*nf]    per-facet accumulators                      */
   double *S;     /* [NMSCR*M]     per-match scratch                           */
+  double *xb;    /* [Dn_pad]      LM backup of the node positions (push/pop)  */
   int *mfac;     /* [M]  facet<<6 | slot0 | slot1<<2 | slot2<<4               */
   int *mperm;    /* [M]  matches grouped by facet                             */
   int *fptr;     /* [nf+1] */
@@ -92,7 +93,7 @@ struct Workspace {
 };
 
 struct WorkspaceSizes {
-  size_t band, dinv, cg, F, S, M, nf; /* element counts (max over the batch) */
+  size_t band, dinv, cg, F, S, M, nf, dp; /* element counts (max over the batch) */
 };
 
 static inline
@@ -100,7 +101,7 @@ static inline
 __host__ __device__
 #endif
 size_t workspace_bytes(const WorkspaceSizes &z) {
-  size_t b = sizeof(double) * (2 * z.band + z.dinv + 2 * z.cg + z.F + z.S) + sizeof(int) * (2 * z.M + 2 * z.nf + 2);
+  size_t b = sizeof(double) * (2 * z.band + z.dinv + 2 * z.cg + z.F + z.S + z.dp) + sizeof(int) * (2 * z.M + 2 * z.nf + 2);
   return (b + 255) & ~(size_t)255;
 }
 
@@ -118,6 +119,7 @@ Workspace carve_workspace(uint8_t *base, const WorkspaceSizes &z) {
   w.Eg = d; d += z.cg;
   w.F = d; d += z.F;
   w.S = d; d += z.S;
+  w.xb = d; d += z.dp;
   int *i = (int *)d;
   w.mfac = i; i += z.M;
   w.mperm = i; i += z.M;
@@ -149,7 +151,7 @@ SmemLayout smem_layout(int n_nodes, int n_edges, int Dn_pad, int bwp, int ld, in
   L.E = o;    o += e_in_smem ? 8 * ES : 0;
   L.P = o;    o += (NB * (bwp + 8) > 216 ? NB * (bwp + 8) : 216); o = (o + 1) & ~1;
   L.x = o;    o += Dn_pad;
-  L.xb = o;   o += Dn_pad;
+  L.xb = o;   /* (backup lives in global memory) */
   L.dx = o;   o += Dn_pad + 8;
   L.Lkk = o;  o += 64;
   L.invL = o; o += 96;   /* inv(L_kk), row stride 12 */
@@ -167,9 +169,6 @@ struct Ctx {
   ProbView pb;
   Workspace ws;
   SmemLayout sl;
-  double *sm;      /* shared memory base */
-  double *E;       /* working border rows (smem or global) */
-  uint8_t *viewed, *freev;
   int n_optlap, n_viewed, n_str;
   double info_ref, info_curv, info_str;
   double hub_delta, hub_dsqr;
@@ -180,10 +179,31 @@ struct Ctx {
   uint64_t mbar[8]; /* 0: forward window, 1..4: backward ring (fixed address for the whole launch) */
 };
 
+/* doubles reserved at the head of shared memory for the CTA-wide context */
+constexpr int CTX_DOUBLES = (int)((sizeof(Ctx) + 15) / 16) * 2;
+
+/* All shared-memory pointers are derived from the kernel's dynamic shared array
+ * inside each function, never carried through the context: that way the
+ * compiler knows the address space and emits LDS/STS with 32-bit addressing
+ * instead of generic 64-bit loads. */
+#if DS_CUDA
+extern __shared__ __align__(16) double ds_smem_raw[];
+#define DS_SMEM ds_smem_raw
+#else
+static double *ds_smem_emu = nullptr;
+#define DS_SMEM ds_smem_emu
+#endif
+DS_FN Ctx &ctx_ref() { return *(Ctx *)DS_SMEM; }
+DS_FN double *sm_base() { return DS_SMEM + CTX_DOUBLES; }
+DS_FN uint8_t *viewed_ptr(const Ctx &c) { return (uint8_t *)(sm_base() + c.sl.flags); }
+DS_FN uint8_t *freev_ptr(const Ctx &c) { return (uint8_t *)(sm_base() + c.sl.flags) + c.pl.n_nodes; }
+
 /* phase-cycle accounting (diagnostics; enabled by DEFSLAM_PROFILE=1 on the host side) */
 enum { PF_PROLOGUE = 0, PF_EVAL_STORE, PF_BUILD, PF_FS_INIT, PF_S1, PF_S1_WAIT, PF_S2, PF_S3, PF_SCHUR, PF_BWD_INIT,
        PF_BWD, PF_UPDATE, PF_EVAL_TRIAL, PF_LM_SCALAR, PF_FINALIZE, PF_COUNT };
-DS_FN void prof_mark(const Team team, Ctx &c, int idx) {
+DS_FN void prof_mark(const Team team, Ctx &cx, int idx) {
+  Ctx &c = ctx_ref();
+  (void)cx;
 #if DS_CUDA
   if (c.prof != nullptr && team.tid == 0) {
     const long long now = clock64();
@@ -208,21 +228,24 @@ DS_FN int pidx(int cc, int r, int HS) { return (cc >> 2) * HS + r * 4 + (cc & 3)
 /* ------------------------------------------------------------ prologue -- */
 
 /* returns 0 or an error code (uniform over the team) */
-DS_FN_NOINLINE int prologue(const Team team, Ctx &c) {
+DS_FN_NOINLINE int prologue(const Team team, Ctx &cx) {
+  Ctx &c = ctx_ref();
+  (void)cx;
   const PlanView &pl = c.pl;
   const ProbView &pb = c.pb;
   const int n = pl.n_nodes, nf = pl.n_facets, M = pb.n_matches;
-  double *x = c.sm + c.sl.x;
-  double *red = c.sm + c.sl.red;
+  double *x = sm_base() + c.sl.x;
+  double *red = sm_base() + c.sl.red;
 
   DS_FOR(i, pl.Dn_pad) x[i] = i < pl.Dn ? pb.node_xyz[i] : 0.0;
-  DS_FOR(i, pl.Dn_pad + 8) c.sm[c.sl.dx + i] = 0.0;
-  DS_FOR(i, 2 * n) c.viewed[i] = 0; /* viewed + freev are contiguous */
+  DS_FOR(i, pl.Dn_pad + 8) sm_base()[c.sl.dx + i] = 0.0;
+  DS_FOR(i, 96) sm_base()[c.sl.invL + i] = 0.0;
+  DS_FOR(i, 2 * n) viewed_ptr(c)[i] = 0; /* viewed + freev are contiguous */
   DS_FOR(f, nf) c.ws.fcnt[f] = 0;
   if (team.tid == 0) {
     Pose P;
     pose_from_Tcw(pb.Tcw, P);
-    double *ps = c.sm + c.sl.pose;
+    double *ps = sm_base() + c.sl.pose;
     for (int k = 0; k < 4; k++) ps[k] = P.q[k];
     for (int k = 0; k < 3; k++) ps[4 + k] = P.t[k];
   }
@@ -258,7 +281,7 @@ DS_FN_NOINLINE int prologue(const Team team, Ctx &c) {
     if (code < 0) bad++;
     else {
       atomic_inc_int(&c.ws.fcnt[code >> 6]);
-      c.viewed[v[0]] = 1; c.viewed[v[1]] = 1; c.viewed[v[2]] = 1;
+      viewed_ptr(c)[v[0]] = 1; viewed_ptr(c)[v[1]] = 1; viewed_ptr(c)[v[2]] = 1;
     }
   }
   bad = team_sum_int(team, bad, red);
@@ -266,10 +289,10 @@ DS_FN_NOINLINE int prologue(const Team team, Ctx &c) {
 
   /* OptLap = Viewed U ring1(Viewed)  (DefOptimizer.cc:384-406, quirk C3) */
   DS_FOR(v, n) {
-    int fr = c.viewed[v];
+    int fr = viewed_ptr(c)[v];
     if (!fr && pb.layers >= 1)
-      for (int k = pl.nbr_ptr[v]; k < pl.nbr_ptr[v + 1]; k++) fr |= c.viewed[pl.nbr_idx[k]];
-    c.freev[v] = (uint8_t)fr;
+      for (int k = pl.nbr_ptr[v]; k < pl.nbr_ptr[v + 1]; k++) fr |= viewed_ptr(c)[pl.nbr_idx[k]];
+    freev_ptr(c)[v] = (uint8_t)fr;
   }
   if (team.tid == 0) { /* exclusive scan of the facet histogram */
     int s = 0;
@@ -278,8 +301,8 @@ DS_FN_NOINLINE int prologue(const Team team, Ctx &c) {
   }
   team.sync();
   int cnt_v = 0, cnt_o = 0, cnt_s = 0;
-  DS_FOR(v, n) { cnt_v += c.viewed[v]; cnt_o += c.freev[v]; }
-  DS_FOR(e, pl.n_edges) cnt_s += (c.freev[pl.edge_ab[2 * e]] | c.freev[pl.edge_ab[2 * e + 1]]);
+  DS_FOR(v, n) { cnt_v += viewed_ptr(c)[v]; cnt_o += freev_ptr(c)[v]; }
+  DS_FOR(e, pl.n_edges) cnt_s += (freev_ptr(c)[pl.edge_ab[2 * e]] | freev_ptr(c)[pl.edge_ab[2 * e + 1]]);
   DS_FOR(f, nf) c.ws.fcnt[f] = 0;
   const int n_viewed = team_sum_int(team, cnt_v, red);
   const int n_optlap = team_sum_int(team, cnt_o, red);
@@ -358,13 +381,16 @@ DS_FN double curv_residual(const Ctx &c, const double *x, int i, double d[3], do
  * store=true additionally fills everything build_system() gathers from:
  * per-match scratch S, per-node A / centre / edge quantities (overlaid on the
  * window region of shared memory). */
-DS_FN_NOINLINE double eval_state(const Team team, Ctx &c, const double *x, const double *ps, bool store) {
+DS_FN_NOINLINE double eval_state(const Team team, Ctx &cx, bool store) {
+  Ctx &c = ctx_ref();
+  (void)cx;
+  const double *x = sm_base() + c.sl.x, *ps = sm_base() + c.sl.pose;
   const PlanView &pl = c.pl;
   const ProbView &pb = c.pb;
   const int n = pl.n_nodes, ne = pl.n_edges, M = pb.n_matches;
   Pose P;
   load_pose(ps, P);
-  double *A = c.sm + c.sl.W;      /* [6n] */
+  double *A = sm_base() + c.sl.W;      /* [6n] */
   double *cd = A + 6 * n;         /* [3n] unit Laplacian direction */
   double *cg = cd + 3 * n;        /* [n]  info_curv * S_i (0 if inactive) */
   double *cr = cg + n;            /* [n]  |delta| - kappa0 */
@@ -421,12 +447,12 @@ DS_FN_NOINLINE double eval_state(const Team team, Ctx &c, const double *x, const
   }
   /* temporal (EdgesReference sft_types.h:403-408), curvature, per-node A */
   DS_FOR(v, n) {
-    if (c.viewed[v]) {
+    if (viewed_ptr(c)[v]) {
       const double e0 = x[3 * v] - pl.rest[3 * v], e1 = x[3 * v + 1] - pl.rest[3 * v + 1],
                    e2 = x[3 * v + 2] - pl.rest[3 * v + 2];
       chi += (e0 * e0 + e1 * e1 + e2 * e2) * c.info_ref;
     }
-    const bool active = c.freev[v] && !pl.boundary[v] && (pl.nbr_ptr[v + 1] > pl.nbr_ptr[v]);
+    const bool active = freev_ptr(c)[v] && !pl.boundary[v] && (pl.nbr_ptr[v + 1] > pl.nbr_ptr[v]);
     if (active) {
       double d[3], nrm;
       const double r = curv_residual(c, x, v, d, nrm);
@@ -453,7 +479,7 @@ DS_FN_NOINLINE double eval_state(const Team team, Ctx &c, const double *x, const
   /* stretch (EdgesStreching sft_types.h:353-378) */
   DS_FOR(e, ne) {
     const int a = pl.edge_ab[2 * e], b = pl.edge_ab[2 * e + 1];
-    const bool active = c.freev[a] || c.freev[b];
+    const bool active = freev_ptr(c)[a] || freev_ptr(c)[b];
     if (active) {
       const double d0 = x[3 * a] - x[3 * b], d1 = x[3 * a + 1] - x[3 * b + 1], d2 = x[3 * a + 2] - x[3 * b + 2];
       const double nrm = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
@@ -469,7 +495,7 @@ DS_FN_NOINLINE double eval_state(const Team team, Ctx &c, const double *x, const
       eu[3 * e] = eu[3 * e + 1] = eu[3 * e + 2] = 0.0; er[e] = 0.0; es[e] = 0.0;
     }
   }
-  return team_sum(team, chi, c.sm + c.sl.red);
+  return team_sum(team, chi, sm_base() + c.sl.red);
 }
 
 /* ------------------------------------------------ normal equations ----- */
@@ -478,15 +504,17 @@ DS_FN_NOINLINE double eval_state(const Team team, Ctx &c, const double *x, const
  * same state.  Produces Hb (band), Cg rows 0-5 (camera border), Cg row 6 (b_n),
  * Hcc/bc (shared).  Returns max |diag| over the free variables
  * (computeLambdaInit, optimization_algorithm_levenberg.cpp:166-180). */
-DS_FN_NOINLINE double build_system(const Team team, Ctx &c) {
+DS_FN_NOINLINE double build_system(const Team team, Ctx &cx) {
+  Ctx &c = ctx_ref();
+  (void)cx;
   const PlanView &pl = c.pl;
   const int n = pl.n_nodes, ne = pl.n_edges, nf = pl.n_facets, M = c.pb.n_matches;
   const int bwE = pl.bwE, ld = pl.ld, ES = pl.ES;
-  const double *A = c.sm + c.sl.W;
+  const double *A = sm_base() + c.sl.W;
   const double *cd = A + 6 * n, *cg = cd + 3 * n, *cr = cg + n, *eu = cr + n, *er = eu + 3 * ne, *es = er + ne;
   double *F = c.ws.F;
   const double *S = c.ws.S;
-  double *Hcc = c.sm + c.sl.Hcc;
+  double *Hcc = sm_base() + c.sl.Hcc;
   team.sync();
 
   /* (1) per-facet sums.  item = (facet, group) */
@@ -565,7 +593,7 @@ DS_FN_NOINLINE double build_system(const Team team, Ctx &c) {
    * 27 sums x NPART partial ranges, then the partials in order. */
   {
     constexpr int NPART = 8;
-    double *part = c.sm + c.sl.P; /* 27*NPART doubles, free outside factor_solve */
+    double *part = sm_base() + c.sl.P; /* 27*NPART doubles, free outside factor_solve */
     const int chunk = (nf + NPART - 1) / NPART;
     DS_FOR(it, 27 * NPART) {
       const int k = it % 27, pt = it / 27;
@@ -596,7 +624,7 @@ DS_FN_NOINLINE double build_system(const Team team, Ctx &c) {
     const int p = pl.blk_pq[2 * bi], q = pl.blk_pq[2 * bi + 1];
     double h[9];
     for (int k = 0; k < 9; k++) h[k] = 0.0;
-    const bool fp = c.freev[p], fq = c.freev[q];
+    const bool fp = freev_ptr(c)[p], fq = freev_ptr(c)[q];
     if (fp && fq) {
       /* reprojection: (sum over shared facets of sum_m w b_p b_q) * A_p^T A_q */
       double beta = 0.0;
@@ -629,7 +657,7 @@ DS_FN_NOINLINE double build_system(const Team team, Ctx &c) {
           for (int r = 0; r < 3; r++)
             for (int s = 0; s < 3; s++) h[3 * r + s] += w * u[r] * u[s];
         }
-        if (c.viewed[p]) { h[0] += c.info_ref; h[4] += c.info_ref; h[8] += c.info_ref; }
+        if (viewed_ptr(c)[p]) { h[0] += c.info_ref; h[4] += c.info_ref; h[8] += c.info_ref; }
       } else if (pl.blk_edge[bi] >= 0) {
         const int e = pl.blk_edge[bi];
         const double w = es[e];
@@ -656,7 +684,7 @@ DS_FN_NOINLINE double build_system(const Team team, Ctx &c) {
   DS_FOR(p, n) {
     double b[3] = {0, 0, 0}, C[18];
     for (int k = 0; k < 18; k++) C[k] = 0.0;
-    if (c.freev[p]) {
+    if (freev_ptr(c)[p]) {
       const double *Ap = &A[6 * p];
       double be0 = 0, be1 = 0, bj[12];
       for (int k = 0; k < 12; k++) bj[k] = 0.0;
@@ -670,8 +698,8 @@ DS_FN_NOINLINE double build_system(const Team team, Ctx &c) {
       /* C[a][r] = sum_rows bj[row][a] * Ap[row][r] */
       for (int a = 0; a < 6; a++)
         for (int r = 0; r < 3; r++) C[3 * a + r] = bj[a] * Ap[r] + bj[6 + a] * Ap[3 + r];
-      if (c.viewed[p])
-        for (int r = 0; r < 3; r++) b[r] -= c.info_ref * ((c.sm + c.sl.x)[3 * p + r] - pl.rest[3 * p + r]);
+      if (viewed_ptr(c)[p])
+        for (int r = 0; r < 3; r++) b[r] -= c.info_ref * ((sm_base() + c.sl.x)[3 * p + r] - pl.rest[3 * p + r]);
       for (int k = pl.nc_ptr[p]; k < pl.nc_ptr[p + 1]; k++) {
         const int i = pl.nc_ent[2 * k], ip = pl.nc_ent[2 * k + 1];
         const double g = cg[i];
@@ -691,7 +719,7 @@ DS_FN_NOINLINE double build_system(const Team team, Ctx &c) {
       for (int a = 0; a < 6; a++) c.ws.Cg[a * ES + 3 * p + r] = C[3 * a + r];
     }
   }
-  maxd = team_max(team, maxd, c.sm + c.sl.red); /* also a barrier: Hcc complete */
+  maxd = team_max(team, maxd, sm_base() + c.sl.red); /* also a barrier: Hcc complete */
   for (int k = 0; k < 6; k++) maxd = fmax(maxd, fabs(Hcc[7 * k]));
   return maxd;
 }
@@ -746,8 +774,8 @@ constexpr int ILS = 12; /* row stride of inv(L_kk) in shared memory */
  * arithmetic on registers, so the dependent chain (8 x rsqrt-mul-fma) has no
  * shuffle or shared-memory hop on it.  Phase 2: lane j builds column j of the
  * inverse by forward substitution from the shared copy. */
-DS_FN void diag_factor(const Team team, double *W, int kslot, int Wr, int ld, int bwE, double lambda, double *Lkk,
-                       double *invL, int *flag) {
+DS_FN void diag_factor(const Team team, double *W, int kslot, int Wr, int ld, int bwE, double lambda, double *invL,
+                       int *flag) {
   const int lane = team.lane();
   double *rowp[NB]; /* rowp[a][t] = entry (a, a - (bwE - t)); diagonal at rowp[a][bwE] */
 #pragma unroll
@@ -780,9 +808,7 @@ DS_FN void diag_factor(const Team team, double *W, int kslot, int Wr, int ld, in
   for (int a = 0; a < 4; a++)
 #pragma unroll
     for (int b = 0; b < NB; b++) {
-      const double v = b <= a ? A11[a * (a + 1) / 2 + b] : 0.0;
-      Lkk[a * NB + b] = v;
-      if (b <= a) rowp[a][b] = v;
+      if (b <= a) rowp[a][b] = A11[a * (a + 1) / 2 + b];
     }
 #pragma unroll
   for (int a = 0; a < 4; a++)
@@ -798,9 +824,7 @@ DS_FN void diag_factor(const Team team, double *W, int kslot, int Wr, int ld, in
   for (int a = 0; a < 4; a++)
 #pragma unroll
     for (int b = 0; b < NB; b++) {
-      const double v = b < 4 ? L21[a * 4 + b] : (b - 4 <= a ? A22[a * (a + 1) / 2 + (b - 4)] : 0.0);
-      Lkk[(4 + a) * NB + b] = v;
-      if (b <= 4 + a) rowp[4 + a][b] = v;
+      if (b <= 4 + a) rowp[4 + a][b] = b < 4 ? L21[a * 4 + b] : A22[a * (a + 1) / 2 + (b - 4)];
     }
   if (bad && lane == 0) *flag = 1;
   team.warp_sync();
@@ -811,10 +835,10 @@ DS_FN void diag_factor(const Team team, double *W, int kslot, int Wr, int ld, in
     for (int i = 0; i < NB; i++) sacc[i] = (i == j) ? 1.0 : 0.0;
 #pragma unroll
     for (int m = 0; m < NB; m++) {
-      const double xm = sacc[m] * Lkk[m * NB + m];
-      invL[m * ILS + j] = xm;
+      const double xm = sacc[m] * rowp[m][m];
+      if (m >= j) invL[m * ILS + j] = xm; /* the strict upper part stays zero (prologue) */
 #pragma unroll
-      for (int i = m + 1; i < NB; i++) sacc[i] -= Lkk[i * NB + m] * xm;
+      for (int i = m + 1; i < NB; i++) sacc[i] -= rowp[i][m] * xm;
     }
   }
 }
@@ -823,7 +847,7 @@ DS_FN void diag_factor(const Team team, double *W, int kslot, int Wr, int ld, in
 /* D(8x8) += A(8x4) B(4x8) on the FP64 tensor cores.  Lane T holds a = A[T/4][T%4],
  * b = B[T%4][T/4], and d0,d1 = D[T/4][2*(T%4)], D[T/4][2*(T%4)+1]. */
 DS_FN void dmma884(double &d0, double &d1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(d0), "+d"(d1)
                : "d"(a), "d"(b));
 }
@@ -867,18 +891,70 @@ DS_FN void tile_mul_pp(int lane, const double *P, int HS, int rA, int rB, double
 #endif
 }
 
+/* One 8-row tile of the panel solve: X = A inv(L_kk)^T, in place, and into the
+ * panel buffer.  base[g*rs + cc] = A[g][cc]; the entry is inside the band iff
+ * o0 + og*g + cc >= lo (always, for the border rows). */
+DS_FN void panel_tile(const Team team, double *base, int rs, int o0, int og, int lo, const double *invL, double *P,
+                      int HS, int r0) {
+#if DS_CUDA
+  const int lane = team.tid & 31, g = lane >> 2, q = lane & 3;
+  const int o = o0 + og * g;
+  const double a0 = (o + q >= lo) ? base[g * rs + q] : 0.0;
+  const double a1 = (o + 4 + q >= lo) ? base[g * rs + 4 + q] : 0.0;
+  double d0 = 0.0, d1 = 0.0;
+  dmma884(d0, d1, a0, invL[g * ILS + q]);
+  dmma884(d0, d1, a1, invL[g * ILS + 4 + q]);
+  /* mma.sync is warp-synchronous: every lane has read its operands */
+  if (o + 2 * q >= lo) base[g * rs + 2 * q] = d0;
+  if (o + 2 * q + 1 >= lo) base[g * rs + 2 * q + 1] = d1;
+  *(dbl2 *)&P[pidx(2 * q, r0 + g, HS)] = dbl2{d0, d1};
+#else
+  (void)team;
+  double X[NB][NB];
+  for (int g = 0; g < NB; g++) {
+    const int o = o0 + og * g;
+    for (int cc = 0; cc < NB; cc++) {
+      double sx = 0.0;
+      for (int m = 0; m < NB; m++) {
+        const double a = (o + m >= lo) ? base[g * rs + m] : 0.0;
+        sx += a * invL[cc * ILS + m];
+      }
+      X[g][cc] = sx;
+    }
+  }
+  for (int g = 0; g < NB; g++) {
+    const int o = o0 + og * g;
+    for (int cc = 0; cc < NB; cc++) {
+      if (o + cc >= lo) base[g * rs + cc] = X[g][cc];
+      P[pidx(cc, r0 + g, HS)] = X[g][cc];
+    }
+  }
+#endif
+}
+
+/* C(pair) -= d for the 16-byte pair a DMMA accumulator lane owns */
+DS_FN void sub_pair(double *dst, double d0, double d1) {
+  dbl2 *p2 = (dbl2 *)dst;
+  dbl2 cv = *p2;
+  cv.x -= d0; cv.y -= d1;
+  *p2 = cv;
+}
+
 /* Solve (H + lambda I) dx = b.  dx -> sm[sl.dx] (nodes, then camera at Dn_pad).
  * Returns false if a pivot is not positive (LinearSolverDense::solve returning
  * false, linear_solver_dense.h:107-112); dx is then left untouched (stale), as
  * in the reference. */
-DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &c, double lambda) {
+DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
+  Ctx &c = ctx_ref();
+  (void)cx;
   const int bw = c.pl.bw, bwE = c.pl.bwE, ld = c.pl.ld, Dp = c.pl.Dn_pad, Wr = c.pl.Wr, bwp = c.pl.bwp,
             nblk = c.pl.nblk, ES = c.pl.ES;
   const int PR = bwp + 8, HS = 4 * PR; /* panel rows: trailing rows, then the 8 border rows */
-  double *const sm = c.sm;
-  double *W = sm + c.sl.W, *P = sm + c.sl.P, *Lkk = sm + c.sl.Lkk, *invL = sm + c.sl.invL;
+  double *const sm = sm_base();
+  double *W = sm + c.sl.W, *P = sm + c.sl.P, *invL = sm + c.sl.invL;
   double *G = sm + c.sl.G, *Hcc = sm + c.sl.Hcc, *dx = sm + c.sl.dx;
-  double *E = c.E;
+  const bool e_smem = c.pb.e_in_smem != 0;
+  double *Es = sm_base() + c.sl.E, *Eg = c.ws.Eg;
   const double *Hb = c.ws.Hb;
   double *Lb = c.ws.Lb;
   int *flag = (int *)(sm + c.sl.red + 36);
@@ -888,7 +964,6 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &c, double lambda) {
 #else
   const int warp = 0, nwarp = 1;
 #endif
-  (void)Lkk;
 
   /* Everything H/border related in global memory was written with plain stores
    * (build_system); order them before the TMA reads. */
@@ -899,17 +974,16 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &c, double lambda) {
   /* window <- first Wr rows of H; border/rhs working copy (bulk async); corner */
   {
     const int rows = Wr < Dp ? Wr : Dp;
-    const bool e_smem = c.pb.e_in_smem != 0;
     if (team.tid == 0) {
       const uint32_t bw_bytes = (uint32_t)(rows * ld * sizeof(double));
       const uint32_t e_bytes = e_smem ? (uint32_t)(8 * ES * sizeof(double)) : 0u;
       mbar_expect_tx(bar0, bw_bytes + e_bytes);
       tma_load_1d(W, Hb, bw_bytes, bar0);
-      if (e_smem) tma_load_1d(E, c.ws.Cg, e_bytes, bar0);
+      if (e_smem) tma_load_1d(Es, c.ws.Cg, e_bytes, bar0);
     }
     if (!e_smem) {
       const double *Cg = c.ws.Cg;
-      DS_FOR(i, 8 * ES) E[i] = Cg[i];
+      DS_FOR(i, 8 * ES) Eg[i] = Cg[i];
     }
     DS_FOR(i, 64) {
       const int a = i >> 3, b = i & 7;
@@ -929,7 +1003,7 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &c, double lambda) {
   for (int kb = 0; kb < nblk; kb++) {
     const int k = kb * NB;
     /* S1: factor the diagonal block (warp 0) */
-    if (team.warp0()) diag_factor(team, W, kslot, Wr, ld, bwE, lambda, Lkk, invL, flag);
+    if (team.warp0()) diag_factor(team, W, kslot, Wr, ld, bwE, lambda, invL, flag);
     team.sync();
     prof_mark(team, c, PF_S1);
     /* rows requested during the previous step (they enter this step's panel) */
@@ -944,51 +1018,18 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &c, double lambda) {
       const bool erow = rt == nt8;
       if (!erow && rt >= nrt) continue; /* rows beyond the matrix: never read by S3 */
       const int r0 = erow ? bwp : rt * NB; /* first panel row of this tile */
-      /* trailing rows i = k+8+r0+g: column k+cc sits at band offset o0+cc with
-       * o0 = bwE-8-r0-g; offsets below lo = bwE-bw are outside the band (zero).
-       * The 8 rows of a tile never wrap inside the ring (Wr, r0 multiples of 8). */
-      int s0 = kslot + NB + r0;
-      if (s0 >= Wr) s0 -= Wr;
-      double *base = erow ? (E + k) : (W + s0 * ld + (bwE - NB - r0));
-      const int rs = erow ? ES : (ld - 1); /* stride between the tile's rows at a fixed column */
-      const int lo = bwE - bw;
-#if DS_CUDA
-      {
-        const int g = lane >> 2, q = lane & 3;
-        const int o0 = erow ? bwE : (bwE - NB - r0 - g);
-        const double a0 = (o0 + q >= lo) ? base[g * rs + q] : 0.0;
-        const double a1 = (o0 + 4 + q >= lo) ? base[g * rs + 4 + q] : 0.0;
-        double d0 = 0.0, d1 = 0.0;
-        dmma884(d0, d1, a0, invL[g * ILS + q]);
-        dmma884(d0, d1, a1, invL[g * ILS + 4 + q]);
-        /* mma.sync is warp-synchronous: every lane has read its operands */
-        if (o0 + 2 * q >= lo) base[g * rs + 2 * q] = d0;
-        if (o0 + 2 * q + 1 >= lo) base[g * rs + 2 * q + 1] = d1;
-        *(dbl2 *)&P[pidx(2 * q, r0 + g, HS)] = dbl2{d0, d1};
+      if (!erow) {
+        /* trailing rows i = k+8+r0+g: column k+cc sits at band offset o0+cc with
+         * o0 = bwE-8-r0-g; offsets below lo = bwE-bw are outside the band (zero).
+         * The 8 rows of a tile never wrap inside the ring (Wr, r0 multiples of 8). */
+        int s0 = kslot + NB + r0;
+        if (s0 >= Wr) s0 -= Wr;
+        panel_tile(team, W + s0 * ld + (bwE - NB - r0), ld - 1, bwE - NB - r0, -1, bwE - bw, invL, P, HS, r0);
+      } else if (e_smem) {
+        panel_tile(team, Es + k, ES, bwE, 0, bwE - bw, invL, P, HS, r0);
+      } else {
+        panel_tile(team, Eg + k, ES, bwE, 0, bwE - bw, invL, P, HS, r0);
       }
-#else
-      {
-        double X[NB][NB];
-        for (int g = 0; g < NB; g++) {
-          const int o0 = erow ? bwE : (bwE - NB - r0 - g);
-          for (int cc = 0; cc < NB; cc++) {
-            double sx = 0.0;
-            for (int m = 0; m < NB; m++) {
-              const double a = (o0 + m >= lo) ? base[g * rs + m] : 0.0;
-              sx += a * invL[cc * ILS + m];
-            }
-            X[g][cc] = sx;
-          }
-        }
-        for (int g = 0; g < NB; g++) {
-          const int o0 = erow ? bwE : (bwE - NB - r0 - g);
-          for (int cc = 0; cc < NB; cc++) {
-            if (o0 + cc >= lo) base[g * rs + cc] = X[g][cc];
-            P[pidx(cc, r0 + g, HS)] = X[g][cc];
-          }
-        }
-      }
-#endif
     }
     /* finished rows k..k+7 (final after S1) -> L band in global memory */
     {
@@ -1006,48 +1047,61 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &c, double lambda) {
       tma_load_1d(W + kslot * ld, Hb + (k + Wr) * ld, bytes, bar0);
     }
 
-    /* S3: trailing update, one 8x8 tile per warp iteration: C -= P_I P_J^T */
+    /* S3: trailing update C -= P_I P_J^T on 8x8 tiles, tiles dealt round-robin to
+     * the warps (row-major over the lower triangle of tile rows, the border tile
+     * row last).  A warp keeps S3U tiles in flight: all operand fragments are
+     * loaded and all DMMAs issued before the first read-modify-write, so the
+     * latencies of independent tiles overlap. */
     {
-      const int nrow = nt8 + 1; /* tile rows: trailing tiles, then the border tile row */
+      constexpr int S3U = 1;
+      const int nrow = nt8 + 1;
       const int ntiles = nrow * (nrow + 1) / 2;
-      for (int t = warp; t < ntiles; t += nwarp) {
-        int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-        while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
-        while (ti * (ti + 1) / 2 > t) ti--;
-        const int tj = t - ti * (ti + 1) / 2;
-        const bool erow = ti == nt8, ecol = tj == nt8;
-        if (!erow && ti >= nrt) continue;
-        if (!ecol && tj >= nrt) continue;
-        const int rA = erow ? bwp : ti * NB, rB = ecol ? bwp : tj * NB;
+      const int lo = bwE - bw;
+      int ti = 0, tj = warp;
+      while (tj > ti) { tj -= ti + 1; ti++; }
+      for (int t0 = warp; t0 < ntiles; t0 += S3U * nwarp) {
+        int rA[S3U], rB[S3U], kind[S3U]; /* kind: 0 skip, 1 window, 2 border row, 3 corner */
+#pragma unroll
+        for (int u = 0; u < S3U; u++) {
+          const int cti = ti, ctj = tj;
+          const bool in = t0 + u * nwarp < ntiles;
+          tj += nwarp;
+          while (tj > ti) { tj -= ti + 1; ti++; }
+          const bool erow = cti == nt8, ecol = ctj == nt8;
+          const bool skip = !in || (!erow && cti >= nrt) || (!ecol && ctj >= nrt);
+          kind[u] = skip ? 0 : (!erow ? 1 : (!ecol ? 2 : 3));
+          rA[u] = erow ? bwp : cti * NB;
+          rB[u] = ecol ? bwp : ctj * NB;
+        }
         DS_WARP_FOR(T, 32) {
           const int g = T >> 2, q = T & 3;
-          double d0, d1;
-          tile_mul_pp(T, P, HS, rA, rB, d0, d1);
-          if (!erow) {
-            /* entry (i, j): i = k+8+rA+g, j = k+8+rB+2q(+1); band offset j-i+bwE */
-            int s0 = kslot + NB + rA;
-            if (s0 >= Wr) s0 -= Wr;
-            const int off = rB + 2 * q - rA - g + bwE;
-            double *dst = W + (s0 + g) * ld + off;
-            const int lo = bwE - bw;
-            const bool v0 = off <= bwE && off >= lo, v1 = off + 1 <= bwE && off + 1 >= lo;
-            if (v0 && v1) {
-              dbl2 *p2 = (dbl2 *)dst;
-              dbl2 cv = *p2;
-              cv.x -= d0; cv.y -= d1;
-              *p2 = cv;
-            } else {
-              if (v0) dst[0] -= d0;
-              if (v1) dst[1] -= d1;
+          double d0[S3U], d1[S3U];
+#pragma unroll
+          for (int u = 0; u < S3U; u++)
+            if (kind[u] != 0) tile_mul_pp(T, P, HS, rA[u], rB[u], d0[u], d1[u]);
+#pragma unroll
+          for (int u = 0; u < S3U; u++) {
+            if (kind[u] == 1) {
+              /* entry (i, j): i = k+8+rA+g, j = k+8+rB+2q(+1); band offset j-i+bwE */
+              int s0 = kslot + NB + rA[u];
+              if (s0 >= Wr) s0 -= Wr;
+              const int off = rB[u] + 2 * q - rA[u] - g + bwE;
+              double *dst = W + (s0 + g) * ld + off;
+              const bool v0 = off <= bwE && off >= lo, v1 = off + 1 <= bwE && off + 1 >= lo;
+              if (v0 && v1) {
+                sub_pair(dst, d0[u], d1[u]);
+              } else {
+                if (v0) dst[0] -= d0[u];
+                if (v1) dst[1] -= d1[u];
+              }
+            } else if (kind[u] == 2) {
+              const int eo = g * ES + k + NB + rB[u] + 2 * q;
+              if (e_smem) sub_pair(Es + eo, d0[u], d1[u]);
+              else sub_pair(Eg + eo, d0[u], d1[u]);
+            } else if (kind[u] == 3) {
+              if (2 * q <= g) G[g * 8 + 2 * q] -= d0[u];
+              if (2 * q + 1 <= g) G[g * 8 + 2 * q + 1] -= d1[u];
             }
-          } else if (!ecol) {
-            dbl2 *p2 = (dbl2 *)(E + g * ES + k + NB + rB + 2 * q);
-            dbl2 cv = *p2;
-            cv.x -= d0; cv.y -= d1;
-            *p2 = cv;
-          } else {
-            if (2 * q <= g) G[g * 8 + 2 * q] -= d0;
-            if (2 * q + 1 <= g) G[g * 8 + 2 * q + 1] -= d1;
           }
         }
       }
@@ -1099,11 +1153,20 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &c, double lambda) {
   if (*flag != 0) { team.sync(); return false; }
 
   /* v = z - Y^T dc */
-  DS_FOR(i, Dp) {
-    double s = E[6 * ES + i];
+  if (e_smem) {
+    DS_FOR(i, Dp) {
+      double s = Es[6 * ES + i];
 #pragma unroll
-    for (int e = 0; e < 6; e++) s -= E[e * ES + i] * dx[Dp + e];
-    dx[i] = s;
+      for (int e = 0; e < 6; e++) s -= Es[e * ES + i] * dx[Dp + e];
+      dx[i] = s;
+    }
+  } else {
+    DS_FOR(i, Dp) {
+      double s = Eg[6 * ES + i];
+#pragma unroll
+      for (int e = 0; e < 6; e++) s -= Eg[e * ES + i] * dx[Dp + e];
+      dx[i] = s;
+    }
   }
   /* backward sweep  L^T dn = v, one block of NB rows per step.  Rows of L stream
    * back from global memory through a ring of NBUF buffers in the (now free)
@@ -1141,34 +1204,46 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &c, double lambda) {
     for (int b = 0; b < NBUF; b++)
       if (b == buf) { mbar_wait(&c.mbar[1 + b], phb[b]); phb[b] ^= 1u; }
     /* d = L_kk^-T y by backward substitution (1/L_ii on the diagonal); every
-     * thread that needs d computes it redundantly from shared memory */
+     * thread that needs d (the updaters of dx[k-bw .. k+7]) computes it
+     * redundantly from shared memory: no barrier between solve and update */
+    const int j0 = k - bw > 0 ? k - bw : 0;
+    const int nupd = k - j0; /* entries left of the block that change */
+    const bool active = team.tid < (nupd > NB ? nupd : NB);
     double d[NB];
+    if (active) {
 #pragma unroll
-    for (int a = 0; a < NB; a++) d[a] = dx[k + a];
+      for (int a = 0; a < NB; a++) d[a] = dx[k + a];
+      /* the 36 entries of L_kk first (independent loads), then the dependent chain */
+      double Lk[NB * (NB + 1) / 2];
 #pragma unroll
-    for (int a = NB - 1; a >= 0; a--) {
-      d[a] *= LR[a * ld + bwE];
+      for (int a = 0; a < NB; a++)
 #pragma unroll
-      for (int m = 0; m < a; m++) d[m] -= d[a] * LR[a * ld + bwE - a + m];
+        for (int m = 0; m <= a; m++) Lk[a * (a + 1) / 2 + m] = LR[a * ld + bwE - a + m];
+#pragma unroll
+      for (int a = NB - 1; a >= 0; a--) {
+        d[a] *= Lk[a * (a + 1) / 2 + a];
+#pragma unroll
+        for (int m = 0; m < a; m++) d[m] -= d[a] * Lk[a * (a + 1) / 2 + m];
+      }
     }
     team.sync(); /* everybody has read dx[k..k+7] */
+    if (active) {
 #pragma unroll
-    for (int a = 0; a < NB; a++) {
+      for (int a = 0; a < NB; a++) {
 #if DS_CUDA
-      if (team.tid == a) dx[k + a] = d[a];
+        if (team.tid == a) dx[k + a] = d[a];
 #else
-      dx[k + a] = d[a];
+        dx[k + a] = d[a];
 #endif
-    }
-    {
-      const int j0 = k - bw > 0 ? k - bw : 0;
-      DS_FOR(jj, k - j0) {
+      }
+      DS_FOR(jj, nupd) {
         const int jc = j0 + jj;
         double s = dx[jc];
+        const double *Lc = LR + (jc - k + bwE); /* Lc[a*(ld-1)] = L[k+a][jc] */
+        const int lo = bwE - bw;
 #pragma unroll
         for (int a = 0; a < NB; a++) {
-          const int off = jc - (k + a) + bwE;
-          if (off >= bwE - bw) s -= LR[a * ld + off] * d[a];
+          if (jc - k - a + bwE >= lo) s -= Lc[a * (ld - 1)] * d[a];
         }
         dx[jc] = s;
       }
@@ -1185,26 +1260,30 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &c, double lambda) {
 
 /* ------------------------------------------------------------- LM ------ */
 
-DS_FN void apply_update(const Team team, Ctx &c) {
+DS_FN void apply_update(const Team team, Ctx &cx) {
+  Ctx &c = ctx_ref();
+  (void)cx;
   const PlanView &pl = c.pl;
-  double *x = c.sm + c.sl.x, *dx = c.sm + c.sl.dx;
+  double *x = sm_base() + c.sl.x, *dx = sm_base() + c.sl.dx;
   /* VertexSBAPointXYZ::oplusImpl (types_sba.h:52-56); fixed nodes have dx = 0 */
   DS_FOR(i, pl.Dn) x[i] += dx[i];
   if (team.tid == 0) { /* VertexSE3Expmap::oplusImpl */
     Pose P;
-    load_pose(c.sm + c.sl.pose, P);
+    load_pose(sm_base() + c.sl.pose, P);
     pose_oplus(P, &dx[pl.Dn_pad]);
-    double *ps = c.sm + c.sl.pose;
+    double *ps = sm_base() + c.sl.pose;
     for (int k = 0; k < 4; k++) ps[k] = P.q[k];
     for (int k = 0; k < 3; k++) ps[4 + k] = P.t[k];
   }
   team.sync();
 }
 
-DS_FN void expand_dense(const Team team, Ctx &c, double chi) {
+DS_FN void expand_dense(const Team team, Ctx &cx, double chi) {
+  Ctx &c = ctx_ref();
+  (void)cx;
   const PlanView &pl = c.pl;
   const int Dn = pl.Dn, D = Dn + 6, bw = pl.bw, bwE = pl.bwE, ld = pl.ld, ES = pl.ES;
-  const double *Hcc = c.sm + c.sl.Hcc;
+  const double *Hcc = sm_base() + c.sl.Hcc;
   team.sync();
   if (c.pb.out_H) {
     DS_FOR(idx, D * D) {
@@ -1220,7 +1299,7 @@ DS_FN void expand_dense(const Team team, Ctx &c, double chi) {
   if (c.pb.out_b) {
     DS_FOR(i, D) {
       double v = i < Dn ? c.ws.Cg[6 * ES + i] : Hcc[36 + (i - Dn)];
-      if (i < Dn && !c.freev[i / 3]) v = 0.0;
+      if (i < Dn && !freev_ptr(c)[i / 3]) v = 0.0;
       c.pb.out_b[i] = v;
     }
   }
@@ -1234,15 +1313,17 @@ DS_FN void expand_dense(const Team team, Ctx &c, double chi) {
 }
 
 /* DefOptimizer.cc:515-577 */
-DS_FN_NOINLINE void finalize(const Team team, Ctx &c, bool last_rejected, int iterations, int trials, double chi_ini,
+DS_FN_NOINLINE void finalize(const Team team, Ctx &cx, bool last_rejected, int iterations, int trials, double chi_ini,
                              double chi_fin, double lambda) {
+  Ctx &c = ctx_ref();
+  (void)cx;
   const PlanView &pl = c.pl;
   const ProbView &pb = c.pb;
   const int M = pb.n_matches, n = pl.n_nodes;
-  const double *x = c.sm + c.sl.x, *xb = c.sm + c.sl.xb;
+  const double *x = sm_base() + c.sl.x, *xb = c.ws.xb;
   Pose P, Pb;
-  load_pose(c.sm + c.sl.pose, P);
-  load_pose(c.sm + c.sl.pose + 8, Pb);
+  load_pose(sm_base() + c.sl.pose, P);
+  load_pose(sm_base() + c.sl.pose + 8, Pb);
   /* e->chi2() is the error of the LAST computeActiveErrors, i.e. of the last LM
    * trial whether it was accepted or not (the state was popped, the edges were
    * not re-evaluated). */
@@ -1264,11 +1345,11 @@ DS_FN_NOINLINE void finalize(const Team team, Ctx &c, bool last_rejected, int it
       cnt++;
     }
   }
-  nbad = team_sum_int(team, nbad, c.sm + c.sl.red);
-  cnt = team_sum_int(team, cnt, c.sm + c.sl.red);
-  sum = team_sum(team, sum, c.sm + c.sl.red);
+  nbad = team_sum_int(team, nbad, sm_base() + c.sl.red);
+  cnt = team_sum_int(team, cnt, sm_base() + c.sl.red);
+  sum = team_sum(team, sum, sm_base() + c.sl.red);
   if (pb.out_nodes) DS_FOR(i, pl.Dn) pb.out_nodes[i] = x[i];
-  if (pb.out_role) DS_FOR(v, n) pb.out_role[v] = (uint8_t)(c.viewed[v] | (c.freev[v] << 1));
+  if (pb.out_role) DS_FOR(v, n) pb.out_role[v] = (uint8_t)(viewed_ptr(c)[v] | (freev_ptr(c)[v] << 1));
   if (team.tid == 0) {
     ResultScalars *r = pb.out_res;
     pose_to_Tcw(P, r->Tcw);
@@ -1286,12 +1367,14 @@ DS_FN_NOINLINE void finalize(const Team team, Ctx &c, bool last_rejected, int it
 }
 
 /* One frame, start to finish.  All threads of the team call this. */
-DS_FN_NOINLINE void sft_solve_one(const Team team, Ctx &c) {
+DS_FN_NOINLINE void sft_solve_one(const Team team, Ctx &cx) {
+  Ctx &c = ctx_ref();
+  (void)cx;
   const PlanView &pl = c.pl;
   const ProbView &pb = c.pb;
-  double *x = c.sm + c.sl.x, *xb = c.sm + c.sl.xb, *dx = c.sm + c.sl.dx;
-  double *ps = c.sm + c.sl.pose, *psb = ps + 8;
-  double *red = c.sm + c.sl.red;
+  double *x = sm_base() + c.sl.x, *xb = c.ws.xb, *dx = sm_base() + c.sl.dx;
+  double *ps = sm_base() + c.sl.pose, *psb = ps + 8;
+  double *red = sm_base() + c.sl.red;
   const int Dp = pl.Dn_pad;
 
   const int rc = prologue(team, c);
@@ -1301,7 +1384,7 @@ DS_FN_NOINLINE void sft_solve_one(const Team team, Ctx &c) {
     return;
   }
   if (pb.mode == MODE_NORMAL_EQ) {
-    const double chi = eval_state(team, c, x, ps, true);
+    const double chi = eval_state(team, c, true);
     build_system(team, c);
     expand_dense(team, c, chi);
     return;
@@ -1316,7 +1399,7 @@ DS_FN_NOINLINE void sft_solve_one(const Team team, Ctx &c) {
   int nBad = 0, iterations = 0, trials = 0;
   bool last_rejected = false;
   for (int it = 0; it < max_it; it++) {
-    double currentChi = eval_state(team, c, x, ps, true);
+    double currentChi = eval_state(team, c, true);
     prof_mark(team, c, PF_EVAL_STORE);
     double tempChi = currentChi;
     const double iniChi = currentChi;
@@ -1336,14 +1419,14 @@ DS_FN_NOINLINE void sft_solve_one(const Team team, Ctx &c) {
       const bool ok2 = factor_solve(team, c, lambda);
       apply_update(team, c);
       prof_mark(team, c, PF_UPDATE);
-      tempChi = eval_state(team, c, x, ps, false);
+      tempChi = eval_state(team, c, false);
       prof_mark(team, c, PF_EVAL_TRIAL);
       if (!ok2) tempChi = DBL_MAX;
       rho = currentChi - tempChi;
       double scale = 0.; /* computeScale :182-189 */
       DS_FOR(j, pl.Dn) scale += dx[j] * (lambda * dx[j] + c.ws.Cg[6 * pl.ES + j]);
       scale = team_sum(team, scale, red);
-      for (int j = 0; j < 6; j++) scale += dx[Dp + j] * (lambda * dx[Dp + j] + (c.sm + c.sl.Hcc)[36 + j]);
+      for (int j = 0; j < 6; j++) scale += dx[Dp + j] * (lambda * dx[Dp + j] + (sm_base() + c.sl.Hcc)[36 + j]);
       scale += 1e-3;
       rho /= scale;
       if (rho > 0 && isfinite(tempChi)) {
@@ -1383,17 +1466,19 @@ DS_FN_NOINLINE void sft_solve_one(const Team team, Ctx &c) {
   prof_mark(team, c, PF_FINALIZE);
 }
 
-/* doubles reserved at the head of shared memory for the CTA-wide context */
-constexpr int CTX_DOUBLES = (int)((sizeof(Ctx) + 15) / 16) * 2;
-
 /* Entry shared by the CUDA kernel and the emulation: bind a problem to a team,
  * its shared memory and its global workspace, then solve it.  The context is
  * kept in shared memory (one copy per CTA): with the shared-memory carve-out
  * this kernel uses there is almost no L1 left for a per-thread stack copy. */
 DS_FN void sft_run_problem(const Team &team, const ProbView &pv, double *smem, uint8_t *ws_base,
                            const WorkspaceSizes &z, bool first_of_launch, long long *prof) {
-  Ctx &c = *(Ctx *)smem;
-  double *sm = smem + CTX_DOUBLES;
+#if !DS_CUDA
+  ds_smem_emu = smem;
+#else
+  (void)smem;
+#endif
+  Ctx &c = ctx_ref();
+  double *sm = sm_base();
   team.sync();
   if (team.tid == 0) {
     if (first_of_launch) {
@@ -1408,10 +1493,6 @@ DS_FN void sft_run_problem(const Team &team, const ProbView &pv, double *smem, u
     c.pl = *pv.plan;
     c.ws = carve_workspace(ws_base, z);
     c.sl = smem_layout(c.pl.n_nodes, c.pl.n_edges, c.pl.Dn_pad, c.pl.bwp, c.pl.ld, c.pl.Wr, c.pl.ES, pv.e_in_smem != 0);
-    c.sm = sm;
-    c.E = pv.e_in_smem ? sm + c.sl.E : c.ws.Eg;
-    c.viewed = (uint8_t *)(sm + c.sl.flags);
-    c.freev = c.viewed + c.pl.n_nodes;
   }
   team.sync();
   sft_solve_one(team, c);

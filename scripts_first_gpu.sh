@@ -3,7 +3,7 @@
 set -x
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv
-timeout 900 python -m pytest tests/test_gpu_sft.py -x -q -m gpu 2>&1 | tail -30
+
 timeout 600 python - <<'PY' 2>&1 | tee gpurun_out/first_timing.log
 import time, numpy as np
 from defslam_b200 import sft, synthetic

@@ -1,4 +1,3 @@
 #!/bin/bash
-set -x
 mkdir -p gpurun_out
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:sft_lm_kernel -c 1 -f -o gpurun_out/prof_sft_c2 python tools/prof_run.py C2 296 1 2>&1 | tail -5
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:sft_lm_kernel -c 1 -f -o gpurun_out/prof_sft_c2 python tools/prof_run.py C2 148 1 2>&1 | tail -3
