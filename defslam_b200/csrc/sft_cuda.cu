@@ -22,17 +22,23 @@ constexpr int SFT_THREADS = 256;
 
 __global__ void __launch_bounds__(SFT_THREADS, 2)
 sft_lm_kernel(const ProbView *__restrict__ probs, int nprob, uint8_t *ws_base, size_t ws_stride, WorkspaceSizes z,
-              long long *prof) {
+              long long *prof, int *work_counter) {
   extern __shared__ __align__(16) double smem[];
   Team team;
   team.tid = threadIdx.x;
   team.nthr = blockDim.x;
   uint8_t *ws = ws_base + (size_t)blockIdx.x * ws_stride;
+  /* frames are handed out dynamically: LM trial counts differ per frame */
+  __shared__ int next_problem;
   bool first = true;
-  for (int pi = blockIdx.x; pi < nprob; pi += gridDim.x) {
+  int pi = blockIdx.x;
+  while (pi < nprob) {
     sft_run_problem(team, probs[pi], smem, ws, z, first, blockIdx.x == 0 ? prof : nullptr);
     first = false;
     __syncthreads();
+    if (threadIdx.x == 0) next_problem = (int)gridDim.x + atomicAdd(work_counter, 1);
+    __syncthreads();
+    pi = next_problem;
   }
 }
 
@@ -97,7 +103,7 @@ static int template_make(const defslam_template_desc *desc, DevCtx *ctx, defslam
 struct defslam_sft_batch {
   DevCtx *ctx = nullptr;
   BatchMarshal bm;
-  DevBuf h_in, h_out, d_in, d_out, d_views, d_ws, d_prof;
+  DevBuf h_in, h_out, d_in, d_out, d_views, d_ws, d_prof, d_counter;
   std::vector<defslam_template *> temps;
   int nprob = 0, grid = 0, smem_bytes = 0, mode = MODE_SOLVE;
   size_t ws_stride = 0;
@@ -110,7 +116,7 @@ struct defslam_sft_batch {
   ~defslam_sft_batch() {
     drop_temps();
     h_in.release(); h_out.release(); d_in.release(); d_out.release(); d_views.release(); d_ws.release();
-    d_prof.release();
+    d_prof.release(); d_counter.release();
   }
 };
 
@@ -178,9 +184,14 @@ static int batch_launch(defslam_sft_batch *B) {
     prof = (long long *)B->d_prof.p;
     DS_CUDA_TRY(cudaMemsetAsync(prof, 0, sizeof(long long) * PF_COUNT, ctx->stream));
   }
+  {
+    int rc = B->d_counter.ensure(sizeof(int));
+    if (rc) return rc;
+    DS_CUDA_TRY(cudaMemsetAsync(B->d_counter.p, 0, sizeof(int), ctx->stream));
+  }
   DS_CUDA_TRY(cudaEventRecord(ctx->e0, ctx->stream));
-  sft_lm_kernel<<<B->grid, SFT_THREADS, B->smem_bytes, ctx->stream>>>((const ProbView *)B->d_views.p, B->nprob,
-                                                                      (uint8_t *)B->d_ws.p, B->ws_stride, z, prof);
+  sft_lm_kernel<<<B->grid, SFT_THREADS, B->smem_bytes, ctx->stream>>>(
+      (const ProbView *)B->d_views.p, B->nprob, (uint8_t *)B->d_ws.p, B->ws_stride, z, prof, (int *)B->d_counter.p);
   DS_CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1);
   DS_CUDA_TRY(cudaEventRecord(ctx->e1, ctx->stream));

@@ -89,6 +89,24 @@ def _results(frames):
     return outs, arr
 
 
+class HostBatch:
+    """Descriptor arrays (defslam_sft_problem / defslam_sft_result) over HOST buffers, prepared
+    once; solve() is exactly one defslam_sft_solve_batched call: marshalling into pinned memory,
+    H2D, the kernel, D2H and the scatter into the result arrays all happen inside it."""
+
+    def __init__(self, frames, template: Template | None = None, device: int = -1):
+        self.lib = _capi.load()
+        self.frames = frames
+        self.device = device
+        self.probs = _problems(frames, template)
+        self.outs, self.res = _results(frames)
+
+    def solve(self):
+        _check("defslam_sft_solve_batched",
+               self.lib.defslam_sft_solve_batched(len(self.frames), self.probs, self.res, self.device))
+        return self.outs
+
+
 def solve_batched(frames, template: Template | None = None, device: int = -1):
     """defslam_sft_solve_batched on host buffers (H2D + kernel + D2H inside the call)."""
     lib = _capi.load()

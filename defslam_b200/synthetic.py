@@ -191,27 +191,39 @@ def _point_in_triangle32(q, p0, p1, p2):
 
 
 def embed_points(tmpl_nodes: np.ndarray, facets: np.ndarray, pts32: np.ndarray):
-    """calculateFeaturesCoordinates: closest node, then its incident facets in index order."""
+    """calculateFeaturesCoordinates: closest node, then its incident facets in index order
+    (vectorised over the points: slot s of every point's incident-facet list at a time)."""
     n = tmpl_nodes.shape[0]
+    npts = len(pts32)
     inc = [[] for _ in range(n)]
     for fi, f in enumerate(facets):
         for v in f:
             inc[int(v)].append(fi)
+    max_inc = max((len(x) for x in inc), default=0)
+    inc_tab = np.full((n, max(max_inc, 1)), -1, dtype=np.int64)
+    for v, lst in enumerate(inc):
+        inc_tab[v, :len(lst)] = lst
     dist = np.sqrt(((tmpl_nodes[None, :, :] - pts32[:, None, :].astype(np.float64)) ** 2).sum(-1))
     closest = dist.argmin(1)
-    out_f = np.full(len(pts32), -1, dtype=np.int32)
-    out_nodes = np.full((len(pts32), 3), -1, dtype=np.int32)
-    out_b = np.zeros((len(pts32), 3), dtype=np.float32)
+    near = dist[np.arange(npts), closest] < 100
+    out_f = np.full(npts, -1, dtype=np.int32)
+    out_nodes = np.full((npts, 3), -1, dtype=np.int32)
+    out_b = np.zeros((npts, 3), dtype=np.float32)
     nodes32 = tmpl_nodes.astype(np.float32)
-    for i in range(len(pts32)):
-        if dist[i, closest[i]] >= 100:
+    fsorted = np.sort(facets, axis=1)
+    todo = near.copy()
+    for s in range(max_inc):
+        cand = inc_tab[closest, s]
+        sel = np.flatnonzero(todo & (cand >= 0))
+        if len(sel) == 0:
             continue
-        for fi in inc[int(closest[i])]:
-            v = np.sort(facets[fi])
-            ok, b = _point_in_triangle32(pts32[i:i + 1], nodes32[v[0]][None], nodes32[v[1]][None], nodes32[v[2]][None])
-            if ok[0]:
-                out_f[i], out_nodes[i], out_b[i] = fi, v, b[0]
-                break
+        v = fsorted[cand[sel]]
+        ok, b = _point_in_triangle32(pts32[sel], nodes32[v[:, 0]], nodes32[v[:, 1]], nodes32[v[:, 2]])
+        hit = sel[ok]
+        out_f[hit] = cand[hit]
+        out_nodes[hit] = v[ok]
+        out_b[hit] = b[ok]
+        todo[hit] = False
     return out_f, out_nodes, out_b
 
 

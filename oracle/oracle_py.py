@@ -109,3 +109,162 @@ def sft_normal_equations(frame, lib=None):
     if rc != 0:
         raise RuntimeError(f"oracle_sft_normal_equations rc={rc}")
     return H, b, chi.value
+
+
+# ------------------------------------------------------------------ BBS ------------------
+def _bbs_struct(umin, umax, nptsu, vmin, vmax, nptsv, valdim):
+    b = _capi.Bbs()
+    b.umin, b.umax, b.nptsu, b.vmin, b.vmax, b.nptsv, b.valdim = umin, umax, nptsu, vmin, vmax, nptsv, valdim
+    return b
+
+
+def _bind_bbs(lib, prefix="oracle_"):
+    P = _capi
+    f = getattr(lib, prefix + "bbs_eval")
+    f.restype = C.c_int
+    f.argtypes = [C.POINTER(P.Bbs), P.c_double_p, C.c_int32, P.c_double_p, P.c_double_p, C.c_int32, C.c_int32,
+                  P.c_double_p]
+    f = getattr(lib, prefix + "bbs_coloc")
+    f.restype = C.c_int
+    f.argtypes = [C.POINTER(P.Bbs), C.c_int32, P.c_double_p, P.c_double_p, C.c_int32, C.c_int32, P.c_double_p]
+    f = getattr(lib, prefix + "bbs_bending")
+    f.restype = C.c_int
+    f.argtypes = [C.POINTER(P.Bbs), P.c_double_p]
+    f = getattr(lib, prefix + "surface_vertices")
+    f.restype = C.c_int
+    f.argtypes = [C.POINTER(P.Bbs), P.c_double_p, C.c_int32, C.c_int32, P.c_float_p]
+
+
+class BbsApi:
+    """eval / coloc / bending / surface_vertices behind one of: the oracle ("oracle_"), the
+    emulated kernel sources ("emu_") or the CUDA library ("defslam_")."""
+
+    def __init__(self, lib, prefix):
+        self.lib, self.prefix = lib, prefix
+        if prefix != "defslam_":
+            _bind_bbs(lib, prefix)
+
+    def _f(self, name):
+        return getattr(self.lib, self.prefix + name)
+
+    def eval(self, bbs, ctrl, u, v, du=0, dv=0):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        ctrl = np.ascontiguousarray(ctrl, dtype=np.float64)
+        out = np.zeros((len(u), bbs.valdim))
+        rc = self._f("bbs_eval")(C.byref(bbs), _capi.as_ptr(ctrl, C.c_double), len(u), _capi.as_ptr(u, C.c_double),
+                                 _capi.as_ptr(v, C.c_double), du, dv, _capi.as_ptr(out, C.c_double))
+        return rc, out
+
+    def coloc(self, bbs, u, v, du=0, dv=0):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        out = np.zeros((len(u), bbs.nptsu * bbs.nptsv))
+        rc = self._f("bbs_coloc")(C.byref(bbs), len(u), _capi.as_ptr(u, C.c_double), _capi.as_ptr(v, C.c_double),
+                                  du, dv, _capi.as_ptr(out, C.c_double))
+        return rc, out
+
+    def bending(self, bbs):
+        NC = bbs.nptsu * bbs.nptsv
+        out = np.zeros((NC, NC))
+        rc = self._f("bbs_bending")(C.byref(bbs), _capi.as_ptr(out, C.c_double))
+        return rc, out
+
+    def surface_vertices(self, bbs, ctrl, xs, ys):
+        ctrl = np.ascontiguousarray(ctrl, dtype=np.float64)
+        out = np.zeros((xs * ys, 3), dtype=np.float32)
+        rc = self._f("surface_vertices")(C.byref(bbs), _capi.as_ptr(ctrl, C.c_double), xs, ys,
+                                         _capi.as_ptr(out, C.c_float))
+        return rc, out
+
+
+def bbs_oracle():
+    return BbsApi(load(), "oracle_")
+
+
+class BbsReference:
+    """The reference's own Thirdparty/BBS/bbs.cc, compiled where it lies (oracle/_ref/).
+    C++ symbols are called through their mangled names; all arguments are plain pointers."""
+
+    class _bbs_t(C.Structure):
+        _fields_ = [("umin", C.c_double), ("umax", C.c_double), ("nptsu", C.c_int), ("vmin", C.c_double),
+                    ("vmax", C.c_double), ("nptsv", C.c_int), ("valdim", C.c_int)]
+
+    def __init__(self):
+        path = os.path.join(_DIR, "_ref", "libbbs_ref.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = C.CDLL(path)
+        self._eval = self.lib._ZN3BBS4evalEPNS_6_bbs_tEPdS2_S2_iS2_ii
+        self._eval.restype = None
+        self._eval.argtypes = [C.POINTER(self._bbs_t), _capi.c_double_p, _capi.c_double_p, _capi.c_double_p,
+                               C.c_int, _capi.c_double_p, C.c_int, C.c_int]
+        self._coloc_deriv = self.lib._ZN3BBS11coloc_derivEPNS_6_bbs_tEPdS2_iiiS2_PmS3_
+        self._coloc_deriv.restype = C.c_int
+        self._coloc_deriv.argtypes = [C.POINTER(self._bbs_t), _capi.c_double_p, _capi.c_double_p, C.c_int, C.c_int,
+                                      C.c_int, _capi.c_double_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+        self._coloc = self.lib._ZN3BBS5colocEPNS_6_bbs_tEPdS2_iS2_PmS3_
+        self._coloc.restype = C.c_int
+        self._coloc.argtypes = [C.POINTER(self._bbs_t), _capi.c_double_p, _capi.c_double_p, C.c_int,
+                                _capi.c_double_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+        self._bending = self.lib._ZN3BBS10bending_urEPNS_6_bbs_tEdPdPmS3_
+        self._bending.restype = None
+        self._bending.argtypes = [C.POINTER(self._bbs_t), C.c_double, _capi.c_double_p, C.POINTER(C.c_size_t),
+                                  C.POINTER(C.c_size_t)]
+
+    def _t(self, b):
+        t = self._bbs_t()
+        t.umin, t.umax, t.nptsu, t.vmin, t.vmax, t.nptsv, t.valdim = b.umin, b.umax, b.nptsu, b.vmin, b.vmax, \
+            b.nptsv, b.valdim
+        return t
+
+    def eval(self, bbs, ctrl, u, v, du=0, dv=0):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        ctrl = np.ascontiguousarray(ctrl, dtype=np.float64)
+        out = np.zeros((len(u), bbs.valdim))
+        t = self._t(bbs)
+        self._eval(C.byref(t), _capi.as_ptr(ctrl, C.c_double), _capi.as_ptr(u, C.c_double),
+                   _capi.as_ptr(v, C.c_double), len(u), _capi.as_ptr(out, C.c_double), du, dv)
+        return 0, out
+
+    def coloc(self, bbs, u, v, du=0, dv=0):
+        """sparse (pr, ir, jc) of the reference expanded to dense rows"""
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        n, NC = len(u), bbs.nptsu * bbs.nptsv
+        pr = np.zeros(16 * n)
+        ir = np.zeros(16 * n, dtype=np.uint64)
+        jc = np.zeros(NC + 1, dtype=np.uint64)
+        t = self._t(bbs)
+        if du == 0 and dv == 0:
+            rc = self._coloc(C.byref(t), _capi.as_ptr(u, C.c_double), _capi.as_ptr(v, C.c_double), n,
+                             _capi.as_ptr(pr, C.c_double), ir.ctypes.data_as(C.POINTER(C.c_size_t)),
+                             jc.ctypes.data_as(C.POINTER(C.c_size_t)))
+        else:
+            rc = self._coloc_deriv(C.byref(t), _capi.as_ptr(u, C.c_double), _capi.as_ptr(v, C.c_double), n, du, dv,
+                                   _capi.as_ptr(pr, C.c_double), ir.ctypes.data_as(C.POINTER(C.c_size_t)),
+                                   jc.ctypes.data_as(C.POINTER(C.c_size_t)))
+        out = np.zeros((n, NC))
+        if rc == 0:
+            for col in range(NC):
+                for k in range(int(jc[col]), int(jc[col + 1])):
+                    out[int(ir[k]), col] = pr[k]
+        return rc, out
+
+    def bending(self, bbs, lam=1.0):
+        """upper-right sparse matrix of bending_ur, symmetrised to dense"""
+        NC = bbs.nptsu * bbs.nptsv
+        cap = NC * 49
+        pr = np.zeros(cap)
+        ir = np.zeros(cap, dtype=np.uint64)
+        jc = np.zeros(NC + 1, dtype=np.uint64)
+        t = self._t(bbs)
+        self._bending(C.byref(t), lam, _capi.as_ptr(pr, C.c_double), ir.ctypes.data_as(C.POINTER(C.c_size_t)),
+                      jc.ctypes.data_as(C.POINTER(C.c_size_t)))
+        out = np.zeros((NC, NC))
+        for col in range(NC):
+            for k in range(int(jc[col]), int(jc[col + 1])):
+                out[int(ir[k]), col] = pr[k]
+                out[col, int(ir[k])] = pr[k]
+        return 0, out

@@ -27,6 +27,14 @@ int oracle_embed_points(int32_t n_nodes, const double *node_xyz, int32_t n_facet
                         int32_t n_points, const float *point_xyz, int32_t *out_facet, int32_t *out_nodes,
                         float *out_bary);
 
+/* ---- bicubic B-splines (bbs_oracle.c) ---- */
+int oracle_bbs_eval(const defslam_bbs *s, const double *ctrl, int32_t nsites, const double *u, const double *v,
+                    int32_t du, int32_t dv, double *val);
+int oracle_bbs_coloc(const defslam_bbs *s, int32_t nsites, const double *u, const double *v, int32_t du, int32_t dv,
+                     double *C);
+int oracle_bbs_bending(const defslam_bbs *s, double *B);
+int oracle_surface_vertices(const defslam_bbs *s, const double *ctrl, int32_t xs, int32_t ys, float *out);
+
 #ifdef __cplusplus
 }
 #endif

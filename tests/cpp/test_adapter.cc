@@ -1,0 +1,144 @@
+// Compiles adapter/DefOptimizerB200.h against mock types that carry the member names the
+// reference body uses (Frame, DefMap, Template, Node, Edge, Facet, DefMapPoint), runs the
+// drop-in, and checks it against the CPU oracle.  Exit code 0 = pass.  Without a CUDA device
+// the library must fail loudly: the adapter then returns 0 inliers and leaves the state untouched.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <random>
+#include <set>
+#include <vector>
+
+#include "../../adapter/DefOptimizerB200.h"
+#include "../../oracle/sft_oracle.h"
+
+struct Node {
+  int idx; double x, y, z, xO, yO, zO; bool boundary = false; int role = 0;
+  std::set<Node *> nbrs; std::map<Node *, double> weights;
+  int getIndex() const { return idx; }
+  std::vector<double> getInitialPose() const { return {xO, yO, zO}; }
+  bool isBoundary() const { return boundary; }
+  std::set<Node *> GetNeighbours() const { return nbrs; }
+  void getXYZ(double &a, double &b, double &c) const { a = x; b = y; c = z; }
+  void setXYZ(double a, double b, double c) { x = a; y = b; z = c; }
+  void resetRole() { role = 0; }
+  void setViewed() { role = 1; }
+  void setLocal() { role = 2; }
+};
+struct Edge { Node *a, *b; double d; std::pair<Node *, Node *> get_pair_nodes() const { return {a, b}; } double getDist() const { return d; } };
+struct Facet { std::set<Node *> nodes; std::set<Node *> getNodes() const { return nodes; } };
+struct Template {
+  std::set<Node *> nodes; std::set<Edge *> edges; std::set<Facet *> facets; std::map<Node *, double> kappa; double median;
+  std::set<Node *> get_nodes() const { return nodes; }
+  std::set<Edge *> get_edges() const { return edges; }
+  std::set<Facet *> get_facets() const { return facets; }
+  double GetMeanCurvatureInitial(Node *n) { return kappa[n]; }
+  double getEdgeMeanSize() const { return median; }
+};
+struct MapPoint { virtual ~MapPoint() {} bool bad = false; bool isBad() const { return bad; } };
+struct DefMapPoint : MapPoint {
+  Facet *facet = nullptr; double b1, b2, b3; float pos[3];
+  Facet *getFacet() const { return facet; }
+  void RecalculatePosition() {
+    int k = 0; double b[3] = {b1, b2, b3}; double p[3] = {0, 0, 0};
+    for (Node *n : facet->getNodes()) { p[0] += b[k] * n->x; p[1] += b[k] * n->y; p[2] += b[k] * n->z; k++; }
+    for (int c = 0; c < 3; c++) pos[c] = (float)p[c];
+  }
+};
+struct KeyPoint { struct { float x, y; } pt; int octave; };
+struct Frame {
+  int N; std::vector<MapPoint *> mvpMapPoints; std::vector<bool> mvbOutlier; std::vector<KeyPoint> mvKeysUn;
+  std::vector<float> mvInvLevelSigma2; double fx, fy, cx, cy; float Tcw[16]; float repError = 0;
+  void getPoseRowMajor(float *o) const { memcpy(o, Tcw, sizeof(Tcw)); }
+  void SetPoseRowMajor(const float *i) { memcpy(Tcw, i, sizeof(Tcw)); }
+};
+struct DefMap {
+  Template *t; std::vector<MapPoint *> pts;
+  Template *GetTemplate() { return t; }
+  std::vector<MapPoint *> GetAllMapPoints() { return pts; }
+};
+
+int main() {
+  const int G = 8; const double fx = 435.2, fy = 435.2, cx = 367.45, cy = 252.2;
+  std::mt19937 rng(5); std::uniform_real_distribution<double> U(0, 1); std::normal_distribution<double> Nn(0, 1);
+  // mesh on a curved surface, grid index = x*G + y
+  std::vector<Node> nodes(G * G);
+  std::vector<double> X(3 * G * G); std::vector<int32_t> F;
+  for (int x = 0; x < G; x++) for (int y = 0; y < G; y++) {
+    const double u = -0.8 + 1.4 * x / (G - 1), v = -0.6 + 1.1 * y / (G - 1), d = 1.0 + 0.05 * std::sin(6.28 * u) * std::cos(6.28 * v);
+    Node &n = nodes[x * G + y]; n.idx = x * G + y + 1;  // reference indices start at 1 (vertex 0 is the camera)
+    n.x = n.xO = (float)(u * d); n.y = n.yO = (float)(v * d); n.z = n.zO = (float)d;
+    X[3 * (x * G + y)] = n.x; X[3 * (x * G + y) + 1] = n.y; X[3 * (x * G + y) + 2] = n.z;
+  }
+  F.resize(2 * (G - 1) * (G - 1) * 3);
+  const int nf = oracle_regular_triangulation(G, G, F.data());
+  // template constants from the oracle's mesh Laplacian (the reference's LaplacianMesh)
+  const int n = G * G, R = 8;
+  std::vector<int32_t> cnt(n), idx(n * R), ab(2 * 3 * nf); std::vector<double> w(n * R), k0(n), l0(3 * nf); std::vector<uint8_t> bd(n);
+  int32_t ne = 0; double med = 0;
+  if (oracle_mesh_laplacian(n, X.data(), nf, F.data(), R, cnt.data(), idx.data(), w.data(), bd.data(), k0.data(), &ne, ab.data(), l0.data(), &med)) return 2;
+  Template T; T.median = med;
+  std::vector<Edge> edges(ne); std::vector<Facet> facets(nf);
+  for (int i = 0; i < n; i++) {
+    T.nodes.insert(&nodes[i]); nodes[i].boundary = bd[i]; T.kappa[&nodes[i]] = k0[i];
+    for (int k = 0; k < cnt[i]; k++) { nodes[i].nbrs.insert(&nodes[idx[i * R + k]]); nodes[i].weights[&nodes[idx[i * R + k]]] = w[i * R + k]; }
+  }
+  for (int e = 0; e < ne; e++) { edges[e] = {&nodes[ab[2 * e]], &nodes[ab[2 * e + 1]], l0[e]}; T.edges.insert(&edges[e]); }
+  for (int f = 0; f < nf; f++) { for (int k = 0; k < 3; k++) facets[f].nodes.insert(&nodes[F[3 * f + k]]); T.facets.insert(&facets[f]); }
+  // frame: 150 matches with random barycentrics, observations from a shifted camera + noise, some unmatched keypoints
+  const int M = 150, N = 400;
+  Frame fr; fr.N = N; fr.fx = fx; fr.fy = fy; fr.cx = cx; fr.cy = cy;
+  fr.mvpMapPoints.assign(N, nullptr); fr.mvbOutlier.assign(N, false); fr.mvKeysUn.resize(N);
+  fr.mvInvLevelSigma2 = {1.0f, 0.694444f, 0.482253f, 0.334898f, 0.232568f, 0.161506f};
+  const float I4[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}; memcpy(fr.Tcw, I4, sizeof(I4));
+  std::vector<DefMapPoint> mps(M); DefMap map; map.t = &T;
+  for (int m = 0; m < M; m++) {
+    Facet *f = &facets[rng() % nf];
+    double a = U(rng), b = U(rng); if (a + b > 1) { a = 1 - a; b = 1 - b; }
+    mps[m].facet = f; mps[m].b1 = (float)(1 - a - b); mps[m].b2 = (float)a; mps[m].b3 = (float)b;
+    mps[m].RecalculatePosition();
+    const int slot = 2 * m + 1; fr.mvpMapPoints[slot] = &mps[m]; map.pts.push_back(&mps[m]);
+    const double px = mps[m].pos[0] + 0.01, py = mps[m].pos[1] - 0.005, pz = mps[m].pos[2] + 0.01 * std::sin(3.0 * mps[m].pos[0]);
+    fr.mvKeysUn[slot].pt.x = (float)(fx * px / pz + cx + Nn(rng)); fr.mvKeysUn[slot].pt.y = (float)(fy * py / pz + cy + Nn(rng));
+    fr.mvKeysUn[slot].octave = rng() % 6;
+  }
+  // the same problem, flat, for the oracle
+  defslam_template_desc d; std::vector<int32_t> ptr(n + 1, 0), nidx; std::vector<double> nw, rest(X);
+  for (int i = 0; i < n; i++) { for (int k = 0; k < cnt[i]; k++) { nidx.push_back(idx[i * R + k]); nw.push_back(w[i * R + k]); } ptr[i + 1] = (int)nidx.size(); }
+  std::vector<int32_t> Fs(F);
+  d.n_nodes = n; d.n_edges = ne; d.n_facets = nf; d.node_rest_xyz = rest.data(); d.node_boundary = bd.data(); d.nbr_ptr = ptr.data();
+  d.nbr_idx = nidx.data(); d.nbr_w = nw.data(); d.node_kappa0 = k0.data(); d.edge_ab = ab.data(); d.edge_len0 = l0.data(); d.facets = Fs.data(); d.edge_median_len = med;
+  std::vector<int32_t> mn; std::vector<double> mb; std::vector<float> uv, is;
+  for (int i = 0; i < N; i++) if (fr.mvpMapPoints[i]) {
+    DefMapPoint *p = static_cast<DefMapPoint *>(fr.mvpMapPoints[i]);
+    for (Node *nd : p->facet->getNodes()) mn.push_back((int)(nd - &nodes[0]));
+    mb.push_back(p->b1); mb.push_back(p->b2); mb.push_back(p->b3);
+    uv.push_back(fr.mvKeysUn[i].pt.x); uv.push_back(fr.mvKeysUn[i].pt.y); is.push_back(fr.mvInvLevelSigma2[fr.mvKeysUn[i].octave]);
+  }
+  defslam_sft_problem p = {}; p.tmpl_desc = &d; p.node_xyz = X.data(); p.n_matches = M; p.n_frame_keypoints = N;
+  p.match_nodes = mn.data(); p.match_bary = mb.data(); p.match_uv = uv.data(); p.match_inv_sigma2 = is.data();
+  p.fx = fx; p.fy = fy; p.cx = cx; p.cy = cy; memcpy(p.T_cw, I4, sizeof(I4)); p.reg_lap = 700; p.reg_inex = 12000; p.reg_temp = 0.05;
+  p.neighbour_layers = 2; p.max_iterations = 50;
+  std::vector<double> onodes(3 * n); std::vector<uint8_t> ooutl(M); defslam_sft_result r = {}; r.node_xyz_out = onodes.data(); r.outlier_out = ooutl.data();
+  if (oracle_sft_solve(&p, &r)) return 3;
+
+  defslam_b200::PlanCache<Template, Node> cache;
+  const int inl = defslam_b200::DefPoseOptimization<Frame, DefMap, Template, Node, DefMapPoint>(&fr, &map, cache, 700, 12000, 0.05, 2);
+  if (defslam_device_count() == 0) {
+    // no GPU: must fail loudly and leave everything untouched
+    bool same = inl == 0 && memcmp(fr.Tcw, I4, sizeof(I4)) == 0;
+    for (int i = 0; i < n; i++) same = same && nodes[i].x == X[3 * i];
+    printf("no CUDA device: adapter returned %d inliers, state %s\n", inl, same ? "untouched" : "MODIFIED");
+    return same ? 0 : 4;
+  }
+  double err = 0, nrm = 0;
+  for (int i = 0; i < n; i++) { err = std::max(err, std::fabs(nodes[i].x - onodes[3 * i])); err = std::max(err, std::fabs(nodes[i].y - onodes[3 * i + 1])); err = std::max(err, std::fabs(nodes[i].z - onodes[3 * i + 2])); nrm += onodes[3 * i + 2] * onodes[3 * i + 2]; }
+  double terr = 0; for (int k = 0; k < 16; k++) terr = std::max(terr, (double)std::fabs(fr.Tcw[k] - r.T_cw_out[k]));
+  int k = 0, outl_diff = 0; for (int i = 0; i < N; i++) if (fr.mvpMapPoints[i]) { outl_diff += (fr.mvbOutlier[i] != (ooutl[k] != 0)); k++; }
+  DefMapPoint chk = mps[7]; chk.RecalculatePosition();
+  const bool mp_ok = memcmp(chk.pos, mps[7].pos, sizeof(chk.pos)) == 0;
+  printf("adapter: inliers %d (oracle %d), max node err %.3g, pose err %.3g, outlier diff %d, repError %.4f (oracle %.4f)\n", inl, r.n_inliers, err, terr, outl_diff, fr.repError, r.rep_error);
+  return (inl == r.n_inliers && err < 1e-8 && terr < 1e-6 && outl_diff == 0 && mp_ok && std::fabs(fr.repError - r.rep_error) < 1e-4) ? 0 : 5;
+}

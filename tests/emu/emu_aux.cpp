@@ -1,0 +1,92 @@
+/*
+ * emu_aux.cpp -- TEST INFRASTRUCTURE ONLY (see emu_sft.cpp).  Host-compiled copies of
+ * the device functions in mesh_core.h / bbs_core.h behind the same argument lists as the
+ * C ABI, so that the CPU-only test tier can check them against the oracle and against the
+ * reference's own bbs.cc.
+ */
+#define DS_EMULATE 1
+#include <vector>
+
+#include "../../include/defslam_b200.h"
+#include "../../defslam_b200/csrc/mesh_core.h"
+
+using namespace ds;
+
+static BbsView view_of(const defslam_bbs *b) {
+  BbsView s;
+  s.umin = b->umin; s.umax = b->umax; s.vmin = b->vmin; s.vmax = b->vmax;
+  s.nptsu = b->nptsu; s.nptsv = b->nptsv; s.valdim = b->valdim;
+  return s;
+}
+
+extern "C" {
+
+int emu_mesh_laplacian(int32_t n_nodes, const double *node_xyz, int32_t n_facets, const int32_t *facets,
+                       int32_t max_ring, int32_t *nbr_cnt, int32_t *nbr_idx, double *nbr_w, uint8_t *node_boundary,
+                       double *node_kappa0, int32_t *n_edges_out, int32_t *edge_ab, double *edge_len0,
+                       double *edge_median_len) {
+  std::vector<int> cf(3 * (size_t)n_facets + 1), cp(3 * (size_t)n_facets + 1);
+  int status = 0;
+  double red[40];
+  MeshLapArgs A;
+  A.n = n_nodes; A.nf = n_facets; A.max_ring = max_ring;
+  A.X = node_xyz; A.facets = facets;
+  A.nbr_cnt = nbr_cnt; A.nbr_idx = nbr_idx; A.nbr_w = nbr_w; A.boundary = node_boundary; A.kappa0 = node_kappa0;
+  A.n_edges = n_edges_out; A.edge_ab = edge_ab; A.edge_len0 = edge_len0; A.median = edge_median_len;
+  A.status = &status; A.cand_first = cf.data(); A.cand_pos = cp.data();
+  Team team;
+  team.tid = 0; team.nthr = 1;
+  mesh_laplacian_team(team, A, red);
+  return status;
+}
+
+int emu_embed_points(int32_t n_nodes, const double *node_xyz, int32_t n_facets, const int32_t *facets,
+                     int32_t n_points, const float *point_xyz, int32_t *out_facet, int32_t *out_nodes,
+                     float *out_bary) {
+  for (int i = 0; i < n_points; i++)
+    embed_point(n_nodes, node_xyz, n_facets, facets, &point_xyz[3 * i], &out_facet[i], &out_nodes[3 * i],
+                &out_bary[3 * i]);
+  return 0;
+}
+
+int emu_mappoints_recalculate(int32_t n_nodes, const double *node_xyz, int32_t n_points, const int32_t *point_nodes,
+                              const double *point_bary, float *out) {
+  (void)n_nodes;
+  for (int i = 0; i < n_points; i++) mappoint_position(node_xyz, &point_nodes[3 * i], &point_bary[3 * i], &out[3 * i]);
+  return 0;
+}
+
+int emu_bbs_eval(const defslam_bbs *bbs, const double *ctrl, int32_t nsites, const double *u, const double *v,
+                 int32_t du, int32_t dv, double *val) {
+  const BbsView s = view_of(bbs);
+  for (int i = 0; i < nsites; i++) bbs_eval_site(s, ctrl, u[i], v[i], du, dv, &val[(size_t)i * s.valdim]);
+  return 0;
+}
+
+int emu_bbs_coloc(const defslam_bbs *bbs, int32_t nsites, const double *u, const double *v, int32_t du, int32_t dv,
+                  double *Cm) {
+  const BbsView s = view_of(bbs);
+  const size_t NC = (size_t)s.nptsu * s.nptsv;
+  for (size_t i = 0; i < (size_t)nsites * NC; i++) Cm[i] = 0.0;
+  int bad = 0;
+  for (int i = 0; i < nsites; i++)
+    if (!bbs_coloc_row(s, u[i], v[i], du, dv, &Cm[(size_t)i * NC])) bad = 1;
+  if (bad) /* like the ABI wrapper: the reference aborts leaving an empty matrix */
+    for (size_t i = 0; i < (size_t)nsites * NC; i++) Cm[i] = 0.0;
+  return bad ? DEFSLAM_EBADARG : 0;
+}
+
+int emu_bbs_bending(const defslam_bbs *bbs, double *B) {
+  const BbsView s = view_of(bbs);
+  const int NC = s.nptsu * s.nptsv;
+  for (int i = 0; i < NC; i++)
+    for (int j = 0; j < NC; j++) B[(size_t)i * NC + j] = bbs_bending_entry(s, i, j);
+  return 0;
+}
+
+int emu_surface_vertices(const defslam_bbs *bbs, const double *ctrl, int32_t xs, int32_t ys, float *out) {
+  const BbsView s = view_of(bbs);
+  for (int i = 0; i < xs * ys; i++) surface_vertex(s, ctrl, xs, ys, i, &out[3 * i]);
+  return 0;
+}
+}

@@ -1,0 +1,41 @@
+"""The C++ host side (adapter/DefOptimizerB200.h, same signature and side effects as the reference's
+Optimizer::DefPoseOptimization) compiled against mock DefSLAM types and run end to end."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "_emu", "test_adapter")
+
+
+def _build(oracle):
+    oracle.load()
+    os.makedirs(os.path.dirname(EXE), exist_ok=True)
+    cmd = ["g++", "-O1", "-std=c++17", "-o", EXE, os.path.join(ROOT, "tests", "cpp", "test_adapter.cc"),
+           "-L" + os.path.join(ROOT, "defslam_b200"), "-ldefslam_b200",
+           "-L" + os.path.join(ROOT, "oracle", "_build"), "-loracle",
+           "-Wl,-rpath," + os.path.join(ROOT, "defslam_b200"), "-Wl,-rpath," + os.path.join(ROOT, "oracle", "_build")]
+    subprocess.run(cmd, check=True, capture_output=True)
+
+
+def _run():
+    r = subprocess.run([EXE], capture_output=True, text=True, timeout=300)
+    return r.returncode, r.stdout + r.stderr
+
+
+def test_adapter_compiles_and_fails_loudly_without_a_device(oracle, cuda_lib):
+    _build(oracle)
+    if cuda_lib.defslam_device_count() > 0:
+        pytest.skip("device present: covered by the gpu test")
+    rc, out = _run()
+    assert rc == 0, out
+    assert "untouched" in out
+
+
+@pytest.mark.gpu
+def test_adapter_matches_oracle_on_gpu(oracle, cuda_lib):
+    _build(oracle)
+    rc, out = _run()
+    assert rc == 0, out
+    assert "max node err" in out
