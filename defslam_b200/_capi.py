@@ -192,7 +192,7 @@ PROTOTYPES = {
 }
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libdefslam_b200.so")
+LIB_PATH = os.environ.get("DEFSLAM_LIB", os.path.join(_PKG_DIR, "libdefslam_b200.so"))
 _lib = None
 
 

@@ -34,6 +34,18 @@ DS_FN void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uin
                "l"(__cvta_generic_to_global(src_gmem)), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+DS_FN void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+/* shared -> global bulk store (bulk async-group completion) */
+DS_FN void tma_store_1d(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(__cvta_generic_to_global(dst_gmem)),
+               "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+/* all committed bulk stores have finished READING their shared-memory source */
+DS_FN void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+/* all committed bulk stores are complete (writes visible) */
+DS_FN void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 DS_FN void mbar_wait(uint64_t *bar, uint32_t parity) {
   asm volatile(
       "{\n"
@@ -54,6 +66,10 @@ DS_FN void fence_proxy_async() {}
 DS_FN void mbar_expect_tx(uint64_t *, uint32_t) {}
 DS_FN void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *) { memcpy(dst, src, bytes); }
 DS_FN void mbar_wait(uint64_t *, uint32_t) {}
+DS_FN void fence_proxy_async_smem() {}
+DS_FN void tma_store_1d(void *dst, const void *src, uint32_t bytes) { memcpy(dst, src, bytes); }
+DS_FN void tma_store_wait_read() {}
+DS_FN void tma_store_wait_all() {}
 #endif
 
 }  // namespace ds

@@ -131,7 +131,7 @@ Workspace carve_workspace(uint8_t *base, const WorkspaceSizes &z) {
 /* shared-memory carve-up (offsets in doubles) -- same function on host (size)
  * and device (pointers) */
 struct SmemLayout {
-  int W, E, P, x, xb, dx, Lkk, invL, G, Hcc, red, pose, flags, total;
+  int W, E, P, x, xb, dx, Lkk, invL, G, Hcc, red, pose, tiles, flags, total;
 };
 
 DS_FN int asm_scratch_doubles(int n, int ne) { return 11 * n + 5 * ne; }
@@ -159,6 +159,10 @@ SmemLayout smem_layout(int n_nodes, int n_edges, int Dn_pad, int bwp, int ld, in
   L.Hcc = o;  o += 48;   /* 36 Hcc + 6 bc + 6 dc(stale) */
   L.red = o;  o += 40;
   L.pose = o; o += 16;   /* pose (7) + backup (7) */
+  {
+    const int nrow = bwp / NB + 1;
+    L.tiles = o; o += 2 * (nrow * (nrow + 1) / 2); /* one int4 per trailing-update tile */
+  }
   L.flags = o; o += (2 * n_nodes + 7) / 8 + 1;
   L.total = o;
   return L;
@@ -204,7 +208,7 @@ enum { PF_PROLOGUE = 0, PF_EVAL_STORE, PF_BUILD, PF_FS_INIT, PF_S1, PF_S1_WAIT, 
 DS_FN void prof_mark(const Team team, Ctx &cx, int idx) {
   Ctx &c = ctx_ref();
   (void)cx;
-#if DS_CUDA
+#if DS_CUDA && defined(DS_PROFILE)
   if (c.prof != nullptr && team.tid == 0) {
     const long long now = clock64();
     c.prof[idx] += now - c.prof_last;
@@ -940,6 +944,32 @@ DS_FN void sub_pair(double *dst, double d0, double d1) {
   *p2 = cv;
 }
 
+/* One trailing-update tile: panel rows of its two operands and where it lands. */
+struct alignas(16) TileDesc {
+  int rA, rB;   /* first panel row of the A / B operand (multiples of 8; bwp = border rows) */
+  int kind;     /* 1 window tile, all 64 entries inside the band and below the diagonal;
+                   2 window tile that needs per-entry checks; 3 border-row tile; 4 corner */
+  int dcol;     /* rB - rA */
+};
+
+/* Tiles in the order the warps consume them (row-major over the lower triangle of
+ * tile rows, the border tile row last); built once per problem. */
+DS_FN void build_tile_table(const Team team, TileDesc *tt, int nt8, int bwp, int bw) {
+  const int nrow = nt8 + 1, ntiles = nrow * (nrow + 1) / 2;
+  DS_FOR(t, ntiles) {
+    int ti = 0, tj = t;
+    while (tj > ti) { tj -= ti + 1; ti++; }
+    const bool erow = ti == nt8, ecol = tj == nt8;
+    TileDesc d;
+    d.rA = erow ? bwp : ti * NB;
+    d.rB = ecol ? bwp : tj * NB;
+    d.dcol = d.rB - d.rA;
+    if (erow) d.kind = ecol ? 4 : 3;
+    else d.kind = (ti > tj && NB * (ti - tj) + (NB - 1) <= bw) ? 1 : 2;
+    tt[t] = d;
+  }
+}
+
 /* Solve (H + lambda I) dx = b.  dx -> sm[sl.dx] (nodes, then camera at Dn_pad).
  * Returns false if a pivot is not positive (LinearSolverDense::solve returning
  * false, linear_solver_dense.h:107-112); dx is then left untouched (stale), as
@@ -959,6 +989,7 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
   double *Lb = c.ws.Lb;
   int *flag = (int *)(sm + c.sl.red + 36);
   const int nt8 = bwp / NB;
+  const TileDesc *tiles = (const TileDesc *)(sm + c.sl.tiles);
 #if DS_CUDA
   const int warp = team.tid >> 5, nwarp = team.nthr >> 5, lane = team.tid & 31;
 #else
@@ -1003,8 +1034,13 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
   for (int kb = 0; kb < nblk; kb++) {
     const int k = kb * NB;
     /* S1: factor the diagonal block (warp 0) */
-    if (team.warp0()) diag_factor(team, W, kslot, Wr, ld, bwE, lambda, invL, flag);
+    if (team.warp0()) {
+      diag_factor(team, W, kslot, Wr, ld, bwE, lambda, invL, flag);
+      fence_proxy_async_smem(); /* rows k..k+7 are final: they leave through the async proxy */
+    }
     team.sync();
+    /* finished rows k..k+7 -> L band in global memory (TMA bulk store) */
+    if (team.tid == 0) tma_store_1d(Lb + k * ld, W + kslot * ld, (uint32_t)(NB * ld * sizeof(double)));
     prof_mark(team, c, PF_S1);
     /* rows requested during the previous step (they enter this step's panel) */
     if (kb > 0 && (k - NB) + Wr < Dp) { mbar_wait(bar0, ph0); ph0 ^= 1u; }
@@ -1031,81 +1067,62 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
         panel_tile(team, Eg + k, ES, bwE, 0, bwE - bw, invL, P, HS, r0);
       }
     }
-    /* finished rows k..k+7 (final after S1) -> L band in global memory */
-    {
-      const double *src = W + kslot * ld;
-      double *dst = Lb + k * ld;
-      DS_FOR(i, NB * ld) dst[i] = src[i];
-    }
     team.sync();
     prof_mark(team, c, PF_S2);
-    /* refill the freed slot with rows k+Wr.. (needed by the next step's panel).
-     * All reads of the slot happened before the barrier above. */
-    if (team.tid == 0 && k + Wr < Dp) {
-      const uint32_t bytes = (uint32_t)(NB * ld * sizeof(double));
-      mbar_expect_tx(bar0, bytes);
-      tma_load_1d(W + kslot * ld, Hb + (k + Wr) * ld, bytes, bar0);
+    /* the bulk store of rows k..k+7 (issued after S1) has read its source by now:
+     * refill the freed slot with rows k+Wr.. (needed by the next step's panel) */
+    if (team.tid == 0) {
+      tma_store_wait_read();
+      if (k + Wr < Dp) {
+        const uint32_t bytes = (uint32_t)(NB * ld * sizeof(double));
+        mbar_expect_tx(bar0, bytes);
+        tma_load_1d(W + kslot * ld, Hb + (k + Wr) * ld, bytes, bar0);
+      }
     }
 
-    /* S3: trailing update C -= P_I P_J^T on 8x8 tiles, tiles dealt round-robin to
-     * the warps (row-major over the lower triangle of tile rows, the border tile
-     * row last).  A warp keeps S3U tiles in flight: all operand fragments are
-     * loaded and all DMMAs issued before the first read-modify-write, so the
-     * latencies of independent tiles overlap. */
+    /* S3: trailing update C -= P_I P_J^T on 8x8 tiles (FP64 tensor cores), tiles
+     * dealt round-robin to the warps from the per-problem tile table */
     {
-      constexpr int S3U = 1;
       const int nrow = nt8 + 1;
       const int ntiles = nrow * (nrow + 1) / 2;
       const int lo = bwE - bw;
-      int ti = 0, tj = warp;
-      while (tj > ti) { tj -= ti + 1; ti++; }
-      for (int t0 = warp; t0 < ntiles; t0 += S3U * nwarp) {
-        int rA[S3U], rB[S3U], kind[S3U]; /* kind: 0 skip, 1 window, 2 border row, 3 corner */
-#pragma unroll
-        for (int u = 0; u < S3U; u++) {
-          const int cti = ti, ctj = tj;
-          const bool in = t0 + u * nwarp < ntiles;
-          tj += nwarp;
-          while (tj > ti) { tj -= ti + 1; ti++; }
-          const bool erow = cti == nt8, ecol = ctj == nt8;
-          const bool skip = !in || (!erow && cti >= nrt) || (!ecol && ctj >= nrt);
-          kind[u] = skip ? 0 : (!erow ? 1 : (!ecol ? 2 : 3));
-          rA[u] = erow ? bwp : cti * NB;
-          rB[u] = ecol ? bwp : ctj * NB;
-        }
+      for (int t = warp; t < ntiles; t += nwarp) {
+        const TileDesc td = tiles[t];
+        if (td.kind <= 2 ? td.rA >= n_trail : (td.kind == 3 && td.rB >= n_trail)) continue;
+        if (td.kind <= 2 && td.rB >= n_trail) continue;
         DS_WARP_FOR(T, 32) {
           const int g = T >> 2, q = T & 3;
-          double d0[S3U], d1[S3U];
-#pragma unroll
-          for (int u = 0; u < S3U; u++)
-            if (kind[u] != 0) tile_mul_pp(T, P, HS, rA[u], rB[u], d0[u], d1[u]);
-#pragma unroll
-          for (int u = 0; u < S3U; u++) {
-            if (kind[u] == 1) {
-              /* entry (i, j): i = k+8+rA+g, j = k+8+rB+2q(+1); band offset j-i+bwE */
-              int s0 = kslot + NB + rA[u];
-              if (s0 >= Wr) s0 -= Wr;
-              const int off = rB[u] + 2 * q - rA[u] - g + bwE;
-              double *dst = W + (s0 + g) * ld + off;
+          double d0, d1;
+          tile_mul_pp(T, P, HS, td.rA, td.rB, d0, d1);
+          if (td.kind <= 2) {
+            /* entry (i, j): i = k+8+rA+g, j = k+8+rB+2q(+1); band offset j-i+bwE */
+            int s0 = kslot + NB + td.rA;
+            if (s0 >= Wr) s0 -= Wr;
+            const int off = td.dcol + 2 * q - g + bwE;
+            double *dst = W + (s0 + g) * ld + off;
+            if (td.kind == 1) {
+              sub_pair(dst, d0, d1);
+            } else {
               const bool v0 = off <= bwE && off >= lo, v1 = off + 1 <= bwE && off + 1 >= lo;
-              if (v0 && v1) {
-                sub_pair(dst, d0[u], d1[u]);
-              } else {
-                if (v0) dst[0] -= d0[u];
-                if (v1) dst[1] -= d1[u];
+              if (v0 && v1) sub_pair(dst, d0, d1);
+              else {
+                if (v0) dst[0] -= d0;
+                if (v1) dst[1] -= d1;
               }
-            } else if (kind[u] == 2) {
-              const int eo = g * ES + k + NB + rB[u] + 2 * q;
-              if (e_smem) sub_pair(Es + eo, d0[u], d1[u]);
-              else sub_pair(Eg + eo, d0[u], d1[u]);
-            } else if (kind[u] == 3) {
-              if (2 * q <= g) G[g * 8 + 2 * q] -= d0[u];
-              if (2 * q + 1 <= g) G[g * 8 + 2 * q + 1] -= d1[u];
             }
+          } else if (td.kind == 3) {
+            const int eo = g * ES + k + NB + td.rB + 2 * q;
+            if (e_smem) sub_pair(Es + eo, d0, d1);
+            else sub_pair(Eg + eo, d0, d1);
+          } else {
+            if (2 * q <= g) G[g * 8 + 2 * q] -= d0;
+            if (2 * q + 1 <= g) G[g * 8 + 2 * q + 1] -= d1;
           }
         }
       }
     }
+    /* rows written here are bulk-stored (async proxy) after a later barrier */
+    fence_proxy_async_smem();
     team.sync();
     prof_mark(team, c, PF_S3);
     kslot += NB;
@@ -1144,9 +1161,8 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
       for (int i = 0; i < 6; i++) dx[Dp + i] = y[i];
     }
   }
-  /* every thread wrote part of L with plain stores: order them before the TMA
-   * reads of the backward sweep */
-  fence_proxy_async();
+  /* all bulk stores of L must have landed before the TMA reads of the backward sweep */
+  if (team.tid == 0) tma_store_wait_all();
   team.sync();
   if (team.tid == 0) c.ph[0] = ph0;
   prof_mark(team, c, PF_SCHUR);
@@ -1378,6 +1394,8 @@ DS_FN_NOINLINE void sft_solve_one(const Team team, Ctx &cx) {
   const int Dp = pl.Dn_pad;
 
   const int rc = prologue(team, c);
+  build_tile_table(team, (TileDesc *)(sm_base() + c.sl.tiles), pl.bwp / NB, pl.bwp, pl.bw);
+  team.sync();
   prof_mark(team, c, PF_PROLOGUE);
   if (rc != 0) {
     if (team.tid == 0) pb.out_res->status = rc;
