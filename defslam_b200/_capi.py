@@ -102,8 +102,10 @@ class SchwarpProblem(C.Structure):
         ("lambda_", C.c_double),
         ("fx", C.c_double),
         ("fy", C.c_double),
+        ("px_fx", C.c_double),
+        ("px_fy", C.c_double),
         ("max_iterations", C.c_int32),
-        ("init_from_affine", C.c_int32),
+        ("initialize", C.c_int32),
         ("x", c_double_p),
     ]
 
@@ -118,6 +120,7 @@ class DiffProp(C.Structure):
         ("cost_initial", C.c_double),
         ("cost_final", C.c_double),
         ("iterations", C.c_int32),
+        ("accepted", C.c_int32),
     ]
 
 
@@ -126,11 +129,16 @@ class NormalsProblem(C.Structure):
         ("n_points", C.c_int32),
         ("pair_ptr", c_int32_p),
         ("J12", c_float_p),
+        ("J21", c_float_p),
         ("H12", c_float_p),
         ("I1", c_float_p),
         ("I2", c_float_p),
+        ("pair_from_ref", c_uint8_p),
+        ("k_first", c_float_p),
         ("k_init", c_double_p),
+        ("ref_uv", c_float_p),
         ("max_iterations", C.c_int32),
+        ("corrected_t2", C.c_int32),
     ]
 
 
@@ -144,8 +152,14 @@ class SfnProblem(C.Structure):
         ("mean_depth", C.c_double),
         ("n_eval", C.c_int32),
         ("eval_uv", c_float_p),
+        ("ctrl_out", c_double_p),
+        ("xyz_out", c_float_p),
     ]
 
+
+NORMALS_ARGS = [C.POINTER(NormalsProblem), c_double_p, c_double_p, c_float_p, c_uint8_p, c_int32_p, c_float_p,
+                c_uint8_p]
+POLY_ARGS = [C.c_int32, c_float_p, c_float_p, c_float_p, c_float_p, c_double_p, c_double_p]
 
 # name -> (restype, argtypes); kept in one table so the "every declared symbol is
 # exported" test can iterate it next to the header.
@@ -180,10 +194,14 @@ PROTOTYPES = {
         C.c_int, [C.POINTER(Bbs), C.c_int32, c_double_p, c_double_p, C.c_int32, C.c_int32, c_double_p]),
     "defslam_bbs_bending": (C.c_int, [C.POINTER(Bbs), c_double_p]),
     "defslam_schwarp_fit": (C.c_int, [C.POINTER(SchwarpProblem), C.POINTER(DiffProp)]),
+    "defslam_schwarp_fit_batched": (
+        C.c_int, [C.c_int32, C.POINTER(SchwarpProblem), C.POINTER(DiffProp), C.c_int32]),
     "defslam_schwarp_evaluate": (C.c_int, [C.POINTER(SchwarpProblem), c_double_p, c_double_p]),
-    "defslam_normals_batched": (
-        C.c_int, [C.POINTER(NormalsProblem), c_double_p, c_double_p, c_float_p, c_int32_p]),
-    "defslam_sfn_solve": (C.c_int, [C.POINTER(SfnProblem), c_double_p, c_float_p]),
+    "defslam_normals_batched": (C.c_int, NORMALS_ARGS),
+    "defslam_polysolver_coefficients": (C.c_int, POLY_ARGS),
+    "defslam_sfn_solve": (C.c_int, [C.POINTER(SfnProblem)]),
+    "defslam_sfn_solve_batched": (C.c_int, [C.c_int32, C.POINTER(SfnProblem), c_int32_p, C.c_int32]),
+    "defslam_sfn_system": (C.c_int, [C.POINTER(SfnProblem), c_double_p, c_double_p]),
     "defslam_surface_vertices": (C.c_int, [C.POINTER(Bbs), c_double_p, C.c_int32, C.c_int32, c_float_p]),
     "defslam_version": (C.c_char_p, []),
     "defslam_kernel_launch_count": (C.c_int64, []),

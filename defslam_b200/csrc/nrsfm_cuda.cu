@@ -1,0 +1,512 @@
+/*
+ * nrsfm_cuda.cu -- CUDA kernels + C ABI of the NRSfM mapping stages
+ * (Schwarp fit, isometric normals, shape-from-normals).  Device arithmetic lives
+ * in nrsfm_core.h; include/defslam_b200.h says what each entry point replaces.
+ *
+ * Every batched call packs its inputs into one pinned arena (one H2D copy),
+ * launches one kernel and reads one output arena back (one D2H copy).  Units
+ * (keyframe pairs / map points / keyframes) are independent: persistent CTAs
+ * take the next unit from an atomic counter.
+ */
+#include <string.h>
+
+#include <vector>
+
+#include "ds_runtime.h"
+#include "nrsfm_core.h"
+
+using namespace ds;
+
+namespace {
+
+struct Scratch {
+  DevBuf dev, host, ws;
+  Scratch() { host.pinned = true; }
+};
+Scratch &tl_scratch(int device) {
+  static thread_local std::map<int, std::unique_ptr<Scratch>> tl;
+  auto &s = tl[device];
+  if (!s) s.reset(new Scratch);
+  return *s;
+}
+
+struct Packer {
+  size_t total = 0;
+  size_t add(size_t bytes) { size_t o = total; total += (bytes + 255) & ~(size_t)255; return o; }
+};
+
+constexpr int NRSFM_THREADS = 256;
+
+BbsView to_view(const defslam_bbs *b) {
+  BbsView s;
+  s.umin = b->umin; s.umax = b->umax; s.vmin = b->vmin; s.vmax = b->vmax;
+  s.nptsu = b->nptsu; s.nptsv = b->nptsv; s.valdim = b->valdim;
+  return s;
+}
+bool bbs_ok(const defslam_bbs *b, int valdim) {
+  return b->nptsu >= 4 && b->nptsv >= 4 && b->valdim == valdim && b->umax > b->umin && b->vmax > b->vmin &&
+         b->nptsu <= 64 && b->nptsv <= 64;
+}
+
+/* ------------------------------------------------------------------ kernels ---------- */
+
+__global__ void __launch_bounds__(NRSFM_THREADS, 1)
+schwarp_fit_kernel(const SchwarpProb *probs, int nprob, uint8_t *ws_base, size_t ws_stride, int ws_nu, int ws_nv,
+                   int ws_nmax, int *counter) {
+  extern __shared__ double sh[];
+  __shared__ int s_next;
+  Team team;
+  team.tid = threadIdx.x;
+  team.nthr = blockDim.x;
+  uint8_t *b = ws_base + (size_t)blockIdx.x * ws_stride;
+  const SchwarpSizes z = schwarp_ws_sizes(ws_nu, ws_nv, ws_nmax);
+  SchwarpWs ws;
+  ws.cell = (int *)(b + z.cell); ws.cstart = (int *)(b + z.cstart); ws.perm = (int *)(b + z.perm);
+  ws.taps = (double *)(b + z.taps); ws.CtC = (double *)(b + z.CtC); ws.Hb = (double *)(b + z.Hb);
+  ws.Lb = (double *)(b + z.Lb); ws.Js = (double *)(b + z.Js); ws.rdata = (double *)(b + z.rdata);
+  ws.sdv = (double *)(b + z.sdv);
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_next = atomicAdd(counter, 1);
+    __syncthreads();
+    const int i = s_next;
+    if (i >= nprob) break;
+    schwarp_fit_one(team, probs[i], ws, sh);
+  }
+}
+
+__global__ void schwarp_rows_kernel(SchwarpProb P, int nrows, double *r, double *J) {
+  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < nrows; row += gridDim.x * blockDim.x)
+    schwarp_row(P, row, r, J);
+}
+
+__global__ void normals_kernel(NormalsProb P) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n_points; i += gridDim.x * blockDim.x) normals_point(P, i);
+}
+
+__global__ void poly_kernel(int npairs, const float *J12, const float *H12, const float *I1, const float *I2,
+                            double *eq1, double *eq2) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += gridDim.x * blockDim.x)
+    pair_polynomials(J12 + 4 * i, H12 + 6 * i, I1 + 2 * i, I2 + 2 * i, 0, eq1 + 10 * i, eq2 + 10 * i, 1);
+}
+
+__global__ void __launch_bounds__(NRSFM_THREADS, 1)
+sfn_solve_kernel(const SfnProb *probs, int nprob, uint8_t *ws_base, size_t ws_stride, int ws_nu, int ws_nv,
+                 int ws_nmax, int n_in_smem, int *counter) {
+  extern __shared__ double sh[];
+  __shared__ int s_next;
+  Team team;
+  team.tid = threadIdx.x;
+  team.nthr = blockDim.x;
+  uint8_t *b = ws_base + (size_t)blockIdx.x * ws_stride;
+  const SfnSizes z = sfn_ws_sizes(ws_nu, ws_nv, ws_nmax);
+  SfnWs ws;
+  ws.cell = (int *)(b + z.cell); ws.cstart = (int *)(b + z.cstart); ws.perm = (int *)(b + z.perm);
+  ws.taps = (double *)(b + z.taps); ws.mrow = (double *)(b + z.mrow); ws.B = (double *)(b + z.B);
+  ws.N = (double *)(b + z.N); ws.res = (double *)(b + z.res);
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_next = atomicAdd(counter, 1);
+    __syncthreads();
+    const int i = s_next;
+    if (i >= nprob) break;
+    sfn_solve_one(team, probs[i], ws, sh, n_in_smem != 0);
+  }
+}
+
+__global__ void sfn_rows_kernel(SfnProb P, int nrows, double *A, double *b) {
+  __shared__ double ci[48];
+  Team team;
+  team.tid = threadIdx.x;
+  team.nthr = blockDim.x;
+  fill_cell_integrals(team, ci);
+  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < nrows; row += gridDim.x * blockDim.x)
+    sfn_system_row(P, ci, row, A, b);
+}
+
+int grid_for(int n, int sm) {
+  int g = (n + 255) / 256;
+  if (g > sm * 8) g = sm * 8;
+  return g < 1 ? 1 : g;
+}
+
+int persistent_grid(int nprob, int sm) { return nprob < sm ? nprob : sm; }
+
+}  // namespace
+
+extern "C" {
+
+/* ------------------------------------------------------------------ Schwarp ---------- */
+
+int defslam_schwarp_fit_batched(int32_t nprob, const defslam_schwarp_problem *p, defslam_diffprop *out,
+                                int32_t device) {
+  if (nprob < 0 || (nprob > 0 && (!p || !out))) return DEFSLAM_EBADARG;
+  int nu = 0, nv = 0, nmax = 0;
+  for (int i = 0; i < nprob; i++) {
+    if (!bbs_ok(&p[i].bbs, 2) || p[i].n_matches <= 0 || !p[i].kp1 || !p[i].kp2 || !p[i].inv_sigma || !p[i].x ||
+        p[i].max_iterations < 0)
+      return DEFSLAM_EBADARG;
+    if (p[i].bbs.nptsu > nu) nu = p[i].bbs.nptsu;
+    if (p[i].bbs.nptsv > nv) nv = p[i].bbs.nptsv;
+    if (p[i].n_matches > nmax) nmax = p[i].n_matches;
+  }
+  DevCtx *ctx = get_ctx(device);
+  if (!ctx) return DEFSLAM_ECUDA;
+  if (nprob == 0) return DEFSLAM_OK;
+  const size_t smem = sizeof(double) * (size_t)schwarp_smem(nu, nv).total;
+  if (smem > (size_t)ctx->smem_optin) return DEFSLAM_ETOOLARGE;
+
+  /* arenas */
+  Packer in, outp;
+  std::vector<size_t> o_kp1(nprob), o_kp2(nprob), o_sig(nprob), o_x(nprob), o_uv(nprob), o_j12(nprob), o_j21(nprob),
+      o_h12(nprob), o_keep(nprob), o_sc(nprob);
+  const size_t o_probs = in.add(sizeof(SchwarpProb) * nprob);
+  const size_t o_counter = in.add(sizeof(int));
+  /* x travels in and comes back: all x first in the output arena, so that the upload is one
+   * contiguous span (inputs + x) */
+  for (int i = 0; i < nprob; i++) o_x[i] = outp.add(16 * (size_t)p[i].bbs.nptsu * p[i].bbs.nptsv);
+  const size_t x_total = outp.total;
+  for (int i = 0; i < nprob; i++) {
+    const size_t n = p[i].n_matches;
+    o_kp1[i] = in.add(8 * n); o_kp2[i] = in.add(8 * n); o_sig[i] = in.add(4 * n);
+    o_uv[i] = outp.add(8 * n); o_j12[i] = outp.add(16 * n); o_j21[i] = outp.add(16 * n); o_h12[i] = outp.add(24 * n);
+    o_keep[i] = outp.add(n); o_sc[i] = outp.add(8 * 8);
+  }
+  const int grid = persistent_grid(nprob, ctx->sm_count);
+  const size_t ws_stride = schwarp_ws_sizes(nu, nv, nmax).total;
+  Scratch &S = tl_scratch(ctx->device);
+  int rc;
+  if ((rc = S.host.ensure(in.total + outp.total)) || (rc = S.dev.ensure(in.total + outp.total)) ||
+      (rc = S.ws.ensure(ws_stride * grid)))
+    return rc;
+  uint8_t *h = (uint8_t *)S.host.p, *d_in = (uint8_t *)S.dev.p, *d_out = d_in + in.total, *h_out = h + in.total;
+  SchwarpProb *hp = (SchwarpProb *)(h + o_probs);
+  for (int i = 0; i < nprob; i++) {
+    const size_t n = p[i].n_matches, NC = (size_t)p[i].bbs.nptsu * p[i].bbs.nptsv;
+    memcpy(h + o_kp1[i], p[i].kp1, 8 * n);
+    memcpy(h + o_kp2[i], p[i].kp2, 8 * n);
+    memcpy(h + o_sig[i], p[i].inv_sigma, 4 * n);
+    memcpy(h_out + o_x[i], p[i].x, 16 * NC);
+    SchwarpProb &P = hp[i];
+    P.bbs = to_view(&p[i].bbs);
+    P.n = p[i].n_matches;
+    P.kp1 = (const float *)(d_in + o_kp1[i]); P.kp2 = (const float *)(d_in + o_kp2[i]);
+    P.isig = (const float *)(d_in + o_sig[i]);
+    P.lambda = p[i].lambda; P.fx = p[i].fx; P.fy = p[i].fy; P.px_fx = p[i].px_fx; P.px_fy = p[i].px_fy;
+    P.max_iterations = p[i].max_iterations; P.initialize = p[i].initialize;
+    P.x = (double *)(d_out + o_x[i]);
+    P.warp_uv = (float *)(d_out + o_uv[i]); P.J12 = (float *)(d_out + o_j12[i]); P.J21 = (float *)(d_out + o_j21[i]);
+    P.H12 = (float *)(d_out + o_h12[i]); P.keep = d_out + o_keep[i]; P.scalars = (double *)(d_out + o_sc[i]);
+  }
+  *(int *)(h + o_counter) = 0;
+  DS_CUDA_TRY(cudaMemcpyAsync(d_in, h, in.total + x_total, cudaMemcpyHostToDevice, ctx->stream));
+  DS_CUDA_TRY(cudaFuncSetAttribute(schwarp_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DS_CUDA_TRY(cudaEventRecord(ctx->e0, ctx->stream));
+  schwarp_fit_kernel<<<grid, NRSFM_THREADS, smem, ctx->stream>>>((const SchwarpProb *)(d_in + o_probs), nprob,
+                                                                 (uint8_t *)S.ws.p, ws_stride, nu, nv, nmax,
+                                                                 (int *)(d_in + o_counter));
+  DS_CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  DS_CUDA_TRY(cudaEventRecord(ctx->e1, ctx->stream));
+  DS_CUDA_TRY(cudaMemcpyAsync(h_out, d_out, outp.total, cudaMemcpyDeviceToHost, ctx->stream));
+  DS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ctx->e0, ctx->e1);
+  g_last_kernel_ms = ms;
+  int worst = DEFSLAM_OK;
+  for (int i = 0; i < nprob; i++) {
+    const size_t n = p[i].n_matches, NC = (size_t)p[i].bbs.nptsu * p[i].bbs.nptsv;
+    const double *sc = (const double *)(h_out + o_sc[i]);
+    const int st = (int)sc[4];
+    out[i].cost_initial = sc[0]; out[i].cost_final = sc[1];
+    out[i].iterations = (int)sc[2]; out[i].accepted = (int)sc[3];
+    if (st != SCHWARP_OK) {
+      /* outputs untouched, like the reference keeping its previous estimate */
+      const int e = st == SCHWARP_OUT_OF_DOMAIN ? DEFSLAM_EBADARG : DEFSLAM_ENUMERIC;
+      if (worst == DEFSLAM_OK) worst = e;
+      continue;
+    }
+    memcpy(p[i].x, h_out + o_x[i], 16 * NC);
+    if (out[i].warp_uv) memcpy(out[i].warp_uv, h_out + o_uv[i], 8 * n);
+    if (out[i].J12) memcpy(out[i].J12, h_out + o_j12[i], 16 * n);
+    if (out[i].J21) memcpy(out[i].J21, h_out + o_j21[i], 16 * n);
+    if (out[i].H12) memcpy(out[i].H12, h_out + o_h12[i], 24 * n);
+    if (out[i].keep) memcpy(out[i].keep, h_out + o_keep[i], n);
+  }
+  return worst;
+}
+
+int defslam_schwarp_fit(const defslam_schwarp_problem *p, defslam_diffprop *out) {
+  return defslam_schwarp_fit_batched(1, p, out, -1);
+}
+
+int defslam_schwarp_evaluate(const defslam_schwarp_problem *p, double *r, double *J) {
+  if (!p || !r || !bbs_ok(&p->bbs, 2) || p->n_matches < 0 || !p->x || (p->n_matches > 0 && (!p->kp1 || !p->kp2 || !p->inv_sigma)))
+    return DEFSLAM_EBADARG;
+  DevCtx *ctx = get_ctx(-1);
+  if (!ctx) return DEFSLAM_ECUDA;
+  const size_t n = p->n_matches, NC = (size_t)p->bbs.nptsu * p->bbs.nptsv, NR = 2 * n + 4 * NC, NP = 2 * NC;
+  Packer in, outp;
+  const size_t o_kp1 = in.add(8 * n + 8), o_kp2 = in.add(8 * n + 8), o_sig = in.add(4 * n + 8), o_x = in.add(8 * NP);
+  const size_t o_r = outp.add(8 * NR), o_J = outp.add(J ? 8 * NR * NP : 8);
+  Scratch &S = tl_scratch(ctx->device);
+  int rc;
+  if ((rc = S.host.ensure(in.total > outp.total ? in.total : outp.total)) || (rc = S.dev.ensure(in.total + outp.total)))
+    return rc;
+  uint8_t *h = (uint8_t *)S.host.p, *d_in = (uint8_t *)S.dev.p, *d_out = d_in + in.total;
+  if (n) { memcpy(h + o_kp1, p->kp1, 8 * n); memcpy(h + o_kp2, p->kp2, 8 * n); memcpy(h + o_sig, p->inv_sigma, 4 * n); }
+  memcpy(h + o_x, p->x, 8 * NP);
+  DS_CUDA_TRY(cudaMemcpyAsync(d_in, h, in.total, cudaMemcpyHostToDevice, ctx->stream));
+  if (J) DS_CUDA_TRY(cudaMemsetAsync(d_out + o_J, 0, 8 * NR * NP, ctx->stream));
+  SchwarpProb P;
+  memset(&P, 0, sizeof(P));
+  P.bbs = to_view(&p->bbs);
+  P.n = p->n_matches;
+  P.kp1 = (const float *)(d_in + o_kp1); P.kp2 = (const float *)(d_in + o_kp2); P.isig = (const float *)(d_in + o_sig);
+  P.lambda = p->lambda; P.fx = p->fx; P.fy = p->fy;
+  P.x = (double *)(d_in + o_x);
+  schwarp_rows_kernel<<<grid_for((int)NR, ctx->sm_count), 256, 0, ctx->stream>>>(
+      P, (int)NR, (double *)(d_out + o_r), J ? (double *)(d_out + o_J) : nullptr);
+  DS_CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  DS_CUDA_TRY(cudaMemcpyAsync(h, d_out, outp.total, cudaMemcpyDeviceToHost, ctx->stream));
+  DS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  memcpy(r, h + o_r, 8 * NR);
+  if (J) memcpy(J, h + o_J, 8 * NR * NP);
+  return DEFSLAM_OK;
+}
+
+/* ------------------------------------------------------------------ normals ---------- */
+
+int defslam_normals_batched(const defslam_normals_problem *p, double *k_out, double *cov_out, float *normal_out,
+                            uint8_t *status_out, int32_t *iters_out, float *pair_normal_out,
+                            uint8_t *pair_valid_out) {
+  if (!p || p->n_points < 0 || (p->n_points > 0 && (!p->pair_ptr || !p->ref_uv)) || p->max_iterations < 0)
+    return DEFSLAM_EBADARG;
+  DevCtx *ctx = get_ctx(-1);
+  if (!ctx) return DEFSLAM_ECUDA;
+  const size_t n = p->n_points;
+  if (n == 0) return DEFSLAM_OK;
+  const size_t np = (size_t)p->pair_ptr[n];
+  for (size_t i = 0; i < n; i++)
+    if (p->pair_ptr[i + 1] < p->pair_ptr[i]) return DEFSLAM_EBADARG;
+  if (np > 0 && (!p->J12 || !p->J21 || !p->H12 || !p->I1 || !p->I2)) return DEFSLAM_EBADARG;
+  Packer in, outp, scr;
+  const size_t o_ptr = in.add(4 * (n + 1)), o_j12 = in.add(16 * np + 16), o_j21 = in.add(16 * np + 16),
+               o_h12 = in.add(24 * np + 24), o_i1 = in.add(8 * np + 8), o_i2 = in.add(8 * np + 8),
+               o_fr = in.add(np + 8), o_kf = in.add(8 * np + 8), o_ki = in.add(16 * n), o_uv = in.add(8 * n);
+  const size_t o_k = outp.add(16 * n), o_cov = outp.add(32 * n), o_nrm = outp.add(12 * n), o_st = outp.add(n),
+               o_it = outp.add(4 * n), o_pn = outp.add(12 * np + 12), o_pv = outp.add(np + 8);
+  const size_t o_Q = scr.add(160 * np + 160);
+  Scratch &S = tl_scratch(ctx->device);
+  int rc;
+  if ((rc = S.host.ensure(in.total > outp.total ? in.total : outp.total)) ||
+      (rc = S.dev.ensure(in.total + outp.total)) || (rc = S.ws.ensure(scr.total)))
+    return rc;
+  uint8_t *h = (uint8_t *)S.host.p, *d_in = (uint8_t *)S.dev.p, *d_out = d_in + in.total;
+  memcpy(h + o_ptr, p->pair_ptr, 4 * (n + 1));
+  if (np) {
+    memcpy(h + o_j12, p->J12, 16 * np); memcpy(h + o_j21, p->J21, 16 * np); memcpy(h + o_h12, p->H12, 24 * np);
+    memcpy(h + o_i1, p->I1, 8 * np); memcpy(h + o_i2, p->I2, 8 * np);
+    if (p->pair_from_ref) memcpy(h + o_fr, p->pair_from_ref, np);
+    if (p->k_first) memcpy(h + o_kf, p->k_first, 8 * np);
+  }
+  if (p->k_init) memcpy(h + o_ki, p->k_init, 16 * n);
+  memcpy(h + o_uv, p->ref_uv, 8 * n);
+  DS_CUDA_TRY(cudaMemcpyAsync(d_in, h, in.total, cudaMemcpyHostToDevice, ctx->stream));
+  NormalsProb P;
+  P.n_points = (int)n; P.npairs = (int)np;
+  P.pair_ptr = (const int *)(d_in + o_ptr);
+  P.J12 = (const float *)(d_in + o_j12); P.J21 = (const float *)(d_in + o_j21); P.H12 = (const float *)(d_in + o_h12);
+  P.I1 = (const float *)(d_in + o_i1); P.I2 = (const float *)(d_in + o_i2);
+  P.from_ref = p->pair_from_ref ? d_in + o_fr : nullptr;
+  P.k_first = p->k_first ? (const float *)(d_in + o_kf) : nullptr;
+  P.k_init = p->k_init ? (const double *)(d_in + o_ki) : nullptr;
+  P.ref_uv = (const float *)(d_in + o_uv);
+  P.max_iterations = p->max_iterations; P.corrected_t2 = p->corrected_t2;
+  P.Q = (double *)((uint8_t *)S.ws.p + o_Q);
+  P.k_out = (double *)(d_out + o_k); P.cov_out = (double *)(d_out + o_cov); P.normal_out = (float *)(d_out + o_nrm);
+  P.status_out = d_out + o_st; P.iters_out = (int *)(d_out + o_it);
+  P.pair_normal_out = (float *)(d_out + o_pn); P.pair_valid_out = d_out + o_pv;
+  DS_CUDA_TRY(cudaMemsetAsync(d_out, 0, outp.total, ctx->stream));
+  DS_CUDA_TRY(cudaEventRecord(ctx->e0, ctx->stream));
+  int g = (int)((n + 127) / 128);
+  normals_kernel<<<g < 1 ? 1 : g, 128, 0, ctx->stream>>>(P);
+  DS_CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  DS_CUDA_TRY(cudaEventRecord(ctx->e1, ctx->stream));
+  DS_CUDA_TRY(cudaMemcpyAsync(h, d_out, outp.total, cudaMemcpyDeviceToHost, ctx->stream));
+  DS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ctx->e0, ctx->e1);
+  g_last_kernel_ms = ms;
+  if (k_out) memcpy(k_out, h + o_k, 16 * n);
+  if (status_out) memcpy(status_out, h + o_st, n);
+  if (iters_out) memcpy(iters_out, h + o_it, 4 * n);
+  const uint8_t *st = h + o_st;
+  /* covariance / normal only where estimated (the reference leaves the rest untouched) */
+  for (size_t i = 0; i < n; i++) {
+    if (st[i] != 1) continue;
+    if (cov_out) memcpy(cov_out + 4 * i, h + o_cov + 32 * i, 32);
+    if (normal_out) memcpy(normal_out + 3 * i, h + o_nrm + 12 * i, 12);
+  }
+  const uint8_t *pv = h + o_pv;
+  if (pair_valid_out && np) memcpy(pair_valid_out, pv, np);
+  if (pair_normal_out)
+    for (size_t j = 0; j < np; j++)
+      if (pv[j]) memcpy(pair_normal_out + 3 * j, h + o_pn + 12 * j, 12);
+  return DEFSLAM_OK;
+}
+
+int defslam_polysolver_coefficients(int32_t npairs, const float *J12, const float *H12, const float *I1,
+                                    const float *I2, double *eq1, double *eq2) {
+  if (npairs < 0 || (npairs > 0 && (!J12 || !H12 || !I1 || !I2 || !eq1 || !eq2))) return DEFSLAM_EBADARG;
+  DevCtx *ctx = get_ctx(-1);
+  if (!ctx) return DEFSLAM_ECUDA;
+  if (npairs == 0) return DEFSLAM_OK;
+  const size_t np = npairs;
+  Packer in, outp;
+  const size_t o_j = in.add(16 * np), o_h = in.add(24 * np), o_1 = in.add(8 * np), o_2 = in.add(8 * np);
+  const size_t o_e1 = outp.add(80 * np), o_e2 = outp.add(80 * np);
+  Scratch &S = tl_scratch(ctx->device);
+  int rc;
+  if ((rc = S.host.ensure(in.total > outp.total ? in.total : outp.total)) || (rc = S.dev.ensure(in.total + outp.total)))
+    return rc;
+  uint8_t *h = (uint8_t *)S.host.p, *d_in = (uint8_t *)S.dev.p, *d_out = d_in + in.total;
+  memcpy(h + o_j, J12, 16 * np); memcpy(h + o_h, H12, 24 * np); memcpy(h + o_1, I1, 8 * np); memcpy(h + o_2, I2, 8 * np);
+  DS_CUDA_TRY(cudaMemcpyAsync(d_in, h, in.total, cudaMemcpyHostToDevice, ctx->stream));
+  poly_kernel<<<grid_for(npairs, ctx->sm_count), 256, 0, ctx->stream>>>(
+      npairs, (const float *)(d_in + o_j), (const float *)(d_in + o_h), (const float *)(d_in + o_1),
+      (const float *)(d_in + o_2), (double *)(d_out + o_e1), (double *)(d_out + o_e2));
+  DS_CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  DS_CUDA_TRY(cudaMemcpyAsync(h, d_out, outp.total, cudaMemcpyDeviceToHost, ctx->stream));
+  DS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  memcpy(eq1, h + o_e1, 80 * np);
+  memcpy(eq2, h + o_e2, 80 * np);
+  return DEFSLAM_OK;
+}
+
+/* ------------------------------------------------------------------ shape from normals */
+
+static int sfn_check(const defslam_sfn_problem *p) {
+  if (!bbs_ok(&p->bbs, 1) || p->n_normals < 0 || p->n_eval < 0 || (p->n_normals > 0 && (!p->uv || !p->normals)) ||
+      (p->n_eval > 0 && (!p->eval_uv || !p->xyz_out)))
+    return DEFSLAM_EBADARG;
+  return 0;
+}
+
+int defslam_sfn_solve_batched(int32_t nprob, const defslam_sfn_problem *p, int32_t *rc_out, int32_t device) {
+  if (nprob < 0 || (nprob > 0 && !p)) return DEFSLAM_EBADARG;
+  int nu = 0, nv = 0, nmax = 0;
+  for (int i = 0; i < nprob; i++) {
+    if (sfn_check(&p[i])) return DEFSLAM_EBADARG;
+    if (p[i].bbs.nptsu > nu) nu = p[i].bbs.nptsu;
+    if (p[i].bbs.nptsv > nv) nv = p[i].bbs.nptsv;
+    if (p[i].n_normals > nmax) nmax = p[i].n_normals;
+  }
+  DevCtx *ctx = get_ctx(device);
+  if (!ctx) return DEFSLAM_ECUDA;
+  if (nprob == 0) return DEFSLAM_OK;
+  const size_t NCmax = (size_t)nu * nv;
+  const size_t fixed = sizeof(double) * (size_t)sfn_smem_fixed((int)NCmax);
+  const size_t packed = sizeof(double) * NCmax * (NCmax + 1) / 2;
+  if (fixed > (size_t)ctx->smem_optin) return DEFSLAM_ETOOLARGE;
+  const int n_in_smem = fixed + packed <= (size_t)ctx->smem_optin;
+  const size_t smem = fixed + (n_in_smem ? packed : 0);
+  Packer in, outp;
+  std::vector<size_t> o_uv(nprob), o_nr(nprob), o_ev(nprob), o_ct(nprob), o_xyz(nprob), o_rc(nprob);
+  const size_t o_probs = in.add(sizeof(SfnProb) * nprob), o_counter = in.add(sizeof(int));
+  for (int i = 0; i < nprob; i++) {
+    const size_t n = p[i].n_normals, NC = (size_t)p[i].bbs.nptsu * p[i].bbs.nptsv, ne = p[i].n_eval;
+    o_uv[i] = in.add(8 * n + 8); o_nr[i] = in.add(12 * n + 12); o_ev[i] = in.add(8 * ne + 8);
+    o_ct[i] = outp.add(8 * NC); o_xyz[i] = outp.add(12 * ne + 12); o_rc[i] = outp.add(8);
+  }
+  const int grid = persistent_grid(nprob, ctx->sm_count);
+  const size_t ws_stride = sfn_ws_sizes(nu, nv, nmax).total;
+  Scratch &S = tl_scratch(ctx->device);
+  int rc;
+  if ((rc = S.host.ensure(in.total > outp.total ? in.total : outp.total)) ||
+      (rc = S.dev.ensure(in.total + outp.total)) || (rc = S.ws.ensure(ws_stride * grid)))
+    return rc;
+  uint8_t *h = (uint8_t *)S.host.p, *d_in = (uint8_t *)S.dev.p, *d_out = d_in + in.total;
+  SfnProb *hp = (SfnProb *)(h + o_probs);
+  for (int i = 0; i < nprob; i++) {
+    const size_t n = p[i].n_normals, ne = p[i].n_eval;
+    if (n) { memcpy(h + o_uv[i], p[i].uv, 8 * n); memcpy(h + o_nr[i], p[i].normals, 12 * n); }
+    if (ne) memcpy(h + o_ev[i], p[i].eval_uv, 8 * ne);
+    SfnProb &P = hp[i];
+    P.bbs = to_view(&p[i].bbs);
+    P.n = p[i].n_normals; P.n_eval = p[i].n_eval;
+    P.uv = (const float *)(d_in + o_uv[i]); P.normals = (const float *)(d_in + o_nr[i]);
+    P.eval_uv = (const float *)(d_in + o_ev[i]);
+    P.bending = p[i].bending; P.mean_depth = p[i].mean_depth;
+    P.ctrl_out = (double *)(d_out + o_ct[i]); P.xyz_out = (float *)(d_out + o_xyz[i]); P.rc_out = (int *)(d_out + o_rc[i]);
+  }
+  *(int *)(h + o_counter) = 0;
+  DS_CUDA_TRY(cudaMemcpyAsync(d_in, h, in.total, cudaMemcpyHostToDevice, ctx->stream));
+  DS_CUDA_TRY(cudaMemsetAsync(d_out, 0xff, outp.total, ctx->stream));
+  DS_CUDA_TRY(cudaFuncSetAttribute(sfn_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DS_CUDA_TRY(cudaEventRecord(ctx->e0, ctx->stream));
+  sfn_solve_kernel<<<grid, NRSFM_THREADS, smem, ctx->stream>>>((const SfnProb *)(d_in + o_probs), nprob,
+                                                               (uint8_t *)S.ws.p, ws_stride, nu, nv, nmax, n_in_smem,
+                                                               (int *)(d_in + o_counter));
+  DS_CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  DS_CUDA_TRY(cudaEventRecord(ctx->e1, ctx->stream));
+  DS_CUDA_TRY(cudaMemcpyAsync(h, d_out, outp.total, cudaMemcpyDeviceToHost, ctx->stream));
+  DS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ctx->e0, ctx->e1);
+  g_last_kernel_ms = ms;
+  int worst = DEFSLAM_OK;
+  for (int i = 0; i < nprob; i++) {
+    const size_t NC = (size_t)p[i].bbs.nptsu * p[i].bbs.nptsv, ne = p[i].n_eval;
+    int r = *(const int *)(h + o_rc[i]);
+    if (r != 0 && r != DEFSLAM_EBADARG && r != DEFSLAM_ENUMERIC) r = DEFSLAM_ECUDA;
+    if (rc_out) rc_out[i] = r;
+    if (r) { if (worst == DEFSLAM_OK) worst = r; continue; }
+    if (p[i].ctrl_out) memcpy(p[i].ctrl_out, h + o_ct[i], 8 * NC);
+    if (ne) memcpy(p[i].xyz_out, h + o_xyz[i], 12 * ne);
+  }
+  return worst;
+}
+
+int defslam_sfn_solve(const defslam_sfn_problem *p) {
+  if (!p) return DEFSLAM_EBADARG;
+  return defslam_sfn_solve_batched(1, p, nullptr, -1);
+}
+
+int defslam_sfn_system(const defslam_sfn_problem *p, double *A, double *b) {
+  if (!p || !A || !b || sfn_check(p)) return DEFSLAM_EBADARG;
+  DevCtx *ctx = get_ctx(-1);
+  if (!ctx) return DEFSLAM_ECUDA;
+  const size_t n = p->n_normals, NC = (size_t)p->bbs.nptsu * p->bbs.nptsv, rows = 2 * n + NC + 1;
+  Packer in, outp;
+  const size_t o_uv = in.add(8 * n + 8), o_nr = in.add(12 * n + 12);
+  const size_t o_A = outp.add(8 * rows * NC), o_b = outp.add(8 * rows);
+  Scratch &S = tl_scratch(ctx->device);
+  int rc;
+  if ((rc = S.host.ensure(in.total > outp.total ? in.total : outp.total)) || (rc = S.dev.ensure(in.total + outp.total)))
+    return rc;
+  uint8_t *h = (uint8_t *)S.host.p, *d_in = (uint8_t *)S.dev.p, *d_out = d_in + in.total;
+  if (n) { memcpy(h + o_uv, p->uv, 8 * n); memcpy(h + o_nr, p->normals, 12 * n); }
+  DS_CUDA_TRY(cudaMemcpyAsync(d_in, h, in.total, cudaMemcpyHostToDevice, ctx->stream));
+  SfnProb P;
+  memset(&P, 0, sizeof(P));
+  P.bbs = to_view(&p->bbs);
+  P.n = p->n_normals;
+  P.uv = (const float *)(d_in + o_uv); P.normals = (const float *)(d_in + o_nr);
+  P.bending = p->bending; P.mean_depth = p->mean_depth;
+  sfn_rows_kernel<<<grid_for((int)rows, ctx->sm_count), 256, 0, ctx->stream>>>(P, (int)rows, (double *)(d_out + o_A),
+                                                                                (double *)(d_out + o_b));
+  DS_CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  DS_CUDA_TRY(cudaMemcpyAsync(h, d_out, outp.total, cudaMemcpyDeviceToHost, ctx->stream));
+  DS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  memcpy(A, h + o_A, 8 * rows * NC);
+  memcpy(b, h + o_b, 8 * rows);
+  return DEFSLAM_OK;
+}
+
+}

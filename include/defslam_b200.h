@@ -243,79 +243,126 @@ int defslam_bbs_coloc(const defslam_bbs *bbs, int32_t nsites, const double *u,
 int defslam_bbs_bending(const defslam_bbs *bbs, double *B);
 
 /* ------------------------------------------------------------------------- *
- *  NRSfM stages
+ *  NRSfM stages (mapping thread).  All three are batched: the units (keyframe
+ *  pairs, map points, keyframes) are independent.
  * ------------------------------------------------------------------------- */
 /* Schwarp fit between two keyframes.
  * replaces: SchwarpDatabase::calculateSchwarps  Modules/Mapping/SchwarpDatabase.cc:145-349
  *           Warps::Warp / Warps::Schwarzian     Modules/Mapping/Schwarp.cc
- *           DefORBmatcher::CalculateInitialSchwarp (init only) DefORBmatcher.cc:111-187
- */
+ *           Warps::Warp::initialize             Modules/Mapping/Schwarp.cc:99-160
+ * The trust-region iteration is Ceres' Levenberg-Marquardt with its default
+ * options (Jacobi scaling, initial radius 1e4, min_relative_decrease 1e-3,
+ * tolerances 1e-6/1e-8/1e-10) and the HuberLoss(5.77) corrector on the data
+ * block; Ceres itself is an unpinned external dependency of the reference.
+ * Reference quirk C6 (Schwarp.cc:291-299) is reproduced: the Jacobian rows of
+ * the y residuals are the rows of the x residuals, without the 1/sigma factor. */
 typedef struct defslam_schwarp_problem {
   defslam_bbs bbs;            /* domain of KF1 (DefKeyFrame umin..vmax), valdim=2 */
   int32_t n_matches;
   const float *kp1;           /* [n*2] normalised keypoints in KF1               */
   const float *kp2;           /* [n*2] normalised keypoints in KF2               */
-  const float *inv_sigma;     /* [n]   invSigma per match                        */
+  const float *inv_sigma;     /* [n]   sqrt(invLevelSigma2) per match            */
   double lambda;              /* LocalMapping.Schwarp.Regularizer                */
-  double fx, fy;              /* as passed by the reference (fy,fx swap is the
-                                 caller's business, quirk C6)                   */
+  double fx, fy;              /* as handed to Warps::Warp (the reference passes
+                                 (KF->fy, KF->fx), SchwarpDatabase.cc:199-201)   */
+  double px_fx, px_fy;        /* KF->fx, KF->fy of the 10 px unlink test
+                                 SchwarpDatabase.cc:283-293                      */
   int32_t max_iterations;     /* 3 in the reference                              */
-  int32_t init_from_affine;   /* 1: x0 = (C'C + lambda*B)^-1 C' q2 (Warp::initialize) */
+  int32_t initialize;         /* 1: x0 = (C'C + lambda*B)^-1 C' q2 (Warp::initialize) */
   double *x;                  /* in/out [2*NC] control points, [all x; all y]    */
 } defslam_schwarp_problem;
 
 typedef struct defslam_diffprop {
   /* per match, fp32 like Modules/Mapping/diffProp.h:52-88 */
   float *warp_uv;   /* [n*2] warped position of kp1                             */
-  float *J12;       /* [n*4] a,b,c,d                                            */
-  float *J21;       /* [n*4] inverse                                            */
+  float *J12;       /* [n*4] a,b,c,d = du/du, dv/du, du/dv, dv/dv               */
+  float *J21;       /* [n*4] a,b,c,d of the inverse                             */
   float *H12;       /* [n*6] uux,uuy,uvx,uvy,vvx,vvy                            */
-  uint8_t *keep;    /* [n]   0 if reprojection > 10 px (unlinked)               */
-  double cost_initial, cost_final;
-  int32_t iterations;
+  uint8_t *keep;    /* [n]   0 if the warp error exceeds 10 px (unlinked)       */
+  double cost_initial, cost_final; /* Ceres cost = 0.5*sum rho                  */
+  int32_t iterations;              /* trust-region steps taken (<= max)         */
+  int32_t accepted;                /* how many of them were accepted            */
 } defslam_diffprop;
 
 int defslam_schwarp_fit(const defslam_schwarp_problem *p, defslam_diffprop *out);
+/* nprob independent keyframe pairs, one CTA each. device: CUDA ordinal, -1 = current */
+int defslam_schwarp_fit_batched(int32_t nprob, const defslam_schwarp_problem *p,
+                                defslam_diffprop *out, int32_t device);
 
-/* Residuals/Jacobian of the Schwarp cost at x (parity hook).
+/* Residuals / Jacobian of the Schwarp cost at p->x, before the loss corrector (parity hook).
  * replaces: Warp::Evaluate Schwarp.cc:235-303 + Schwarzian::Evaluate :368-543
  * r: [2n + 4NC]; J: [(2n+4NC) * 2NC] row-major dense or NULL                 */
 int defslam_schwarp_evaluate(const defslam_schwarp_problem *p, double *r, double *J);
 
-/* Batched isometric-NRSfM normal estimation: one 2-unknown LM per map point.
+/* Batched isometric-NRSfM normal estimation: one 2-unknown LM per map point,
+ * then the transfer of the normal to the second keyframe of every pair.
  * replaces: NormalEstimator::ObtainK1K2  Modules/Mapping/NormalEstimator.cc:38-229
- *           PolySolver::getCoefficients/Evaluate Modules/Mapping/PolySolver.cc
- * pair data is CSR by point. */
+ *           PolySolver::getCoefficients/Evaluate Modules/Mapping/PolySolver.cc:50-193
+ * Pair data (the DiffProp records of WarpDatabase) is CSR by point. */
 typedef struct defslam_normals_problem {
   int32_t n_points;
   const int32_t *pair_ptr; /* [n_points+1]                                      */
   const float *J12;        /* [npairs*4] a,b,c,d                                */
+  const float *J21;        /* [npairs*4] a,b,c,d of the inverse (transfer)      */
   const float *H12;        /* [npairs*6] uux,uuy,uvx,uvy,vvx,vvy                */
-  const float *I1;         /* [npairs*2] point in KF1 (u,v)                     */
-  const float *I2;         /* [npairs*2] point in KF2 (u,v)                     */
-  const double *k_init;    /* [n_points*2] initial (k1,k2)                      */
+  const float *I1;         /* [npairs*2] point in the pair's first KF (u,v)     */
+  const float *I2;         /* [npairs*2] point in the pair's second KF (u,v)    */
+  const uint8_t *pair_from_ref; /* [npairs] 1: first KF == the point's reference
+                                   KF (the pair enters the polynomial system)   */
+  const float *k_first;    /* [npairs*2] (k1,k2) stored for the point in the
+                              pair's first KF, read when pair_from_ref==0;
+                              NaN = no normal there (pair skipped); may be NULL */
+  const double *k_init;    /* [n_points*2] initial (k1,k2): last estimate or 0  */
+  const float *ref_uv;     /* [n_points*2] normalised keypoint in the ref KF    */
   int32_t max_iterations;  /* 200                                               */
+  int32_t corrected_t2;    /* 0 = reference-compatible (default): the polynomial
+                              build takes t2 = (c*H12vvy - d*H12vvx)/2
+                              (NormalEstimator.cc:96-97), which vanishes for any
+                              projective warp; 1 = the definition of the transfer
+                              step t2 = (d*H12uux - c*H12uuy)/2 (:210), with which
+                              the polynomials vanish on an isometric pair (quirk C7) */
 } defslam_normals_problem;
 
+/* status_out[i]: 0 no equation for the point (nothing estimated), 1 estimated,
+ *                2 covariance rank deficient (reference `continue`s: no normal, no transfer)
+ * pair_valid_out[j]: 1 if pair_normal_out[j*3..] was written                  */
 int defslam_normals_batched(const defslam_normals_problem *p,
                             double *k_out /*[n*2]*/, double *cov_out /*[n*4]*/,
-                            float *normal_out /*[n*3]*/, int32_t *iters_out);
+                            float *normal_out /*[n*3]*/, uint8_t *status_out /*[n]*/,
+                            int32_t *iters_out /*[n]*/,
+                            float *pair_normal_out /*[npairs*3]*/,
+                            uint8_t *pair_valid_out /*[npairs]*/);
+
+/* PolySolver::getCoefficients for one pair (parity hook)  PolySolver.cc:50-149 */
+int defslam_polysolver_coefficients(int32_t npairs, const float *J12, const float *H12,
+                                    const float *I1, const float *I2,
+                                    double *eq1 /*[npairs*10]*/, double *eq2 /*[npairs*10]*/);
 
 /* Shape-from-normals depth-spline solve.
- * replaces: ShapeFromNormals::{obtainM,estimate}  Modules/Mapping/ShapeFromNormals.cc:81-260 */
+ * replaces: ShapeFromNormals::{ShapeFromNormals,obtainM,estimate}
+ *           Modules/Mapping/ShapeFromNormals.cc:38-76,178-260,81-171
+ * Least squares [M; bending*B; 1'] X = [0; 0; NC*mean_depth]; the reference
+ * uses a dense Householder QR, here: normal equations + Cholesky with two
+ * corrected-semi-normal-equation refinement sweeps (same minimiser). */
 typedef struct defslam_sfn_problem {
   defslam_bbs bbs;          /* valdim = 1                                       */
   int32_t n_normals;
   const float *uv;          /* [n*2] normalised keypoint                        */
-  const float *normals;     /* [n*3]                                            */
+  const float *normals;     /* [n*3] (not normalised)                           */
   double bending;           /* LocalMapping.Bending                             */
   double mean_depth;        /* DefKeyFrame::accMean (=1)                        */
   int32_t n_eval;           /* sites where depth is evaluated afterwards        */
   const float *eval_uv;     /* [n_eval*2]                                       */
+  double *ctrl_out;         /* [NC] control depths after the median rescale     */
+  float *xyz_out;           /* [n_eval*3] (u d, v d, d)                         */
 } defslam_sfn_problem;
 
-int defslam_sfn_solve(const defslam_sfn_problem *p, double *ctrl_out /*[NC]*/,
-                      float *xyz_out /*[n_eval*3] (u d, v d, d)*/);
+/* DEFSLAM_ENUMERIC when the solution is not finite (reference: estimate() == false) */
+int defslam_sfn_solve(const defslam_sfn_problem *p);
+int defslam_sfn_solve_batched(int32_t nprob, const defslam_sfn_problem *p, int32_t *rc_out /*[nprob] or NULL*/,
+                              int32_t device);
+/* The stacked system itself (parity hook): A [(2n+NC+1) * NC] row-major, b [2n+NC+1] */
+int defslam_sfn_system(const defslam_sfn_problem *p, double *A, double *b);
 
 /* Surface -> template nodes.
  * replaces: Surface::getVertex  Modules/Mapping/Surface.cc:125-161

@@ -35,6 +35,18 @@ int oracle_bbs_coloc(const defslam_bbs *s, int32_t nsites, const double *u, cons
 int oracle_bbs_bending(const defslam_bbs *s, double *B);
 int oracle_surface_vertices(const defslam_bbs *s, const double *ctrl, int32_t xs, int32_t ys, float *out);
 
+/* ---- NRSfM stages (nrsfm_oracle.c) ---- */
+int oracle_schwarp_evaluate(const defslam_schwarp_problem *p, double *r, double *J);
+int oracle_schwarp_init(const defslam_schwarp_problem *p, double *x0);
+int oracle_schwarp_fit(const defslam_schwarp_problem *p, defslam_diffprop *out);
+int oracle_polysolver_coefficients(int32_t npairs, const float *J12, const float *H12, const float *I1,
+                                   const float *I2, double *eq1, double *eq2);
+int oracle_normals_batched(const defslam_normals_problem *p, double *k_out, double *cov_out, float *normal_out,
+                           uint8_t *status_out, int32_t *iters_out, float *pair_normal_out,
+                           uint8_t *pair_valid_out);
+int oracle_sfn_system(const defslam_sfn_problem *p, double *A, double *b);
+int oracle_sfn_solve(const defslam_sfn_problem *p);
+
 #ifdef __cplusplus
 }
 #endif

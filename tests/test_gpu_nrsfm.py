@@ -1,0 +1,128 @@
+"""GPU parity tests of the NRSfM stages: CUDA path (through the C ABI) vs the CPU oracle."""
+import copy
+
+import numpy as np
+import pytest
+
+from defslam_b200 import nrsfm
+from tests import nrsfm_checks as ck
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def apis(oracle, cuda_lib):
+    return nrsfm.Api(cuda_lib, "defslam_"), nrsfm.Api(oracle.load(), "oracle_")
+
+
+def test_schwarp_evaluate_matches_oracle(apis):
+    api, orc = apis
+    win = nrsfm.make_window(3, n_keypoints=300, n_views=1)
+    c = nrsfm.schwarp_cases(win)[0]
+    x = orc.schwarp_init(c)
+    ck.check_schwarp_evaluate(api, orc, c, x)
+    ck.check_schwarp_evaluate(api, orc, c, ck.identity_grid(c.bbs))
+
+
+@pytest.mark.parametrize("grid", [(13, 15), (9, 9), (17, 17)])
+def test_window_chain_matches_oracle(apis, grid):
+    api, orc = apis
+    ck.window_chain(api, orc, seed=5, n_keypoints=500, n_views=2, nptsu=grid[0], nptsv=grid[1])
+
+
+def test_schwarp_accepted_steps(apis):
+    api, orc = apis
+    win = nrsfm.make_window(7, n_keypoints=600, n_views=1)
+    c = ck.accepted_steps_case(nrsfm.schwarp_cases(win)[0])
+    fa, fo = ck.check_schwarp_fit(api, orc, c)
+    assert fo.d.accepted >= 1
+
+
+def test_schwarp_batched_equals_single(apis):
+    api, orc = apis
+    win = nrsfm.make_window(11, n_keypoints=800, n_views=5, match_frac=0.4)
+    cases = nrsfm.schwarp_cases(win)
+    cases[2] = ck.accepted_steps_case(cases[2])
+    outs = api.schwarp_fit_batched(cases * 40)  # 200 pairs > 148 CTAs: exercises the work counter
+    for i, c in enumerate(cases):
+        single = api.schwarp_fit(c)
+        for rep in (i, i + 5 * 39):
+            assert np.array_equal(outs[rep].x, single.x)
+            assert np.array_equal(outs[rep].J12, single.J12)
+            assert outs[rep].d.iterations == single.d.iterations
+
+
+def test_schwarp_out_of_domain_is_rejected(apis):
+    api, _ = apis
+    win = nrsfm.make_window(2, n_keypoints=200, n_views=1)
+    c = nrsfm.schwarp_cases(win)[0]
+    c.kp1 = c.kp1.copy()
+    c.kp1[3, 0] = c.bbs.umax + 0.5
+    with pytest.raises(nrsfm.DefslamError) as e:
+        api.schwarp_fit(c)
+    assert e.value.rc == -1
+
+
+def test_normals_large_batch_and_mixed_pairs(apis):
+    api, orc = apis
+    win = nrsfm.make_window(13, n_keypoints=3000, n_views=6, match_frac=0.6)
+    fits = [orc.schwarp_fit(c) for c in nrsfm.schwarp_cases(win)]
+    nc = nrsfm.normals_case(win, fits)
+    # some pairs do not start at the reference keyframe: they only receive a transferred normal
+    rng = np.random.default_rng(0)
+    nc.pair_from_ref = (rng.uniform(size=nc.npairs) > 0.2).astype(np.uint8)
+    nc.k_first = rng.normal(size=(nc.npairs, 2)).astype(np.float32) * 0.1
+    nc.k_first[rng.uniform(size=nc.npairs) > 0.7] = np.nan
+    ck.check_normals(api, orc, nc)
+    nc2 = copy.copy(nc)
+    nc2.corrected_t2 = 1
+    ck.check_normals(api, orc, nc2)
+
+
+def test_polysolver_coefficients_match_oracle(apis):
+    api, orc = apis
+    rng = np.random.default_rng(1)
+    n = 4096
+    J12 = (np.eye(2).reshape(1, 4) + rng.normal(size=(n, 4)) * 0.2).astype(np.float32)
+    H12 = (rng.normal(size=(n, 6)) * 0.3).astype(np.float32)
+    I1 = rng.uniform(-0.7, 0.7, (n, 2)).astype(np.float32)
+    I2 = rng.uniform(-0.7, 0.7, (n, 2)).astype(np.float32)
+    a1, a2 = api.polysolver_coefficients(J12, H12, I1, I2)
+    o1, o2 = orc.polysolver_coefficients(J12, H12, I1, I2)
+    s = np.maximum(np.abs(o1).max(1), np.abs(o2).max(1))[:, None]
+    assert (np.abs(a1 - o1) / s).max() < 1e-13 and (np.abs(a2 - o2) / s).max() < 1e-13
+
+
+def test_sfn_batched_and_few_normals(apis):
+    api, orc = apis
+    cases = []
+    for seed in range(3):
+        win = nrsfm.make_window(20 + seed, n_keypoints=300, n_views=2)
+        fits = [orc.schwarp_fit(c) for c in nrsfm.schwarp_cases(win)]
+        no = orc.normals(nrsfm.normals_case(win, fits))
+        cases.append(nrsfm.sfn_case(win, no))
+    few = copy.copy(cases[0])
+    few.uv, few.normals = few.uv[:10].copy(), few.normals[:10].copy()
+    cases.append(few)
+    refs = []
+    for c in cases:
+        co, xo = orc.sfn_solve(c)
+        refs.append((co.copy(), xo.copy()))
+    rcs = api.sfn_solve_batched(cases)
+    assert (rcs == 0).all()
+    for c, (co, xo) in zip(cases, refs):
+        assert np.abs(c.ctrl - co).max() <= ck.CTRL_TOL
+        assert np.abs(c.xyz - xo).max() <= 1e-6
+
+
+def test_sfn_nan_normals_fail_loudly(apis):
+    api, orc = apis
+    win = nrsfm.make_window(4, n_keypoints=200, n_views=1)
+    fits = [orc.schwarp_fit(c) for c in nrsfm.schwarp_cases(win)]
+    no = orc.normals(nrsfm.normals_case(win, fits))
+    c = nrsfm.sfn_case(win, no)
+    c.normals = c.normals.copy()
+    c.normals[0] = np.nan
+    with pytest.raises(nrsfm.DefslamError) as e:
+        api.sfn_solve(c)
+    assert e.value.rc == -3
