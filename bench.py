@@ -149,6 +149,105 @@ def cpu_solve_rate(frames, n_threads: int):
     return len(work) / dt, dt, build
 
 
+# ------------------------------------------------------------------ NRSfM stages -----------
+NRSFM_WINDOWS = 8        # distinct synthetic keyframe windows (1200 keypoints, 4 later views each)
+NRSFM_PAIRS = 592        # Schwarp fits per step  (148 SMs x 4 waves)
+NRSFM_POINTS = 480000    # map points per normals step
+NRSFM_KEYFRAMES = 296    # shape-from-normals solves per step
+
+
+def nrsfm_workload():
+    """One mapping workload per stage, built from NRSFM_WINDOWS keyframe windows (inputs of the later
+    stages come from the oracle-independent product path itself: fits -> normals -> SfN)."""
+    from defslam_b200 import nrsfm
+    api = nrsfm.Api()
+    wins = [nrsfm.make_window(100 + i, n_keypoints=1200, n_views=4) for i in range(NRSFM_WINDOWS)]
+    cases = [c for w in wins for c in nrsfm.schwarp_cases(w)]
+    fits = api.schwarp_fit_batched(cases)
+    ncs = [nrsfm.normals_case(w, fits[4 * i:4 * i + 4]) for i, w in enumerate(wins)]
+    reps = max(1, NRSFM_POINTS // sum(nc.n for nc in ncs))
+    ptr = [0]
+    for _ in range(reps):
+        for nc in ncs:
+            ptr.extend((nc.pair_ptr[1:] + ptr[-1]).tolist())
+
+    def cat(name, per_point=False):
+        return np.ascontiguousarray(np.concatenate(
+            [getattr(nc, name) if per_point else getattr(nc, name)[:nc.npairs] for nc in ncs] * reps))
+    big = nrsfm.NormalsCase(pair_ptr=np.array(ptr, np.int32), J12=cat("J12"), J21=cat("J21"), H12=cat("H12"),
+                            I1=cat("I1"), I2=cat("I2"), pair_from_ref=cat("pair_from_ref"), k_first=cat("k_first"),
+                            k_init=cat("k_init", True), ref_uv=cat("ref_uv", True))
+    scs = [nrsfm.sfn_case(w, api.normals(nc)) for w, nc in zip(wins, ncs)]
+    return dict(api=api, wins=wins, pairs=cases * max(1, NRSFM_PAIRS // len(cases)), pair_base=cases, normals=big,
+                normals_base=ncs, keyframes=scs * max(1, NRSFM_KEYFRAMES // len(scs)), keyframes_base=scs)
+
+
+def nrsfm_gpu(lib, wl, steps, warmup, flush_fn):
+    """[units per step, device ms, wall s] per stage; device time = CUDA events around the stage's
+    kernel on the library's stream, wall = the whole C-ABI call on host buffers."""
+    api = wl["api"]
+    # descriptors over the host arrays are built once; each call below is ONE C-ABI call
+    stages = {"schwarp_fit": (len(wl["pairs"]), api.schwarp_prepare(wl["pairs"])),
+              "normals": (wl["normals"].n, api.normals_prepare(wl["normals"])),
+              "sfn": (len(wl["keyframes"]), api.sfn_prepare(wl["keyframes"]))}
+    res = {}
+    for name, (units, call) in stages.items():
+        for _ in range(min(warmup, 2)):
+            call()
+        dev_ms, wall_s = 0.0, 0.0
+        for _ in range(steps):
+            flush_fn()
+            t0 = time.perf_counter()
+            call()
+            wall_s += time.perf_counter() - t0
+            dev_ms += lib.defslam_last_kernel_ms()
+        res[name] = [units, dev_ms, wall_s]
+    return res
+
+
+def _threaded(fn, items, n_threads):
+    lock, pos = threading.Lock(), [0]
+
+    def worker():
+        while True:
+            with lock:
+                i = pos[0]
+                pos[0] += 1
+            if i >= len(items):
+                return
+            fn(items[i])
+    t0 = time.perf_counter()
+    th = [threading.Thread(target=worker) for _ in range(n_threads)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    return time.perf_counter() - t0
+
+
+def nrsfm_cpu(wl, cores):
+    """The oracle (dense Jacobians / dense Cholesky / Householder QR like the reference's Ceres+Eigen
+    path) on a bounded sample of the same units, one unit per host thread."""
+    from defslam_b200 import nrsfm
+    from oracle import oracle_py
+    try:
+        lib = oracle_py.load(native=True)
+    except Exception:
+        lib = oracle_py.load()
+    orc = nrsfm.Api(lib, "oracle_")
+    out = {}
+    pairs = (wl["pair_base"] * 8)[:max(cores, 32)]
+    out["schwarp_fit"] = len(pairs) / _threaded(orc.schwarp_fit, pairs, cores)
+    ncs = (wl["normals_base"] * 64)[:max(cores, 64) * 4]
+    out["normals"] = sum(nc.n for nc in ncs) / _threaded(orc.normals, ncs, cores)
+    import copy
+    kfs = [copy.copy(k) for k in (wl["keyframes_base"] * 8)[:max(cores, 16)]]
+    for k in kfs:
+        k.ctrl = None
+    out["sfn"] = len(kfs) / _threaded(orc.sfn_solve, kfs, cores)
+    return out
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -189,6 +288,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-nrsfm", action="store_true", help="skip the NRSfM stage measurements")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -261,6 +361,19 @@ def main():
     barrier()
     assert all(o.r.status == 0 for o in e2e_outs)
 
+    # ---- NRSfM stages (same timing rules; reported next to the headline metric) ---------
+    nr = None
+    if not args.no_nrsfm:
+        def _flush():
+            flush.fill_(1)
+            torch.cuda.synchronize()
+        wl = nrsfm_workload()
+        barrier()
+        l0 = lib.defslam_kernel_launch_count()
+        nr = nrsfm_gpu(lib, wl, max(2, args.steps // 2), args.warmup, _flush)
+        nrsfm_launches = lib.defslam_kernel_launch_count() - l0
+        barrier()
+
     # ---- parity spot check against the oracle (not timed) ----------------------------
     rel = None
     if rank == 0:
@@ -280,6 +393,17 @@ def main():
     else:
         e2e_ms = e2e_s * 1e3
         iters_all, trials_all = iters, trials
+
+    nr_line = None
+    if nr is not None:
+        names = sorted(nr)
+        tt = torch.tensor([[nr[k][1], nr[k][2] * 1e3] for k in names], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        nsteps = max(2, args.steps // 2)
+        nr_line = {k: {"units_per_step_per_gpu": nr[k][0],
+                       "value": nr[k][0] * world * nsteps / (float(tt[i, 0]) * 1e-3),
+                       "e2e": nr[k][0] * world * nsteps / (float(tt[i, 1]) * 1e-3)} for i, k in enumerate(names)}
 
     if rank == 0:
         n_frames_job = args.frames * world
@@ -322,6 +446,20 @@ def main():
                          "note": "the fused LM kernel is bound by the FP64 latency chain of the banded "
                                  "factorisation, not by HBM; see DESIGN.md"},
         }
+        if nr_line is not None:
+            units = {"schwarp_fit": "keyframe-pair fits/s", "normals": "map-point normals/s", "sfn": "keyframe solves/s"}
+            for k in nr_line:
+                nr_line[k]["unit"] = units[k]
+            line["nrsfm"] = {"stages": nr_line, "gpu_launches": int(nrsfm_launches),
+                             "workload": f"{NRSFM_WINDOWS} distinct synthetic keyframe windows (1200 keypoints, 4 views, "
+                                         "13x15 control grid) tiled; value = units / device time of the stage kernel "
+                                         "(CUDA events), e2e = units / wall time of the C-ABI call on host buffers"}
+            if not args.no_cpu_baseline:
+                cpu = nrsfm_cpu(wl, os.cpu_count() or 1)
+                for k, v in cpu.items():
+                    line["nrsfm"]["stages"][k]["cpu_baseline"] = v
+                line["nrsfm"]["cpu_baseline"] = {"cores": os.cpu_count() or 1, "kind": "port",
+                                                 "sample": "32 fits / 256 point sets / 16 keyframes, one unit per thread"}
         if not args.no_cpu_baseline and world >= 1:
             cores = os.cpu_count() or 1
             n_sample = max(cores, min(CPU_SAMPLE_FRAMES, 8 * cores))

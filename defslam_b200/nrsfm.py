@@ -243,19 +243,33 @@ class Api:
         self._check("schwarp_fit", self._f("schwarp_fit")(C.byref(p), C.byref(out.d)))
         return out
 
-    def schwarp_fit_batched(self, cases, device: int = -1):
+    def schwarp_prepare(self, cases):
+        """Descriptors over the host arrays, built once (HostBatch-style): calling the returned
+        function is exactly one C-ABI call."""
         n = len(cases)
         outs = [DiffPropOut(c.n) for c in cases]
         probs = (_capi.SchwarpProblem * n)()
         dps = (_capi.DiffProp * n)()
+        x0 = []
         for i, (c, o) in enumerate(zip(cases, outs)):
             o.x = np.zeros(2 * c.NC) if c.x0 is None else np.array(c.x0, dtype=np.float64)
+            x0.append(o.x.copy())
             probs[i] = c.problem(o.x)
             dps[i] = o.d
-        self._check("schwarp_fit_batched", self._f("schwarp_fit_batched")(n, probs, dps, device))
-        for i, o in enumerate(outs):
-            o.d = dps[i]
-        return outs
+        fn = self._f("schwarp_fit_batched")
+
+        def call(device: int = -1):
+            for o, x in zip(outs, x0):   # x is in/out
+                o.x[:] = x
+            self._check("schwarp_fit_batched", fn(n, probs, dps, device))
+            for i, o in enumerate(outs):
+                o.d = dps[i]
+            return outs
+        call.keepalive = (cases, outs, probs, dps)
+        return call
+
+    def schwarp_fit_batched(self, cases, device: int = -1):
+        return self.schwarp_prepare(cases)(device)
 
     # -- normals
     def polysolver_coefficients(self, J12, H12, I1, I2):
@@ -267,11 +281,20 @@ class Api:
             _capi.as_ptr(I2, C.c_float), _capi.as_ptr(e1, C.c_double), _capi.as_ptr(e2, C.c_double)))
         return e1, e2
 
-    def normals(self, case: NormalsCase) -> NormalsOut:
+    def normals_prepare(self, case: NormalsCase):
         out = NormalsOut(case.n, case.npairs)
         p = case.problem()
-        self._check("normals_batched", self._f("normals_batched")(C.byref(p), *out.args()))
-        return out
+        args = out.args()
+        fn = self._f("normals_batched")
+
+        def call():
+            self._check("normals_batched", fn(C.byref(p), *args))
+            return out
+        call.keepalive = (case, out, p, args)
+        return call
+
+    def normals(self, case: NormalsCase) -> NormalsOut:
+        return self.normals_prepare(case)()
 
     # -- shape from normals
     def sfn_system(self, case: SfnCase):
@@ -287,14 +310,22 @@ class Api:
         self._check("sfn_solve", self._f("sfn_solve")(C.byref(p)))
         return case.ctrl, case.xyz
 
-    def sfn_solve_batched(self, cases, device: int = -1):
+    def sfn_prepare(self, cases):
         n = len(cases)
         probs = (_capi.SfnProblem * n)()
         for i, c in enumerate(cases):
             probs[i] = c.problem()
         rcs = np.zeros(n, np.int32)
-        self._check("sfn_solve_batched", self._f("sfn_solve_batched")(n, probs, _capi.as_ptr(rcs, C.c_int32), device))
-        return rcs
+        fn = self._f("sfn_solve_batched")
+
+        def call(device: int = -1):
+            self._check("sfn_solve_batched", fn(n, probs, _capi.as_ptr(rcs, C.c_int32), device))
+            return rcs
+        call.keepalive = (cases, probs, rcs)
+        return call
+
+    def sfn_solve_batched(self, cases, device: int = -1):
+        return self.sfn_prepare(cases)(device)
 
 
 # ----------------------------------------------------------------------------- synthetic
