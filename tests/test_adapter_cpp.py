@@ -9,18 +9,21 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "tests", "_emu", "test_adapter")
 
 
-def _build(oracle):
+EXE2 = os.path.join(ROOT, "tests", "_emu", "test_adapter_nrsfm")
+
+
+def _build(oracle, src="test_adapter.cc", exe=EXE):
     oracle.load()
-    os.makedirs(os.path.dirname(EXE), exist_ok=True)
-    cmd = ["g++", "-O1", "-std=c++17", "-o", EXE, os.path.join(ROOT, "tests", "cpp", "test_adapter.cc"),
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    cmd = ["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "cpp", src),
            "-L" + os.path.join(ROOT, "defslam_b200"), "-ldefslam_b200",
            "-L" + os.path.join(ROOT, "oracle", "_build"), "-loracle",
            "-Wl,-rpath," + os.path.join(ROOT, "defslam_b200"), "-Wl,-rpath," + os.path.join(ROOT, "oracle", "_build")]
     subprocess.run(cmd, check=True, capture_output=True)
 
 
-def _run():
-    r = subprocess.run([EXE], capture_output=True, text=True, timeout=300)
+def _run(exe=EXE):
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     return r.returncode, r.stdout + r.stderr
 
 
@@ -39,3 +42,21 @@ def test_adapter_matches_oracle_on_gpu(oracle, cuda_lib):
     rc, out = _run()
     assert rc == 0, out
     assert "max node err" in out
+
+
+def test_nrsfm_adapter_compiles_and_fails_loudly_without_a_device(oracle, cuda_lib):
+    """adapter/NrsfmB200.h: calculateSchwarps / ObtainK1K2 / estimateSurface against mock DefSLAM types."""
+    _build(oracle, "test_adapter_nrsfm.cc", EXE2)
+    if cuda_lib.defslam_device_count() > 0:
+        pytest.skip("device present: covered by the gpu test")
+    rc, out = _run(EXE2)
+    assert rc == 0, out
+    assert "untouched" in out
+
+
+@pytest.mark.gpu
+def test_nrsfm_adapter_matches_oracle_on_gpu(oracle, cuda_lib):
+    _build(oracle, "test_adapter_nrsfm.cc", EXE2)
+    rc, out = _run(EXE2)
+    assert rc == 0, out
+    assert "nrsfm adapter ok" in out
