@@ -128,9 +128,19 @@ DS_FN_NOINLINE bool bband_solve(const Team team, const BandDims bd, const double
         const double a = W[(size_t)row * ldw + pj] * inv;
         const int cmax = ii < nrow ? ii : nrow - 1;
         double *wr = W + (size_t)row * ldw;
-        for (int c = j + 1 + tx; c <= cmax; c += TX) {
-          const int pc = DS_P(c);
-          wr[pc] -= a * W[(size_t)pc * ldw + pj];
+        const double *wc = W + pj; /* column pj */
+        /* the ring wraps at most once inside [j+1, cmax]: two plain strided segments */
+        const int e1 = cmax < Wn - off - 1 ? cmax : Wn - off - 1;
+        int c = j + 1 + tx;
+#pragma unroll 4
+        for (; c <= e1; c += TX) {
+          const int pc = c + off;
+          wr[pc] -= a * wc[(size_t)pc * ldw];
+        }
+#pragma unroll 4
+        for (; c <= cmax; c += TX) {
+          const int pc = c + off - Wn;
+          wr[pc] -= a * wc[(size_t)pc * ldw];
         }
       }
       team.sync();

@@ -35,7 +35,7 @@ struct Packer {
   size_t add(size_t bytes) { size_t o = total; total += (bytes + 255) & ~(size_t)255; return o; }
 };
 
-constexpr int NRSFM_THREADS = 256;
+constexpr int NRSFM_THREADS = 512;
 
 BbsView to_view(const defslam_bbs *b) {
   BbsView s;

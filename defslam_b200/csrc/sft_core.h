@@ -1031,14 +1031,15 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
   prof_mark(team, c, PF_FS_INIT);
 
   int kslot = 0; /* k mod Wr */
+  /* S1 of the first block; every later diagonal block is factored by warp 0 during the
+   * trailing update of the step before it (look-ahead), off the critical path */
+  if (team.warp0()) {
+    diag_factor(team, W, 0, Wr, ld, bwE, lambda, invL, flag);
+    fence_proxy_async_smem(); /* rows 0..7 are final: they leave through the async proxy */
+  }
+  team.sync();
   for (int kb = 0; kb < nblk; kb++) {
     const int k = kb * NB;
-    /* S1: factor the diagonal block (warp 0) */
-    if (team.warp0()) {
-      diag_factor(team, W, kslot, Wr, ld, bwE, lambda, invL, flag);
-      fence_proxy_async_smem(); /* rows k..k+7 are final: they leave through the async proxy */
-    }
-    team.sync();
     /* finished rows k..k+7 -> L band in global memory (TMA bulk store) */
     if (team.tid == 0) tma_store_1d(Lb + k * ld, W + kslot * ld, (uint32_t)(NB * ld * sizeof(double)));
     prof_mark(team, c, PF_S1);
@@ -1086,38 +1087,58 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
       const int nrow = nt8 + 1;
       const int ntiles = nrow * (nrow + 1) / 2;
       const int lo = bwE - bw;
-      for (int t = warp; t < ntiles; t += nwarp) {
+      /* Look-ahead: tile 0 is the next diagonal block and the only tile that touches rows
+       * k+8..k+15.  Warp 0 updates it first and factors it (S1 of step kb+1, worth ~5 tiles)
+       * while the other warps work through the remaining tiles; warp 0 then takes n0 tiles
+       * from the tail so that all warps finish together. */
+      int n0 = (10 * (ntiles - 1) - 54 * (nwarp - 1)) / (10 * nwarp);
+      if (n0 < 0) n0 = 0;
+      const int nshared = ntiles - n0; /* tiles 1..nshared-1 go round-robin to warps 1.. */
+      const int t_first = warp == 0 ? 0 : warp, t_step = nwarp > 1 ? nwarp - 1 : 1;
+      for (int t = t_first; t < ntiles;) {
         const TileDesc td = tiles[t];
-        if (td.kind <= 2 ? td.rA >= n_trail : (td.kind == 3 && td.rB >= n_trail)) continue;
-        if (td.kind <= 2 && td.rB >= n_trail) continue;
-        DS_WARP_FOR(T, 32) {
-          const int g = T >> 2, q = T & 3;
-          double d0, d1;
-          tile_mul_pp(T, P, HS, td.rA, td.rB, d0, d1);
-          if (td.kind <= 2) {
-            /* entry (i, j): i = k+8+rA+g, j = k+8+rB+2q(+1); band offset j-i+bwE */
-            int s0 = kslot + NB + td.rA;
-            if (s0 >= Wr) s0 -= Wr;
-            const int off = td.dcol + 2 * q - g + bwE;
-            double *dst = W + (s0 + g) * ld + off;
-            if (td.kind == 1) {
-              sub_pair(dst, d0, d1);
-            } else {
-              const bool v0 = off <= bwE && off >= lo, v1 = off + 1 <= bwE && off + 1 >= lo;
-              if (v0 && v1) sub_pair(dst, d0, d1);
-              else {
-                if (v0) dst[0] -= d0;
-                if (v1) dst[1] -= d1;
+        const int t_cur = t;
+        if (warp == 0) t = (t == 0) ? nshared : t + 1;
+        else { t += t_step; if (t >= nshared) t = ntiles; }
+        bool skip = td.kind <= 2 ? td.rA >= n_trail : (td.kind == 3 && td.rB >= n_trail);
+        skip = skip || (td.kind <= 2 && td.rB >= n_trail);
+        if (!skip) {
+          DS_WARP_FOR(T, 32) {
+            const int g = T >> 2, q = T & 3;
+            double d0, d1;
+            tile_mul_pp(T, P, HS, td.rA, td.rB, d0, d1);
+            if (td.kind <= 2) {
+              /* entry (i, j): i = k+8+rA+g, j = k+8+rB+2q(+1); band offset j-i+bwE */
+              int s0 = kslot + NB + td.rA;
+              if (s0 >= Wr) s0 -= Wr;
+              const int off = td.dcol + 2 * q - g + bwE;
+              double *dst = W + (s0 + g) * ld + off;
+              if (td.kind == 1) {
+                sub_pair(dst, d0, d1);
+              } else {
+                const bool v0 = off <= bwE && off >= lo, v1 = off + 1 <= bwE && off + 1 >= lo;
+                if (v0 && v1) sub_pair(dst, d0, d1);
+                else {
+                  if (v0) dst[0] -= d0;
+                  if (v1) dst[1] -= d1;
+                }
               }
+            } else if (td.kind == 3) {
+              const int eo = g * ES + k + NB + td.rB + 2 * q;
+              if (e_smem) sub_pair(Es + eo, d0, d1);
+              else sub_pair(Eg + eo, d0, d1);
+            } else {
+              if (2 * q <= g) G[g * 8 + 2 * q] -= d0;
+              if (2 * q + 1 <= g) G[g * 8 + 2 * q + 1] -= d1;
             }
-          } else if (td.kind == 3) {
-            const int eo = g * ES + k + NB + td.rB + 2 * q;
-            if (e_smem) sub_pair(Es + eo, d0, d1);
-            else sub_pair(Eg + eo, d0, d1);
-          } else {
-            if (2 * q <= g) G[g * 8 + 2 * q] -= d0;
-            if (2 * q + 1 <= g) G[g * 8 + 2 * q + 1] -= d1;
           }
+        }
+        if (t_cur == 0 && warp == 0 && kb + 1 < nblk) {
+          /* S1 of the next step on the block tile 0 just produced */
+          team.warp_sync();
+          int ns = kslot + NB;
+          if (ns >= Wr) ns -= Wr;
+          diag_factor(team, W, ns, Wr, ld, bwE, lambda, invL, flag);
         }
       }
     }
