@@ -9,6 +9,8 @@
  *                         Modules/Mapping/NormalEstimator.cc:38-229    -> ObtainK1K2()
  *   ShapeFromNormals::estimate()  (+ ctor / obtainM)
  *                         Modules/Mapping/ShapeFromNormals.cc:38-260   -> estimateSurface()
+ *   SurfaceRegistration::registerSurfaces()  (+ Optimizer::OptimizeHorn, scaleMinMedian)
+ *                         Modules/Mapping/SurfaceRegistration.cc:48-153 -> registerSurfaces()
  *
  * Like DefOptimizerB200.h they are templates over the reference's types, written against the member
  * names the reference bodies use, so they compile unchanged against the DefSLAM headers
@@ -217,6 +219,71 @@ bool estimateSurface(KeyFrame *refKf_, double bendingWeight_) {
   bbs.umin = p.bbs.umin; bbs.umax = p.bbs.umax; bbs.nptsu = p.bbs.nptsu;
   bbs.vmin = p.bbs.vmin; bbs.vmax = p.bbs.vmax; bbs.nptsv = p.bbs.nptsv; bbs.valdim = 1;
   kf->surface->saveArray(ctrl, bbs);                                 /* :164 */
+  return true;
+}
+
+/* SurfaceRegistration(refKF, chiLimit, check_chi).registerSurfaces()
+ * (Modules/Mapping/SurfaceRegistration.cc:48-153).  cv::Mat never crosses the adapter: the keyframe
+ * exposes getPoseInverseRowMajor(float[16]) / SetPoseRowMajor(const float[16]) (one-line wrappers of
+ * GetPoseInverse / SetPose) and the map point getPositionInKeyframe(KeyFrame*, float[3]) (the
+ * PosesKeyframes[refKF] entry, false when empty).  `seed` replaces the reference's unseeded rand(). */
+template <class DefKeyFrame, class KeyFrame, class DefMapPoint, class Vec3f>
+bool registerSurfaces(KeyFrame *refKF, double chiLimit_, bool check_chi, uint64_t seed = 1) {
+  DefKeyFrame *kf = static_cast<DefKeyFrame *>(refKF);
+  float Twc[16];
+  refKF->getPoseInverseRowMajor(Twc);
+  std::vector<float> cloud1, cloud2; /* cloud1pc: stored map points; cloud2pc: surface points in the world frame */
+  for (size_t i = 0; i < refKF->mvKeysUn.size(); i++) {               /* :60-103 */
+    auto *pMP = refKF->GetMapPoint(i);
+    if (!pMP || pMP->isBad()) continue;
+    DefMapPoint *dmp = static_cast<DefMapPoint *>(pMP);
+    if (!dmp->getFacet()) continue;
+    float pos[3];
+    if (!dmp->getPositionInKeyframe(refKF, pos)) continue;
+    Vec3f x;
+    kf->surface->get3DSurfacePoint(i, x);
+    cloud1.insert(cloud1.end(), pos, pos + 3);
+    for (int r = 0; r < 3; r++) cloud2.push_back(Twc[4 * r] * x(0) + Twc[4 * r + 1] * x(1) + Twc[4 * r + 2] * x(2) + Twc[4 * r + 3]);
+  }
+  const int n = (int)(cloud1.size() / 3);
+  if (n < 15) return false;                                            /* :105-106 */
+  float scale = 0.f;
+  if (defslam_scale_min_median(n, cloud2.data(), cloud1.data(), seed, &scale) != DEFSLAM_OK) return false;
+  defslam_sim3_problem p;
+  p.n_points = n; p.pts1 = cloud2.data(); p.pts2 = cloud1.data();
+  p.rot[0] = p.rot[1] = p.rot[2] = 0.0; p.rot[3] = 1.0;
+  p.trans[0] = p.trans[1] = p.trans[2] = 0.0;
+  p.scale = scale; p.chi = chiLimit_ * chiLimit_; p.huber = 0.01; p.max_iterations = 50;
+  defslam_sim3_result r;
+  if (defslam_sim3_register_batched(1, &p, &r, -1) != DEFSLAM_OK) return false;
+  if (!r.acceptable && check_chi) return false;                        /* :129-130 */
+  /* mScw = [s R | t] in fp32 (Converter::toCvMat(g2o::Sim3)); Twc' = mScw * Twc  (:132-136) */
+  const double x = r.rot[0], y = r.rot[1], z = r.rot[2], w = r.rot[3];
+  const double R[9] = {1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                       2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                       2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)};
+  float S[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1}, T[16];
+  for (int a = 0; a < 3; a++) {
+    for (int b = 0; b < 3; b++) S[4 * a + b] = (float)(r.scale * R[3 * a + b]);
+    S[4 * a + 3] = (float)r.trans[a];
+  }
+  for (int a = 0; a < 4; a++)
+    for (int b = 0; b < 4; b++) {
+      float acc = 0.f;
+      for (int k = 0; k < 4; k++) acc += S[4 * a + k] * Twc[4 * k + b];
+      T[4 * a + b] = acc;
+    }
+  const double s22 = std::sqrt((double)(T[0] * T[0] + T[1] * T[1] + T[2] * T[2]));  /* :138-140 */
+  kf->surface->applyScale(s22);
+  for (int a = 0; a < 3; a++)
+    for (int b = 0; b < 3; b++) T[4 * a + b] = (float)(T[4 * a + b] / s22);
+  /* Tcw = inverse of the rigid Twc' (:142-145) */
+  float Tcw[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1};
+  for (int a = 0; a < 3; a++) {
+    for (int b = 0; b < 3; b++) Tcw[4 * a + b] = T[4 * b + a];
+    Tcw[4 * a + 3] = -(T[a] * T[3] + T[4 + a] * T[7] + T[8 + a] * T[11]);
+  }
+  refKF->SetPoseRowMajor(Tcw);
   return true;
 }
 

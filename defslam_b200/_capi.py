@@ -157,6 +157,32 @@ class SfnProblem(C.Structure):
     ]
 
 
+class Sim3Problem(C.Structure):
+    _fields_ = [
+        ("n_points", C.c_int32),
+        ("pts1", c_float_p),
+        ("pts2", c_float_p),
+        ("rot", C.c_double * 4),
+        ("trans", C.c_double * 3),
+        ("scale", C.c_double),
+        ("chi", C.c_double),
+        ("huber", C.c_double),
+        ("max_iterations", C.c_int32),
+    ]
+
+
+class Sim3Result(C.Structure):
+    _fields_ = [
+        ("rot", C.c_double * 4),
+        ("trans", C.c_double * 3),
+        ("scale", C.c_double),
+        ("chi2", C.c_double),
+        ("inliers", C.c_int32),
+        ("acceptable", C.c_int32),
+        ("iterations", C.c_int32 * 2),
+    ]
+
+
 NORMALS_ARGS = [C.POINTER(NormalsProblem), c_double_p, c_double_p, c_float_p, c_uint8_p, c_int32_p, c_float_p,
                 c_uint8_p]
 POLY_ARGS = [C.c_int32, c_float_p, c_float_p, c_float_p, c_float_p, c_double_p, c_double_p]
@@ -202,6 +228,9 @@ PROTOTYPES = {
     "defslam_sfn_solve": (C.c_int, [C.POINTER(SfnProblem)]),
     "defslam_sfn_solve_batched": (C.c_int, [C.c_int32, C.POINTER(SfnProblem), c_int32_p, C.c_int32]),
     "defslam_sfn_system": (C.c_int, [C.POINTER(SfnProblem), c_double_p, c_double_p]),
+    "defslam_sim3_register_batched": (
+        C.c_int, [C.c_int32, C.POINTER(Sim3Problem), C.POINTER(Sim3Result), C.c_int32]),
+    "defslam_scale_min_median": (C.c_int, [C.c_int32, c_float_p, c_float_p, C.c_uint64, c_float_p]),
     "defslam_surface_vertices": (C.c_int, [C.POINTER(Bbs), c_double_p, C.c_int32, C.c_int32, c_float_p]),
     "defslam_version": (C.c_char_p, []),
     "defslam_kernel_launch_count": (C.c_int64, []),

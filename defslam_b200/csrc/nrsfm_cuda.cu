@@ -14,6 +14,7 @@
 
 #include "ds_runtime.h"
 #include "nrsfm_core.h"
+#include "sim3_core.h"
 
 using namespace ds;
 
@@ -122,6 +123,31 @@ __global__ void sfn_rows_kernel(SfnProb P, int nrows, double *A, double *b) {
   fill_cell_integrals(team, ci);
   for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < nrows; row += gridDim.x * blockDim.x)
     sfn_system_row(P, ci, row, A, b);
+}
+
+constexpr int SIM3_THREADS = 256;
+
+__global__ void __launch_bounds__(SIM3_THREADS)
+sim3_register_kernel(const Sim3Prob *probs, int nprob) {
+  __shared__ double red[36 + 36 * (SIM3_THREADS / 32) + 40];
+  Team team;
+  team.tid = threadIdx.x;
+  team.nthr = blockDim.x;
+  for (int i = blockIdx.x; i < nprob; i += gridDim.x) {
+    __syncthreads();
+    sim3_register_one(team, probs[i], red);
+  }
+}
+
+__global__ void __launch_bounds__(512)
+scale_min_median_kernel(int n, const float *mono, const float *stereo, uint64_t seed, float *out) {
+  extern __shared__ float mm_buf[];
+  __shared__ int cnt;
+  __shared__ double sc[4];
+  Team team;
+  team.tid = threadIdx.x;
+  team.nthr = blockDim.x;
+  scale_min_median_team(team, n, mono, stereo, seed, mm_buf, &cnt, sc, out);
 }
 
 int grid_for(int n, int sm) {
@@ -506,6 +532,94 @@ int defslam_sfn_system(const defslam_sfn_problem *p, double *A, double *b) {
   DS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   memcpy(A, h + o_A, 8 * rows * NC);
   memcpy(b, h + o_b, 8 * rows);
+  return DEFSLAM_OK;
+}
+
+/* ------------------------------------------------------------------ Sim(3) registration */
+
+int defslam_sim3_register_batched(int32_t nprob, const defslam_sim3_problem *p, defslam_sim3_result *out,
+                                  int32_t device) {
+  if (nprob < 0 || (nprob > 0 && (!p || !out))) return DEFSLAM_EBADARG;
+  for (int i = 0; i < nprob; i++)
+    if (p[i].n_points <= 0 || !p[i].pts1 || !p[i].pts2 || p[i].max_iterations < 0 || !(p[i].huber > 0)) return DEFSLAM_EBADARG;
+  DevCtx *ctx = get_ctx(device);
+  if (!ctx) return DEFSLAM_ECUDA;
+  if (nprob == 0) return DEFSLAM_OK;
+  Packer in, outp;
+  std::vector<size_t> o1(nprob), o2(nprob), oo(nprob);
+  const size_t o_probs = in.add(sizeof(Sim3Prob) * nprob);
+  for (int i = 0; i < nprob; i++) {
+    const size_t n = p[i].n_points;
+    o1[i] = in.add(12 * n); o2[i] = in.add(12 * n); oo[i] = outp.add(16 * 8);
+  }
+  Scratch &S = tl_scratch(ctx->device);
+  int rc;
+  if ((rc = S.host.ensure(in.total > outp.total ? in.total : outp.total)) || (rc = S.dev.ensure(in.total + outp.total)))
+    return rc;
+  uint8_t *h = (uint8_t *)S.host.p, *d_in = (uint8_t *)S.dev.p, *d_out = d_in + in.total;
+  Sim3Prob *hp = (Sim3Prob *)(h + o_probs);
+  for (int i = 0; i < nprob; i++) {
+    const size_t n = p[i].n_points;
+    memcpy(h + o1[i], p[i].pts1, 12 * n);
+    memcpy(h + o2[i], p[i].pts2, 12 * n);
+    Sim3Prob &P = hp[i];
+    P.n = p[i].n_points;
+    P.p1 = (const float *)(d_in + o1[i]); P.p2 = (const float *)(d_in + o2[i]);
+    for (int k = 0; k < 4; k++) P.init.q[k] = p[i].rot[k];
+    for (int k = 0; k < 3; k++) P.init.t[k] = p[i].trans[k];
+    P.init.s = p[i].scale;
+    P.chi = p[i].chi; P.huber = p[i].huber; P.max_iterations = p[i].max_iterations;
+    P.out = (double *)(d_out + oo[i]);
+  }
+  DS_CUDA_TRY(cudaMemcpyAsync(d_in, h, in.total, cudaMemcpyHostToDevice, ctx->stream));
+  DS_CUDA_TRY(cudaEventRecord(ctx->e0, ctx->stream));
+  const int grid = nprob < ctx->sm_count * 4 ? nprob : ctx->sm_count * 4;
+  sim3_register_kernel<<<grid, SIM3_THREADS, 0, ctx->stream>>>((const Sim3Prob *)(d_in + o_probs), nprob);
+  DS_CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  DS_CUDA_TRY(cudaEventRecord(ctx->e1, ctx->stream));
+  DS_CUDA_TRY(cudaMemcpyAsync(h, d_out, outp.total, cudaMemcpyDeviceToHost, ctx->stream));
+  DS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ctx->e0, ctx->e1);
+  g_last_kernel_ms = ms;
+  for (int i = 0; i < nprob; i++) {
+    const double *o = (const double *)(h + oo[i]);
+    for (int k = 0; k < 4; k++) out[i].rot[k] = o[k];
+    for (int k = 0; k < 3; k++) out[i].trans[k] = o[4 + k];
+    out[i].scale = o[7]; out[i].chi2 = o[8];
+    out[i].inliers = (int)o[9]; out[i].acceptable = (int)o[10];
+    out[i].iterations[0] = (int)o[11]; out[i].iterations[1] = (int)o[12];
+  }
+  return DEFSLAM_OK;
+}
+
+int defslam_scale_min_median(int32_t n, const float *mono_xyz, const float *stereo_xyz, uint64_t seed,
+                             float *scale_out) {
+  if (n <= 0 || !mono_xyz || !stereo_xyz || !scale_out) return DEFSLAM_EBADARG;
+  DevCtx *ctx = get_ctx(-1);
+  if (!ctx) return DEFSLAM_ECUDA;
+  if ((size_t)n * 4 > (size_t)ctx->smem_optin - 1024) return DEFSLAM_ETOOLARGE;
+  Packer in, outp;
+  const size_t om = in.add(12 * (size_t)n), os = in.add(12 * (size_t)n), oo = outp.add(16);
+  Scratch &S = tl_scratch(ctx->device);
+  int rc;
+  if ((rc = S.host.ensure(in.total > outp.total ? in.total : outp.total)) || (rc = S.dev.ensure(in.total + outp.total)))
+    return rc;
+  uint8_t *h = (uint8_t *)S.host.p, *d_in = (uint8_t *)S.dev.p, *d_out = d_in + in.total;
+  memcpy(h + om, mono_xyz, 12 * (size_t)n);
+  memcpy(h + os, stereo_xyz, 12 * (size_t)n);
+  DS_CUDA_TRY(cudaMemcpyAsync(d_in, h, in.total, cudaMemcpyHostToDevice, ctx->stream));
+  const size_t smem = 4 * (size_t)n;
+  if (smem > 48 * 1024)
+    DS_CUDA_TRY(cudaFuncSetAttribute(scale_min_median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  scale_min_median_kernel<<<1, 512, smem, ctx->stream>>>(n, (const float *)(d_in + om), (const float *)(d_in + os), seed,
+                                                         (float *)(d_out + oo));
+  DS_CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  DS_CUDA_TRY(cudaMemcpyAsync(h, d_out, outp.total, cudaMemcpyDeviceToHost, ctx->stream));
+  DS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  *scale_out = *(const float *)(h + oo);
   return DEFSLAM_OK;
 }
 

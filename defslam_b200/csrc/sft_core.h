@@ -1095,41 +1095,59 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
       if (n0 < 0) n0 = 0;
       const int nshared = ntiles - n0; /* tiles 1..nshared-1 go round-robin to warps 1.. */
       const int t_first = warp == 0 ? 0 : warp, t_step = nwarp > 1 ? nwarp - 1 : 1;
+      /* two tiles in flight per warp: both products are issued before either write-back, so
+       * the shared-memory and DMMA latencies of one tile hide behind the other */
       for (int t = t_first; t < ntiles;) {
-        const TileDesc td = tiles[t];
+        TileDesc td[2];
+        bool live[2];
         const int t_cur = t;
+        td[0] = tiles[t];
         if (warp == 0) t = (t == 0) ? nshared : t + 1;
         else { t += t_step; if (t >= nshared) t = ntiles; }
-        bool skip = td.kind <= 2 ? td.rA >= n_trail : (td.kind == 3 && td.rB >= n_trail);
-        skip = skip || (td.kind <= 2 && td.rB >= n_trail);
-        if (!skip) {
-          DS_WARP_FOR(T, 32) {
-            const int g = T >> 2, q = T & 3;
-            double d0, d1;
-            tile_mul_pp(T, P, HS, td.rA, td.rB, d0, d1);
-            if (td.kind <= 2) {
+        const bool second = t < ntiles && !(t_cur == 0 && warp == 0); /* S1 follows tile 0 at once */
+        td[1] = second ? tiles[t] : td[0];
+        if (second) {
+          if (warp == 0) t = t + 1;
+          else { t += t_step; if (t >= nshared) t = ntiles; }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          bool skip = td[u].kind <= 2 ? td[u].rA >= n_trail : (td[u].kind == 3 && td[u].rB >= n_trail);
+          skip = skip || (td[u].kind <= 2 && td[u].rB >= n_trail);
+          live[u] = !skip && (u == 0 || second);
+        }
+        DS_WARP_FOR(T, 32) {
+          const int g = T >> 2, q = T & 3;
+          double d0[2], d1[2];
+#pragma unroll
+          for (int u = 0; u < 2; u++)
+            if (live[u]) tile_mul_pp(T, P, HS, td[u].rA, td[u].rB, d0[u], d1[u]);
+#pragma unroll
+          for (int u = 0; u < 2; u++) {
+            if (!live[u]) continue;
+            if (td[u].kind <= 2) {
               /* entry (i, j): i = k+8+rA+g, j = k+8+rB+2q(+1); band offset j-i+bwE */
-              int s0 = kslot + NB + td.rA;
+              int s0 = kslot + NB + td[u].rA;
               if (s0 >= Wr) s0 -= Wr;
-              const int off = td.dcol + 2 * q - g + bwE;
+              const int off = td[u].dcol + 2 * q - g + bwE;
               double *dst = W + (s0 + g) * ld + off;
-              if (td.kind == 1) {
-                sub_pair(dst, d0, d1);
+              if (td[u].kind == 1) {
+                sub_pair(dst, d0[u], d1[u]);
               } else {
                 const bool v0 = off <= bwE && off >= lo, v1 = off + 1 <= bwE && off + 1 >= lo;
-                if (v0 && v1) sub_pair(dst, d0, d1);
+                if (v0 && v1) sub_pair(dst, d0[u], d1[u]);
                 else {
-                  if (v0) dst[0] -= d0;
-                  if (v1) dst[1] -= d1;
+                  if (v0) dst[0] -= d0[u];
+                  if (v1) dst[1] -= d1[u];
                 }
               }
-            } else if (td.kind == 3) {
-              const int eo = g * ES + k + NB + td.rB + 2 * q;
-              if (e_smem) sub_pair(Es + eo, d0, d1);
-              else sub_pair(Eg + eo, d0, d1);
+            } else if (td[u].kind == 3) {
+              const int eo = g * ES + k + NB + td[u].rB + 2 * q;
+              if (e_smem) sub_pair(Es + eo, d0[u], d1[u]);
+              else sub_pair(Eg + eo, d0[u], d1[u]);
             } else {
-              if (2 * q <= g) G[g * 8 + 2 * q] -= d0;
-              if (2 * q + 1 <= g) G[g * 8 + 2 * q + 1] -= d1;
+              if (2 * q <= g) G[g * 8 + 2 * q] -= d0[u];
+              if (2 * q + 1 <= g) G[g * 8 + 2 * q + 1] -= d1[u];
             }
           }
         }

@@ -194,6 +194,33 @@ class SfnCase:
         return p
 
 
+# ----------------------------------------------------------------------------- Sim(3) ---
+@dataclass
+class Sim3Case:
+    pts1: np.ndarray  # f32 [n,3] surface points (world frame)
+    pts2: np.ndarray  # f32 [n,3] stored map-point positions
+    scale: float = 1.0
+    rot: tuple = (0.0, 0.0, 0.0, 1.0)
+    trans: tuple = (0.0, 0.0, 0.0)
+    chi: float = 0.07 ** 2
+    huber: float = 0.01
+    max_iterations: int = 50
+
+    def __post_init__(self):
+        self.pts1 = np.ascontiguousarray(self.pts1, dtype=np.float32)
+        self.pts2 = np.ascontiguousarray(self.pts2, dtype=np.float32)
+
+    def problem(self) -> _capi.Sim3Problem:
+        p = _capi.Sim3Problem()
+        p.n_points = len(self.pts1)
+        p.pts1 = _capi.as_ptr(self.pts1, C.c_float)
+        p.pts2 = _capi.as_ptr(self.pts2, C.c_float)
+        p.rot = (C.c_double * 4)(*self.rot)
+        p.trans = (C.c_double * 3)(*self.trans)
+        p.scale, p.chi, p.huber, p.max_iterations = self.scale, self.chi, self.huber, self.max_iterations
+        return p
+
+
 # ----------------------------------------------------------------------------- API ------
 class Api:
     """The NRSfM entry points of one library under one symbol prefix."""
@@ -204,7 +231,8 @@ class Api:
         if prefix != "defslam_":
             P = _capi.PROTOTYPES
             for name in ("schwarp_fit", "schwarp_evaluate", "normals_batched", "polysolver_coefficients",
-                         "sfn_solve", "sfn_system", "schwarp_fit_batched", "sfn_solve_batched"):
+                         "sfn_solve", "sfn_system", "schwarp_fit_batched", "sfn_solve_batched",
+                         "sim3_register_batched", "scale_min_median"):
                 if hasattr(self.lib, prefix + name):
                     f = getattr(self.lib, prefix + name)
                     f.restype, f.argtypes = P["defslam_" + name]
@@ -326,6 +354,39 @@ class Api:
 
     def sfn_solve_batched(self, cases, device: int = -1):
         return self.sfn_prepare(cases)(device)
+
+
+    # -- Sim(3) registration
+    def sim3_register(self, cases, device: int = -1):
+        n = len(cases)
+        probs = (_capi.Sim3Problem * n)()
+        for i, c in enumerate(cases):
+            probs[i] = c.problem()
+        res = (_capi.Sim3Result * n)()
+        self._check("sim3_register_batched", self._f("sim3_register_batched")(n, probs, res, device))
+        return [dict(rot=np.array(r.rot[:]), trans=np.array(r.trans[:]), scale=r.scale, chi2=r.chi2, inliers=r.inliers,
+                     acceptable=r.acceptable, iterations=tuple(r.iterations[:])) for r in res]
+
+    def scale_min_median(self, mono, stereo, seed: int = 1):
+        mono = np.ascontiguousarray(mono, np.float32)
+        stereo = np.ascontiguousarray(stereo, np.float32)
+        out = C.c_float(0)
+        self._check("scale_min_median", self._f("scale_min_median")(
+            len(mono), _capi.as_ptr(mono, C.c_float), _capi.as_ptr(stereo, C.c_float), C.c_uint64(seed),
+            C.cast(C.byref(out), _capi.c_float_p)))
+        return out.value
+
+
+def sim3_case(seed: int, n: int = 600, noise: float = 0.003, outlier_frac: float = 0.05) -> Sim3Case:
+    """surface cloud vs map cloud related by a similarity close to identity (what NRSfM registers)"""
+    rng = np.random.default_rng(seed)
+    P = np.stack([rng.uniform(-0.8, 0.8, n), rng.uniform(-0.6, 0.6, n), rng.uniform(0.8, 1.3, n)], 1)
+    R = _rot(rng.normal(size=3), np.deg2rad(rng.uniform(1, 5)))
+    s, t = rng.uniform(0.7, 1.4), rng.normal(size=3) * 0.05
+    Q = s * (R @ P.T).T + t + rng.normal(size=P.shape) * noise
+    bad = rng.uniform(size=n) < outlier_frac
+    Q[bad] += rng.normal(size=(int(bad.sum()), 3)) * 0.3
+    return Sim3Case(pts1=P.astype(np.float32), pts2=Q.astype(np.float32), scale=float(s * rng.uniform(0.9, 1.1)))
 
 
 # ----------------------------------------------------------------------------- synthetic

@@ -364,6 +364,50 @@ int defslam_sfn_solve_batched(int32_t nprob, const defslam_sfn_problem *p, int32
 /* The stacked system itself (parity hook): A [(2n+NC+1) * NC] row-major, b [2n+NC+1] */
 int defslam_sfn_system(const defslam_sfn_problem *p, double *A, double *b);
 
+/* Sim(3) surface registration (last stage of DefLocalMapping::NRSfM).
+ * replaces: Optimizer::OptimizeHorn          Modules/Tracking/DefOptimizer.cc:840-922
+ *           EdgeSim3Simple / VertexSim3ExpmapNoProj
+ *                                            Thirdparty/g2o/g2o/types/types_seven_dof_expmap.h:96-188
+ *           Sim3(update) / map / operator*   Thirdparty/g2o/g2o/types/sim3.h:70-160,270-277
+ *           called from SurfaceRegistration::registerSurfaces
+ *                                            Modules/Mapping/SurfaceRegistration.cc:48-153
+ * Two runs of g2o's Levenberg-Marquardt (<= max_iterations each) over the 7-dof vertex with one
+ * Huber edge e = p2 - S.map(p1) per point.  The reference differentiates numerically (central
+ * differences, delta 1e-9, base_unary_edge.hpp:82-118); the kernel uses the analytic Jacobian those
+ * differences approximate. */
+typedef struct defslam_sim3_problem {
+  int32_t n_points;
+  const float *pts1;      /* [n*3] cloud moved by the transform (surface points, world frame) */
+  const float *pts2;      /* [n*3] target cloud (stored map-point positions)                  */
+  double rot[4];          /* initial Sim3: unit quaternion x,y,z,w                            */
+  double trans[3];
+  double scale;           /* GroundTruthTools::scaleMinMedian                                 */
+  double chi;             /* chiLimit^2                                                       */
+  double huber;           /* 0.01; the kernel width is sqrt(huber)                            */
+  int32_t max_iterations; /* 50                                                               */
+} defslam_sim3_problem;
+
+typedef struct defslam_sim3_result {
+  double rot[4], trans[3], scale; /* estimate after the FIRST run: what the reference copies
+                                     back into g2oS12 (DefOptimizer.cc:896)                   */
+  double chi2;                    /* optimizer.chi2() after the second run                    */
+  int32_t inliers;                /* edges with chi2 <= chi after the first run               */
+  int32_t acceptable;             /* chi2 finite and chi2 / inliers < chi                     */
+  int32_t iterations[2];
+} defslam_sim3_result;
+
+int defslam_sim3_register_batched(int32_t nprob, const defslam_sim3_problem *p, defslam_sim3_result *out,
+                                  int32_t device);
+
+/* Min-median scale between two clouds.
+ * replaces: GroundTruthTools::scaleMinMedian  Modules/GroundTruth/GroundTruthCalculator.cc:54-159
+ * The reference subsamples candidates and residuals with unseeded rand() (quirk C10); here the
+ * same 25 % Bernoulli draws come from a counter-based hash of (seed, i, j), so the result is
+ * reproducible.  Returns the scale in *scale_out (0 when a candidate has no sampled residual,
+ * like the reference). */
+int defslam_scale_min_median(int32_t n, const float *mono_xyz, const float *stereo_xyz, uint64_t seed,
+                             float *scale_out);
+
 /* Surface -> template nodes.
  * replaces: Surface::getVertex  Modules/Mapping/Surface.cc:125-161
  * nodes_out: [xs*ys*3] fp32 (u d, v d, d), x-major outer loop */

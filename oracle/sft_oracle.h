@@ -47,6 +47,11 @@ int oracle_normals_batched(const defslam_normals_problem *p, double *k_out, doub
 int oracle_sfn_system(const defslam_sfn_problem *p, double *A, double *b);
 int oracle_sfn_solve(const defslam_sfn_problem *p);
 
+/* ---- Sim(3) surface registration (sim3_oracle.c) ---- */
+int oracle_sim3_register_batched(int32_t nprob, const defslam_sim3_problem *p, defslam_sim3_result *out, int32_t dev);
+int oracle_sim3_jacobian(const defslam_sim3_problem *p, int i, double *J21);
+int oracle_scale_min_median(int32_t n, const float *mono, const float *stereo, uint64_t seed, float *scale_out);
+
 #ifdef __cplusplus
 }
 #endif

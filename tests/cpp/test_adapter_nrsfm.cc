@@ -18,7 +18,9 @@ struct Vec3f { float v[3] = {0, 0, 0}; float &operator()(int i) { return v[i]; }
 struct KeyPoint { struct { float x, y; } pt; int octave = 0; };
 struct BbsT { double umin, umax; int nptsu; double vmin, vmax; int nptsv; int valdim; };
 struct Surface {
-  std::vector<Vec3f> normals, pts; std::vector<bool> has; std::vector<double> ctrl; bool saved = false;
+  std::vector<Vec3f> normals, pts; std::vector<bool> has; std::vector<double> ctrl; bool saved = false; double applied = 0;
+  void get3DSurfacePoint(size_t i, Vec3f &x) { x = pts[i]; }
+  void applyScale(double s) { applied = s; for (auto &p : pts) for (int c = 0; c < 3; c++) p(c) = (float)(p(c) * s); }
   explicit Surface(size_t n) : normals(n), pts(n), has(n, false) {}
   bool getNormalSurfacePoint(size_t i, Vec3f &N) { if (!has[i]) return false; N = normals[i]; return true; }
   void setNormalSurfacePoint(size_t i, Vec3f &N) { normals[i] = N; has[i] = true; }
@@ -28,13 +30,18 @@ struct Surface {
 struct KeyFrame;
 struct MapPoint {
   bool bad = false; KeyFrame *ref = nullptr; std::map<KeyFrame *, size_t> obs; double covNorm[4] = {0, 0, 0, 0};
+  float kfpos[3] = {0, 0, 0}; bool facet = true;
+  bool getFacet() const { return facet; }
+  bool getPositionInKeyframe(KeyFrame *, float *o) { memcpy(o, kfpos, sizeof(kfpos)); return true; }
   bool isBad() const { return bad; }
   KeyFrame *GetReferenceKeyFrame() { return ref; }
   size_t GetIndexInKeyFrame(KeyFrame *k) { return obs[k]; }
   void EraseObservation(KeyFrame *k) { obs.erase(k); }
 };
 struct KeyFrame {
-  std::vector<KeyPoint> mvKeysUn; std::vector<MapPoint *> mps;
+  std::vector<KeyPoint> mvKeysUn; std::vector<MapPoint *> mps; float Twc[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}, Tcw[16];
+  void getPoseInverseRowMajor(float *o) const { memcpy(o, Twc, sizeof(Twc)); }
+  void SetPoseRowMajor(const float *i) { memcpy(Tcw, i, sizeof(Tcw)); }
   MapPoint *GetMapPoint(size_t i) { return mps[i]; }
   void EraseMapPointMatch(size_t i) { mps[i] = nullptr; }
   virtual ~KeyFrame() {}
@@ -106,7 +113,8 @@ int main() {
   if (defslam_device_count() <= 0) {
     const bool untouched = rc != 0 && db.empty() && fresh.empty() && x == x0;
     const int rc2 = defslam_b200::ObtainK1K2<DefKeyFrame, KeyFrame, MapPoint, DiffProp, Vec3f>(db, fresh);
-    const bool ok3 = !defslam_b200::estimateSurface<DefKeyFrame, KeyFrame, Vec3f, BbsT>((KeyFrame *)&kf1, 0.7) && !s1.saved;
+    const bool ok3 = !defslam_b200::estimateSurface<DefKeyFrame, KeyFrame, Vec3f, BbsT>((KeyFrame *)&kf1, 0.7) && !s1.saved &&
+                     !defslam_b200::registerSurfaces<DefKeyFrame, KeyFrame, MapPoint, Vec3f>((KeyFrame *)&kf1, 0.07, true) && s1.applied == 0;
     printf("no CUDA device: rc=%d rc2=%d state %s\n", rc, rc2, untouched && ok3 ? "untouched" : "MODIFIED");
     return untouched && ok3 ? 0 : 1;
   }
@@ -178,6 +186,12 @@ int main() {
   for (int i = 0; i < N; i++) for (int c = 0; c < 3; c++) ep = std::fmax(ep, std::fabs(oxyz[3 * i + c] - s1.pts[i](c)));
   printf("sfn: max ctrl err %.3e, max point err %.3e\n", ec, ep);
   if (ec > 1e-7 || ep > 1e-5) return 1;
+  // ---- Sim(3) registration: stored map points = 1.3 x the estimated surface, shifted
+  for (int i = 0; i < N; i++) for (int c = 0; c < 3; c++) mps[i].kfpos[c] = 1.3f * s1.pts[i](c) + (c == 2 ? 0.02f : 0.f);
+  const std::vector<Vec3f> before = s1.pts;
+  if (!defslam_b200::registerSurfaces<DefKeyFrame, KeyFrame, MapPoint, Vec3f>((KeyFrame *)&kf1, 0.07, true)) { printf("registerSurfaces failed\n"); return 1; }
+  printf("registration: surface scaled by %.6f, camera moved to (%.4f %.4f %.4f)\n", s1.applied, kf1.Tcw[3], kf1.Tcw[7], kf1.Tcw[11]);
+  if (std::fabs(s1.applied - 1.3) > 1e-3 || std::fabs(kf1.Tcw[11] + 0.02) > 2e-3) return 1;
   printf("nrsfm adapter ok\n");
   return 0;
 }

@@ -9,6 +9,7 @@
 
 #include "../../include/defslam_b200.h"
 #include "../../defslam_b200/csrc/nrsfm_core.h"
+#include "../../defslam_b200/csrc/sim3_core.h"
 
 using namespace ds;
 
@@ -127,6 +128,36 @@ int emu_sfn_system(const defslam_sfn_problem *p, double *A, double *b) {
   team.tid = 0; team.nthr = 1;
   fill_cell_integrals(team, ci);
   for (int row = 0; row < 2 * P.n + NC + 1; row++) sfn_system_row(P, ci, row, A, b);
+  return 0;
+}
+
+int emu_sim3_register_batched(int32_t nprob, const defslam_sim3_problem *p, defslam_sim3_result *out, int32_t) {
+  Team team;
+  team.tid = 0; team.nthr = 1;
+  for (int i = 0; i < nprob; i++) {
+    double o[16] = {0}, red[200];
+    Sim3Prob P;
+    P.n = p[i].n_points; P.p1 = p[i].pts1; P.p2 = p[i].pts2;
+    for (int k = 0; k < 4; k++) P.init.q[k] = p[i].rot[k];
+    for (int k = 0; k < 3; k++) P.init.t[k] = p[i].trans[k];
+    P.init.s = p[i].scale; P.chi = p[i].chi; P.huber = p[i].huber; P.max_iterations = p[i].max_iterations;
+    P.out = o;
+    sim3_register_one(team, P, red);
+    for (int k = 0; k < 4; k++) out[i].rot[k] = o[k];
+    for (int k = 0; k < 3; k++) out[i].trans[k] = o[4 + k];
+    out[i].scale = o[7]; out[i].chi2 = o[8]; out[i].inliers = (int)o[9]; out[i].acceptable = (int)o[10];
+    out[i].iterations[0] = (int)o[11]; out[i].iterations[1] = (int)o[12];
+  }
+  return 0;
+}
+
+int emu_scale_min_median(int32_t n, const float *mono, const float *stereo, uint64_t seed, float *scale_out) {
+  std::vector<float> buf(n + 1);
+  int cnt = 0;
+  double sc[4];
+  Team team;
+  team.tid = 0; team.nthr = 1;
+  scale_min_median_team(team, n, mono, stereo, seed, buf.data(), &cnt, sc, scale_out);
   return 0;
 }
 }

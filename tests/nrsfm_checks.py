@@ -116,3 +116,17 @@ def window_chain(api, orc, seed=1, n_keypoints=400, n_views=3, nptsu=nrsfm.NCU, 
     scase = nrsfm.sfn_case(win, no)
     check_sfn(api, orc, scase)
     return win
+
+
+def check_sim3(api, orc, cases):
+    ro = orc.sim3_register(cases)
+    ra = api.sim3_register(cases)
+    for a, o in zip(ra, ro):
+        # the oracle differentiates numerically (delta 1e-9) like the reference, the kernel analytically:
+        # the first run's trajectory is the same, the estimates agree to the noise of those differences
+        assert a["iterations"][0] == o["iterations"][0]
+        assert np.abs(a["rot"] - o["rot"]).max() < 1e-7 and np.abs(a["trans"] - o["trans"]).max() < 1e-7
+        assert abs(a["scale"] - o["scale"]) < 1e-7 * o["scale"]
+        assert abs(a["chi2"] - o["chi2"]) < 1e-6 * o["chi2"]
+        assert a["inliers"] == o["inliers"] and a["acceptable"] == o["acceptable"]
+    return ra, ro

@@ -63,3 +63,12 @@ def test_normals_mixed_pairs(apis):
     nc2 = copy.copy(nc)
     nc2.corrected_t2 = 1
     ck.check_normals(api, orc, nc2)
+
+
+def test_sim3_registration_and_min_median_scale(apis):
+    api, orc = apis
+    cases = [nrsfm.sim3_case(s) for s in range(3)] + [nrsfm.sim3_case(9, n=40, noise=1e-4, outlier_frac=0.0)]
+    ra, ro = ck.check_sim3(api, orc, cases)
+    assert ro[-1]["acceptable"] == 1 and ro[0]["acceptable"] == 0
+    for c in cases:
+        assert api.scale_min_median(c.pts1, c.pts2, seed=7) == orc.scale_min_median(c.pts1, c.pts2, seed=7)

@@ -126,3 +126,13 @@ def test_sfn_nan_normals_fail_loudly(apis):
     with pytest.raises(nrsfm.DefslamError) as e:
         api.sfn_solve(c)
     assert e.value.rc == -3
+
+
+def test_sim3_registration_and_min_median_scale(apis):
+    api, orc = apis
+    cases = [nrsfm.sim3_case(s, n=1200) for s in range(6)] + [nrsfm.sim3_case(9, n=40, noise=1e-4, outlier_frac=0.0)]
+    ra, ro = ck.check_sim3(api, orc, cases * 30)       # 210 keyframes in one launch
+    assert ro[6]["acceptable"] == 1 and ro[0]["acceptable"] == 0
+    for c in cases[:3]:
+        a, o = api.scale_min_median(c.pts1, c.pts2, seed=7), orc.scale_min_median(c.pts1, c.pts2, seed=7)
+        assert abs(a - o) <= 1e-6 * abs(o)

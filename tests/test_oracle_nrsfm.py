@@ -219,3 +219,52 @@ def test_oracle_reproduces_committed_vectors(orc, win):
     assert np.abs(no.k - g["normals_k"])[ok[:len(no.k)]].max() < 1e-8
     ctrl, xyz = orc.sfn_solve(nrsfm.sfn_case(win, no))
     assert np.abs(ctrl - g["sfn_ctrl"]).max() < 1e-7
+
+
+# --------------------------------------------------------------------------- Sim(3) --------
+def test_sim3_numeric_jacobian_is_the_analytic_one(orc, oracle):
+    """g2o differentiates EdgeSim3Simple numerically (delta 1e-9); the kernel uses the limit
+    [y]x | -I | -y with y = S.map(p1)."""
+    c = nrsfm.sim3_case(1, n=20)
+    q = np.array([0.02, -0.01, 0.03, 1.0]); q /= np.linalg.norm(q)
+    c.rot, c.trans, c.scale = tuple(q), (0.01, -0.02, 0.03), 1.1
+    lib = oracle.load()
+    lib.oracle_sim3_jacobian.restype = C.c_int
+    lib.oracle_sim3_jacobian.argtypes = [C.POINTER(_capi.Sim3Problem), C.c_int, _capi.c_double_p]
+    p = c.problem()
+    x, y, z, w = q
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    for i in range(5):
+        J = np.zeros((3, 7))
+        lib.oracle_sim3_jacobian(C.byref(p), i, _capi.as_ptr(J, C.c_double))
+        yv = c.scale * R @ c.pts1[i].astype(float) + np.array(c.trans)
+        skew = np.array([[0, -yv[2], yv[1]], [yv[2], 0, -yv[0]], [-yv[1], yv[0], 0]])
+        Ja = np.concatenate([skew, -np.eye(3), -yv[:, None]], 1)
+        assert np.abs(J - Ja).max() < 5e-7
+
+
+def test_sim3_recovers_a_noise_free_similarity(orc):
+    rng = np.random.default_rng(4)
+    P = rng.uniform(-0.5, 0.5, (100, 3)) + [0, 0, 1]
+    R = nrsfm._rot([0.3, -0.2, 0.9], 0.04)
+    s, t = 1.23, np.array([0.02, -0.03, 0.05])
+    # values exactly representable in fp32 on both sides keep the residual at rounding level
+    P32 = P.astype(np.float32)
+    Q32 = (s * (R @ P32.astype(float).T).T + t).astype(np.float32)
+    c = nrsfm.Sim3Case(pts1=P32, pts2=Q32, scale=1.0)
+    r = orc.sim3_register([c])[0]
+    assert abs(r["scale"] - s) < 1e-6 and np.abs(r["trans"] - t).max() < 1e-6
+    assert r["acceptable"] == 1 and r["inliers"] == 100
+
+
+def test_min_median_scale_is_robust_and_reproducible(orc):
+    rng = np.random.default_rng(8)
+    mono = rng.uniform(0.5, 1.5, (400, 3)).astype(np.float32)
+    stereo = (1.7 * mono + rng.normal(size=mono.shape) * 0.002).astype(np.float32)
+    stereo[:40] += 1.0                                  # gross outliers
+    s1 = orc.scale_min_median(mono, stereo, seed=3)
+    assert abs(s1 - 1.7) < 5e-3
+    assert s1 == orc.scale_min_median(mono, stereo, seed=3)
+    assert abs(orc.scale_min_median(mono, stereo, seed=4) - 1.7) < 5e-3
