@@ -34,6 +34,30 @@ DS_FN void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uin
                "l"(__cvta_generic_to_global(src_gmem)), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+/* L2 eviction policy for data that is streamed once per use (the H / L bands: 2 x 365 KB per CTA,
+ * far more than the CTAs' share of L2): evict-first keeps the small re-read scratch (per-match and
+ * per-facet sums, border rows, inputs) resident instead */
+DS_FN uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+DS_FN void tma_load_1d_stream(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(__cvta_generic_to_global(src_gmem)), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
+}
+DS_FN void tma_store_1d_stream(void *dst_gmem, const void *src_smem, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(
+                   __cvta_generic_to_global(dst_gmem)),
+               "r"(smem_u32(src_smem)), "r"(bytes), "l"(pol)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+/* plain store with the streaming (evict-first) cache operator */
+DS_FN void st_stream(double *p, double v) { __stcs(p, v); }
 DS_FN void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 /* shared -> global bulk store (bulk async-group completion) */
 DS_FN void tma_store_1d(void *dst_gmem, const void *src_smem, uint32_t bytes) {
@@ -65,6 +89,10 @@ DS_FN void fence_mbar_init() {}
 DS_FN void fence_proxy_async() {}
 DS_FN void mbar_expect_tx(uint64_t *, uint32_t) {}
 DS_FN void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *) { memcpy(dst, src, bytes); }
+DS_FN uint64_t l2_policy_evict_first() { return 0; }
+DS_FN void st_stream(double *p, double v) { *p = v; }
+DS_FN void tma_load_1d_stream(void *dst, const void *src, uint32_t bytes, uint64_t *, uint64_t) { memcpy(dst, src, bytes); }
+DS_FN void tma_store_1d_stream(void *dst, const void *src, uint32_t bytes, uint64_t) { memcpy(dst, src, bytes); }
 DS_FN void mbar_wait(uint64_t *, uint32_t) {}
 DS_FN void fence_proxy_async_smem() {}
 DS_FN void tma_store_1d(void *dst, const void *src, uint32_t bytes) { memcpy(dst, src, bytes); }

@@ -678,7 +678,7 @@ DS_FN_NOINLINE double build_system(const Team team, Ctx &cx) {
       for (int s = 0; s < 3; s++) {
         const int j = 3 * q + s;
         if (j > i) continue;
-        c.ws.Hb[i * ld + (j - i + bwE)] = h[3 * r + s];
+        st_stream(&c.ws.Hb[i * ld + (j - i + bwE)], h[3 * r + s]);
       }
       if (p == q && fp) maxd = fmax(maxd, fabs(h[4 * r]));
     }
@@ -1002,6 +1002,7 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
   team.sync();
   uint64_t *bar0 = &c.mbar[0];
   uint32_t ph0 = c.ph[0];
+  const uint64_t pol = l2_policy_evict_first();
   /* window <- first Wr rows of H; border/rhs working copy (bulk async); corner */
   {
     const int rows = Wr < Dp ? Wr : Dp;
@@ -1009,7 +1010,7 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
       const uint32_t bw_bytes = (uint32_t)(rows * ld * sizeof(double));
       const uint32_t e_bytes = e_smem ? (uint32_t)(8 * ES * sizeof(double)) : 0u;
       mbar_expect_tx(bar0, bw_bytes + e_bytes);
-      tma_load_1d(W, Hb, bw_bytes, bar0);
+      tma_load_1d_stream(W, Hb, bw_bytes, bar0, pol);
       if (e_smem) tma_load_1d(Es, c.ws.Cg, e_bytes, bar0);
     }
     if (!e_smem) {
@@ -1041,7 +1042,7 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
   for (int kb = 0; kb < nblk; kb++) {
     const int k = kb * NB;
     /* finished rows k..k+7 -> L band in global memory (TMA bulk store) */
-    if (team.tid == 0) tma_store_1d(Lb + k * ld, W + kslot * ld, (uint32_t)(NB * ld * sizeof(double)));
+    if (team.tid == 0) tma_store_1d_stream(Lb + k * ld, W + kslot * ld, (uint32_t)(NB * ld * sizeof(double)), pol);
     prof_mark(team, c, PF_S1);
     /* rows requested during the previous step (they enter this step's panel) */
     if (kb > 0 && (k - NB) + Wr < Dp) { mbar_wait(bar0, ph0); ph0 ^= 1u; }
@@ -1077,7 +1078,7 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
       if (k + Wr < Dp) {
         const uint32_t bytes = (uint32_t)(NB * ld * sizeof(double));
         mbar_expect_tx(bar0, bytes);
-        tma_load_1d(W + kslot * ld, Hb + (k + Wr) * ld, bytes, bar0);
+        tma_load_1d_stream(W + kslot * ld, Hb + (k + Wr) * ld, bytes, bar0, pol);
       }
     }
 
@@ -1095,59 +1096,41 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
       if (n0 < 0) n0 = 0;
       const int nshared = ntiles - n0; /* tiles 1..nshared-1 go round-robin to warps 1.. */
       const int t_first = warp == 0 ? 0 : warp, t_step = nwarp > 1 ? nwarp - 1 : 1;
-      /* two tiles in flight per warp: both products are issued before either write-back, so
-       * the shared-memory and DMMA latencies of one tile hide behind the other */
       for (int t = t_first; t < ntiles;) {
-        TileDesc td[2];
-        bool live[2];
+        const TileDesc td = tiles[t];
         const int t_cur = t;
-        td[0] = tiles[t];
         if (warp == 0) t = (t == 0) ? nshared : t + 1;
         else { t += t_step; if (t >= nshared) t = ntiles; }
-        const bool second = t < ntiles && !(t_cur == 0 && warp == 0); /* S1 follows tile 0 at once */
-        td[1] = second ? tiles[t] : td[0];
-        if (second) {
-          if (warp == 0) t = t + 1;
-          else { t += t_step; if (t >= nshared) t = ntiles; }
-        }
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-          bool skip = td[u].kind <= 2 ? td[u].rA >= n_trail : (td[u].kind == 3 && td[u].rB >= n_trail);
-          skip = skip || (td[u].kind <= 2 && td[u].rB >= n_trail);
-          live[u] = !skip && (u == 0 || second);
-        }
-        DS_WARP_FOR(T, 32) {
-          const int g = T >> 2, q = T & 3;
-          double d0[2], d1[2];
-#pragma unroll
-          for (int u = 0; u < 2; u++)
-            if (live[u]) tile_mul_pp(T, P, HS, td[u].rA, td[u].rB, d0[u], d1[u]);
-#pragma unroll
-          for (int u = 0; u < 2; u++) {
-            if (!live[u]) continue;
-            if (td[u].kind <= 2) {
+        bool skip = td.kind <= 2 ? td.rA >= n_trail : (td.kind == 3 && td.rB >= n_trail);
+        skip = skip || (td.kind <= 2 && td.rB >= n_trail);
+        if (!skip) {
+          DS_WARP_FOR(T, 32) {
+            const int g = T >> 2, q = T & 3;
+            double d0, d1;
+            tile_mul_pp(T, P, HS, td.rA, td.rB, d0, d1);
+            if (td.kind <= 2) {
               /* entry (i, j): i = k+8+rA+g, j = k+8+rB+2q(+1); band offset j-i+bwE */
-              int s0 = kslot + NB + td[u].rA;
+              int s0 = kslot + NB + td.rA;
               if (s0 >= Wr) s0 -= Wr;
-              const int off = td[u].dcol + 2 * q - g + bwE;
+              const int off = td.dcol + 2 * q - g + bwE;
               double *dst = W + (s0 + g) * ld + off;
-              if (td[u].kind == 1) {
-                sub_pair(dst, d0[u], d1[u]);
+              if (td.kind == 1) {
+                sub_pair(dst, d0, d1);
               } else {
                 const bool v0 = off <= bwE && off >= lo, v1 = off + 1 <= bwE && off + 1 >= lo;
-                if (v0 && v1) sub_pair(dst, d0[u], d1[u]);
+                if (v0 && v1) sub_pair(dst, d0, d1);
                 else {
-                  if (v0) dst[0] -= d0[u];
-                  if (v1) dst[1] -= d1[u];
+                  if (v0) dst[0] -= d0;
+                  if (v1) dst[1] -= d1;
                 }
               }
-            } else if (td[u].kind == 3) {
-              const int eo = g * ES + k + NB + td[u].rB + 2 * q;
-              if (e_smem) sub_pair(Es + eo, d0[u], d1[u]);
-              else sub_pair(Eg + eo, d0[u], d1[u]);
+            } else if (td.kind == 3) {
+              const int eo = g * ES + k + NB + td.rB + 2 * q;
+              if (e_smem) sub_pair(Es + eo, d0, d1);
+              else sub_pair(Eg + eo, d0, d1);
             } else {
-              if (2 * q <= g) G[g * 8 + 2 * q] -= d0[u];
-              if (2 * q + 1 <= g) G[g * 8 + 2 * q + 1] -= d1[u];
+              if (2 * q <= g) G[g * 8 + 2 * q] -= d0;
+              if (2 * q + 1 <= g) G[g * 8 + 2 * q + 1] -= d1;
             }
           }
         }
@@ -1237,7 +1220,7 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
     for (int j = 0; j < NBUF - 1 && j < nblk; j++) {
       const int kbj = nblk - 1 - j;
       mbar_expect_tx(&c.mbar[1 + (j % NBUF)], row_bytes);
-      tma_load_1d(W + (j % NBUF) * bufsz, Lb + kbj * NB * ld, row_bytes, &c.mbar[1 + (j % NBUF)]);
+      tma_load_1d_stream(W + (j % NBUF) * bufsz, Lb + kbj * NB * ld, row_bytes, &c.mbar[1 + (j % NBUF)], pol);
     }
   }
   prof_mark(team, c, PF_BWD_INIT);
@@ -1251,7 +1234,7 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
       if (jn < nblk) {
         const int kbn = nblk - 1 - jn, bn = jn % NBUF;
         mbar_expect_tx(&c.mbar[1 + bn], row_bytes);
-        tma_load_1d(W + bn * bufsz, Lb + kbn * NB * ld, row_bytes, &c.mbar[1 + bn]);
+        tma_load_1d_stream(W + bn * bufsz, Lb + kbn * NB * ld, row_bytes, &c.mbar[1 + bn], pol);
       }
     }
     const double *LR = W + buf * bufsz;
