@@ -108,6 +108,17 @@ struct defslam_sft_batch {
   int nprob = 0, grid = 0, smem_bytes = 0, mode = MODE_SOLVE;
   size_t ws_stride = 0;
   float last_ms = 0.f;
+  cudaEvent_t k0 = nullptr, k1 = nullptr, done = nullptr, up = nullptr; /* pipelined host path: per-chunk events */
+  int ensure_events() {
+    if (k0) return 0;
+    if (cudaEventCreate(&k0) != cudaSuccess || cudaEventCreate(&k1) != cudaSuccess ||
+        cudaEventCreateWithFlags(&done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&up, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      return DEFSLAM_ECUDA;
+    }
+    return 0;
+  }
   defslam_sft_batch() { h_in.pinned = true; h_out.pinned = true; }
   void drop_temps() {
     for (auto *t : temps) template_free(t);
@@ -121,8 +132,10 @@ struct defslam_sft_batch {
 };
 
 /* marshal + upload; after this the batch is resident on the device */
-static int batch_load(defslam_sft_batch *B, int nprob, const defslam_sft_problem *p, int mode) {
+static int batch_load(defslam_sft_batch *B, int nprob, const defslam_sft_problem *p, int mode,
+                      cudaStream_t copy_stream = nullptr) {
   DevCtx *ctx = B->ctx;
+  if (!copy_stream) copy_stream = ctx->stream;
   B->drop_temps();
   B->nprob = nprob;
   B->mode = mode;
@@ -168,14 +181,15 @@ static int batch_load(defslam_sft_batch *B, int nprob, const defslam_sft_problem
   B->ws_stride = workspace_bytes(z);
   if ((rc = B->d_ws.ensure(B->ws_stride * (size_t)B->grid))) return rc;
 
-  DS_CUDA_TRY(cudaMemcpyAsync(B->d_in.p, B->h_in.p, B->bm.in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  DS_CUDA_TRY(cudaMemcpyAsync(B->d_in.p, B->h_in.p, B->bm.in_bytes, cudaMemcpyHostToDevice, copy_stream));
   DS_CUDA_TRY(cudaMemcpyAsync(B->d_views.p, B->bm.views.data(), sizeof(ProbView) * (size_t)nprob,
-                              cudaMemcpyHostToDevice, ctx->stream));
+                              cudaMemcpyHostToDevice, copy_stream));
   return 0;
 }
 
-static int batch_launch(defslam_sft_batch *B) {
+static int batch_launch(defslam_sft_batch *B, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr) {
   DevCtx *ctx = B->ctx;
+  if (!ev0) { ev0 = ctx->e0; ev1 = ctx->e1; }
   const WorkspaceSizes z = B->bm.ws_sizes();
   long long *prof = nullptr;
   if (getenv("DEFSLAM_PROFILE")) { /* diagnostics: per-phase cycles of CTA 0 */
@@ -189,12 +203,12 @@ static int batch_launch(defslam_sft_batch *B) {
     if (rc) return rc;
     DS_CUDA_TRY(cudaMemsetAsync(B->d_counter.p, 0, sizeof(int), ctx->stream));
   }
-  DS_CUDA_TRY(cudaEventRecord(ctx->e0, ctx->stream));
+  DS_CUDA_TRY(cudaEventRecord(ev0, ctx->stream));
   sft_lm_kernel<<<B->grid, SFT_THREADS, B->smem_bytes, ctx->stream>>>(
       (const ProbView *)B->d_views.p, B->nprob, (uint8_t *)B->d_ws.p, B->ws_stride, z, prof, (int *)B->d_counter.p);
   DS_CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1);
-  DS_CUDA_TRY(cudaEventRecord(ctx->e1, ctx->stream));
+  DS_CUDA_TRY(cudaEventRecord(ev1, ctx->stream));
   return 0;
 }
 
@@ -226,11 +240,63 @@ static int batch_download(defslam_sft_batch *B) {
   return 0;
 }
 
-static defslam_sft_batch *tl_batch(DevCtx *ctx) {
+static defslam_sft_batch *tl_batch(DevCtx *ctx, int which = 0) {
   static thread_local std::map<int, std::unique_ptr<defslam_sft_batch>> tl;
-  auto &b = tl[ctx->device];
+  auto &b = tl[ctx->device * 4 + which];
   if (!b) { b.reset(new defslam_sft_batch); b->ctx = ctx; }
   return b.get();
+}
+
+/* Large host batches are cut into chunks that ping-pong between two batch objects: while the
+ * kernel of chunk c runs on the library's stream, the host marshals chunk c+1 into the other pinned
+ * arena, a copy stream uploads it and brings the results of chunk c-1 back, and the host scatters
+ * them -- only the first marshal+upload and the last download+scatter are exposed. */
+static cudaStream_t tl_copy_stream(DevCtx *ctx, int which) {
+  static thread_local std::map<int, cudaStream_t> tl;
+  const int key = ctx->device * 2 + which;
+  auto it = tl.find(key);
+  if (it != tl.end()) return it->second;
+  cudaStream_t s = nullptr;
+  if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  tl[key] = s;
+  return s;
+}
+static int solve_pipelined(DevCtx *ctx, int nprob, const defslam_sft_problem *p, defslam_sft_result *r, int chunk) {
+  defslam_sft_batch *Bs[2] = {tl_batch(ctx, 1), tl_batch(ctx, 2)};
+  cudaStream_t cs = tl_copy_stream(ctx, 0), cs_down = tl_copy_stream(ctx, 1); /* uploads / downloads */
+  if (!cs || !cs_down) return DEFSLAM_ECUDA;
+  int rc;
+  for (int k = 0; k < 2; k++)
+    if ((rc = Bs[k]->ensure_events())) return rc;
+  const int nchunks = (nprob + chunk - 1) / chunk;
+  int first_err = DEFSLAM_OK;
+  float total_ms = 0.f;
+  auto finish = [&](int c) -> int {
+    defslam_sft_batch *B = Bs[c & 1];
+    DS_CUDA_TRY(cudaEventSynchronize(B->done));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, B->k0, B->k1) == cudaSuccess) total_ms += ms;
+    const int e = B->bm.unpack((const uint8_t *)B->h_out.p, r + (size_t)c * chunk);
+    if (e && first_err == DEFSLAM_OK) first_err = e;
+    B->drop_temps();
+    return 0;
+  };
+  for (int c = 0; c < nchunks; c++) {
+    defslam_sft_batch *B = Bs[c & 1];
+    if (c >= 2 && (rc = finish(c - 2))) return rc;
+    const int off = c * chunk, cnt = nprob - off < chunk ? nprob - off : chunk;
+    if ((rc = batch_load(B, cnt, p + off, MODE_SOLVE, cs))) return rc;
+    DS_CUDA_TRY(cudaEventRecord(B->up, cs));
+    DS_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, B->up, 0));
+    if ((rc = batch_launch(B, B->k0, B->k1))) return rc;
+    DS_CUDA_TRY(cudaStreamWaitEvent(cs_down, B->k1, 0));
+    DS_CUDA_TRY(cudaMemcpyAsync(B->h_out.p, B->d_out.p, B->bm.out_bytes, cudaMemcpyDeviceToHost, cs_down));
+    DS_CUDA_TRY(cudaEventRecord(B->done, cs_down));
+  }
+  for (int c = nchunks >= 2 ? nchunks - 2 : 0; c < nchunks; c++)
+    if ((rc = finish(c))) return rc;
+  g_last_kernel_ms = total_ms;
+  return first_err;
 }
 
 /* ------------------------------------------------------------------ ABI -- */
@@ -266,6 +332,10 @@ int defslam_sft_solve_batched(int32_t nprob, const defslam_sft_problem *p, defsl
   DevCtx *ctx = get_ctx(device);
   if (!ctx) return DEFSLAM_ECUDA;
   if (nprob == 0) return DEFSLAM_OK;
+  {
+    const int chunk = 4 * ctx->sm_count; /* two waves at two CTAs per SM */
+    if (nprob >= 3 * chunk && getenv("DEFSLAM_NO_PIPELINE") == nullptr) return solve_pipelined(ctx, nprob, p, r, chunk);
+  }
   defslam_sft_batch *B = tl_batch(ctx);
   int rc;
   if ((rc = batch_load(B, nprob, p, MODE_SOLVE))) return rc;

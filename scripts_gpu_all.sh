@@ -1,5 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -5
-bash scripts_first_gpu.sh 2>&1 | grep -E "solves/s"
-timeout 600 python tools/nrsfm_timing.py 8 > gpurun_out/nrsfm_timing.log 2>&1; tail -8 gpurun_out/nrsfm_timing.log
+timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -1 gpurun_out/bench_n1.json | cut -c1-2800; tail -5 gpurun_out/bench_n1.err

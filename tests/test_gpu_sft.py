@@ -72,3 +72,19 @@ def test_bad_match_is_rejected(cuda_lib):
     with pytest.raises(sft.DefslamError) as e:
         sft.solve_batched([f])
     assert e.value.rc == -1
+
+
+def test_pipelined_host_path_equals_single_launch(cuda_lib, monkeypatch):
+    """large host batches are cut into chunks that overlap marshalling with the kernel: same results"""
+    tmpl, base = synthetic.make_config_frames("C1", nframes=8)
+    frames = [base[i % 8] for i in range(3 * 4 * 148 + 37)]
+    T = sft.Template(tmpl)
+    piped = sft.solve_batched(frames, template=T)
+    monkeypatch.setenv("DEFSLAM_NO_PIPELINE", "1")
+    single = sft.solve_batched(frames, template=T)
+    for a, b in zip(piped, single):
+        assert a.r.status == 0 and b.r.status == 0
+        assert np.array_equal(a.nodes, b.nodes)
+        assert a.r.lm_trials == b.r.lm_trials and a.r.n_inliers == b.r.n_inliers
+        assert np.array_equal(a.outlier, b.outlier)
+    T.close()
