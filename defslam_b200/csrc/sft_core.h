@@ -161,7 +161,7 @@ SmemLayout smem_layout(int n_nodes, int n_edges, int Dn_pad, int bwp, int ld, in
   L.pose = o; o += 16;   /* pose (7) + backup (7) */
   {
     const int nrow = bwp / NB + 1;
-    L.tiles = o; o += 2 * (nrow * (nrow + 1) / 2); /* one int4 per trailing-update tile */
+    L.tiles = o; o += 2 * (nrow * (nrow + 1) / 2) + 10; /* one int4 per trailing-update tile + per-warp ranges */
   }
   L.flags = o; o += (2 * n_nodes + 7) / 8 + 1;
   L.total = o;
@@ -204,7 +204,18 @@ DS_FN uint8_t *freev_ptr(const Ctx &c) { return (uint8_t *)(sm_base() + c.sl.fla
 
 /* phase-cycle accounting (diagnostics; enabled by DEFSLAM_PROFILE=1 on the host side) */
 enum { PF_PROLOGUE = 0, PF_EVAL_STORE, PF_BUILD, PF_FS_INIT, PF_S1, PF_S1_WAIT, PF_S2, PF_S3, PF_SCHUR, PF_BWD_INIT,
-       PF_BWD, PF_UPDATE, PF_EVAL_TRIAL, PF_LM_SCALAR, PF_FINALIZE, PF_COUNT };
+       PF_BWD, PF_UPDATE, PF_EVAL_TRIAL, PF_LM_SCALAR, PF_FINALIZE, PF_COUNT,
+       /* extras (not part of the total): busy cycles of each warp inside S3, look-ahead factor, steps */
+       PF_X_WARP = PF_COUNT, PF_X_DIAG = PF_COUNT + 16, PF_X_STEPS, PF_X_S2W, PF_TOTAL = PF_X_S2W + 16 };
+#if DS_CUDA && defined(DS_PROFILE)
+#define DS_PROF_T0(var) const long long var = clock64()
+#define DS_PROF_ADD(idx, t0, cond) do { if (ctx_ref().prof != nullptr && (cond)) ctx_ref().prof[idx] += clock64() - (t0); } while (0)
+#define DS_PROF_INC(idx, cond) do { if (ctx_ref().prof != nullptr && (cond)) ctx_ref().prof[idx] += 1; } while (0)
+#else
+#define DS_PROF_T0(var) do {} while (0)
+#define DS_PROF_ADD(idx, t0, cond) do {} while (0)
+#define DS_PROF_INC(idx, cond) do {} while (0)
+#endif
 DS_FN void prof_mark(const Team team, Ctx &cx, int idx) {
   Ctx &c = ctx_ref();
   (void)cx;
@@ -885,13 +896,13 @@ DS_FN void tile_mul_pp(int lane, const double *P, int HS, int rA, int rB, double
   dmma884(d0, d1, P[(rA + g) * 4 + q], P[(rB + g) * 4 + q]);
   dmma884(d0, d1, P[HS + (rA + g) * 4 + q], P[HS + (rB + g) * 4 + q]);
 #else
-  double s0 = 0.0, s1 = 0.0;
+  double s0[2] = {0.0, 0.0}, s1[2] = {0.0, 0.0}; /* k = 0..3 and k = 4..7 summed separately, like the kernel */
   for (int cc = 0; cc < NB; cc++) {
     const double a = P[pidx(cc, rA + g, HS)];
-    s0 += a * P[pidx(cc, rB + 2 * q, HS)];
-    s1 += a * P[pidx(cc, rB + 2 * q + 1, HS)];
+    s0[cc >> 2] += a * P[pidx(cc, rB + 2 * q, HS)];
+    s1[cc >> 2] += a * P[pidx(cc, rB + 2 * q + 1, HS)];
   }
-  d0 = s0; d1 = s1;
+  d0 = s0[0] + s0[1]; d1 = s1[0] + s1[1];
 #endif
 }
 
@@ -944,31 +955,134 @@ DS_FN void sub_pair(double *dst, double d0, double d1) {
   *p2 = cv;
 }
 
-/* One trailing-update tile: panel rows of its two operands and where it lands. */
+/* One trailing-update tile, in the form the inner loop consumes it. */
 struct alignas(16) TileDesc {
-  int rA, rB;   /* first panel row of the A / B operand (multiples of 8; bwp = border rows) */
+  int pa, pb;   /* 32 * first panel row of the A / B operand = its byte offset into P (rows are
+                   multiples of 8, the border rows start at bwp) */
   int kind;     /* 1 window tile, all 64 entries inside the band and below the diagonal;
                    2 window tile that needs per-entry checks; 3 border-row tile; 4 corner */
-  int dcol;     /* rB - rA */
+  int doff;     /* 8 * (kinds 1-2: rB - rA + bwE, the band offset of the tile's first column in its first
+                   row; kind 3: NB + rB, the column of the border rows relative to k) = byte offset */
 };
 
-/* Tiles in the order the warps consume them (row-major over the lower triangle of
- * tile rows, the border tile row last); built once per problem. */
-DS_FN void build_tile_table(const Team team, TileDesc *tt, int nt8, int bwp, int bw) {
+/* cost of the look-ahead diagonal factorisation in units of one trailing-update tile (measured:
+ * ~2.8 k cycles against ~320 per tile with two resident CTAs) */
+constexpr int LOOKAHEAD_TILES = 9;
+
+/* Tiles in row-major order over the lower triangle of tile rows, the border tile row last; built
+ * once per problem.  Warp w > 0 owns the contiguous range [wstart[w], wstart[w+1]) of tiles
+ * 1..nshared-1 (consecutive tiles of a tile row share their A operand); warp 0 owns tile 0 -- the
+ * next diagonal block, which it then factors (look-ahead) -- and the n0 tiles
+ * [nshared, ntiles) so that all warps finish together.  wstart[nwarp] = nshared. */
+DS_FN void build_tile_table(const Team team, TileDesc *tt, int *wstart, int nwarp, int nt8, int bwp, int bw, int bwE) {
   const int nrow = nt8 + 1, ntiles = nrow * (nrow + 1) / 2;
   DS_FOR(t, ntiles) {
     int ti = 0, tj = t;
     while (tj > ti) { tj -= ti + 1; ti++; }
     const bool erow = ti == nt8, ecol = tj == nt8;
+    const int rA = erow ? bwp : ti * NB, rB = ecol ? bwp : tj * NB;
     TileDesc d;
-    d.rA = erow ? bwp : ti * NB;
-    d.rB = ecol ? bwp : tj * NB;
-    d.dcol = d.rB - d.rA;
-    if (erow) d.kind = ecol ? 4 : 3;
-    else d.kind = (ti > tj && NB * (ti - tj) + (NB - 1) <= bw) ? 1 : 2;
+    d.pa = 32 * rA;
+    d.pb = 32 * rB;
+    if (erow) { d.kind = ecol ? 4 : 3; d.doff = 8 * (NB + rB); }
+    else { d.kind = (ti > tj && NB * (ti - tj) + (NB - 1) <= bw) ? 1 : 2; d.doff = 8 * (rB - rA + bwE); }
     tt[t] = d;
   }
+  int n0 = ((ntiles - 1) - LOOKAHEAD_TILES * (nwarp - 1)) / nwarp;
+  if (n0 < 0) n0 = 0;
+  const int nshared = ntiles - n0, cnt = nshared - 1;
+  DS_FOR(w, nwarp + 1) {
+    if (w == 0) wstart[0] = nshared;
+    else wstart[w] = nwarp > 1 ? 1 + ((w - 1) * cnt) / (nwarp - 1) : nshared;
+  }
 }
+
+#if DS_CUDA
+/* C -= X for the 8x8 product a trailing-update tile produced (d0, d1 = this lane's pair) */
+DS_FN void s3_store(const TileDesc td, double d0, double d1, double *W, double *Eb, double *G, int ks8, int k, int Wr,
+                    int ld, int ES, int bwE, int lo, int g, int q) {
+  if (td.kind <= 2) {
+    /* entry (i, j): i = k+8+rA+g, j = k+8+rB+2q(+1); band offset j-i+bwE */
+    int s0 = ks8 + (td.pa >> 5);
+    if (s0 >= Wr) s0 -= Wr;
+    const int off = (td.doff >> 3) + 2 * q - g;
+    double *dst = W + (s0 + g) * ld + off;
+    if (td.kind == 1) {
+      sub_pair(dst, d0, d1);
+    } else {
+      const bool v0 = off <= bwE && off >= lo, v1 = off + 1 <= bwE && off + 1 >= lo;
+      if (v0 && v1) sub_pair(dst, d0, d1);
+      else {
+        if (v0) dst[0] -= d0;
+        if (v1) dst[1] -= d1;
+      }
+    }
+  } else if (td.kind == 3) {
+    sub_pair(Eb + g * ES + k + (td.doff >> 3) + 2 * q, d0, d1);
+  } else {
+    if (2 * q <= g) G[g * 8 + 2 * q] -= d0;
+    if (2 * q + 1 <= g) G[g * 8 + 2 * q + 1] -= d1;
+  }
+}
+
+/* tiles [beg, end) of the table, two at a time: the operand loads, the loads of the two
+ * destination pairs and the four DMMAs of a pair of tiles are independent, and consecutive tiles
+ * of a tile row reuse the A fragments.  All shared-memory traffic of the common case (kind 1)
+ * goes through 32-bit shared addresses.  CHECK: steps near the end of the matrix, where the
+ * tiles of rows beyond it are skipped. */
+template <bool CHECK>
+DS_FN void s3_range(const TileDesc *tt, int beg, int end, const double *P, int HS, double *W, double *Eb, double *G,
+                    int ks8, int k, int Wr, int ld, int ES, int bwE, int lo, int n_trail, int lane) {
+  const int g = lane >> 2, q = lane & 3;
+  const uint32_t tt_s = smem_u32(tt);
+  const uint32_t Plo = smem_u32(P) + 8u * (uint32_t)(g * 4 + q), Phi = Plo + 8u * (uint32_t)HS;
+  const uint32_t Wl = smem_u32(W) + 8u * (uint32_t)(g * ld + 2 * q - g); /* lane's pair in row g of a tile */
+  const uint32_t ldb = 8u * (uint32_t)ld;
+  const int nt4 = 32 * n_trail;
+  for (int i = beg; i < end; i += 2) {
+    const bool two = i + 1 < end;
+    const int4 u0 = lds_v4s32(tt_s + 16u * (uint32_t)i), u1 = lds_v4s32(tt_s + 16u * (uint32_t)(two ? i + 1 : i));
+    bool do0 = true, do1 = two;
+    if (CHECK) {
+      do0 = u0.z == 4 || (u0.y < nt4 && (u0.z == 3 || u0.x < nt4));
+      do1 = two && (u1.z == 4 || (u1.y < nt4 && (u1.z == 3 || u1.x < nt4)));
+      if (!do0 && !do1) continue;
+    }
+    const double a0l = lds_f64(Plo + u0.x), a0h = lds_f64(Phi + u0.x);
+    const double b0l = lds_f64(Plo + u0.y), b0h = lds_f64(Phi + u0.y);
+    double a1l = a0l, a1h = a0h;
+    if (u1.x != u0.x) { a1l = lds_f64(Plo + u1.x); a1h = lds_f64(Phi + u1.x); }
+    const double b1l = lds_f64(Plo + u1.y), b1h = lds_f64(Phi + u1.y);
+    /* destination of a window tile: row slot of its first row in the ring, band offset doff */
+    int s0 = ks8 + (u0.x >> 5), s1 = ks8 + (u1.x >> 5);
+    if (s0 >= Wr) s0 -= Wr;
+    if (s1 >= Wr) s1 -= Wr;
+    const uint32_t d0 = Wl + ldb * (uint32_t)s0 + (uint32_t)u0.w, d1 = Wl + ldb * (uint32_t)s1 + (uint32_t)u1.w;
+    const bool f0 = do0 && u0.z == 1, f1 = do1 && u1.z == 1;
+    dbl2 v0 = {0.0, 0.0}, v1 = {0.0, 0.0};
+    if (f0) v0 = lds_v2f64(d0);
+    if (f1) v1 = lds_v2f64(d1);
+    /* four independent DMMAs (k = 0..3 and k = 4..7 of each tile), summed afterwards: no
+     * accumulator dependency between tensor-core instructions */
+    double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0, e00 = 0.0, e01 = 0.0, e10 = 0.0, e11 = 0.0;
+    dmma884(c00, c01, a0l, b0l);
+    dmma884(c10, c11, a1l, b1l);
+    dmma884(e00, e01, a0h, b0h);
+    dmma884(e10, e11, a1h, b1h);
+    c00 += e00; c01 += e01; c10 += e10; c11 += e11;
+    if (f0) sts_v2f64(d0, v0.x - c00, v0.y - c01);
+    else if (do0) {
+      TileDesc td; td.pa = u0.x; td.pb = u0.y; td.kind = u0.z; td.doff = u0.w;
+      s3_store(td, c00, c01, W, Eb, G, ks8, k, Wr, ld, ES, bwE, lo, g, q);
+    }
+    if (f1) sts_v2f64(d1, v1.x - c10, v1.y - c11);
+    else if (do1) {
+      TileDesc td; td.pa = u1.x; td.pb = u1.y; td.kind = u1.z; td.doff = u1.w;
+      s3_store(td, c10, c11, W, Eb, G, ks8, k, Wr, ld, ES, bwE, lo, g, q);
+    }
+  }
+}
+#endif
 
 /* Solve (H + lambda I) dx = b.  dx -> sm[sl.dx] (nodes, then camera at Dn_pad).
  * Returns false if a pivot is not positive (LinearSolverDense::solve returning
@@ -990,6 +1104,7 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
   int *flag = (int *)(sm + c.sl.red + 36);
   const int nt8 = bwp / NB;
   const TileDesc *tiles = (const TileDesc *)(sm + c.sl.tiles);
+  const int *wstart = (const int *)(tiles + (nt8 + 1) * (nt8 + 2) / 2);
 #if DS_CUDA
   const int warp = team.tid >> 5, nwarp = team.nthr >> 5, lane = team.tid & 31;
 #else
@@ -1052,6 +1167,7 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
      * tile per warp: X = A inv(L_kk)^T on the tensor cores */
     const int n_trail = (Dp - (k + NB)) < bwp ? (Dp - (k + NB)) : bwp;
     const int nrt = n_trail / NB; /* trailing row tiles that exist */
+    DS_PROF_T0(s2t0);
     for (int rt = warp; rt <= nt8; rt += nwarp) {
       const bool erow = rt == nt8;
       if (!erow && rt >= nrt) continue; /* rows beyond the matrix: never read by S3 */
@@ -1069,6 +1185,7 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
         panel_tile(team, Eg + k, ES, bwE, 0, bwE - bw, invL, P, HS, r0);
       }
     }
+    DS_PROF_ADD(PF_X_S2W + warp, s2t0, (team.tid & 31) == 0);
     team.sync();
     prof_mark(team, c, PF_S2);
     /* the bulk store of rows k..k+7 (issued after S1) has read its source by now:
@@ -1082,50 +1199,57 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
       }
     }
 
-    /* S3: trailing update C -= P_I P_J^T on 8x8 tiles (FP64 tensor cores), tiles
-     * dealt round-robin to the warps from the per-problem tile table */
+    /* S3: trailing update C -= P_I P_J^T on 8x8 tiles (FP64 tensor cores).  Look-ahead: tile 0 is
+     * the next diagonal block and the only tile that touches rows k+8..k+15; warp 0 updates it
+     * first and factors it (S1 of step kb+1) while the other warps work through their ranges. */
     {
       const int nrow = nt8 + 1;
       const int ntiles = nrow * (nrow + 1) / 2;
       const int lo = bwE - bw;
-      /* Look-ahead: tile 0 is the next diagonal block and the only tile that touches rows
-       * k+8..k+15.  Warp 0 updates it first and factors it (S1 of step kb+1, worth ~5 tiles)
-       * while the other warps work through the remaining tiles; warp 0 then takes n0 tiles
-       * from the tail so that all warps finish together. */
-      int n0 = (10 * (ntiles - 1) - 54 * (nwarp - 1)) / (10 * nwarp);
-      if (n0 < 0) n0 = 0;
-      const int nshared = ntiles - n0; /* tiles 1..nshared-1 go round-robin to warps 1.. */
-      const int t_first = warp == 0 ? 0 : warp, t_step = nwarp > 1 ? nwarp - 1 : 1;
-      for (int t = t_first; t < ntiles;) {
+#if DS_CUDA
+      double *Eb = e_smem ? Es : Eg;
+      const int ks8 = kslot + NB;
+      const bool full = n_trail == bwp;
+      DS_PROF_T0(s3t0);
+      DS_PROF_INC(PF_X_STEPS, team.tid == 0);
+      if (warp == 0) {
+        if (n_trail > 0) s3_range<false>(tiles, 0, 1, P, HS, W, Eb, G, ks8, k, Wr, ld, ES, bwE, lo, n_trail, lane);
+        if (kb + 1 < nblk) {
+          team.warp_sync();
+          int ns = kslot + NB;
+          if (ns >= Wr) ns -= Wr;
+          DS_PROF_T0(dgt0);
+          diag_factor(team, W, ns, Wr, ld, bwE, lambda, invL, flag);
+          DS_PROF_ADD(PF_X_DIAG, dgt0, lane == 0);
+        }
+        if (full) s3_range<false>(tiles, wstart[0], ntiles, P, HS, W, Eb, G, ks8, k, Wr, ld, ES, bwE, lo, n_trail, lane);
+        else s3_range<true>(tiles, wstart[0], ntiles, P, HS, W, Eb, G, ks8, k, Wr, ld, ES, bwE, lo, n_trail, lane);
+      } else {
+        const int beg = wstart[warp], end = wstart[warp + 1];
+        if (full) s3_range<false>(tiles, beg, end, P, HS, W, Eb, G, ks8, k, Wr, ld, ES, bwE, lo, n_trail, lane);
+        else s3_range<true>(tiles, beg, end, P, HS, W, Eb, G, ks8, k, Wr, ld, ES, bwE, lo, n_trail, lane);
+      }
+      DS_PROF_ADD(PF_X_WARP + warp, s3t0, lane == 0);
+#else
+      (void)wstart;
+      for (int t = 0; t < ntiles; t++) {
         const TileDesc td = tiles[t];
-        const int t_cur = t;
-        if (warp == 0) t = (t == 0) ? nshared : t + 1;
-        else { t += t_step; if (t >= nshared) t = ntiles; }
-        bool skip = td.kind <= 2 ? td.rA >= n_trail : (td.kind == 3 && td.rB >= n_trail);
-        skip = skip || (td.kind <= 2 && td.rB >= n_trail);
+        const int rA = td.pa >> 5, rB = td.pb >> 5;
+        bool skip = td.kind <= 2 ? (rA >= n_trail || rB >= n_trail) : (td.kind == 3 && rB >= n_trail);
         if (!skip) {
-          DS_WARP_FOR(T, 32) {
+          for (int T = 0; T < 32; T++) {
             const int g = T >> 2, q = T & 3;
             double d0, d1;
-            tile_mul_pp(T, P, HS, td.rA, td.rB, d0, d1);
+            tile_mul_pp(T, P, HS, rA, rB, d0, d1);
             if (td.kind <= 2) {
-              /* entry (i, j): i = k+8+rA+g, j = k+8+rB+2q(+1); band offset j-i+bwE */
-              int s0 = kslot + NB + td.rA;
+              int s0 = kslot + NB + rA;
               if (s0 >= Wr) s0 -= Wr;
-              const int off = td.dcol + 2 * q - g + bwE;
+              const int off = (td.doff >> 3) + 2 * q - g;
               double *dst = W + (s0 + g) * ld + off;
-              if (td.kind == 1) {
-                sub_pair(dst, d0, d1);
-              } else {
-                const bool v0 = off <= bwE && off >= lo, v1 = off + 1 <= bwE && off + 1 >= lo;
-                if (v0 && v1) sub_pair(dst, d0, d1);
-                else {
-                  if (v0) dst[0] -= d0;
-                  if (v1) dst[1] -= d1;
-                }
-              }
+              if (off <= bwE && off >= lo) dst[0] -= d0;
+              if (off + 1 <= bwE && off + 1 >= lo) dst[1] -= d1;
             } else if (td.kind == 3) {
-              const int eo = g * ES + k + NB + td.rB + 2 * q;
+              const int eo = g * ES + k + (td.doff >> 3) + 2 * q;
               if (e_smem) sub_pair(Es + eo, d0, d1);
               else sub_pair(Eg + eo, d0, d1);
             } else {
@@ -1134,14 +1258,13 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
             }
           }
         }
-        if (t_cur == 0 && warp == 0 && kb + 1 < nblk) {
-          /* S1 of the next step on the block tile 0 just produced */
-          team.warp_sync();
+        if (t == 0 && kb + 1 < nblk) {
           int ns = kslot + NB;
           if (ns >= Wr) ns -= Wr;
           diag_factor(team, W, ns, Wr, ld, bwE, lambda, invL, flag);
         }
       }
+#endif
     }
     /* rows written here are bulk-stored (async proxy) after a later barrier */
     fence_proxy_async_smem();
@@ -1416,7 +1539,16 @@ DS_FN_NOINLINE void sft_solve_one(const Team team, Ctx &cx) {
   const int Dp = pl.Dn_pad;
 
   const int rc = prologue(team, c);
-  build_tile_table(team, (TileDesc *)(sm_base() + c.sl.tiles), pl.bwp / NB, pl.bwp, pl.bw);
+  {
+    TileDesc *tt = (TileDesc *)(sm_base() + c.sl.tiles);
+    const int nt8 = pl.bwp / NB;
+#if DS_CUDA
+    const int nwarp = team.nthr >> 5;
+#else
+    const int nwarp = 1;
+#endif
+    build_tile_table(team, tt, (int *)(tt + (nt8 + 1) * (nt8 + 2) / 2), nwarp, nt8, pl.bwp, pl.bw, pl.bwE);
+  }
   team.sync();
   prof_mark(team, c, PF_PROLOGUE);
   if (rc != 0) {

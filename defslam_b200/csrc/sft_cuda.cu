@@ -193,10 +193,10 @@ static int batch_launch(defslam_sft_batch *B, cudaEvent_t ev0 = nullptr, cudaEve
   const WorkspaceSizes z = B->bm.ws_sizes();
   long long *prof = nullptr;
   if (getenv("DEFSLAM_PROFILE")) { /* diagnostics: per-phase cycles of CTA 0 */
-    int rc = B->d_prof.ensure(sizeof(long long) * PF_COUNT);
+    int rc = B->d_prof.ensure(sizeof(long long) * PF_TOTAL);
     if (rc) return rc;
     prof = (long long *)B->d_prof.p;
-    DS_CUDA_TRY(cudaMemsetAsync(prof, 0, sizeof(long long) * PF_COUNT, ctx->stream));
+    DS_CUDA_TRY(cudaMemsetAsync(prof, 0, sizeof(long long) * PF_TOTAL, ctx->stream));
   }
   {
     int rc = B->d_counter.ensure(sizeof(int));
@@ -220,7 +220,7 @@ static int batch_wait_kernel(defslam_sft_batch *B) {
   B->last_ms = ms;
   g_last_kernel_ms = ms;
   if (getenv("DEFSLAM_PROFILE") && B->d_prof.p) {
-    long long h[PF_COUNT];
+    long long h[PF_TOTAL];
     DS_CUDA_TRY(cudaMemcpy(h, B->d_prof.p, sizeof(h), cudaMemcpyDeviceToHost));
     static const char *names[PF_COUNT] = {"prologue", "eval_store", "build", "fs_init", "S1", "S1_wait", "S2", "S3",
                                           "schur", "bwd_init", "bwd", "update", "eval_trial", "lm_scalar", "finalize"};
@@ -228,6 +228,13 @@ static int batch_wait_kernel(defslam_sft_batch *B) {
     for (int i = 0; i < PF_COUNT; i++) tot += h[i];
     fprintf(stderr, "[defslam profile] CTA0 cycles total %lld:", tot);
     for (int i = 0; i < PF_COUNT; i++) fprintf(stderr, " %s=%.1f%%", names[i], 100.0 * (double)h[i] / (double)(tot ? tot : 1));
+    fprintf(stderr, "\n");
+    const double steps = (double)(h[PF_X_STEPS] ? h[PF_X_STEPS] : 1);
+    fprintf(stderr, "[defslam profile] per step (%lld steps): S3 phase %.0f, look-ahead factor %.0f; S3 busy per warp:",
+            h[PF_X_STEPS], (double)h[PF_S3] / steps, (double)h[PF_X_DIAG] / steps);
+    for (int w = 0; w < 16; w++) if (h[PF_X_WARP + w]) fprintf(stderr, " %.0f", (double)h[PF_X_WARP + w] / steps);
+    fprintf(stderr, "; S2 phase %.0f busy per warp:", (double)h[PF_S2] / steps);
+    for (int w = 0; w < 16; w++) if (h[PF_X_S2W + w]) fprintf(stderr, " %.0f", (double)h[PF_X_S2W + w] / steps);
     fprintf(stderr, "\n");
   }
   return 0;
