@@ -144,7 +144,8 @@ SmemLayout smem_layout(int n_nodes, int n_edges, int Dn_pad, int bwp, int ld, in
   SmemLayout L;
   int o = 0;
   int wsz = Wr * ld;
-  const int asz = 11 * n_nodes + 5 * n_edges, bsz = 4 * (NB * ld);
+  /* assembly scratch; backward sweep: ring of 4 row blocks + the solution vector */
+  const int asz = 11 * n_nodes + 5 * n_edges, bsz = 4 * (NB * ld) + Dn_pad;
   if (asz > wsz) wsz = asz;
   if (bsz > wsz) wsz = bsz;
   L.W = o;    o += wsz; o = (o + 1) & ~1;
@@ -154,7 +155,7 @@ SmemLayout smem_layout(int n_nodes, int n_edges, int Dn_pad, int bwp, int ld, in
   L.xb = o;   /* (backup lives in global memory) */
   L.dx = o;   o += Dn_pad + 8;
   L.Lkk = o;  o += 64;
-  L.invL = o; o += 96;   /* inv(L_kk), row stride 12 */
+  L.invL = o; o += 192;  /* inv(L_kk), row stride 12; two buffers (step parity) */
   L.G = o;    o += 64;
   L.Hcc = o;  o += 48;   /* 36 Hcc + 6 bc + 6 dc(stale) */
   L.red = o;  o += 40;
@@ -206,7 +207,8 @@ DS_FN uint8_t *freev_ptr(const Ctx &c) { return (uint8_t *)(sm_base() + c.sl.fla
 enum { PF_PROLOGUE = 0, PF_EVAL_STORE, PF_BUILD, PF_FS_INIT, PF_S1, PF_S1_WAIT, PF_S2, PF_S3, PF_SCHUR, PF_BWD_INIT,
        PF_BWD, PF_UPDATE, PF_EVAL_TRIAL, PF_LM_SCALAR, PF_FINALIZE, PF_COUNT,
        /* extras (not part of the total): busy cycles of each warp inside S3, look-ahead factor, steps */
-       PF_X_WARP = PF_COUNT, PF_X_DIAG = PF_COUNT + 16, PF_X_STEPS, PF_X_S2W, PF_TOTAL = PF_X_S2W + 16 };
+       PF_X_WARP = PF_COUNT, PF_X_DIAG = PF_COUNT + 16, PF_X_STEPS, PF_X_S2W, PF_X_BUILD = PF_X_S2W + 16,
+       PF_X_BUILDS = PF_X_BUILD + 8, PF_TOTAL };
 #if DS_CUDA && defined(DS_PROFILE)
 #define DS_PROF_T0(var) const long long var = clock64()
 #define DS_PROF_ADD(idx, t0, cond) do { if (ctx_ref().prof != nullptr && (cond)) ctx_ref().prof[idx] += clock64() - (t0); } while (0)
@@ -254,7 +256,7 @@ DS_FN_NOINLINE int prologue(const Team team, Ctx &cx) {
 
   DS_FOR(i, pl.Dn_pad) x[i] = i < pl.Dn ? pb.node_xyz[i] : 0.0;
   DS_FOR(i, pl.Dn_pad + 8) sm_base()[c.sl.dx + i] = 0.0;
-  DS_FOR(i, 96) sm_base()[c.sl.invL + i] = 0.0;
+  DS_FOR(i, 192) sm_base()[c.sl.invL + i] = 0.0;
   DS_FOR(i, 2 * n) viewed_ptr(c)[i] = 0; /* viewed + freev are contiguous */
   DS_FOR(f, nf) c.ws.fcnt[f] = 0;
   if (team.tid == 0) {
@@ -531,33 +533,51 @@ DS_FN_NOINLINE double build_system(const Team team, Ctx &cx) {
   const double *S = c.ws.S;
   double *Hcc = sm_base() + c.sl.Hcc;
   team.sync();
+  DS_PROF_T0(bt0);
+  DS_PROF_INC(PF_X_BUILDS, team.tid == 0);
 
   /* (1) per-facet sums.  item = (facet, group) */
+  /* group-major: the lanes of a warp run the same group on consecutive facets (no divergence
+   * between the four code paths, neighbouring rows of S) */
   DS_FOR(it, nf * 6) {
-    const int f = it / 6, g = it - 6 * f;
+    const int g = it / nf, f = it - g * nf;
     const int sb = c.ws.fptr[f], se = c.ws.fptr[f + 1];
+    /* Two matches per trip: the loads of both are independent, so a facet with n matches costs
+     * ceil(n/2) memory round trips.  The second slot of an odd tail re-reads the last match with
+     * weight 0 (adds +0: the sums are the same as match-by-match). */
     if (g == 0) {
-      double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0, a9 = 0, a10 = 0, a11 = 0;
-      for (int s = sb; s < se; s++) {
-        const double w = S[2 * M + s], e0 = S[s], e1 = S[M + s];
-        const double b0 = S[15 * M + s], b1 = S[16 * M + s], b2 = S[17 * M + s];
-        a0 += w * b0 * b0; a1 += w * b0 * b1; a2 += w * b0 * b2;
-        a3 += w * b1 * b1; a4 += w * b1 * b2; a5 += w * b2 * b2;
-        a6 += w * b0 * e0; a7 += w * b0 * e1;
-        a8 += w * b1 * e0; a9 += w * b1 * e1;
-        a10 += w * b2 * e0; a11 += w * b2 * e1;
+      double a[12];
+#pragma unroll
+      for (int k = 0; k < 12; k++) a[k] = 0.0;
+      for (int s0 = sb; s0 < se; s0 += 2) {
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          const bool ok = s0 + u < se;
+          const int s = ok ? s0 + u : s0;
+          const double w = ok ? S[2 * M + s] : 0.0, e0 = S[s], e1 = S[M + s];
+          const double b0 = S[15 * M + s], b1 = S[16 * M + s], b2 = S[17 * M + s];
+          a[0] += w * b0 * b0; a[1] += w * b0 * b1; a[2] += w * b0 * b2;
+          a[3] += w * b1 * b1; a[4] += w * b1 * b2; a[5] += w * b2 * b2;
+          a[6] += w * b0 * e0; a[7] += w * b0 * e1;
+          a[8] += w * b1 * e0; a[9] += w * b1 * e1;
+          a[10] += w * b2 * e0; a[11] += w * b2 * e1;
+        }
       }
-      F[0 * nf + f] = a0; F[1 * nf + f] = a1; F[2 * nf + f] = a2; F[3 * nf + f] = a3;
-      F[4 * nf + f] = a4; F[5 * nf + f] = a5; F[6 * nf + f] = a6; F[7 * nf + f] = a7;
-      F[8 * nf + f] = a8; F[9 * nf + f] = a9; F[10 * nf + f] = a10; F[11 * nf + f] = a11;
+#pragma unroll
+      for (int k = 0; k < 12; k++) F[k * nf + f] = a[k];
     } else if (g <= 3) {
       double a[12];
 #pragma unroll
       for (int k = 0; k < 12; k++) a[k] = 0.0;
-      for (int s = sb; s < se; s++) {
-        const double wb = S[2 * M + s] * S[(14 + g) * M + s];
+      for (int s0 = sb; s0 < se; s0 += 2) {
 #pragma unroll
-        for (int k = 0; k < 12; k++) a[k] += wb * S[(3 + k) * M + s];
+        for (int u = 0; u < 2; u++) {
+          const bool ok = s0 + u < se;
+          const int s = ok ? s0 + u : s0;
+          const double wb = (ok ? S[2 * M + s] : 0.0) * S[(14 + g) * M + s];
+#pragma unroll
+          for (int k = 0; k < 12; k++) a[k] += wb * S[(3 + k) * M + s];
+        }
       }
 #pragma unroll
       for (int k = 0; k < 12; k++) F[(12 * g + k) * nf + f] = a[k];
@@ -566,15 +586,20 @@ DS_FN_NOINLINE double build_system(const Team team, Ctx &cx) {
       double a[11];
 #pragma unroll
       for (int k = 0; k < 11; k++) a[k] = 0.0;
-      for (int s = sb; s < se; s++) {
-        const double w = S[2 * M + s];
-        double J[12];
+      for (int s0 = sb; s0 < se; s0 += 2) {
 #pragma unroll
-        for (int k = 0; k < 12; k++) J[k] = S[(3 + k) * M + s];
+        for (int u = 0; u < 2; u++) {
+          const bool ok = s0 + u < se;
+          const int s = ok ? s0 + u : s0;
+          const double w = ok ? S[2 * M + s] : 0.0;
+          double J[12];
 #pragma unroll
-        for (int q = 0; q < 6; q++) a[q] += w * (J[0] * J[q] + J[6] * J[6 + q]);
+          for (int k = 0; k < 12; k++) J[k] = S[(3 + k) * M + s];
 #pragma unroll
-        for (int q = 1; q < 6; q++) a[5 + q] += w * (J[1] * J[q] + J[7] * J[6 + q]);
+          for (int q = 0; q < 6; q++) a[q] += w * (J[0] * J[q] + J[6] * J[6 + q]);
+#pragma unroll
+          for (int q = 1; q < 6; q++) a[5 + q] += w * (J[1] * J[q] + J[7] * J[6 + q]);
+        }
       }
 #pragma unroll
       for (int k = 0; k < 11; k++) F[(48 + k) * nf + f] = a[k];
@@ -583,26 +608,33 @@ DS_FN_NOINLINE double build_system(const Team team, Ctx &cx) {
       double a[16];
 #pragma unroll
       for (int k = 0; k < 16; k++) a[k] = 0.0;
-      for (int s = sb; s < se; s++) {
-        const double w = S[2 * M + s], e0 = S[s], e1 = S[M + s];
-        double J[12];
+      for (int s0 = sb; s0 < se; s0 += 2) {
 #pragma unroll
-        for (int k = 0; k < 12; k++) J[k] = S[(3 + k) * M + s];
+        for (int u = 0; u < 2; u++) {
+          const bool ok = s0 + u < se;
+          const int s = ok ? s0 + u : s0;
+          const double w = ok ? S[2 * M + s] : 0.0, e0 = S[s], e1 = S[M + s];
+          double J[12];
 #pragma unroll
-        for (int q = 2; q < 6; q++) a[q - 2] += w * (J[2] * J[q] + J[8] * J[6 + q]);
+          for (int k = 0; k < 12; k++) J[k] = S[(3 + k) * M + s];
 #pragma unroll
-        for (int q = 3; q < 6; q++) a[4 + q - 3] += w * (J[3] * J[q] + J[9] * J[6 + q]);
+          for (int q = 2; q < 6; q++) a[q - 2] += w * (J[2] * J[q] + J[8] * J[6 + q]);
 #pragma unroll
-        for (int q = 4; q < 6; q++) a[7 + q - 4] += w * (J[4] * J[q] + J[10] * J[6 + q]);
-        a[9] += w * (J[5] * J[5] + J[11] * J[11]);
+          for (int q = 3; q < 6; q++) a[4 + q - 3] += w * (J[3] * J[q] + J[9] * J[6 + q]);
 #pragma unroll
-        for (int r = 0; r < 6; r++) a[10 + r] += w * (J[r] * e0 + J[6 + r] * e1);
+          for (int q = 4; q < 6; q++) a[7 + q - 4] += w * (J[4] * J[q] + J[10] * J[6 + q]);
+          a[9] += w * (J[5] * J[5] + J[11] * J[11]);
+#pragma unroll
+          for (int r = 0; r < 6; r++) a[10 + r] += w * (J[r] * e0 + J[6 + r] * e1);
+        }
       }
 #pragma unroll
       for (int k = 0; k < 16; k++) F[(59 + k) * nf + f] = a[k];
     }
   }
   team.sync();
+  DS_PROF_ADD(PF_X_BUILD + 0, bt0, team.tid == 0);
+  DS_PROF_T0(bt1);
 
   /* (2) camera-camera block and b_c: fixed two-level reduction over facets.
    * 27 sums x NPART partial ranges, then the partials in order. */
@@ -633,6 +665,8 @@ DS_FN_NOINLINE double build_system(const Team team, Ctx &cx) {
     }
   }
 
+  DS_PROF_ADD(PF_X_BUILD + 1, bt1, team.tid == 0);
+  DS_PROF_T0(bt2);
   /* (3) node-node blocks: gather */
   double maxd = 0.0;
   DS_FOR(bi, pl.n_blk) {
@@ -652,16 +686,36 @@ DS_FN_NOINLINE double build_system(const Team team, Ctx &cx) {
       const double *Ap = &A[6 * p], *Aq = &A[6 * q];
       for (int r = 0; r < 3; r++)
         for (int s = 0; s < 3; s++) h[3 * r + s] = beta * (Ap[r] * Aq[s] + Ap[3 + r] * Aq[3 + s]);
-      /* curvature: g_i c_ip c_iq d_i d_i^T */
-      for (int k = pl.blk_ctr_ptr[bi]; k < pl.blk_ctr_ptr[bi + 1]; k++) {
-        const int i = pl.blk_ctr[3 * k], ip = pl.blk_ctr[3 * k + 1], iq = pl.blk_ctr[3 * k + 2];
-        const double g = cg[i];
-        if (g == 0.0) continue;
-        const double cp = ip < 0 ? 1.0 : -pl.nbr_c[ip], cq = iq < 0 ? 1.0 : -pl.nbr_c[iq];
-        const double gc = g * cp * cq;
-        const double *d = &cd[3 * i];
-        for (int r = 0; r < 3; r++)
-          for (int s = 0; s < 3; s++) h[3 * r + s] += gc * d[r] * d[s];
+      /* curvature: g_i c_ip c_iq d_i d_i^T.  Four centres at a time: the index loads and the
+       * coefficient loads of a batch are independent (one memory round trip each instead of
+       * one per centre); accumulation order unchanged. */
+      {
+        const int c0 = pl.blk_ctr_ptr[bi], c1 = pl.blk_ctr_ptr[bi + 1];
+        for (int kb4 = c0; kb4 < c1; kb4 += 4) {
+          int ci[4], cip[4], ciq[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int k = kb4 + u < c1 ? kb4 + u : c1 - 1;
+            ci[u] = pl.blk_ctr[3 * k]; cip[u] = pl.blk_ctr[3 * k + 1]; ciq[u] = pl.blk_ctr[3 * k + 2];
+          }
+          double cpv[4], cqv[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            cpv[u] = cip[u] < 0 ? 1.0 : -pl.nbr_c[cip[u]];
+            cqv[u] = ciq[u] < 0 ? 1.0 : -pl.nbr_c[ciq[u]];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            if (kb4 + u >= c1) break;
+            const int i = ci[u];
+            const double g = cg[i];
+            if (g == 0.0) continue;
+            const double gc = g * cpv[u] * cqv[u];
+            const double *d = &cd[3 * i];
+            for (int r = 0; r < 3; r++)
+              for (int s = 0; s < 3; s++) h[3 * r + s] += gc * d[r] * d[s];
+          }
+        }
       }
       /* stretch */
       if (p == q) {
@@ -695,6 +749,8 @@ DS_FN_NOINLINE double build_system(const Team team, Ctx &cx) {
     }
   }
 
+  DS_PROF_ADD(PF_X_BUILD + 2, bt2, team.tid == 0);
+  DS_PROF_T0(bt3);
   /* (4) per-node gradient b_n and camera border C */
   DS_FOR(p, n) {
     double b[3] = {0, 0, 0}, C[18];
@@ -734,7 +790,10 @@ DS_FN_NOINLINE double build_system(const Team team, Ctx &cx) {
       for (int a = 0; a < 6; a++) c.ws.Cg[a * ES + 3 * p + r] = C[3 * a + r];
     }
   }
+  DS_PROF_ADD(PF_X_BUILD + 3, bt3, team.tid == 0);
+  DS_PROF_T0(bt4);
   maxd = team_max(team, maxd, sm_base() + c.sl.red); /* also a barrier: Hcc complete */
+  DS_PROF_ADD(PF_X_BUILD + 4, bt4, team.tid == 0);
   for (int k = 0; k < 6; k++) maxd = fmax(maxd, fabs(Hcc[7 * k]));
   return maxd;
 }
@@ -778,6 +837,28 @@ DS_FN bool chol4(double t[10]) {
 }
 
 constexpr int ILS = 12; /* row stride of inv(L_kk) in shared memory */
+
+/* entry (i, m), i > m, of the factor held as [A11 0; L21 A22] (packed triangles, reciprocal
+ * diagonals); indices are compile-time constants after unrolling */
+DS_FN double lreg(const double *A11, const double *L21, const double *A22, int i, int m) {
+  return i < 4 ? A11[i * (i + 1) / 2 + m] : (m < 4 ? L21[(i - 4) * 4 + m] : A22[(i - 4) * (i - 3) / 2 + (m - 4)]);
+}
+
+/* column j of X = inv(L): s_i = delta_ij - sum_{m<i} L[i][m] X[m];  X[i] = s_i / L_ii.
+ * The strict upper part of invL stays zero (prologue). */
+DS_FN void inv_column(const double *A11, const double *L21, const double *A22, int j, bool store, double *invL) {
+  double sacc[NB];
+#pragma unroll
+  for (int i = 0; i < NB; i++) sacc[i] = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+  for (int m = 0; m < NB; m++) {
+    const double rd = m < 4 ? A11[m * (m + 1) / 2 + m] : A22[(m - 4) * (m - 3) / 2 + (m - 4)];
+    const double xm = sacc[m] * rd;
+    if (store && m >= j) invL[m * ILS + j] = xm;
+#pragma unroll
+    for (int i = m + 1; i < NB; i++) sacc[i] -= lreg(A11, L21, A22, i, m) * xm;
+  }
+}
 
 /* Cholesky of one NB x NB diagonal block + inverse of its factor, by warp 0.
  * in : the block's lower triangle in the window (lambda is added to the diagonal)
@@ -842,20 +923,14 @@ DS_FN void diag_factor(const Team team, double *W, int kslot, int Wr, int ld, in
       if (b <= 4 + a) rowp[4 + a][b] = b < 4 ? L21[a * 4 + b] : A22[a * (a + 1) / 2 + (b - 4)];
     }
   if (bad && lane == 0) *flag = 1;
-  team.warp_sync();
-  /* column j of X = inv(L): s_i = delta_ij - sum_{m<i} L[i][m] X[m];  X[i] = s_i / L_ii */
-  DS_WARP_FOR(j, NB) {
-    double sacc[NB];
-#pragma unroll
-    for (int i = 0; i < NB; i++) sacc[i] = (i == j) ? 1.0 : 0.0;
-#pragma unroll
-    for (int m = 0; m < NB; m++) {
-      const double xm = sacc[m] * rowp[m][m];
-      if (m >= j) invL[m * ILS + j] = xm; /* the strict upper part stays zero (prologue) */
-#pragma unroll
-      for (int i = m + 1; i < NB; i++) sacc[i] -= rowp[i][m] * xm;
-    }
-  }
+  /* Phase 2 from the registers of phase 1 (no shared-memory round trip, no warp barrier): the
+   * substitution for column lane%8 is straight-line code the scheduler interleaves with the
+   * elimination above, one step behind it. */
+#if DS_CUDA
+  inv_column(A11, L21, A22, lane & 7, lane < NB, invL);
+#else
+  for (int j = 0; j < NB; j++) inv_column(A11, L21, A22, j, true, invL);
+#endif
 }
 
 #if DS_CUDA
@@ -988,7 +1063,9 @@ DS_FN void build_tile_table(const Team team, TileDesc *tt, int *wstart, int nwar
     else { d.kind = (ti > tj && NB * (ti - tj) + (NB - 1) <= bw) ? 1 : 2; d.doff = 8 * (rB - rA + bwE); }
     tt[t] = d;
   }
-  int n0 = ((ntiles - 1) - LOOKAHEAD_TILES * (nwarp - 1)) / nwarp;
+  /* warp 0's fixed load per step: its panel tile, tile 0 and the look-ahead factorisation; the other
+   * warps share nt8 panel tiles and the remaining trailing tiles */
+  int n0 = ((ntiles - 1) + nt8 - (LOOKAHEAD_TILES + 2) * (nwarp - 1)) / nwarp;
   if (n0 < 0) n0 = 0;
   const int nshared = ntiles - n0, cnt = nshared - 1;
   DS_FOR(w, nwarp + 1) {
@@ -1084,6 +1161,15 @@ DS_FN void s3_range(const TileDesc *tt, int beg, int end, const double *P, int H
 }
 #endif
 
+#if DS_CUDA
+/* named barriers: producers arrive, consumers sync (count = all threads of the CTA) */
+DS_FN void named_arrive(int id, int count) {
+  __threadfence_block();
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+DS_FN void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+#endif
+
 /* Solve (H + lambda I) dx = b.  dx -> sm[sl.dx] (nodes, then camera at Dn_pad).
  * Returns false if a pivot is not positive (LinearSolverDense::solve returning
  * false, linear_solver_dense.h:107-112); dx is then left untouched (stale), as
@@ -1154,10 +1240,24 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
     fence_proxy_async_smem(); /* rows 0..7 are final: they leave through the async proxy */
   }
   team.sync();
+  /* One step per 8-row block.  Warp 0 is the critical path: the panel tile right under the
+   * diagonal block, the update of the next diagonal block (tile 0) and its factorisation (S1 of
+   * step kb+1, look-ahead).  The other warps solve the rest of the panel (S2), meet on a named
+   * barrier that warp 0 only arrives at, and run the trailing update (S3).  One CTA-wide
+   * barrier per step.  inv(L_kk) is double-buffered: warp 0 writes the next one while the
+   * others may still read the current one. */
+#if DS_CUDA
+  const int tma_tid = 32; /* TMA duty (bulk store of finished rows, refill of the freed slot): warp 1 */
+#else
+  const int tma_tid = 0;
+#endif
   for (int kb = 0; kb < nblk; kb++) {
     const int k = kb * NB;
+    const double *invLk = invL + 96 * (kb & 1);
+    double *invLn = invL + 96 * ((kb + 1) & 1);
     /* finished rows k..k+7 -> L band in global memory (TMA bulk store) */
-    if (team.tid == 0) tma_store_1d_stream(Lb + k * ld, W + kslot * ld, (uint32_t)(NB * ld * sizeof(double)), pol);
+    if (team.tid == tma_tid)
+      tma_store_1d_stream(Lb + k * ld, W + kslot * ld, (uint32_t)(NB * ld * sizeof(double)), pol);
     prof_mark(team, c, PF_S1);
     /* rows requested during the previous step (they enter this step's panel) */
     if (kb > 0 && (k - NB) + Wr < Dp) { mbar_wait(bar0, ph0); ph0 ^= 1u; }
@@ -1167,8 +1267,16 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
      * tile per warp: X = A inv(L_kk)^T on the tensor cores */
     const int n_trail = (Dp - (k + NB)) < bwp ? (Dp - (k + NB)) : bwp;
     const int nrt = n_trail / NB; /* trailing row tiles that exist */
+    const int nrow = nt8 + 1;
+    const int ntiles = nrow * (nrow + 1) / 2;
+    const int lo = bwE - bw;
     DS_PROF_T0(s2t0);
-    for (int rt = warp; rt <= nt8; rt += nwarp) {
+#if DS_CUDA
+    const int rt_first = warp == 0 ? 0 : warp, rt_step = warp == 0 ? nt8 + 1 : nwarp - 1;
+#else
+    const int rt_first = 0, rt_step = 1;
+#endif
+    for (int rt = rt_first; rt <= nt8; rt += rt_step) {
       const bool erow = rt == nt8;
       if (!erow && rt >= nrt) continue; /* rows beyond the matrix: never read by S3 */
       const int r0 = erow ? bwp : rt * NB; /* first panel row of this tile */
@@ -1178,94 +1286,100 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
          * The 8 rows of a tile never wrap inside the ring (Wr, r0 multiples of 8). */
         int s0 = kslot + NB + r0;
         if (s0 >= Wr) s0 -= Wr;
-        panel_tile(team, W + s0 * ld + (bwE - NB - r0), ld - 1, bwE - NB - r0, -1, bwE - bw, invL, P, HS, r0);
+        panel_tile(team, W + s0 * ld + (bwE - NB - r0), ld - 1, bwE - NB - r0, -1, bwE - bw, invLk, P, HS, r0);
       } else if (e_smem) {
-        panel_tile(team, Es + k, ES, bwE, 0, bwE - bw, invL, P, HS, r0);
+        panel_tile(team, Es + k, ES, bwE, 0, bwE - bw, invLk, P, HS, r0);
       } else {
-        panel_tile(team, Eg + k, ES, bwE, 0, bwE - bw, invL, P, HS, r0);
+        panel_tile(team, Eg + k, ES, bwE, 0, bwE - bw, invLk, P, HS, r0);
       }
     }
     DS_PROF_ADD(PF_X_S2W + warp, s2t0, (team.tid & 31) == 0);
-    team.sync();
-    prof_mark(team, c, PF_S2);
-    /* the bulk store of rows k..k+7 (issued after S1) has read its source by now:
-     * refill the freed slot with rows k+Wr.. (needed by the next step's panel) */
-    if (team.tid == 0) {
-      tma_store_wait_read();
-      if (k + Wr < Dp) {
-        const uint32_t bytes = (uint32_t)(NB * ld * sizeof(double));
-        mbar_expect_tx(bar0, bytes);
-        tma_load_1d_stream(W + kslot * ld, Hb + (k + Wr) * ld, bytes, bar0, pol);
-      }
-    }
-
-    /* S3: trailing update C -= P_I P_J^T on 8x8 tiles (FP64 tensor cores).  Look-ahead: tile 0 is
-     * the next diagonal block and the only tile that touches rows k+8..k+15; warp 0 updates it
-     * first and factors it (S1 of step kb+1) while the other warps work through their ranges. */
-    {
-      const int nrow = nt8 + 1;
-      const int ntiles = nrow * (nrow + 1) / 2;
-      const int lo = bwE - bw;
 #if DS_CUDA
+    {
       double *Eb = e_smem ? Es : Eg;
       const int ks8 = kslot + NB;
       const bool full = n_trail == bwp;
-      DS_PROF_T0(s3t0);
+      const bool w0_tail = wstart[0] < ntiles; /* warp 0 also owns trailing tiles: it needs the whole panel */
       DS_PROF_INC(PF_X_STEPS, team.tid == 0);
       if (warp == 0) {
+        named_arrive(1, team.nthr); /* panel rows 0..7 are in P */
+        DS_PROF_T0(s3t0);
+        team.warp_sync();
+        /* S3, tile 0: the next diagonal block, the only tile that touches rows k+8..k+15 */
         if (n_trail > 0) s3_range<false>(tiles, 0, 1, P, HS, W, Eb, G, ks8, k, Wr, ld, ES, bwE, lo, n_trail, lane);
         if (kb + 1 < nblk) {
           team.warp_sync();
           int ns = kslot + NB;
           if (ns >= Wr) ns -= Wr;
           DS_PROF_T0(dgt0);
-          diag_factor(team, W, ns, Wr, ld, bwE, lambda, invL, flag);
+          diag_factor(team, W, ns, Wr, ld, bwE, lambda, invLn, flag);
           DS_PROF_ADD(PF_X_DIAG, dgt0, lane == 0);
         }
-        if (full) s3_range<false>(tiles, wstart[0], ntiles, P, HS, W, Eb, G, ks8, k, Wr, ld, ES, bwE, lo, n_trail, lane);
-        else s3_range<true>(tiles, wstart[0], ntiles, P, HS, W, Eb, G, ks8, k, Wr, ld, ES, bwE, lo, n_trail, lane);
+        if (w0_tail) {
+          named_sync(2, team.nthr);
+          if (full) s3_range<false>(tiles, wstart[0], ntiles, P, HS, W, Eb, G, ks8, k, Wr, ld, ES, bwE, lo, n_trail, lane);
+          else s3_range<true>(tiles, wstart[0], ntiles, P, HS, W, Eb, G, ks8, k, Wr, ld, ES, bwE, lo, n_trail, lane);
+        }
+        DS_PROF_ADD(PF_X_WARP + warp, s3t0, lane == 0);
       } else {
+        if (w0_tail) named_arrive(2, team.nthr);
+        named_sync(1, team.nthr); /* the whole panel is in P; every thread is past the mbarrier wait */
+        prof_mark(team, c, PF_S2);
+        /* the bulk store of rows k..k+7 has read its source by now: refill the freed slot with
+         * rows k+Wr.. (needed by the next step's panel) */
+        if (team.tid == tma_tid) {
+          tma_store_wait_read();
+          if (k + Wr < Dp) {
+            const uint32_t bytes = (uint32_t)(NB * ld * sizeof(double));
+            mbar_expect_tx(bar0, bytes);
+            tma_load_1d_stream(W + kslot * ld, Hb + (k + Wr) * ld, bytes, bar0, pol);
+          }
+        }
+        DS_PROF_T0(s3t0);
+        /* S3: trailing update C -= P_I P_J^T on 8x8 tiles (FP64 tensor cores) */
         const int beg = wstart[warp], end = wstart[warp + 1];
         if (full) s3_range<false>(tiles, beg, end, P, HS, W, Eb, G, ks8, k, Wr, ld, ES, bwE, lo, n_trail, lane);
         else s3_range<true>(tiles, beg, end, P, HS, W, Eb, G, ks8, k, Wr, ld, ES, bwE, lo, n_trail, lane);
+        DS_PROF_ADD(PF_X_WARP + warp, s3t0, lane == 0);
       }
-      DS_PROF_ADD(PF_X_WARP + warp, s3t0, lane == 0);
+    }
 #else
-      (void)wstart;
-      for (int t = 0; t < ntiles; t++) {
-        const TileDesc td = tiles[t];
-        const int rA = td.pa >> 5, rB = td.pb >> 5;
-        bool skip = td.kind <= 2 ? (rA >= n_trail || rB >= n_trail) : (td.kind == 3 && rB >= n_trail);
-        if (!skip) {
-          for (int T = 0; T < 32; T++) {
-            const int g = T >> 2, q = T & 3;
-            double d0, d1;
-            tile_mul_pp(T, P, HS, rA, rB, d0, d1);
-            if (td.kind <= 2) {
-              int s0 = kslot + NB + rA;
-              if (s0 >= Wr) s0 -= Wr;
-              const int off = (td.doff >> 3) + 2 * q - g;
-              double *dst = W + (s0 + g) * ld + off;
-              if (off <= bwE && off >= lo) dst[0] -= d0;
-              if (off + 1 <= bwE && off + 1 >= lo) dst[1] -= d1;
-            } else if (td.kind == 3) {
-              const int eo = g * ES + k + (td.doff >> 3) + 2 * q;
-              if (e_smem) sub_pair(Es + eo, d0, d1);
-              else sub_pair(Eg + eo, d0, d1);
-            } else {
-              if (2 * q <= g) G[g * 8 + 2 * q] -= d0;
-              if (2 * q + 1 <= g) G[g * 8 + 2 * q + 1] -= d1;
-            }
+    /* emulation: one thread, the phases in sequence */
+    (void)wstart;
+    if (k + Wr < Dp) tma_load_1d_stream(W + kslot * ld, Hb + (k + Wr) * ld, (uint32_t)(NB * ld * sizeof(double)), bar0, pol);
+    for (int t = 0; t < ntiles; t++) {
+      const TileDesc td = tiles[t];
+      const int rA = td.pa >> 5, rB = td.pb >> 5;
+      bool skip = td.kind <= 2 ? (rA >= n_trail || rB >= n_trail) : (td.kind == 3 && rB >= n_trail);
+      if (!skip) {
+        for (int T = 0; T < 32; T++) {
+          const int g = T >> 2, q = T & 3;
+          double d0, d1;
+          tile_mul_pp(T, P, HS, rA, rB, d0, d1);
+          if (td.kind <= 2) {
+            int s0 = kslot + NB + rA;
+            if (s0 >= Wr) s0 -= Wr;
+            const int off = (td.doff >> 3) + 2 * q - g;
+            double *dst = W + (s0 + g) * ld + off;
+            if (off <= bwE && off >= lo) dst[0] -= d0;
+            if (off + 1 <= bwE && off + 1 >= lo) dst[1] -= d1;
+          } else if (td.kind == 3) {
+            const int eo = g * ES + k + (td.doff >> 3) + 2 * q;
+            if (e_smem) sub_pair(Es + eo, d0, d1);
+            else sub_pair(Eg + eo, d0, d1);
+          } else {
+            if (2 * q <= g) G[g * 8 + 2 * q] -= d0;
+            if (2 * q + 1 <= g) G[g * 8 + 2 * q + 1] -= d1;
           }
         }
-        if (t == 0 && kb + 1 < nblk) {
-          int ns = kslot + NB;
-          if (ns >= Wr) ns -= Wr;
-          diag_factor(team, W, ns, Wr, ld, bwE, lambda, invL, flag);
-        }
       }
-#endif
+      if (t == 0 && kb + 1 < nblk) {
+        int ns = kslot + NB;
+        if (ns >= Wr) ns -= Wr;
+        diag_factor(team, W, ns, Wr, ld, bwE, lambda, invLn, flag);
+      }
     }
+#endif
     /* rows written here are bulk-stored (async proxy) after a later barrier */
     fence_proxy_async_smem();
     team.sync();
@@ -1307,7 +1421,7 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
     }
   }
   /* all bulk stores of L must have landed before the TMA reads of the backward sweep */
-  if (team.tid == 0) tma_store_wait_all();
+  if (team.tid == tma_tid) tma_store_wait_all();
   team.sync();
   if (team.tid == 0) c.ph[0] = ph0;
   prof_mark(team, c, PF_SCHUR);
@@ -1334,6 +1448,7 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
    * window, NBUF-1 steps ahead. */
   constexpr int NBUF = 4;
   const int bufsz = NB * ld;
+  double *sol = W + NBUF * bufsz;
   const uint32_t row_bytes = (uint32_t)(NB * ld * sizeof(double));
   uint32_t phb[NBUF];
 #pragma unroll
@@ -1387,14 +1502,15 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
         for (int m = 0; m < a; m++) d[m] -= d[a] * Lk[a * (a + 1) / 2 + m];
       }
     }
-    team.sync(); /* everybody has read dx[k..k+7] */
+    /* the solution goes to its own vector: dx[k..k+7] is still being read as the right-hand
+     * side by slower threads, and one barrier per step is enough */
     if (active) {
 #pragma unroll
       for (int a = 0; a < NB; a++) {
 #if DS_CUDA
-        if (team.tid == a) dx[k + a] = d[a];
+        if (team.tid == a) sol[k + a] = d[a];
 #else
-        dx[k + a] = d[a];
+        sol[k + a] = d[a];
 #endif
       }
       DS_FOR(jj, nupd) {
@@ -1415,6 +1531,8 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
 #pragma unroll
     for (int b = 0; b < NBUF; b++) c.ph[1 + b] = phb[b];
   }
+  DS_FOR(i, Dp) dx[i] = sol[i];
+  team.sync();
   prof_mark(team, c, PF_BWD);
   return true;
 }

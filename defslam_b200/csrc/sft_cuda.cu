@@ -236,6 +236,11 @@ static int batch_wait_kernel(defslam_sft_batch *B) {
     fprintf(stderr, "; S2 phase %.0f busy per warp:", (double)h[PF_S2] / steps);
     for (int w = 0; w < 16; w++) if (h[PF_X_S2W + w]) fprintf(stderr, " %.0f", (double)h[PF_X_S2W + w] / steps);
     fprintf(stderr, "\n");
+    const double nb = (double)(h[PF_X_BUILDS] ? h[PF_X_BUILDS] : 1);
+    fprintf(stderr, "[defslam profile] per build (%lld builds): phase %.0f; facet sums %.0f, camera reduce %.0f, block gather %.0f, "
+            "per-node %.0f, max-diag reduce %.0f (thread 0)\n", h[PF_X_BUILDS], (double)h[PF_BUILD] / nb,
+            (double)h[PF_X_BUILD] / nb, (double)h[PF_X_BUILD + 1] / nb, (double)h[PF_X_BUILD + 2] / nb,
+            (double)h[PF_X_BUILD + 3] / nb, (double)h[PF_X_BUILD + 4] / nb);
   }
   return 0;
 }
