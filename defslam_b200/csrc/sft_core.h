@@ -208,12 +208,21 @@ enum { PF_PROLOGUE = 0, PF_EVAL_STORE, PF_BUILD, PF_FS_INIT, PF_S1, PF_S1_WAIT, 
        PF_BWD, PF_UPDATE, PF_EVAL_TRIAL, PF_LM_SCALAR, PF_FINALIZE, PF_COUNT,
        /* extras (not part of the total): busy cycles of each warp inside S3, look-ahead factor, steps */
        PF_X_WARP = PF_COUNT, PF_X_DIAG = PF_COUNT + 16, PF_X_STEPS, PF_X_S2W, PF_X_BUILD = PF_X_S2W + 16,
-       PF_X_BUILDS = PF_X_BUILD + 8, PF_TOTAL };
+       PF_X_BUILDS = PF_X_BUILD + 8, PF_X_BWD, PF_TOTAL = PF_X_BWD + 4 };
 #if DS_CUDA && defined(DS_PROFILE)
 #define DS_PROF_T0(var) const long long var = clock64()
 #define DS_PROF_ADD(idx, t0, cond) do { if (ctx_ref().prof != nullptr && (cond)) ctx_ref().prof[idx] += clock64() - (t0); } while (0)
 #define DS_PROF_INC(idx, cond) do { if (ctx_ref().prof != nullptr && (cond)) ctx_ref().prof[idx] += 1; } while (0)
+/* register accumulators for fine-grained sections (a global += per section would stall the warp) */
+#define DS_PROF_LOCALS(name, n) long long name[n] = {}
+#define DS_PROF_LAP(name, i, t) do { const long long now_ = clock64(); name[i] += now_ - t; t = now_; } while (0)
+#define DS_PROF_T0M(var) long long var = clock64()
+#define DS_PROF_FLUSH(name, n, idx, cond) do { if (ctx_ref().prof != nullptr && (cond)) for (int i_ = 0; i_ < n; i_++) ctx_ref().prof[idx + i_] += name[i_]; } while (0)
 #else
+#define DS_PROF_LOCALS(name, n) do {} while (0)
+#define DS_PROF_LAP(name, i, t) do {} while (0)
+#define DS_PROF_T0M(var) do {} while (0)
+#define DS_PROF_FLUSH(name, n, idx, cond) do {} while (0)
 #define DS_PROF_T0(var) do {} while (0)
 #define DS_PROF_ADD(idx, t0, cond) do {} while (0)
 #define DS_PROF_INC(idx, cond) do {} while (0)
@@ -1462,6 +1471,7 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
     }
   }
   prof_mark(team, c, PF_BWD_INIT);
+  DS_PROF_LOCALS(bwacc, 4);
   for (int kb = nblk - 1; kb >= 0; kb--) {
     const int k = kb * NB;
     const int j = nblk - 1 - kb, buf = j % NBUF;
@@ -1476,9 +1486,11 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
       }
     }
     const double *LR = W + buf * bufsz;
+    DS_PROF_T0M(bwt);
 #pragma unroll
     for (int b = 0; b < NBUF; b++)
       if (b == buf) { mbar_wait(&c.mbar[1 + b], phb[b]); phb[b] ^= 1u; }
+    DS_PROF_LAP(bwacc, 0, bwt);
     /* d = L_kk^-T y by backward substitution (1/L_ii on the diagonal); every
      * thread that needs d (the updaters of dx[k-bw .. k+7]) computes it
      * redundantly from shared memory: no barrier between solve and update */
@@ -1502,16 +1514,13 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
         for (int m = 0; m < a; m++) d[m] -= d[a] * Lk[a * (a + 1) / 2 + m];
       }
     }
+    DS_PROF_LAP(bwacc, 1, bwt);
     /* the solution goes to its own vector: dx[k..k+7] is still being read as the right-hand
      * side by slower threads, and one barrier per step is enough */
     if (active) {
+      if (team.tid == 0) {
 #pragma unroll
-      for (int a = 0; a < NB; a++) {
-#if DS_CUDA
-        if (team.tid == a) sol[k + a] = d[a];
-#else
-        sol[k + a] = d[a];
-#endif
+        for (int a = 0; a < NB; a++) sol[k + a] = d[a];
       }
       DS_FOR(jj, nupd) {
         const int jc = j0 + jj;
@@ -1525,8 +1534,11 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
         dx[jc] = s;
       }
     }
+    DS_PROF_LAP(bwacc, 2, bwt);
     team.sync();
+    DS_PROF_LAP(bwacc, 3, bwt);
   }
+  DS_PROF_FLUSH(bwacc, 4, PF_X_BWD, team.tid == 0);
   if (team.tid == 0) {
 #pragma unroll
     for (int b = 0; b < NBUF; b++) c.ph[1 + b] = phb[b];

@@ -408,6 +408,32 @@ int defslam_sim3_register_batched(int32_t nprob, const defslam_sim3_problem *p, 
 int defslam_scale_min_median(int32_t n, const float *mono_xyz, const float *stereo_xyz, uint64_t seed,
                              float *scale_out);
 
+/* New map points from the estimated surface, and the exploration test.
+ * replaces: DefLocalMapping::CreateNewMapPoints  Modules/Mapping/DefLocalMapping.cc:240-347
+ *           DefLocalMapping::needNewTemplate     Modules/Mapping/DefLocalMapping.cc:355-403
+ * The reference paints a rows x cols 8-bit mask with 255 at (int)pt.y,(int)pt.x of every keypoint
+ * that owns a good map point, box-filters it with cv::filter2D (ones kernel of edge cols/20, anchor at
+ * its centre, BORDER_REFLECT_101, saturating) and thresholds at 1: a pixel is "occupied" when a marked
+ * pixel lies in its window.  Here the same predicate is evaluated per keypoint against the list of
+ * marked pixels (no image).  Keypoints outside the image are EBADARG (the reference indexes the mask
+ * out of bounds there).
+ *   kp_state[i]: 0 = no map point, 1 = good map point, 2 = bad map point (isBad())
+ *   action_out[i]: 0 = leave, 1 = move the existing map point to world_xyz_out[i],
+ *                  2 = create a map point at world_xyz_out[i]
+ *   world_xyz_out[i] = (Twc * [surf_xyz[i]; 1])(0..2), fp32 like cv::Mat (double accumulation)
+ *   *n_new_out = number of state-0 keypoints on unoccupied pixels (needNewTemplate's newPoints)
+ * surf_xyz / T_wc / world_xyz_out may be NULL when only the count is wanted. */
+typedef struct defslam_newpoints_problem {
+  int32_t n_keypoints, rows, cols;
+  const float *kp_xy;       /* [n*2] KeyFrame::mvKeysUn[i].pt (x, y)                          */
+  const uint8_t *kp_state;  /* [n]                                                            */
+  const float *surf_xyz;    /* [n*3] Surface::get3DSurfacePoint (camera frame of the keyframe) */
+  const float *T_wc;        /* [16] row-major KeyFrame::GetPoseInverse()                      */
+} defslam_newpoints_problem;
+
+int defslam_new_map_points(const defslam_newpoints_problem *p, uint8_t *action_out, float *world_xyz_out,
+                           int32_t *n_new_out);
+
 /* Surface -> template nodes.
  * replaces: Surface::getVertex  Modules/Mapping/Surface.cc:125-161
  * nodes_out: [xs*ys*3] fp32 (u d, v d, d), x-major outer loop */
