@@ -208,7 +208,7 @@ enum { PF_PROLOGUE = 0, PF_EVAL_STORE, PF_BUILD, PF_FS_INIT, PF_S1, PF_S1_WAIT, 
        PF_BWD, PF_UPDATE, PF_EVAL_TRIAL, PF_LM_SCALAR, PF_FINALIZE, PF_COUNT,
        /* extras (not part of the total): busy cycles of each warp inside S3, look-ahead factor, steps */
        PF_X_WARP = PF_COUNT, PF_X_DIAG = PF_COUNT + 16, PF_X_STEPS, PF_X_S2W, PF_X_BUILD = PF_X_S2W + 16,
-       PF_X_BUILDS = PF_X_BUILD + 8, PF_X_BWD, PF_TOTAL = PF_X_BWD + 4 };
+       PF_X_BUILDS = PF_X_BUILD + 8, PF_X_BWD, PF_X_FS = PF_X_BWD + 4, PF_TOTAL = PF_X_FS + 4 };
 #if DS_CUDA && defined(DS_PROFILE)
 #define DS_PROF_T0(var) const long long var = clock64()
 #define DS_PROF_ADD(idx, t0, cond) do { if (ctx_ref().prof != nullptr && (cond)) ctx_ref().prof[idx] += clock64() - (t0); } while (0)
@@ -545,12 +545,60 @@ DS_FN_NOINLINE double build_system(const Team team, Ctx &cx) {
   DS_PROF_T0(bt0);
   DS_PROF_INC(PF_X_BUILDS, team.tid == 0);
 
-  /* (1) per-facet sums.  item = (facet, group) */
-  /* group-major: the lanes of a warp run the same group on consecutive facets (no divergence
-   * between the four code paths, neighbouring rows of S) */
-  DS_FOR(it, nf * 6) {
-    const int g = it / nf, f = it - g * nf;
-    const int sb = c.ws.fptr[f], se = c.ws.fptr[f + 1];
+  /* (1) per-facet sums.  item = (facet, group).  The per-match scratch of a run of facets is
+   * first staged into the shared memory that is idle during assembly (rest of the window, the
+   * border rows, the panel buffer) by all threads -- coalesced, every load independent -- so the
+   * sums read shared memory instead of paying one L2/HBM round trip per match. */
+  {
+    const int asz = asm_scratch_doubles(n, ne);
+    double *stage = sm_base() + c.sl.W + asz;
+    const int psz = NB * (pl.bwp + 8) > 216 ? NB * (pl.bwp + 8) : 216;
+    /* the tail of the area holds the chunk's facet offsets (nf + 1 ints) */
+    const int avail = (c.sl.P + psz) - (c.sl.W + asz) - (nf + 2) / 2 - 1;
+    const int cap = avail > 0 ? avail / NMSCR : 0; /* matches per chunk */
+    int *fps = (int *)(stage + (avail > 0 ? avail : 0));
+    int fb = 0;
+    DS_PROF_LOCALS(fsacc, 4);
+    DS_PROF_T0M(fst);
+    while (fb < nf) {
+      const int sb0 = c.ws.fptr[fb];
+      int fe = nf, s1 = M;
+      if (M - sb0 > cap) {
+        fe = cap > 0 ? c.ws.mfac[c.ws.mperm[sb0 + cap]] >> 6 : fb; /* first facet that does not fit entirely */
+        s1 = c.ws.fptr[fe];
+      }
+      const double *SS;
+      int sst;
+      if (fe > fb) { /* stage matches sb0..s1 */
+        const int cnt = s1 - sb0;
+        team.sync(); /* the previous chunk has been consumed */
+        DS_PROF_LAP(fsacc, 0, fst);
+        /* plane by plane, all 18 loads of a thread in flight together */
+        DS_FOR(j, cnt) {
+          double v[NMSCR];
+#pragma unroll
+          for (int pln = 0; pln < NMSCR; pln++) v[pln] = S[pln * M + sb0 + j];
+#pragma unroll
+          for (int pln = 0; pln < NMSCR; pln++) stage[pln * cap + j] = v[pln];
+        }
+        /* facet offsets of the chunk, relative to it (int view of the tail of the staging area) */
+        DS_FOR(i, fe - fb + 1) fps[i] = c.ws.fptr[fb + i] - sb0;
+        DS_PROF_LAP(fsacc, 1, fst);
+        team.sync();
+        DS_PROF_LAP(fsacc, 2, fst);
+        SS = stage; sst = cap;
+      } else {      /* a single facet with more matches than the staging area holds: from global */
+        fe = fb + 1;
+        SS = S; sst = M;
+      }
+      const int nfc = fe - fb;
+      /* group-major: the lanes of a warp run the same group on consecutive facets (no divergence
+       * between the four code paths, neighbouring rows of the scratch) */
+      DS_FOR(it, nfc * 6) {
+        const int g = it / nfc, f = fb + (it - g * nfc);
+        int sb, se;
+        if (SS == stage) { sb = fps[f - fb]; se = fps[f - fb + 1]; }
+        else { sb = c.ws.fptr[f]; se = c.ws.fptr[f + 1]; }
     /* Two matches per trip: the loads of both are independent, so a facet with n matches costs
      * ceil(n/2) memory round trips.  The second slot of an odd tail re-reads the last match with
      * weight 0 (adds +0: the sums are the same as match-by-match). */
@@ -563,8 +611,8 @@ DS_FN_NOINLINE double build_system(const Team team, Ctx &cx) {
         for (int u = 0; u < 2; u++) {
           const bool ok = s0 + u < se;
           const int s = ok ? s0 + u : s0;
-          const double w = ok ? S[2 * M + s] : 0.0, e0 = S[s], e1 = S[M + s];
-          const double b0 = S[15 * M + s], b1 = S[16 * M + s], b2 = S[17 * M + s];
+          const double w = ok ? SS[2 * sst + s] : 0.0, e0 = SS[s], e1 = SS[sst + s];
+          const double b0 = SS[15 * sst + s], b1 = SS[16 * sst + s], b2 = SS[17 * sst + s];
           a[0] += w * b0 * b0; a[1] += w * b0 * b1; a[2] += w * b0 * b2;
           a[3] += w * b1 * b1; a[4] += w * b1 * b2; a[5] += w * b2 * b2;
           a[6] += w * b0 * e0; a[7] += w * b0 * e1;
@@ -583,9 +631,9 @@ DS_FN_NOINLINE double build_system(const Team team, Ctx &cx) {
         for (int u = 0; u < 2; u++) {
           const bool ok = s0 + u < se;
           const int s = ok ? s0 + u : s0;
-          const double wb = (ok ? S[2 * M + s] : 0.0) * S[(14 + g) * M + s];
+          const double wb = (ok ? SS[2 * sst + s] : 0.0) * SS[(14 + g) * sst + s];
 #pragma unroll
-          for (int k = 0; k < 12; k++) a[k] += wb * S[(3 + k) * M + s];
+          for (int k = 0; k < 12; k++) a[k] += wb * SS[(3 + k) * sst + s];
         }
       }
 #pragma unroll
@@ -600,10 +648,10 @@ DS_FN_NOINLINE double build_system(const Team team, Ctx &cx) {
         for (int u = 0; u < 2; u++) {
           const bool ok = s0 + u < se;
           const int s = ok ? s0 + u : s0;
-          const double w = ok ? S[2 * M + s] : 0.0;
+          const double w = ok ? SS[2 * sst + s] : 0.0;
           double J[12];
 #pragma unroll
-          for (int k = 0; k < 12; k++) J[k] = S[(3 + k) * M + s];
+          for (int k = 0; k < 12; k++) J[k] = SS[(3 + k) * sst + s];
 #pragma unroll
           for (int q = 0; q < 6; q++) a[q] += w * (J[0] * J[q] + J[6] * J[6 + q]);
 #pragma unroll
@@ -622,10 +670,10 @@ DS_FN_NOINLINE double build_system(const Team team, Ctx &cx) {
         for (int u = 0; u < 2; u++) {
           const bool ok = s0 + u < se;
           const int s = ok ? s0 + u : s0;
-          const double w = ok ? S[2 * M + s] : 0.0, e0 = S[s], e1 = S[M + s];
+          const double w = ok ? SS[2 * sst + s] : 0.0, e0 = SS[s], e1 = SS[sst + s];
           double J[12];
 #pragma unroll
-          for (int k = 0; k < 12; k++) J[k] = S[(3 + k) * M + s];
+          for (int k = 0; k < 12; k++) J[k] = SS[(3 + k) * sst + s];
 #pragma unroll
           for (int q = 2; q < 6; q++) a[q - 2] += w * (J[2] * J[q] + J[8] * J[6 + q]);
 #pragma unroll
@@ -640,6 +688,11 @@ DS_FN_NOINLINE double build_system(const Team team, Ctx &cx) {
 #pragma unroll
       for (int k = 0; k < 16; k++) F[(59 + k) * nf + f] = a[k];
     }
+      }
+      DS_PROF_LAP(fsacc, 3, fst);
+      fb = fe;
+    }
+    DS_PROF_FLUSH(fsacc, 4, PF_X_FS, team.tid == 0);
   }
   team.sync();
   DS_PROF_ADD(PF_X_BUILD + 0, bt0, team.tid == 0);
