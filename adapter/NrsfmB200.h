@@ -11,6 +11,8 @@
  *                         Modules/Mapping/ShapeFromNormals.cc:38-260   -> estimateSurface()
  *   SurfaceRegistration::registerSurfaces()  (+ Optimizer::OptimizeHorn, scaleMinMedian)
  *                         Modules/Mapping/SurfaceRegistration.cc:48-153 -> registerSurfaces()
+ *   DefLocalMapping::needNewTemplate() / CreateNewMapPoints()
+ *                         Modules/Mapping/DefLocalMapping.cc:355-403,240-347 -> needNewTemplate(), CreateNewMapPoints()
  *
  * Like DefOptimizerB200.h they are templates over the reference's types, written against the member
  * names the reference bodies use, so they compile unchanged against the DefSLAM headers
@@ -285,6 +287,78 @@ bool registerSurfaces(KeyFrame *refKF, double chiLimit_, bool check_chi, uint64_
   }
   refKF->SetPoseRowMajor(Tcw);
   return true;
+}
+
+/* Keypoint table of a keyframe in the C ABI's form: pixel positions and map-point state
+ * (0 none, 1 good, 2 bad) -- what both mask loops of DefLocalMapping.cc read. */
+template <class KeyFrame>
+inline void keyframe_keypoint_states(KeyFrame *kf, std::vector<float> &xy, std::vector<uint8_t> &state) {
+  const size_t nval = kf->mvKeysUn.size();
+  xy.resize(2 * nval); state.resize(nval);
+  for (size_t i = 0; i < nval; i++) {
+    xy[2 * i] = kf->mvKeysUn[i].pt.x; xy[2 * i + 1] = kf->mvKeysUn[i].pt.y;
+    auto *pMP = kf->GetMapPoint(i);
+    state[i] = !pMP ? 0 : (pMP->isBad() ? 2 : 1);
+  }
+}
+
+/* DefLocalMapping::needNewTemplate (DefLocalMapping.cc:355-403): rows/cols are imGray.rows/cols.
+ * A failing C-ABI call answers false (no template change), like a frame without new points. */
+template <class KeyFrame>
+bool needNewTemplate(KeyFrame *mpCurrentKeyFrame, int rows, int cols, int pointsToTemplate_, int *newPoints_out = nullptr) {
+  std::vector<float> xy; std::vector<uint8_t> state;
+  keyframe_keypoint_states(mpCurrentKeyFrame, xy, state);
+  defslam_newpoints_problem p;
+  p.n_keypoints = (int32_t)state.size(); p.rows = rows; p.cols = cols;
+  p.kp_xy = xy.data(); p.kp_state = state.data(); p.surf_xyz = nullptr; p.T_wc = nullptr;
+  std::vector<uint8_t> action(state.size() + 1);
+  int32_t newPoints = 0;
+  if (defslam_new_map_points(&p, action.data(), nullptr, &newPoints) != DEFSLAM_OK) return false;
+  if (newPoints_out) *newPoints_out = newPoints;
+  return newPoints > pointsToTemplate_;                               /* :399 */
+}
+
+/* DefLocalMapping::CreateNewMapPoints (DefLocalMapping.cc:240-347).  Existing good map points move
+ * onto the surface (SetWorldPosXYZ(const float[3]), the cv::Mat-free form of SetWorldPos); for every
+ * keypoint without a map point on a free pixel `create_point(i, x3w)` runs the reference's
+ * object-management tail (:329-341: new DefMapPoint, AddObservation, addMapPoint,
+ * ComputeDistinctiveDescriptors, UpdateNormalAndDepth, Map::addMapPoint, mlpRecentAddedMapPoints).
+ * Returns the number of points created, or -1 with nothing touched when the C-ABI call fails. */
+template <class DefKeyFrame, class KeyFrame, class DefMapPoint, class Vec3f, class Create>
+int CreateNewMapPoints(KeyFrame *referenceKF_, int rows, int cols, Create create_point) {
+  DefKeyFrame *kf = static_cast<DefKeyFrame *>(referenceKF_);
+  std::vector<float> xy; std::vector<uint8_t> state;
+  keyframe_keypoint_states(referenceKF_, xy, state);
+  const size_t nval = state.size();
+  std::vector<float> surf(3 * nval + 3, 0.f), world(3 * nval + 3);
+  for (size_t i = 0; i < nval; i++) {
+    if (state[i] == 2) continue;
+    Vec3f x3c;
+    kf->surface->get3DSurfacePoint(i, x3c);
+    for (int c = 0; c < 3; c++) surf[3 * i + c] = x3c(c);
+  }
+  float Twc[16];
+  referenceKF_->getPoseInverseRowMajor(Twc);
+  defslam_newpoints_problem p;
+  p.n_keypoints = (int32_t)nval; p.rows = rows; p.cols = cols;
+  p.kp_xy = xy.data(); p.kp_state = state.data(); p.surf_xyz = surf.data(); p.T_wc = Twc;
+  std::vector<uint8_t> action(nval + 1);
+  int32_t n_new = 0;
+  if (defslam_new_map_points(&p, action.data(), world.data(), &n_new) != DEFSLAM_OK) return -1;
+  int created = 0;
+  for (size_t i = 0; i < nval; i++) {
+    if (action[i] == 1) {                                             /* :281-311 */
+      DefMapPoint *defMP = static_cast<DefMapPoint *>(referenceKF_->GetMapPoint(i));
+      float pos[3];
+      const bool known = defMP->getPositionInKeyframe(referenceKF_, pos);
+      defMP->SetWorldPosXYZ(&world[3 * i]);
+      if (!known) defMP->lastincorporasion = false;
+    } else if (action[i] == 2) {                                      /* :313-342 */
+      create_point(i, (const float *)&world[3 * i]);
+      created++;
+    }
+  }
+  return created;
 }
 
 }  // namespace defslam_b200

@@ -183,6 +183,18 @@ class Sim3Result(C.Structure):
     ]
 
 
+class NewPointsProblem(C.Structure):
+    _fields_ = [
+        ("n_keypoints", C.c_int32),
+        ("rows", C.c_int32),
+        ("cols", C.c_int32),
+        ("kp_xy", c_float_p),
+        ("kp_state", c_uint8_p),
+        ("surf_xyz", c_float_p),
+        ("T_wc", c_float_p),
+    ]
+
+
 NORMALS_ARGS = [C.POINTER(NormalsProblem), c_double_p, c_double_p, c_float_p, c_uint8_p, c_int32_p, c_float_p,
                 c_uint8_p]
 POLY_ARGS = [C.c_int32, c_float_p, c_float_p, c_float_p, c_float_p, c_double_p, c_double_p]
@@ -231,6 +243,7 @@ PROTOTYPES = {
     "defslam_sim3_register_batched": (
         C.c_int, [C.c_int32, C.POINTER(Sim3Problem), C.POINTER(Sim3Result), C.c_int32]),
     "defslam_scale_min_median": (C.c_int, [C.c_int32, c_float_p, c_float_p, C.c_uint64, c_float_p]),
+    "defslam_new_map_points": (C.c_int, [C.POINTER(NewPointsProblem), c_uint8_p, c_float_p, c_int32_p]),
     "defslam_surface_vertices": (C.c_int, [C.POINTER(Bbs), c_double_p, C.c_int32, C.c_int32, c_float_p]),
     "defslam_version": (C.c_char_p, []),
     "defslam_kernel_launch_count": (C.c_int64, []),

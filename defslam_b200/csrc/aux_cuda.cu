@@ -8,6 +8,7 @@
 
 #include "ds_runtime.h"
 #include "mesh_core.h"
+#include "newpts_core.h"
 
 using namespace ds;
 
@@ -53,6 +54,50 @@ __global__ void mappoints_kernel(const double *X, int npts, const int *nodes, co
 __global__ void surface_vertices_kernel(BbsView s, const double *ctrl, int xs, int ys, float *out) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < xs * ys; i += gridDim.x * blockDim.x)
     surface_vertex(s, ctrl, xs, ys, i, &out[3 * i]);
+}
+
+/* One thread per keypoint; the pixels of the keypoints that own a good map point are staged
+ * through shared memory in tiles and every candidate tests its window against them. */
+__global__ void new_map_points_kernel(int n, int rows, int cols, const float *kp_xy, const uint8_t *state,
+                                      const float *surf, const float *Twc, uint8_t *action, float *world,
+                                      int *n_new) {
+  __shared__ int mx[256], my[256];
+  __shared__ float T[16];
+  const int ksz = cols / 20, anc = ksz / 2;
+  if (Twc != nullptr && threadIdx.x < 16) T[threadIdx.x] = Twc[threadIdx.x];
+  const int nblk_iter = (n + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
+  for (int it = 0; it < nblk_iter; it++) {
+    const int i = (it * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+    const bool valid = i < n;
+    const int st = valid ? state[i] : 2;
+    const int cx = valid ? (int)kp_xy[2 * i] : 0, cy = valid ? (int)kp_xy[2 * i + 1] : 0;
+    bool occupied = false;
+    for (int base = 0; base < n; base += blockDim.x) {
+      __syncthreads();
+      const int j = base + threadIdx.x;
+      int px = -1, py = -1;
+      if (j < n && state[j] == 1) { px = (int)kp_xy[2 * j]; py = (int)kp_xy[2 * j + 1]; }
+      mx[threadIdx.x] = px; my[threadIdx.x] = py;
+      __syncthreads();
+      if (st == 0 && !occupied) {
+        const int lim = n - base < (int)blockDim.x ? n - base : (int)blockDim.x;
+        for (int t = 0; t < lim; t++) {
+          if (mx[t] < 0) continue;
+          if (window_hits(cx, mx[t], cols, ksz, anc) && window_hits(cy, my[t], rows, ksz, anc)) { occupied = true; break; }
+        }
+      }
+    }
+    if (valid) {
+      const int act = st == 1 ? 1 : (st == 0 && !occupied ? 2 : 0);
+      action[i] = (uint8_t)act;
+      if (world != nullptr) {
+        float w[3] = {0.f, 0.f, 0.f};
+        if (act != 0) surface_point_to_world(T, &surf[3 * i], w);
+        world[3 * i] = w[0]; world[3 * i + 1] = w[1]; world[3 * i + 2] = w[2];
+      }
+      if (act == 2) atomicAdd(n_new, 1);
+    }
+  }
 }
 
 /* nord derivative orders per site; val laid out [ord][site][valdim] */
@@ -345,6 +390,54 @@ int defslam_surface_vertices(const defslam_bbs *bbs, const double *ctrl_depth, i
   DS_CUDA_TRY(cudaMemcpyAsync(h, d_out, out.total, cudaMemcpyDeviceToHost, ctx->stream));
   DS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   memcpy(nodes_out, h + o_o, nv * 3 * 4);
+  return DEFSLAM_OK;
+}
+
+int defslam_new_map_points(const defslam_newpoints_problem *p, uint8_t *action_out, float *world_xyz_out,
+                           int32_t *n_new_out) {
+  if (!p || p->n_keypoints < 0 || p->rows <= 0 || p->cols <= 0 || !action_out || !n_new_out) return DEFSLAM_EBADARG;
+  const int n = p->n_keypoints, ksz = p->cols / 20;
+  if (n > 0 && (!p->kp_xy || !p->kp_state)) return DEFSLAM_EBADARG;
+  if (ksz < 1 || ksz > p->rows || ksz > p->cols) return DEFSLAM_EBADARG;
+  const bool place = world_xyz_out != nullptr;
+  if (place && (!p->surf_xyz || !p->T_wc)) return DEFSLAM_EBADARG;
+  for (int i = 0; i < n; i++) {
+    const int x = (int)p->kp_xy[2 * i], y = (int)p->kp_xy[2 * i + 1];
+    if (p->kp_state[i] > 2) return DEFSLAM_EBADARG;
+    /* the reference indexes its mask with these: outside the image is out of bounds there */
+    if (p->kp_state[i] != 2 && (x < 0 || x >= p->cols || y < 0 || y >= p->rows || !(p->kp_xy[2 * i] > -1.f) ||
+                                !(p->kp_xy[2 * i + 1] > -1.f)))
+      return DEFSLAM_EBADARG;
+  }
+  DevCtx *ctx = get_ctx(-1);
+  if (!ctx) return DEFSLAM_ECUDA;
+  *n_new_out = 0;
+  if (n == 0) return DEFSLAM_OK;
+  const size_t N = (size_t)n;
+  Packer in, out;
+  const size_t o_xy = in.add(N * 8), o_st = in.add(N), o_sf = in.add(place ? N * 12 : 0), o_T = in.add(64);
+  const size_t o_cnt = out.add(4), o_act = out.add(N), o_w = out.add(place ? N * 12 : 0);
+  Scratch &S = tl_scratch(ctx->device);
+  int rc;
+  if ((rc = S.host.ensure(in.total > out.total ? in.total : out.total)) || (rc = S.dev.ensure(in.total + out.total)))
+    return rc;
+  uint8_t *h = (uint8_t *)S.host.p, *d_in = (uint8_t *)S.dev.p, *d_out = d_in + in.total;
+  memcpy(h + o_xy, p->kp_xy, N * 8);
+  memcpy(h + o_st, p->kp_state, N);
+  if (place) { memcpy(h + o_sf, p->surf_xyz, N * 12); memcpy(h + o_T, p->T_wc, 64); }
+  DS_CUDA_TRY(cudaMemcpyAsync(d_in, h, in.total, cudaMemcpyHostToDevice, ctx->stream));
+  DS_CUDA_TRY(cudaMemsetAsync(d_out + o_cnt, 0, 4, ctx->stream));
+  new_map_points_kernel<<<grid_for(n, ctx->sm_count), 256, 0, ctx->stream>>>(
+      n, p->rows, p->cols, (const float *)(d_in + o_xy), d_in + o_st, place ? (const float *)(d_in + o_sf) : nullptr,
+      place ? (const float *)(d_in + o_T) : nullptr, d_out + o_act, place ? (float *)(d_out + o_w) : nullptr,
+      (int *)(d_out + o_cnt));
+  DS_CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  DS_CUDA_TRY(cudaMemcpyAsync(h, d_out, out.total, cudaMemcpyDeviceToHost, ctx->stream));
+  DS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  memcpy(n_new_out, h + o_cnt, 4);
+  memcpy(action_out, h + o_act, N);
+  if (place) memcpy(world_xyz_out, h + o_w, N * 12);
   return DEFSLAM_OK;
 }
 

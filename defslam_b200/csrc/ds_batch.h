@@ -31,6 +31,7 @@ struct BatchMarshal {
   size_t ws_band = 0, ws_dinv = 0, ws_cg = 0, ws_F = 0, ws_S = 0, ws_M = 0, ws_nf = 0, ws_dp = 0;
   int smem_doubles = 0;
   bool any_e_global = false;
+  bool any_x_global = false; /* then EVERY problem of the batch keeps x/dx in the workspace (one kernel variant per launch) */
 
   WorkspaceSizes ws_sizes() const {
     WorkspaceSizes z;
@@ -49,10 +50,13 @@ struct BatchMarshal {
     ws_band = ws_dinv = ws_cg = ws_F = ws_S = ws_M = ws_nf = ws_dp = 0;
     smem_doubles = 0;
     any_e_global = false;
+    any_x_global = false;
+    std::vector<const PlanView *> hvs(nprob);
     for (int i = 0; i < nprob; i++) {
       const PlanView *hv = nullptr, *dv = nullptr;
       const int rc = resolve(p[i], &hv, &dv);
       if (rc != 0) return rc;
+      hvs[i] = hv;
       if (!p[i].node_xyz || p[i].n_matches < 0 || p[i].n_frame_keypoints <= 0) return DEFSLAM_EBADARG;
       if (p[i].n_matches > 0 && (!p[i].match_nodes || !p[i].match_bary || !p[i].match_uv || !p[i].match_inv_sigma2))
         return DEFSLAM_EBADARG;
@@ -90,12 +94,20 @@ struct BatchMarshal {
       v.reg_lap = p[i].reg_lap; v.reg_inex = p[i].reg_inex; v.reg_temp = p[i].reg_temp;
       for (int k = 0; k < 16; k++) v.Tcw[k] = p[i].T_cw[k];
 
-      SmemLayout L = smem_layout(hv->n_nodes, hv->n_edges, hv->Dn_pad, hv->bwp, hv->ld, hv->Wr, hv->ES, true);
+      /* shared-memory placement, most resident first: border rows and x/dx in smem; border rows in
+       * the global workspace; x/dx there too (large meshes: the window alone fills the SM) */
+      SmemLayout L = smem_layout(hv->n_nodes, hv->n_edges, hv->Dn_pad, hv->bwp, hv->ld, hv->Wr, hv->ES, true, true);
       v.e_in_smem = 1;
+      v.x_in_smem = 1;
       if (L.total + CTX_DOUBLES > smem_limit_doubles) {
-        L = smem_layout(hv->n_nodes, hv->n_edges, hv->Dn_pad, hv->bwp, hv->ld, hv->Wr, hv->ES, false);
+        L = smem_layout(hv->n_nodes, hv->n_edges, hv->Dn_pad, hv->bwp, hv->ld, hv->Wr, hv->ES, false, true);
         v.e_in_smem = 0;
         any_e_global = true;
+      }
+      if (L.total + CTX_DOUBLES > smem_limit_doubles) {
+        L = smem_layout(hv->n_nodes, hv->n_edges, hv->Dn_pad, hv->bwp, hv->ld, hv->Wr, hv->ES, false, false);
+        v.x_in_smem = 0;
+        any_x_global = true;
         if (L.total + CTX_DOUBLES > smem_limit_doubles) return DEFSLAM_ETOOLARGE;
       }
       if (L.total + CTX_DOUBLES > smem_doubles) smem_doubles = L.total + CTX_DOUBLES;
@@ -107,6 +119,16 @@ struct BatchMarshal {
       ws_M = std::max(ws_M, M);
       ws_nf = std::max(ws_nf, (size_t)hv->n_facets + 1);
       ws_dp = std::max(ws_dp, (size_t)hv->Dn_pad);
+    }
+    if (any_x_global) {
+      smem_doubles = 0;
+      for (int i = 0; i < nprob; i++) {
+        const PlanView *hv = hvs[i];
+        views[i].x_in_smem = 0;
+        const SmemLayout L = smem_layout(hv->n_nodes, hv->n_edges, hv->Dn_pad, hv->bwp, hv->ld, hv->Wr, hv->ES,
+                                         views[i].e_in_smem != 0, false);
+        if (L.total + CTX_DOUBLES > smem_doubles) smem_doubles = L.total + CTX_DOUBLES;
+      }
     }
     return 0;
   }

@@ -26,13 +26,34 @@ DS_FN bool window_hits(int c, int m, int n, int k, int a) {
   return false;
 }
 
-/* x3w = (Twc [x3c; 1])(0..2): cv::Mat fp32 product, accumulated in double like cv::gemm */
+/* fp32 multiply / add with one rounding each (never contracted into an FMA) */
+DS_FN float mul_rn(float a, float b) {
+#if DS_CUDA
+  return __fmul_rn(a, b);
+#else
+  volatile float t = a * b;
+  return t;
+#endif
+}
+DS_FN float add_rn(float a, float b) {
+#if DS_CUDA
+  return __fadd_rn(a, b);
+#else
+  volatile float t = a + b;
+  return t;
+#endif
+}
+
+/* x3w = (Twc [x3c; 1])(0..2) as OpenCV computes a CV_32F 4x4 * 4x1 product (cv::gemm's small-
+ * matrix path): fp32 products summed left to right in fp32, no FMA -- checked bit for bit against
+ * cv2.gemm (tests/golden/newpts_cv.npz) */
 DS_FN void surface_point_to_world(const float *Twc, const float *x3c, float *out) {
   for (int r = 0; r < 3; r++) {
-    double s = 0.0;
-    for (int k = 0; k < 3; k++) s += (double)Twc[4 * r + k] * (double)x3c[k];
-    s += (double)Twc[4 * r + 3] * 1.0;
-    out[r] = (float)s;
+    float s = mul_rn(Twc[4 * r], x3c[0]);
+    s = add_rn(s, mul_rn(Twc[4 * r + 1], x3c[1]));
+    s = add_rn(s, mul_rn(Twc[4 * r + 2], x3c[2]));
+    s = add_rn(s, mul_rn(Twc[4 * r + 3], 1.0f));
+    out[r] = s;
   }
 }
 

@@ -59,6 +59,8 @@ struct ProbView {
   int n_matches, n_kp, max_it, layers;
   int trace_cap;
   int e_in_smem;
+  int x_in_smem;           /* node positions / LM step in shared memory (else in the global workspace) */
+  int pad_;
   double fx, fy, cx, cy;
   double reg_lap, reg_inex, reg_temp;
   float Tcw[16];
@@ -86,6 +88,8 @@ struct Workspace {
   double *F;     /* [NFACC*nf]    per-facet accumulators                      */
   double *S;     /* [NMSCR*M]     per-match scratch                           */
   double *xb;    /* [Dn_pad]      LM backup of the node positions (push/pop)  */
+  double *xg;    /* [Dn_pad]      node positions when they do not fit in smem */
+  double *dxg;   /* [Dn_pad+8]    LM step when it does not fit in smem        */
   int *mfac;     /* [M]  facet<<6 | slot0 | slot1<<2 | slot2<<4               */
   int *mperm;    /* [M]  matches grouped by facet                             */
   int *fptr;     /* [nf+1] */
@@ -101,7 +105,7 @@ static inline
 __host__ __device__
 #endif
 size_t workspace_bytes(const WorkspaceSizes &z) {
-  size_t b = sizeof(double) * (2 * z.band + z.dinv + 2 * z.cg + z.F + z.S + z.dp) + sizeof(int) * (2 * z.M + 2 * z.nf + 2);
+  size_t b = sizeof(double) * (2 * z.band + z.dinv + 2 * z.cg + z.F + z.S + 3 * z.dp + 8) + sizeof(int) * (2 * z.M + 2 * z.nf + 2);
   return (b + 255) & ~(size_t)255;
 }
 
@@ -120,6 +124,8 @@ Workspace carve_workspace(uint8_t *base, const WorkspaceSizes &z) {
   w.F = d; d += z.F;
   w.S = d; d += z.S;
   w.xb = d; d += z.dp;
+  w.xg = d; d += z.dp;
+  w.dxg = d; d += z.dp + 8;
   int *i = (int *)d;
   w.mfac = i; i += z.M;
   w.mperm = i; i += z.M;
@@ -140,7 +146,8 @@ static inline
 #if DS_CUDA
 __host__ __device__
 #endif
-SmemLayout smem_layout(int n_nodes, int n_edges, int Dn_pad, int bwp, int ld, int Wr, int ES, bool e_in_smem) {
+SmemLayout smem_layout(int n_nodes, int n_edges, int Dn_pad, int bwp, int ld, int Wr, int ES, bool e_in_smem,
+                       bool x_in_smem = true) {
   SmemLayout L;
   int o = 0;
   int wsz = Wr * ld;
@@ -151,9 +158,9 @@ SmemLayout smem_layout(int n_nodes, int n_edges, int Dn_pad, int bwp, int ld, in
   L.W = o;    o += wsz; o = (o + 1) & ~1;
   L.E = o;    o += e_in_smem ? 8 * ES : 0;
   L.P = o;    o += (NB * (bwp + 8) > 216 ? NB * (bwp + 8) : 216); o = (o + 1) & ~1;
-  L.x = o;    o += Dn_pad;
+  L.x = o;    o += x_in_smem ? Dn_pad : 0;
   L.xb = o;   /* (backup lives in global memory) */
-  L.dx = o;   o += Dn_pad + 8;
+  L.dx = o;   o += x_in_smem ? Dn_pad + 8 : 0;
   L.Lkk = o;  o += 64;
   L.invL = o; o += 192;  /* inv(L_kk), row stride 12; two buffers (step parity) */
   L.G = o;    o += 64;
@@ -200,6 +207,10 @@ static double *ds_smem_emu = nullptr;
 #endif
 DS_FN Ctx &ctx_ref() { return *(Ctx *)DS_SMEM; }
 DS_FN double *sm_base() { return DS_SMEM + CTX_DOUBLES; }
+/* node positions x and LM step dx: shared memory (XS) or, for meshes whose window leaves no room
+ * (25 x 25 and up), the CTA's global workspace.  Compile-time so the common case keeps LDS/STS. */
+template <bool XS> DS_FN double *xvec(const Ctx &c) { return XS ? sm_base() + c.sl.x : c.ws.xg; }
+template <bool XS> DS_FN double *dxvec(const Ctx &c) { return XS ? sm_base() + c.sl.dx : c.ws.dxg; }
 DS_FN uint8_t *viewed_ptr(const Ctx &c) { return (uint8_t *)(sm_base() + c.sl.flags); }
 DS_FN uint8_t *freev_ptr(const Ctx &c) { return (uint8_t *)(sm_base() + c.sl.flags) + c.pl.n_nodes; }
 
@@ -254,17 +265,18 @@ DS_FN int pidx(int cc, int r, int HS) { return (cc >> 2) * HS + r * 4 + (cc & 3)
 /* ------------------------------------------------------------ prologue -- */
 
 /* returns 0 or an error code (uniform over the team) */
+template <bool XS>
 DS_FN_NOINLINE int prologue(const Team team, Ctx &cx) {
   Ctx &c = ctx_ref();
   (void)cx;
   const PlanView &pl = c.pl;
   const ProbView &pb = c.pb;
   const int n = pl.n_nodes, nf = pl.n_facets, M = pb.n_matches;
-  double *x = sm_base() + c.sl.x;
+  double *x = xvec<XS>(c);
   double *red = sm_base() + c.sl.red;
 
   DS_FOR(i, pl.Dn_pad) x[i] = i < pl.Dn ? pb.node_xyz[i] : 0.0;
-  DS_FOR(i, pl.Dn_pad + 8) sm_base()[c.sl.dx + i] = 0.0;
+  DS_FOR(i, pl.Dn_pad + 8) dxvec<XS>(c)[i] = 0.0;
   DS_FOR(i, 192) sm_base()[c.sl.invL + i] = 0.0;
   DS_FOR(i, 2 * n) viewed_ptr(c)[i] = 0; /* viewed + freev are contiguous */
   DS_FOR(f, nf) c.ws.fcnt[f] = 0;
@@ -407,10 +419,11 @@ DS_FN double curv_residual(const Ctx &c, const double *x, int i, double d[3], do
  * store=true additionally fills everything build_system() gathers from:
  * per-match scratch S, per-node A / centre / edge quantities (overlaid on the
  * window region of shared memory). */
+template <bool XS>
 DS_FN_NOINLINE double eval_state(const Team team, Ctx &cx, bool store) {
   Ctx &c = ctx_ref();
   (void)cx;
-  const double *x = sm_base() + c.sl.x, *ps = sm_base() + c.sl.pose;
+  const double *x = xvec<XS>(c), *ps = sm_base() + c.sl.pose;
   const PlanView &pl = c.pl;
   const ProbView &pb = c.pb;
   const int n = pl.n_nodes, ne = pl.n_edges, M = pb.n_matches;
@@ -530,6 +543,7 @@ DS_FN_NOINLINE double eval_state(const Team team, Ctx &cx, bool store) {
  * same state.  Produces Hb (band), Cg rows 0-5 (camera border), Cg row 6 (b_n),
  * Hcc/bc (shared).  Returns max |diag| over the free variables
  * (computeLambdaInit, optimization_algorithm_levenberg.cpp:166-180). */
+template <bool XS>
 DS_FN_NOINLINE double build_system(const Team team, Ctx &cx) {
   Ctx &c = ctx_ref();
   (void)cx;
@@ -832,7 +846,7 @@ DS_FN_NOINLINE double build_system(const Team team, Ctx &cx) {
       for (int a = 0; a < 6; a++)
         for (int r = 0; r < 3; r++) C[3 * a + r] = bj[a] * Ap[r] + bj[6 + a] * Ap[3 + r];
       if (viewed_ptr(c)[p])
-        for (int r = 0; r < 3; r++) b[r] -= c.info_ref * ((sm_base() + c.sl.x)[3 * p + r] - pl.rest[3 * p + r]);
+        for (int r = 0; r < 3; r++) b[r] -= c.info_ref * (xvec<XS>(c)[3 * p + r] - pl.rest[3 * p + r]);
       for (int k = pl.nc_ptr[p]; k < pl.nc_ptr[p + 1]; k++) {
         const int i = pl.nc_ent[2 * k], ip = pl.nc_ent[2 * k + 1];
         const double g = cg[i];
@@ -1236,6 +1250,7 @@ DS_FN void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"
  * Returns false if a pivot is not positive (LinearSolverDense::solve returning
  * false, linear_solver_dense.h:107-112); dx is then left untouched (stale), as
  * in the reference. */
+template <bool XS>
 DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
   Ctx &c = ctx_ref();
   (void)cx;
@@ -1244,7 +1259,7 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
   const int PR = bwp + 8, HS = 4 * PR; /* panel rows: trailing rows, then the 8 border rows */
   double *const sm = sm_base();
   double *W = sm + c.sl.W, *P = sm + c.sl.P, *invL = sm + c.sl.invL;
-  double *G = sm + c.sl.G, *Hcc = sm + c.sl.Hcc, *dx = sm + c.sl.dx;
+  double *G = sm + c.sl.G, *Hcc = sm + c.sl.Hcc, *dx = dxvec<XS>(c);
   const bool e_smem = c.pb.e_in_smem != 0;
   double *Es = sm_base() + c.sl.E, *Eg = c.ws.Eg;
   const double *Hb = c.ws.Hb;
@@ -1604,11 +1619,12 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
 
 /* ------------------------------------------------------------- LM ------ */
 
+template <bool XS>
 DS_FN void apply_update(const Team team, Ctx &cx) {
   Ctx &c = ctx_ref();
   (void)cx;
   const PlanView &pl = c.pl;
-  double *x = sm_base() + c.sl.x, *dx = sm_base() + c.sl.dx;
+  double *x = xvec<XS>(c), *dx = dxvec<XS>(c);
   /* VertexSBAPointXYZ::oplusImpl (types_sba.h:52-56); fixed nodes have dx = 0 */
   DS_FOR(i, pl.Dn) x[i] += dx[i];
   if (team.tid == 0) { /* VertexSE3Expmap::oplusImpl */
@@ -1657,6 +1673,7 @@ DS_FN void expand_dense(const Team team, Ctx &cx, double chi) {
 }
 
 /* DefOptimizer.cc:515-577 */
+template <bool XS>
 DS_FN_NOINLINE void finalize(const Team team, Ctx &cx, bool last_rejected, int iterations, int trials, double chi_ini,
                              double chi_fin, double lambda) {
   Ctx &c = ctx_ref();
@@ -1664,7 +1681,7 @@ DS_FN_NOINLINE void finalize(const Team team, Ctx &cx, bool last_rejected, int i
   const PlanView &pl = c.pl;
   const ProbView &pb = c.pb;
   const int M = pb.n_matches, n = pl.n_nodes;
-  const double *x = sm_base() + c.sl.x, *xb = c.ws.xb;
+  const double *x = xvec<XS>(c), *xb = c.ws.xb;
   Pose P, Pb;
   load_pose(sm_base() + c.sl.pose, P);
   load_pose(sm_base() + c.sl.pose + 8, Pb);
@@ -1711,17 +1728,18 @@ DS_FN_NOINLINE void finalize(const Team team, Ctx &cx, bool last_rejected, int i
 }
 
 /* One frame, start to finish.  All threads of the team call this. */
+template <bool XS>
 DS_FN_NOINLINE void sft_solve_one(const Team team, Ctx &cx) {
   Ctx &c = ctx_ref();
   (void)cx;
   const PlanView &pl = c.pl;
   const ProbView &pb = c.pb;
-  double *x = sm_base() + c.sl.x, *xb = c.ws.xb, *dx = sm_base() + c.sl.dx;
+  double *x = xvec<XS>(c), *xb = c.ws.xb, *dx = dxvec<XS>(c);
   double *ps = sm_base() + c.sl.pose, *psb = ps + 8;
   double *red = sm_base() + c.sl.red;
   const int Dp = pl.Dn_pad;
 
-  const int rc = prologue(team, c);
+  const int rc = prologue<XS>(team, c);
   {
     TileDesc *tt = (TileDesc *)(sm_base() + c.sl.tiles);
     const int nt8 = pl.bwp / NB;
@@ -1739,8 +1757,8 @@ DS_FN_NOINLINE void sft_solve_one(const Team team, Ctx &cx) {
     return;
   }
   if (pb.mode == MODE_NORMAL_EQ) {
-    const double chi = eval_state(team, c, true);
-    build_system(team, c);
+    const double chi = eval_state<XS>(team, c, true);
+    build_system<XS>(team, c);
     expand_dense(team, c, chi);
     return;
   }
@@ -1754,12 +1772,12 @@ DS_FN_NOINLINE void sft_solve_one(const Team team, Ctx &cx) {
   int nBad = 0, iterations = 0, trials = 0;
   bool last_rejected = false;
   for (int it = 0; it < max_it; it++) {
-    double currentChi = eval_state(team, c, true);
+    double currentChi = eval_state<XS>(team, c, true);
     prof_mark(team, c, PF_EVAL_STORE);
     double tempChi = currentChi;
     const double iniChi = currentChi;
     if (it == 0) chi_ini0 = currentChi;
-    const double maxDiag = build_system(team, c);
+    const double maxDiag = build_system<XS>(team, c);
     prof_mark(team, c, PF_BUILD);
     if (it == 0) { lambda = tau * maxDiag; ni = 2; nBad = 0; }
     const double lambda_start = lambda;
@@ -1771,10 +1789,10 @@ DS_FN_NOINLINE void sft_solve_one(const Team team, Ctx &cx) {
       DS_FOR(i, pl.Dn) xb[i] = x[i];
       if (team.tid == 0) for (int k = 0; k < 7; k++) psb[k] = ps[k];
       prof_mark(team, c, PF_LM_SCALAR);
-      const bool ok2 = factor_solve(team, c, lambda);
-      apply_update(team, c);
+      const bool ok2 = factor_solve<XS>(team, c, lambda);
+      apply_update<XS>(team, c);
       prof_mark(team, c, PF_UPDATE);
-      tempChi = eval_state(team, c, false);
+      tempChi = eval_state<XS>(team, c, false);
       prof_mark(team, c, PF_EVAL_TRIAL);
       if (!ok2) tempChi = DBL_MAX;
       rho = currentChi - tempChi;
@@ -1817,7 +1835,7 @@ DS_FN_NOINLINE void sft_solve_one(const Team team, Ctx &cx) {
   }
   team.sync();
   prof_mark(team, c, PF_LM_SCALAR);
-  finalize(team, c, last_rejected, iterations, trials, chi_ini0, chi_fin, lambda);
+  finalize<XS>(team, c, last_rejected, iterations, trials, chi_ini0, chi_fin, lambda);
   prof_mark(team, c, PF_FINALIZE);
 }
 
@@ -1825,6 +1843,7 @@ DS_FN_NOINLINE void sft_solve_one(const Team team, Ctx &cx) {
  * its shared memory and its global workspace, then solve it.  The context is
  * kept in shared memory (one copy per CTA): with the shared-memory carve-out
  * this kernel uses there is almost no L1 left for a per-thread stack copy. */
+template <bool XS>
 DS_FN void sft_run_problem(const Team &team, const ProbView &pv, double *smem, uint8_t *ws_base,
                            const WorkspaceSizes &z, bool first_of_launch, long long *prof) {
 #if !DS_CUDA
@@ -1847,10 +1866,11 @@ DS_FN void sft_run_problem(const Team &team, const ProbView &pv, double *smem, u
     c.pb = pv;
     c.pl = *pv.plan;
     c.ws = carve_workspace(ws_base, z);
-    c.sl = smem_layout(c.pl.n_nodes, c.pl.n_edges, c.pl.Dn_pad, c.pl.bwp, c.pl.ld, c.pl.Wr, c.pl.ES, pv.e_in_smem != 0);
+    c.sl = smem_layout(c.pl.n_nodes, c.pl.n_edges, c.pl.Dn_pad, c.pl.bwp, c.pl.ld, c.pl.Wr, c.pl.ES, pv.e_in_smem != 0,
+                       pv.x_in_smem != 0);
   }
   team.sync();
-  sft_solve_one(team, c);
+  sft_solve_one<XS>(team, c);
 }
 
 }  // namespace ds

@@ -20,6 +20,9 @@ namespace {
 
 constexpr int SFT_THREADS = 256;
 
+/* XS: node positions and LM step in shared memory (every mesh up to ~21 x 21); the other variant
+ * keeps them in the CTA's global workspace for meshes whose factorisation window fills the SM. */
+template <bool XS>
 __global__ void __launch_bounds__(SFT_THREADS, 2)
 sft_lm_kernel(const ProbView *__restrict__ probs, int nprob, uint8_t *ws_base, size_t ws_stride, WorkspaceSizes z,
               long long *prof, int *work_counter) {
@@ -33,7 +36,7 @@ sft_lm_kernel(const ProbView *__restrict__ probs, int nprob, uint8_t *ws_base, s
   bool first = true;
   int pi = blockIdx.x;
   while (pi < nprob) {
-    sft_run_problem(team, probs[pi], smem, ws, z, first, blockIdx.x == 0 ? prof : nullptr);
+    sft_run_problem<XS>(team, probs[pi], smem, ws, z, first, blockIdx.x == 0 ? prof : nullptr);
     first = false;
     __syncthreads();
     if (threadIdx.x == 0) next_problem = (int)gridDim.x + atomicAdd(work_counter, 1);
@@ -171,9 +174,15 @@ static int batch_load(defslam_sft_batch *B, int nprob, const defslam_sft_problem
   B->bm.bind((uint8_t *)B->d_in.p, (uint8_t *)B->d_out.p);
 
   B->smem_bytes = B->bm.smem_doubles * (int)sizeof(double);
-  DS_CUDA_TRY(cudaFuncSetAttribute(sft_lm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B->smem_bytes));
+  const bool xs = !B->bm.any_x_global;
   int occ = 0;
-  DS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sft_lm_kernel, SFT_THREADS, B->smem_bytes));
+  if (xs) {
+    DS_CUDA_TRY(cudaFuncSetAttribute(sft_lm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, B->smem_bytes));
+    DS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sft_lm_kernel<true>, SFT_THREADS, B->smem_bytes));
+  } else {
+    DS_CUDA_TRY(cudaFuncSetAttribute(sft_lm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B->smem_bytes));
+    DS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sft_lm_kernel<false>, SFT_THREADS, B->smem_bytes));
+  }
   if (occ < 1) return DEFSLAM_ETOOLARGE;
   B->grid = ctx->sm_count * occ;
   if (B->grid > nprob) B->grid = nprob;
@@ -204,8 +213,12 @@ static int batch_launch(defslam_sft_batch *B, cudaEvent_t ev0 = nullptr, cudaEve
     DS_CUDA_TRY(cudaMemsetAsync(B->d_counter.p, 0, sizeof(int), ctx->stream));
   }
   DS_CUDA_TRY(cudaEventRecord(ev0, ctx->stream));
-  sft_lm_kernel<<<B->grid, SFT_THREADS, B->smem_bytes, ctx->stream>>>(
-      (const ProbView *)B->d_views.p, B->nprob, (uint8_t *)B->d_ws.p, B->ws_stride, z, prof, (int *)B->d_counter.p);
+  if (!B->bm.any_x_global)
+    sft_lm_kernel<true><<<B->grid, SFT_THREADS, B->smem_bytes, ctx->stream>>>(
+        (const ProbView *)B->d_views.p, B->nprob, (uint8_t *)B->d_ws.p, B->ws_stride, z, prof, (int *)B->d_counter.p);
+  else
+    sft_lm_kernel<false><<<B->grid, SFT_THREADS, B->smem_bytes, ctx->stream>>>(
+        (const ProbView *)B->d_views.p, B->nprob, (uint8_t *)B->d_ws.p, B->ws_stride, z, prof, (int *)B->d_counter.p);
   DS_CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1);
   DS_CUDA_TRY(cudaEventRecord(ev1, ctx->stream));

@@ -232,7 +232,7 @@ class Api:
             P = _capi.PROTOTYPES
             for name in ("schwarp_fit", "schwarp_evaluate", "normals_batched", "polysolver_coefficients",
                          "sfn_solve", "sfn_system", "schwarp_fit_batched", "sfn_solve_batched",
-                         "sim3_register_batched", "scale_min_median"):
+                         "sim3_register_batched", "scale_min_median", "new_map_points"):
                 if hasattr(self.lib, prefix + name):
                     f = getattr(self.lib, prefix + name)
                     f.restype, f.argtypes = P["defslam_" + name]
@@ -375,6 +375,31 @@ class Api:
             len(mono), _capi.as_ptr(mono, C.c_float), _capi.as_ptr(stereo, C.c_float), C.c_uint64(seed),
             C.cast(C.byref(out), _capi.c_float_p)))
         return out.value
+
+
+def _new_map_points(self, kp_xy, kp_state, rows: int, cols: int, surf_xyz=None, T_wc=None):
+    """DefLocalMapping::CreateNewMapPoints / needNewTemplate (DefLocalMapping.cc:240-347,355-403):
+    returns (action[n], world_xyz[n,3] or None, n_new)."""
+    kp_xy = np.ascontiguousarray(kp_xy, np.float32)
+    kp_state = np.ascontiguousarray(kp_state, np.uint8)
+    n = len(kp_state)
+    place = surf_xyz is not None
+    if place:
+        surf_xyz = np.ascontiguousarray(surf_xyz, np.float32)
+        T_wc = np.ascontiguousarray(T_wc, np.float32)
+    p = _capi.NewPointsProblem(n, rows, cols, _capi.as_ptr(kp_xy, C.c_float), _capi.as_ptr(kp_state, C.c_uint8),
+                               _capi.as_ptr(surf_xyz, C.c_float) if place else None,
+                               _capi.as_ptr(T_wc, C.c_float) if place else None)
+    action = np.zeros(max(n, 1), np.uint8)
+    world = np.zeros((max(n, 1), 3), np.float32) if place else None
+    n_new = C.c_int32(0)
+    self._check("new_map_points", self._f("new_map_points")(
+        C.byref(p), _capi.as_ptr(action, C.c_uint8), _capi.as_ptr(world, C.c_float) if place else None,
+        C.cast(C.byref(n_new), _capi.c_int32_p)))
+    return action[:n], (world[:n] if place else None), n_new.value
+
+
+Api.new_map_points = _new_map_points
 
 
 def sim3_case(seed: int, n: int = 600, noise: float = 0.003, outlier_frac: float = 0.05) -> Sim3Case:

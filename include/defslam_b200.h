@@ -420,7 +420,7 @@ int defslam_scale_min_median(int32_t n, const float *mono_xyz, const float *ster
  *   kp_state[i]: 0 = no map point, 1 = good map point, 2 = bad map point (isBad())
  *   action_out[i]: 0 = leave, 1 = move the existing map point to world_xyz_out[i],
  *                  2 = create a map point at world_xyz_out[i]
- *   world_xyz_out[i] = (Twc * [surf_xyz[i]; 1])(0..2), fp32 like cv::Mat (double accumulation)
+ *   world_xyz_out[i] = (Twc * [surf_xyz[i]; 1])(0..2), fp32 products summed in fp32 like cv::gemm
  *   *n_new_out = number of state-0 keypoints on unoccupied pixels (needNewTemplate's newPoints)
  * surf_xyz / T_wc / world_xyz_out may be NULL when only the count is wanted. */
 typedef struct defslam_newpoints_problem {

@@ -54,6 +54,8 @@ def load(native: bool = False):
     lib.oracle_mappoints_recalculate.restype = C.c_int
     lib.oracle_mappoints_recalculate.argtypes = [C.c_int32, P.c_double_p, C.c_int32, P.c_int32_p, P.c_double_p,
                                                  P.c_float_p]
+    lib.oracle_new_map_points.restype = C.c_int
+    lib.oracle_new_map_points.argtypes = _capi.PROTOTYPES["defslam_new_map_points"][1]
     lib.oracle_regular_triangulation.restype = C.c_int
     lib.oracle_regular_triangulation.argtypes = [C.c_int, C.c_int, P.c_int32_p]
     lib.oracle_mesh_laplacian.restype = C.c_int

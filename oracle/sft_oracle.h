@@ -52,6 +52,10 @@ int oracle_sim3_register_batched(int32_t nprob, const defslam_sim3_problem *p, d
 int oracle_sim3_jacobian(const defslam_sim3_problem *p, int i, double *J21);
 int oracle_scale_min_median(int32_t n, const float *mono, const float *stereo, uint64_t seed, float *scale_out);
 
+/* ---- new map points / exploration test (newpts_oracle.c) ---- */
+int oracle_new_map_points(const defslam_newpoints_problem *p, uint8_t *action_out, float *world_xyz_out,
+                          int32_t *n_new_out);
+
 #ifdef __cplusplus
 }
 #endif

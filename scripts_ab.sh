@@ -1,9 +1,8 @@
 #!/bin/bash
-timeout 600 python -m pytest tests/test_gpu_sft.py -x -q -m gpu 2>&1 | tail -2
-for lib in libdefslam_b200_old.so libdefslam_b200.so; do
-  echo "== $lib"
-  DEFSLAM_LIB=$PWD/defslam_b200/$lib timeout 300 python tools/prof_run.py C2 2368 3 2>&1 | tail -1
-  DEFSLAM_LIB=$PWD/defslam_b200/$lib timeout 300 python tools/prof_run.py C4 2368 3 2>&1 | tail -1
-  DEFSLAM_LIB=$PWD/defslam_b200/$lib timeout 300 python tools/prof_run.py C3 1184 3 2>&1 | tail -1
-done
-bash scripts_phase.sh
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+echo "== timings (baseline a22bbe8: C2 52.0  C4 21.7  C3 108.6 ms)"
+timeout 300 python tools/prof_run.py C2 2368 3 2>&1 | tail -1
+timeout 300 python tools/prof_run.py C4 2368 3 2>&1 | tail -1
+timeout 300 python tools/prof_run.py C3 1184 3 2>&1 | tail -1
+echo "== C5 (25x25, 2000 matches), 148 frames"
+timeout 300 python tools/prof_run.py C5 148 2 2>&1 | tail -1

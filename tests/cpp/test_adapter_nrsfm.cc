@@ -30,9 +30,10 @@ struct Surface {
 struct KeyFrame;
 struct MapPoint {
   bool bad = false; KeyFrame *ref = nullptr; std::map<KeyFrame *, size_t> obs; double covNorm[4] = {0, 0, 0, 0};
-  float kfpos[3] = {0, 0, 0}; bool facet = true;
+  float kfpos[3] = {0, 0, 0}; bool facet = true; bool known = true, lastincorporasion = true; float wpos[3] = {0, 0, 0};
   bool getFacet() const { return facet; }
-  bool getPositionInKeyframe(KeyFrame *, float *o) { memcpy(o, kfpos, sizeof(kfpos)); return true; }
+  bool getPositionInKeyframe(KeyFrame *, float *o) { memcpy(o, kfpos, sizeof(kfpos)); return known; }
+  void SetWorldPosXYZ(const float *p) { memcpy(wpos, p, sizeof(wpos)); }
   bool isBad() const { return bad; }
   KeyFrame *GetReferenceKeyFrame() { return ref; }
   size_t GetIndexInKeyFrame(KeyFrame *k) { return obs[k]; }
@@ -55,6 +56,53 @@ struct DiffProp {
   std::pair<KeyFrame *, KeyFrame *> KFToKF; size_t idx1, idx2; float I1u, I1v, I2u, I2v;
   float J12a, J12b, J12c, J12d, J21a, J21b, J21c, J21d, H12uux, H12uuy, H12uvx, H12uvy, H12vvx, H12vvy;
 };
+
+// DefLocalMapping::needNewTemplate / CreateNewMapPoints through the adapter, against the oracle
+static int test_new_points(bool have_device) {
+  const int N = 500, rows = 480, cols = 640;
+  std::mt19937 rng(4); std::uniform_real_distribution<float> U(0, 1);
+  DefKeyFrame kf; Surface sf(N); kf.surface = &sf;
+  std::vector<MapPoint> mps(N);
+  const float T[16] = {0.98f, 0.02f, 0.f, 0.1f, -0.02f, 0.98f, 0.01f, -0.05f, 0.f, -0.01f, 0.99f, 0.2f, 0, 0, 0, 1};
+  memcpy(kf.Twc, T, sizeof(T));
+  std::vector<float> xy(2 * N), surf(3 * N); std::vector<uint8_t> st(N);
+  for (int i = 0; i < N; i++) {
+    KeyPoint k; k.pt.x = U(rng) * (cols - 1); k.pt.y = U(rng) * (rows - 1);
+    const float r = U(rng);
+    st[i] = r < 0.5f ? 0 : (r < 0.9f ? 1 : 2);
+    if (st[i] == 1) k.pt.x *= 0.5f;   // map points cover the left half only
+    kf.mvKeysUn.push_back(k); xy[2 * i] = k.pt.x; xy[2 * i + 1] = k.pt.y;
+    mps[i].bad = st[i] == 2; mps[i].known = (i % 3) != 0;
+    kf.mps.push_back(st[i] ? &mps[i] : nullptr);
+    for (int c = 0; c < 3; c++) { sf.pts[i](c) = U(rng) + (c == 2 ? 1.f : -0.5f); surf[3 * i + c] = sf.pts[i](c); }
+  }
+  std::vector<std::pair<size_t, Vec3f>> made;
+  auto create = [&](size_t i, const float *x) { Vec3f v; for (int c = 0; c < 3; c++) v(c) = x[c]; made.push_back({i, v}); };
+  int newPoints = -7;
+  const bool need = defslam_b200::needNewTemplate((KeyFrame *)&kf, rows, cols, 50, &newPoints);
+  const int created = defslam_b200::CreateNewMapPoints<DefKeyFrame, KeyFrame, MapPoint, Vec3f>((KeyFrame *)&kf, rows, cols, create);
+  if (!have_device) {
+    bool untouched = !need && newPoints == -7 && created == -1 && made.empty();
+    for (auto &m : mps) untouched = untouched && m.wpos[2] == 0.f && m.lastincorporasion;
+    printf("new points, no CUDA device: %s\n", untouched ? "untouched" : "MODIFIED");
+    return untouched ? 0 : 1;
+  }
+  defslam_newpoints_problem p; p.n_keypoints = N; p.rows = rows; p.cols = cols; p.kp_xy = xy.data(); p.kp_state = st.data();
+  p.surf_xyz = surf.data(); p.T_wc = T;
+  std::vector<uint8_t> act(N); std::vector<float> w(3 * N); int32_t nn = 0;
+  if (oracle_new_map_points(&p, act.data(), w.data(), &nn)) { printf("oracle new points failed\n"); return 1; }
+  size_t mi = 0; int bad = 0;
+  for (int i = 0; i < N; i++) {
+    if (act[i] == 1) {
+      if (memcmp(mps[i].wpos, &w[3 * i], 12) || mps[i].lastincorporasion != mps[i].known) bad++;
+    } else if (act[i] == 2) {
+      if (mi >= made.size() || made[mi].first != (size_t)i || memcmp(made[mi].second.v, &w[3 * i], 12)) bad++;
+      mi++;
+    } else if (st[i] && mps[i].wpos[2] != 0.f) bad++;
+  }
+  printf("new points: %d created (oracle %d), needNewTemplate %d, %d mismatches\n", created, (int)nn, (int)need, bad);
+  return (bad == 0 && created == nn && mi == made.size() && newPoints == nn && need == (nn > 50) && nn > 0) ? 0 : 1;
+}
 
 static double depth(double u, double v) { return 1.0 + 0.05 * std::sin(2.0 * u) * std::cos(2.5 * v); }
 
@@ -116,7 +164,7 @@ int main() {
     const bool ok3 = !defslam_b200::estimateSurface<DefKeyFrame, KeyFrame, Vec3f, BbsT>((KeyFrame *)&kf1, 0.7) && !s1.saved &&
                      !defslam_b200::registerSurfaces<DefKeyFrame, KeyFrame, MapPoint, Vec3f>((KeyFrame *)&kf1, 0.07, true) && s1.applied == 0;
     printf("no CUDA device: rc=%d rc2=%d state %s\n", rc, rc2, untouched && ok3 ? "untouched" : "MODIFIED");
-    return untouched && ok3 ? 0 : 1;
+    return (untouched && ok3 ? 0 : 1) | test_new_points(false);
   }
   if (rc) { printf("calculateSchwarps rc=%d\n", rc); return 1; }
 
@@ -192,6 +240,7 @@ int main() {
   if (!defslam_b200::registerSurfaces<DefKeyFrame, KeyFrame, MapPoint, Vec3f>((KeyFrame *)&kf1, 0.07, true)) { printf("registerSurfaces failed\n"); return 1; }
   printf("registration: surface scaled by %.6f, camera moved to (%.4f %.4f %.4f)\n", s1.applied, kf1.Tcw[3], kf1.Tcw[7], kf1.Tcw[11]);
   if (std::fabs(s1.applied - 1.3) > 1e-3 || std::fabs(kf1.Tcw[11] + 0.02) > 2e-3) return 1;
+  if (test_new_points(true)) return 1;
   printf("nrsfm adapter ok\n");
   return 0;
 }

@@ -9,6 +9,7 @@
 
 #include "../../include/defslam_b200.h"
 #include "../../defslam_b200/csrc/mesh_core.h"
+#include "../../defslam_b200/csrc/newpts_core.h"
 
 using namespace ds;
 
@@ -87,6 +88,32 @@ int emu_bbs_bending(const defslam_bbs *bbs, double *B) {
 int emu_surface_vertices(const defslam_bbs *bbs, const double *ctrl, int32_t xs, int32_t ys, float *out) {
   const BbsView s = view_of(bbs);
   for (int i = 0; i < xs * ys; i++) surface_vertex(s, ctrl, xs, ys, i, &out[3 * i]);
+  return 0;
+}
+/* same predicate and arithmetic as new_map_points_kernel, one keypoint at a time */
+int emu_new_map_points(const defslam_newpoints_problem *p, uint8_t *action, float *world, int32_t *n_new) {
+  const int n = p->n_keypoints, ksz = p->cols / 20, anc = ksz / 2;
+  int cnt = 0;
+  for (int i = 0; i < n; i++) {
+    const int st = p->kp_state[i];
+    const int cx = (int)p->kp_xy[2 * i], cy = (int)p->kp_xy[2 * i + 1];
+    bool occupied = false;
+    if (st == 0)
+      for (int j = 0; j < n && !occupied; j++) {
+        if (p->kp_state[j] != 1) continue;
+        const int mx = (int)p->kp_xy[2 * j], my = (int)p->kp_xy[2 * j + 1];
+        occupied = window_hits(cx, mx, p->cols, ksz, anc) && window_hits(cy, my, p->rows, ksz, anc);
+      }
+    const int act = st == 1 ? 1 : (st == 0 && !occupied ? 2 : 0);
+    action[i] = (uint8_t)act;
+    if (world) {
+      float w[3] = {0.f, 0.f, 0.f};
+      if (act != 0) surface_point_to_world(p->T_wc, &p->surf_xyz[3 * i], w);
+      world[3 * i] = w[0]; world[3 * i + 1] = w[1]; world[3 * i + 2] = w[2];
+    }
+    if (act == 2) cnt++;
+  }
+  *n_new = cnt;
   return 0;
 }
 }

@@ -46,7 +46,10 @@ int run(int nprob, const defslam_sft_problem *p, defslam_sft_result *r, int mode
     *dv = &t->view;
     return 0;
   };
-  int rc = bm.plan(nprob, p, mode, 1 << 28, resolve);
+  /* DEFSLAM_EMU_SMEM_LIMIT (doubles) lets a test force the placements the planner falls back to on
+   * the device: border rows, then x/dx, in the global workspace */
+  const char *lim = getenv("DEFSLAM_EMU_SMEM_LIMIT");
+  int rc = bm.plan(nprob, p, mode, lim ? atoi(lim) : 1 << 28, resolve);
   if (rc) return rc;
   std::vector<uint8_t> in(bm.in_bytes + 16), out(bm.out_bytes + 16, 0);
   bm.pack_inputs(p, in.data());
@@ -60,7 +63,8 @@ int run(int nprob, const defslam_sft_problem *p, defslam_sft_result *r, int mode
   for (int i = 0; i < nprob; i++) {
     /* poison the scratch so that stale-state bugs between problems show up */
     for (auto &v : smem) v = 1e300;
-    sft_run_problem(team, bm.views[i], smem.data(), ws.data(), z, true, nullptr);
+    if (bm.any_x_global) sft_run_problem<false>(team, bm.views[i], smem.data(), ws.data(), z, true, nullptr);
+    else sft_run_problem<true>(team, bm.views[i], smem.data(), ws.data(), z, true, nullptr);
   }
   if (mode == MODE_NORMAL_EQ) {
     const ProbSlot &s = bm.slots[0];

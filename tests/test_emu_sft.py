@@ -134,3 +134,44 @@ def test_plan_bandwidth_of_the_regular_grid():
         assert info[0] == 3 * 2 * G + 2          # 2-ring coupling: node half-bandwidth 2G
         assert info[1] % 16 == 9 and info[1] >= info[0] + 1
         lib.emu_template_destroy(h)
+
+
+def test_fallback_placements_give_identical_results(monkeypatch):
+    """The planner's fallbacks for large meshes (border rows, then x/dx, in the global workspace
+    instead of shared memory) run the same arithmetic: bitwise identical solutions."""
+    tmpl, frames = synthetic.make_config_frames("C1", nframes=2)
+    rc, base = emu_solve_batched(frames)
+    assert rc == 0
+    import ctypes as C
+    lib = emu_lib()
+    h = C.c_void_p()
+    assert lib.emu_template_create(C.byref(tmpl.desc()), -1, C.byref(h)) == 0
+    info = (C.c_int32 * 6)()
+    lib.emu_plan_info(h, info)
+    lib.emu_template_destroy(h)
+    # shared-memory need of the default placement; just below it -> border rows move out, far below -> x/dx too
+    need = info[5]
+    for limit in (need - 1, need - 8 * (3 * tmpl.n_nodes) - 64):
+        monkeypatch.setenv("DEFSLAM_EMU_SMEM_LIMIT", str(limit))
+        rc, outs = emu_solve_batched(frames)
+        assert rc == 0
+        for a, b in zip(base, outs):
+            assert np.array_equal(a.nodes, b.nodes)
+            assert a.r.lm_trials == b.r.lm_trials and a.r.n_inliers == b.r.n_inliers
+    monkeypatch.setenv("DEFSLAM_EMU_SMEM_LIMIT", "1000")
+    rc, _ = emu_solve_batched(frames)
+    assert rc == -4  # DEFSLAM_ETOOLARGE
+
+
+def test_stress_mesh_25x25_matches_oracle(oracle):
+    """C5 (BASELINE.json stress config): 25 x 25 mesh, 2000 matches -- the placement the device uses
+    for it (border rows and x/dx in the global workspace)."""
+    tmpl, frames = synthetic.make_config_frames("C5", nframes=1)
+    import os
+    os.environ["DEFSLAM_EMU_SMEM_LIMIT"] = str((227 * 1024 - 1024) // 8)
+    try:
+        rc, outs = emu_solve_batched(frames)
+    finally:
+        del os.environ["DEFSLAM_EMU_SMEM_LIMIT"]
+    assert rc == 0
+    _check(outs[0], oracle.sft_solve(frames[0]), frames[0])

@@ -13,7 +13,7 @@ def _rel_nodes(a, b):
     return np.abs(a - b).max() / np.sqrt((b ** 2).sum(1).mean())
 
 
-@pytest.mark.parametrize("cfg", ["C1", "C2", "C4"])
+@pytest.mark.parametrize("cfg", ["C1", "C2", "C4", "C5"])
 def test_normal_equations_match_oracle(cfg, oracle, cuda_lib):
     tmpl, frames = synthetic.make_config_frames(cfg, nframes=1)
     H, b, chi = sft.normal_equations(frames[0])
@@ -23,7 +23,7 @@ def test_normal_equations_match_oracle(cfg, oracle, cuda_lib):
     assert np.abs(b - bo).max() <= 1e-12 * np.abs(bo).max()
 
 
-@pytest.mark.parametrize("cfg,nframes", [("C1", 3), ("C2", 2), ("C4", 4), ("C3", 1)])
+@pytest.mark.parametrize("cfg,nframes", [("C1", 3), ("C2", 2), ("C4", 4), ("C3", 1), ("C5", 2)])
 def test_solve_matches_oracle(cfg, nframes, oracle, cuda_lib):
     tmpl, frames = synthetic.make_config_frames(cfg, nframes=nframes)
     outs = sft.solve_batched(frames)
