@@ -51,6 +51,20 @@ def algorithmic_bytes_per_iteration(G: int, M: int) -> float:
     return b_in + b_h + 8 * D + 8 * D
 
 
+def fp64_roofline(G: int, trials: float, iters: float, launch_s: float, clocks: dict):
+    """Compute view of the LM kernel: algorithmic FP64 flops (banded Cholesky D*bw^2 + two band sweeps 4*D*bw per
+    trial, assembly ~1 MFLOP per iteration -- SURVEY.md 8(d)) / launch time, against the FP64 peak measured with
+    tools/microbench.cu on this pool's B200 (DFMA and DMMA both 64 FMA/clk/SM) at the SM clock of the run."""
+    Dn = 3 * G * G
+    bw = 3 * 2 * G + 2
+    flops = trials * (Dn * bw * bw + 4.0 * Dn * bw) + iters * 0.96e6 * (G * G) / 169.0
+    mhz = float((clocks or {}).get("sm_mhz") or 1965.0)
+    peak = 64 * 2 * 148 * mhz * 1e6 / 1e12
+    ach = flops / launch_s / 1e12
+    return {"achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            "peak_source": "measured: 64 FP64 FMA/clk/SM (tools/microbench.cu) x 148 SMs x SM clock"}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -248,6 +262,46 @@ def nrsfm_cpu(wl, cores):
     return out
 
 
+def stream_bench(lib, with_cpu: bool):
+    """Config C3 of SURVEY.md 8(d): 300-frame stream, 17x17 mesh, ~600 matches, keyframe every 10 frames,
+    NRSfM (17x17 control grid) every 5th keyframe -- frames/s of the whole loop through the C ABI on
+    host buffers, one frame at a time (this is the latency the tracking thread sees)."""
+    from defslam_b200 import stream
+    cfg = stream.StreamConfig()
+    be = stream.cuda_backend()
+    stream.run_stream(be, stream.StreamConfig(n_frames=12), keep_nodes=False)      # warm-up (context, allocations)
+    l0 = lib.defslam_kernel_launch_count()
+    t0 = time.perf_counter()
+    r = stream.run_stream(be, cfg, keep_nodes=False)
+    dt = time.perf_counter() - t0
+    out = {"workload": f"C3: {cfg.n_frames}-frame stream, G={cfg.G} mesh, {cfg.n_points} map points, keyframe every "
+                       f"{cfg.kf_every} frames, NRSfM ({cfg.nptsu}x{cfg.nptsv} control grid, {cfg.n_views} views) every "
+                       f"{cfg.nrsfm_every_kf}th keyframe; wall clock of the loop incl. synthetic observations",
+           "value": cfg.n_frames / dt, "unit": "frames/s", "ms_per_frame": 1e3 * dt / cfg.n_frames,
+           "nrsfm_events": r.n_nrsfm, "template_updates": r.n_template_updates,
+           "gpu_launches": int(lib.defslam_kernel_launch_count() - l0),
+           "node_rmse_vs_ground_truth": {"median": float(np.median(r.rmse)), "max": float(np.max(r.rmse))},
+           "lm_trials_per_frame": float(np.mean(r.trials))}
+    if with_cpu:
+        from oracle import oracle_py
+        try:
+            olib = oracle_py.load(native=True)
+        except Exception:
+            olib = oracle_py.load()
+        ob = stream.Backend(olib, "oracle_", lambda f: oracle_py.sft_solve(f, olib))
+        n = 12
+        t0 = time.perf_counter()
+        ro = stream.run_stream(ob, stream.StreamConfig(n_frames=n), keep_nodes=True)
+        dto = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": n / dto, "unit": "frames/s", "cores": 1, "kind": "port",
+                               "sample": f"first {n} frames of the same stream (tracking only: the first NRSfM event "
+                                         f"is at frame 50), oracle on one core, {dto:.1f} s"}
+        rg = stream.run_stream(be, stream.StreamConfig(n_frames=n), keep_nodes=True)
+        out["node_rel_err_vs_oracle"] = float(max(np.abs(a - b).max() / np.sqrt((b ** 2).sum(1).mean())
+                                                  for a, b in zip(rg.nodes_cam, ro.nodes_cam)))
+    return out
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -289,6 +343,7 @@ def main():
     ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-nrsfm", action="store_true", help="skip the NRSfM stage measurements")
+    ap.add_argument("--no-stream", action="store_true", help="skip the C3 tracking+mapping stream")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -374,6 +429,11 @@ def main():
         nrsfm_launches = lib.defslam_kernel_launch_count() - l0
         barrier()
 
+    # ---- C3: tracking + mapping loop over a 300-frame stream (rank 0; latency-bound: one frame at a time)
+    st_line = None
+    if not args.no_stream and rank == 0:
+        st_line = stream_bench(lib, not args.no_cpu_baseline)
+
     # ---- parity spot check against the oracle (not timed) ----------------------------
     rel = None
     if rank == 0:
@@ -443,8 +503,10 @@ def main():
                          "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_kind,
                          "kernel": "sft_lm_kernel (persistent LM solve, one CTA per frame)",
                          "algorithmic_bytes_per_lm_iteration_per_frame": b_iter,
-                         "note": "the fused LM kernel is bound by the FP64 latency chain of the banded "
-                                 "factorisation, not by HBM; see DESIGN.md"},
+                         "note": "the fused LM kernel keeps the whole LM loop on chip: it is bound by shared-memory "
+                                 "bandwidth and the FP64 dependency chain of the banded factorisation, not by HBM; "
+                                 "the fp64 object gives the compute view; see DESIGN.md",
+                         "fp64": fp64_roofline(c["G"], trials, iters, avg_launch_s, clocks)},
         }
         if nr_line is not None:
             units = {"schwarp_fit": "keyframe-pair fits/s", "normals": "map-point normals/s", "sfn": "keyframe solves/s"}
@@ -460,6 +522,8 @@ def main():
                     line["nrsfm"]["stages"][k]["cpu_baseline"] = v
                 line["nrsfm"]["cpu_baseline"] = {"cores": os.cpu_count() or 1, "kind": "port",
                                                  "sample": "32 fits / 256 point sets / 16 keyframes, one unit per thread"}
+        if st_line is not None:
+            line["stream"] = st_line
         if not args.no_cpu_baseline and world >= 1:
             cores = os.cpu_count() or 1
             n_sample = max(cores, min(CPU_SAMPLE_FRAMES, 8 * cores))
