@@ -1143,10 +1143,36 @@ DS_FN void build_tile_table(const Team team, TileDesc *tt, int *wstart, int nwar
    * warps share nt8 panel tiles and the remaining trailing tiles */
   int n0 = ((ntiles - 1) + nt8 - (LOOKAHEAD_TILES + 2) * (nwarp - 1)) / nwarp;
   if (n0 < 0) n0 = 0;
-  const int nshared = ntiles - n0, cnt = nshared - 1;
-  DS_FOR(w, nwarp + 1) {
-    if (w == 0) wstart[0] = nshared;
-    else wstart[w] = nwarp > 1 ? 1 + ((w - 1) * cnt) / (nwarp - 1) : nshared;
+  const int nshared = ntiles - n0;
+  team.sync();
+  /* Contiguous ranges of equal COST for warps 1..: a panel tile the warp solves before the update
+   * (S2, row tiles w, w + nwarp-1, ...) counts 1.4 tiles, a tile that needs per-entry checks
+   * (diagonal, corner) 1.5 -- ratios from the per-warp cycle counters of the profile build. */
+  if (team.tid == 0) {
+    wstart[0] = nshared;
+    if (nwarp > 1) {
+      int total = 0;
+      for (int t = 1; t < nshared; t++) total += (tt[t].kind == 2 || tt[t].kind == 4) ? 15 : 10;
+      for (int rt = 1; rt <= nt8; rt++) total += 14;
+      int cur = 1;
+      for (int w = 1; w < nwarp; w++) {
+        wstart[w] = cur;
+        int acc = 0;
+        for (int rt = w; rt <= nt8; rt += nwarp - 1) acc += 14;
+        const int budget = total / (nwarp - w);
+        if (w == nwarp - 1) cur = nshared;
+        while (cur < nshared) {
+          const int cst = (tt[cur].kind == 2 || tt[cur].kind == 4) ? 15 : 10;
+          if (acc + cst / 2 >= budget) break;
+          acc += cst;
+          cur++;
+        }
+        total -= acc;
+      }
+      wstart[nwarp] = nshared;
+    } else {
+      wstart[1] = nshared;
+    }
   }
 }
 
@@ -1185,9 +1211,11 @@ DS_FN void s3_store(const TileDesc td, double d0, double d1, double *W, double *
  * tiles of rows beyond it are skipped. */
 template <bool CHECK>
 DS_FN void s3_range(const TileDesc *tt, int beg, int end, const double *P, int HS, double *W, double *Eb, double *G,
-                    int ks8, int k, int Wr, int ld, int ES, int bwE, int lo, int n_trail, int lane) {
+                    int ks8, int k, int Wr, int ld, int ES, int bwE, int lo, int n_trail, int lane, bool e_smem) {
   const int g = lane >> 2, q = lane & 3;
   const uint32_t tt_s = smem_u32(tt);
+  /* lane's pair in border row g at column k (shared-memory border rows only) */
+  const uint32_t El = e_smem ? smem_u32(Eb) + 8u * (uint32_t)(g * ES + 2 * q + k) : 0u;
   const uint32_t Plo = smem_u32(P) + 8u * (uint32_t)(g * 4 + q), Phi = Plo + 8u * (uint32_t)HS;
   const uint32_t Wl = smem_u32(W) + 8u * (uint32_t)(g * ld + 2 * q - g); /* lane's pair in row g of a tile */
   const uint32_t ldb = 8u * (uint32_t)ld;
@@ -1210,8 +1238,10 @@ DS_FN void s3_range(const TileDesc *tt, int beg, int end, const double *P, int H
     int s0 = ks8 + (u0.x >> 5), s1 = ks8 + (u1.x >> 5);
     if (s0 >= Wr) s0 -= Wr;
     if (s1 >= Wr) s1 -= Wr;
-    const uint32_t d0 = Wl + ldb * (uint32_t)s0 + (uint32_t)u0.w, d1 = Wl + ldb * (uint32_t)s1 + (uint32_t)u1.w;
-    const bool f0 = do0 && u0.z == 1, f1 = do1 && u1.z == 1;
+    const bool e0 = e_smem && u0.z == 3, e1 = e_smem && u1.z == 3;
+    const uint32_t d0 = e0 ? El + (uint32_t)u0.w : Wl + ldb * (uint32_t)s0 + (uint32_t)u0.w;
+    const uint32_t d1 = e1 ? El + (uint32_t)u1.w : Wl + ldb * (uint32_t)s1 + (uint32_t)u1.w;
+    const bool f0 = do0 && (u0.z == 1 || e0), f1 = do1 && (u1.z == 1 || e1);
     dbl2 v0 = {0.0, 0.0}, v1 = {0.0, 0.0};
     if (f0) v0 = lds_v2f64(d0);
     if (f1) v1 = lds_v2f64(d1);
@@ -1383,7 +1413,7 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
         DS_PROF_T0(s3t0);
         team.warp_sync();
         /* S3, tile 0: the next diagonal block, the only tile that touches rows k+8..k+15 */
-        if (n_trail > 0) s3_range<false>(tiles, 0, 1, P, HS, W, Eb, G, ks8, k, Wr, ld, ES, bwE, lo, n_trail, lane);
+        if (n_trail > 0) s3_range<false>(tiles, 0, 1, P, HS, W, Eb, G, ks8, k, Wr, ld, ES, bwE, lo, n_trail, lane, e_smem);
         if (kb + 1 < nblk) {
           team.warp_sync();
           int ns = kslot + NB;
@@ -1394,8 +1424,8 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
         }
         if (w0_tail) {
           named_sync(2, team.nthr);
-          if (full) s3_range<false>(tiles, wstart[0], ntiles, P, HS, W, Eb, G, ks8, k, Wr, ld, ES, bwE, lo, n_trail, lane);
-          else s3_range<true>(tiles, wstart[0], ntiles, P, HS, W, Eb, G, ks8, k, Wr, ld, ES, bwE, lo, n_trail, lane);
+          if (full) s3_range<false>(tiles, wstart[0], ntiles, P, HS, W, Eb, G, ks8, k, Wr, ld, ES, bwE, lo, n_trail, lane, e_smem);
+          else s3_range<true>(tiles, wstart[0], ntiles, P, HS, W, Eb, G, ks8, k, Wr, ld, ES, bwE, lo, n_trail, lane, e_smem);
         }
         DS_PROF_ADD(PF_X_WARP + warp, s3t0, lane == 0);
       } else {
@@ -1415,8 +1445,8 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
         DS_PROF_T0(s3t0);
         /* S3: trailing update C -= P_I P_J^T on 8x8 tiles (FP64 tensor cores) */
         const int beg = wstart[warp], end = wstart[warp + 1];
-        if (full) s3_range<false>(tiles, beg, end, P, HS, W, Eb, G, ks8, k, Wr, ld, ES, bwE, lo, n_trail, lane);
-        else s3_range<true>(tiles, beg, end, P, HS, W, Eb, G, ks8, k, Wr, ld, ES, bwE, lo, n_trail, lane);
+        if (full) s3_range<false>(tiles, beg, end, P, HS, W, Eb, G, ks8, k, Wr, ld, ES, bwE, lo, n_trail, lane, e_smem);
+        else s3_range<true>(tiles, beg, end, P, HS, W, Eb, G, ks8, k, Wr, ld, ES, bwE, lo, n_trail, lane, e_smem);
         DS_PROF_ADD(PF_X_WARP + warp, s3t0, lane == 0);
       }
     }

@@ -157,7 +157,7 @@ class StreamResult:
     template_rmse: list = field(default_factory=list)  # per update: new rest nodes vs ground truth, relative
 
 
-def run_stream(be: Backend, cfg: StreamConfig, keep_nodes: bool = True) -> StreamResult:
+def run_stream(be: Backend, cfg: StreamConfig, keep_nodes: bool = True, logs_dir: str | None = None) -> StreamResult:
     it = cfg.intr
     fx, fy, cx, cy = it["fx"], it["fy"], it["cx"], it["cy"]
     rng = np.random.default_rng(cfg.seed)
@@ -185,6 +185,10 @@ def run_stream(be: Backend, cfg: StreamConfig, keep_nodes: bool = True) -> Strea
     T_cw = np.eye(4, dtype=np.float32)
     res = StreamResult([], [], [], [])
     keyframes = []
+    log = None
+    if logs_dir is not None:
+        from . import logs
+        log = logs.ResultLogs(logs_dir)
     for t in range(cfg.n_frames):
         Tgt = scene.pose(t)
         Pc = scene.points(pu, pv, t) @ Tgt[:3, :3].T + Tgt[:3, 3]
@@ -210,6 +214,11 @@ def run_stream(be: Backend, cfg: StreamConfig, keep_nodes: bool = True) -> Strea
         res.trials.append(int(out.r.lm_trials))
         if keep_nodes:
             res.nodes_cam.append(est_cam)
+        if log is not None:   # Matches.txt / ErrorGTs<frame>.txt like DefTracking.cc:321-328, GroundTruthFrame.cc:259-264
+            n_in = int(out.r.n_inliers)
+            log.frame(t, n_in, len(sel) - n_in, int(valid.sum()))
+            mp_est = (m_bary[sel][:, :, None].astype(np.float64) * nodes[m_nodes[sel]]).sum(1) @ Tc[:3, :3].T + Tc[:3, 3]
+            log.errors(t, np.sqrt(((mp_est - Pc[sel]) ** 2).sum(1)))
         if (t + 1) % cfg.kf_every:
             continue
         # ---- keyframe (normalised keypoints, DefKeyFrame.cc:94-133)
@@ -226,6 +235,8 @@ def run_stream(be: Backend, cfg: StreamConfig, keep_nodes: bool = True) -> Strea
         nodes = tmpl.nodes_rest.copy()
         res.n_template_updates += 1
         res.template_rmse.append(trel)
+    if log is not None:
+        log.close()
     return res
 
 
