@@ -195,6 +195,21 @@ class NewPointsProblem(C.Structure):
     ]
 
 
+class ProjSearchProblem(C.Structure):
+    _fields_ = [
+        ("n_last", C.c_int32), ("n_cur", C.c_int32), ("n_levels", C.c_int32),
+        ("last_state", c_uint8_p), ("last_has_obs", c_uint8_p), ("last_world_xyz", c_float_p), ("last_desc", c_uint8_p),
+        ("last_octave", c_int32_p), ("last_angle", c_float_p),
+        ("cur_xy", c_float_p), ("cur_octave", c_int32_p), ("cur_angle", c_float_p), ("cur_desc", c_uint8_p),
+        ("cur_uright", c_float_p), ("cur_taken", c_uint8_p), ("scale_factors", c_float_p),
+        ("T_cw", C.c_float * 16), ("T_lw", C.c_float * 16),
+        ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("mb", C.c_float), ("mbf", C.c_float),
+        ("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float),
+        ("grid_width_inv", C.c_float), ("grid_height_inv", C.c_float), ("th", C.c_float),
+        ("mono", C.c_int32), ("th_high", C.c_int32), ("check_orientation", C.c_int32),
+    ]
+
+
 NORMALS_ARGS = [C.POINTER(NormalsProblem), c_double_p, c_double_p, c_float_p, c_uint8_p, c_int32_p, c_float_p,
                 c_uint8_p]
 POLY_ARGS = [C.c_int32, c_float_p, c_float_p, c_float_p, c_float_p, c_double_p, c_double_p]
@@ -244,6 +259,7 @@ PROTOTYPES = {
         C.c_int, [C.c_int32, C.POINTER(Sim3Problem), C.POINTER(Sim3Result), C.c_int32]),
     "defslam_scale_min_median": (C.c_int, [C.c_int32, c_float_p, c_float_p, C.c_uint64, c_float_p]),
     "defslam_new_map_points": (C.c_int, [C.POINTER(NewPointsProblem), c_uint8_p, c_float_p, c_int32_p]),
+    "defslam_search_by_projection": (C.c_int, [C.POINTER(ProjSearchProblem), c_int32_p, c_int32_p]),
     "defslam_surface_vertices": (C.c_int, [C.POINTER(Bbs), c_double_p, C.c_int32, C.c_int32, c_float_p]),
     "defslam_version": (C.c_char_p, []),
     "defslam_kernel_launch_count": (C.c_int64, []),

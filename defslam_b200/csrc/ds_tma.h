@@ -63,6 +63,16 @@ DS_FN uint64_t l2_policy_evict_first() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
+DS_FN uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+DS_FN uint64_t l2_policy_evict_normal() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
 DS_FN void tma_load_1d_stream(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, uint64_t pol) {
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
@@ -111,6 +121,8 @@ DS_FN void fence_proxy_async() {}
 DS_FN void mbar_expect_tx(uint64_t *, uint32_t) {}
 DS_FN void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *) { memcpy(dst, src, bytes); }
 DS_FN uint64_t l2_policy_evict_first() { return 0; }
+DS_FN uint64_t l2_policy_evict_last() { return 0; }
+DS_FN uint64_t l2_policy_evict_normal() { return 0; }
 DS_FN void st_stream(double *p, double v) { *p = v; }
 DS_FN void tma_load_1d_stream(void *dst, const void *src, uint32_t bytes, uint64_t *, uint64_t) { memcpy(dst, src, bytes); }
 DS_FN void tma_store_1d_stream(void *dst, const void *src, uint32_t bytes, uint64_t) { memcpy(dst, src, bytes); }

@@ -1,0 +1,217 @@
+/*
+ * match_cuda.cu -- CUDA kernels + C ABI of the projection search (match production for the SfT
+ * solve).  Device arithmetic lives in match_core.h; see include/defslam_b200.h for what the entry
+ * point replaces in the reference.
+ */
+#include <vector>
+
+#include "ds_runtime.h"
+#include "match_core.h"
+
+using namespace ds;
+
+namespace {
+
+struct Scratch {
+  DevBuf dev, host, keys;
+  Scratch() { host.pinned = true; }
+};
+Scratch &tl_scratch(int device) {
+  static thread_local std::map<int, std::unique_ptr<Scratch>> tl;
+  auto &s = tl[device];
+  if (!s) s.reset(new Scratch);
+  return *s;
+}
+struct Packer {
+  size_t total = 0;
+  size_t add(size_t bytes) { size_t o = total; total += (bytes + 255) & ~(size_t)255; return o; }
+};
+int grid_for(int n, int sm) {
+  int g = (n + 127) / 128;
+  if (g > sm * 8) g = sm * 8;
+  return g < 1 ? 1 : g;
+}
+
+__global__ void cell_kernel(ProjView P, int *cell) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < P.n_cur; j += gridDim.x * blockDim.x) cell[j] = keypoint_cell(P, j);
+}
+
+/* FILL = false: projection + candidate count per map point; FILL = true: ranked candidate keys */
+template <bool FILL>
+__global__ void candidates_kernel(ProjView P, const int *cell, Proj *proj, int *cnt, const int *off, uint64_t *keys) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n_last; i += gridDim.x * blockDim.x) {
+    Proj r;
+    if (FILL) r = proj[i];
+    else { r = project_point(P, i); proj[i] = r; }
+    int c = 0;
+    if (r.ok) {
+      uint64_t *out = FILL ? keys + off[i] : nullptr;
+      const uint8_t *d = &P.last_desc[32 * (size_t)i];
+      for (int j = 0; j < P.n_cur; j++) {
+        const int cj = cell[j];
+        if (!candidate_ok(P, r, j, cj)) continue;
+        if (FILL) out[c] = cand_key(hamming256(d, &P.cur_desc[32 * (size_t)j]), cj, j);
+        c++;
+      }
+    }
+    if (!FILL) cnt[i] = c;
+  }
+}
+
+/* exclusive scan of cnt[0..n) by one CTA; total -> off[n] */
+__global__ void scan_kernel(const int *cnt, int *off, int n) {
+  __shared__ int part[1024];
+  const int chunk = (n + blockDim.x - 1) / blockDim.x;
+  const int b = threadIdx.x * chunk, e = min(b + chunk, n);
+  int s = 0;
+  for (int i = b; i < e; i++) s += cnt[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int t = 0; t < (int)blockDim.x; t++) { const int v = part[t]; part[t] = acc; acc += v; }
+    off[n] = acc;
+  }
+  __syncthreads();
+  int acc = part[threadIdx.x];
+  for (int i = b; i < e; i++) { off[i] = acc; acc += cnt[i]; }
+}
+
+/* The order-dependent tail, by one warp: map points in keypoint order, each taking its best-ranked
+ * candidate that is still free; then the rotation-consistency filter. */
+__global__ void resolve_kernel(ProjView P, const int *cnt, const int *off, const uint64_t *keys, uint8_t *taken,
+                               int *match, int *acc_i, int *acc_j, int *nmatches_out) {
+  const int lane = threadIdx.x;
+  int nacc = 0, nmatches = 0;
+  for (int i = 0; i < P.n_last; i++) {
+    const int n = cnt[i];
+    if (n == 0) continue;
+    uint64_t best = ~0ull;
+    for (int b = 0; b < n; b += 32) {
+      uint64_t k = ~0ull;
+      if (b + lane < n) {
+        k = keys[off[i] + b + lane];
+        if (taken[key_index(k)]) k = ~0ull;
+      }
+      best = k < best ? k : best;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const uint64_t other = __shfl_xor_sync(0xffffffffu, best, o);
+      best = other < best ? other : best;
+    }
+    /* bestDist starts at 256 and only a strictly smaller distance replaces it; accept when <= TH_HIGH */
+    if (best != ~0ull && key_dist(best) < 256 && key_dist(best) <= P.th_high) {
+      const int j = key_index(best);
+      if (lane == 0) {
+        match[j] = i;
+        taken[j] = P.last_has_obs[i];
+        acc_i[nacc] = i;
+        acc_j[nacc] = j;
+      }
+      nacc++;
+      nmatches++;
+    }
+    __syncwarp();
+  }
+  if (P.check_orientation) {
+    __shared__ int hist[HISTO_LENGTH];
+    __shared__ int keep[3];
+    if (lane < HISTO_LENGTH) hist[lane] = 0;
+    __syncwarp();
+    if (lane == 0) {
+      for (int a = 0; a < nacc; a++) hist[rotation_bin(P.last_angle[acc_i[a]], P.cur_angle[acc_j[a]])]++;
+      int i1, i2, i3;
+      three_maxima(hist, HISTO_LENGTH, i1, i2, i3);
+      keep[0] = i1; keep[1] = i2; keep[2] = i3;
+      for (int a = 0; a < nacc; a++) {
+        const int bin = rotation_bin(P.last_angle[acc_i[a]], P.cur_angle[acc_j[a]]);
+        if (bin != keep[0] && bin != keep[1] && bin != keep[2]) { match[acc_j[a]] = -1; nmatches--; }
+      }
+    }
+  }
+  if (lane == 0) *nmatches_out = nmatches;
+}
+
+}  // namespace
+
+extern "C" {
+
+int defslam_search_by_projection(const defslam_projsearch_problem *p, int32_t *match_out, int32_t *nmatches_out) {
+  if (!p || !match_out || !nmatches_out || p->n_last < 0 || p->n_cur < 0 || p->n_levels <= 0 || !p->scale_factors)
+    return DEFSLAM_EBADARG;
+  if (p->n_last > 0 && (!p->last_state || !p->last_has_obs || !p->last_world_xyz || !p->last_desc || !p->last_octave ||
+                        !p->last_angle))
+    return DEFSLAM_EBADARG;
+  if (p->n_cur > 0 && (!p->cur_xy || !p->cur_octave || !p->cur_angle || !p->cur_desc || !p->cur_uright || !p->cur_taken))
+    return DEFSLAM_EBADARG;
+  DevCtx *ctx = get_ctx(-1);
+  if (!ctx) return DEFSLAM_ECUDA;
+  *nmatches_out = 0;
+  const size_t NL = (size_t)p->n_last, NC = (size_t)p->n_cur;
+  for (size_t j = 0; j < NC; j++) match_out[j] = -1;
+  if (NL == 0 || NC == 0) return DEFSLAM_OK;
+  Packer in, wk;
+  const size_t o_ls = in.add(NL), o_lo = in.add(NL), o_lx = in.add(NL * 12), o_ld = in.add(NL * 32), o_loc = in.add(NL * 4),
+               o_la = in.add(NL * 4), o_cx = in.add(NC * 8), o_co = in.add(NC * 4), o_ca = in.add(NC * 4),
+               o_cd = in.add(NC * 32), o_cu = in.add(NC * 4), o_ct = in.add(NC), o_sc = in.add((size_t)p->n_levels * 4);
+  const size_t w_cell = wk.add(NC * 4), w_proj = wk.add(NL * sizeof(Proj)), w_cnt = wk.add(NL * 4),
+               w_off = wk.add((NL + 1) * 4), w_ai = wk.add(NL * 4), w_aj = wk.add(NL * 4), w_match = wk.add(NC * 4),
+               w_n = wk.add(4);
+  Scratch &S = tl_scratch(ctx->device);
+  int rc;
+  if ((rc = S.host.ensure(in.total > wk.total ? in.total : wk.total)) || (rc = S.dev.ensure(in.total + wk.total))) return rc;
+  uint8_t *h = (uint8_t *)S.host.p, *d = (uint8_t *)S.dev.p, *w = d + in.total;
+  memcpy(h + o_ls, p->last_state, NL); memcpy(h + o_lo, p->last_has_obs, NL);
+  memcpy(h + o_lx, p->last_world_xyz, NL * 12); memcpy(h + o_ld, p->last_desc, NL * 32);
+  memcpy(h + o_loc, p->last_octave, NL * 4); memcpy(h + o_la, p->last_angle, NL * 4);
+  memcpy(h + o_cx, p->cur_xy, NC * 8); memcpy(h + o_co, p->cur_octave, NC * 4); memcpy(h + o_ca, p->cur_angle, NC * 4);
+  memcpy(h + o_cd, p->cur_desc, NC * 32); memcpy(h + o_cu, p->cur_uright, NC * 4); memcpy(h + o_ct, p->cur_taken, NC);
+  memcpy(h + o_sc, p->scale_factors, (size_t)p->n_levels * 4);
+  DS_CUDA_TRY(cudaMemcpyAsync(d, h, in.total, cudaMemcpyHostToDevice, ctx->stream));
+  ProjView V;
+  V.n_last = p->n_last; V.n_cur = p->n_cur; V.n_levels = p->n_levels;
+  V.last_state = d + o_ls; V.last_has_obs = d + o_lo; V.last_desc = d + o_ld; V.cur_desc = d + o_cd; V.cur_taken = d + o_ct;
+  V.last_xyz = (const float *)(d + o_lx); V.last_angle = (const float *)(d + o_la); V.cur_xy = (const float *)(d + o_cx);
+  V.cur_angle = (const float *)(d + o_ca); V.cur_uright = (const float *)(d + o_cu); V.scale = (const float *)(d + o_sc);
+  V.last_octave = (const int *)(d + o_loc); V.cur_octave = (const int *)(d + o_co);
+  for (int k = 0; k < 16; k++) V.Tcw[k] = p->T_cw[k];
+  V.fx = p->fx; V.fy = p->fy; V.cx = p->cx; V.cy = p->cy; V.mbf = p->mbf;
+  V.min_x = p->min_x; V.max_x = p->max_x; V.min_y = p->min_y; V.max_y = p->max_y;
+  V.gwi = p->grid_width_inv; V.ghi = p->grid_height_inv; V.th = p->th;
+  V.th_high = p->th_high; V.check_orientation = p->check_orientation;
+  {
+    /* twc = -Rcw^T tcw; tlc = Rlw twc + tlw (fp32 cv::Mat products); only the sign tests on tlc.z matter */
+    float twc[3], tlc2;
+    for (int a = 0; a < 3; a++)
+      twc[a] = -(p->T_cw[a] * p->T_cw[3] + p->T_cw[4 + a] * p->T_cw[7] + p->T_cw[8 + a] * p->T_cw[11]);
+    tlc2 = p->T_lw[8] * twc[0] + p->T_lw[9] * twc[1] + p->T_lw[10] * twc[2] + p->T_lw[11];
+    V.forward = tlc2 > p->mb && !p->mono;
+    V.backward = -tlc2 > p->mb && !p->mono;
+  }
+  int *cell = (int *)(w + w_cell), *cnt = (int *)(w + w_cnt), *off = (int *)(w + w_off);
+  Proj *proj = (Proj *)(w + w_proj);
+  DS_CUDA_TRY(cudaMemsetAsync(w + w_match, 0xff, NC * 4, ctx->stream));
+  cell_kernel<<<grid_for(p->n_cur, ctx->sm_count), 128, 0, ctx->stream>>>(V, cell);
+  candidates_kernel<false><<<grid_for(p->n_last, ctx->sm_count), 128, 0, ctx->stream>>>(V, cell, proj, cnt, nullptr, nullptr);
+  scan_kernel<<<1, 1024, 0, ctx->stream>>>(cnt, off, p->n_last);
+  DS_CUDA_TRY(cudaGetLastError());
+  int total = 0;
+  DS_CUDA_TRY(cudaMemcpyAsync(&total, off + NL, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  DS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if ((rc = S.keys.ensure((size_t)(total > 0 ? total : 1) * 8))) return rc;
+  candidates_kernel<true><<<grid_for(p->n_last, ctx->sm_count), 128, 0, ctx->stream>>>(V, cell, proj, cnt, off,
+                                                                                      (uint64_t *)S.keys.p);
+  /* cur_taken is an input copy in the arena: the resolve pass updates it in place */
+  resolve_kernel<<<1, 32, 0, ctx->stream>>>(V, cnt, off, (const uint64_t *)S.keys.p, d + o_ct, (int *)(w + w_match),
+                                            (int *)(w + w_ai), (int *)(w + w_aj), (int *)(w + w_n));
+  DS_CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(5);
+  DS_CUDA_TRY(cudaMemcpyAsync(h, w + w_match, NC * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  DS_CUDA_TRY(cudaMemcpyAsync(h + ((NC * 4 + 255) & ~(size_t)255), w + w_n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  DS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  memcpy(match_out, h, NC * 4);
+  memcpy(nmatches_out, h + ((NC * 4 + 255) & ~(size_t)255), 4);
+  return DEFSLAM_OK;
+}
+
+}  // extern "C"

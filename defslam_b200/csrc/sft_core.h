@@ -1311,6 +1311,11 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
   uint64_t *bar0 = &c.mbar[0];
   uint32_t ph0 = c.ph[0];
   const uint64_t pol = l2_policy_evict_first();
+  /* the factor is written top-down and read back bottom-up within the same trial (LIFO) */
+#ifndef DS_LB_POLICY
+#define DS_LB_POLICY 0
+#endif
+  const uint64_t polL = DS_LB_POLICY == 0 ? pol : (DS_LB_POLICY == 1 ? l2_policy_evict_normal() : l2_policy_evict_last());
   /* window <- first Wr rows of H; border/rhs working copy (bulk async); corner */
   {
     const int rows = Wr < Dp ? Wr : Dp;
@@ -1364,7 +1369,7 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
     double *invLn = invL + 96 * ((kb + 1) & 1);
     /* finished rows k..k+7 -> L band in global memory (TMA bulk store) */
     if (team.tid == tma_tid)
-      tma_store_1d_stream(Lb + k * ld, W + kslot * ld, (uint32_t)(NB * ld * sizeof(double)), pol);
+      tma_store_1d_stream(Lb + k * ld, W + kslot * ld, (uint32_t)(NB * ld * sizeof(double)), polL);
     prof_mark(team, c, PF_S1);
     /* rows requested during the previous step (they enter this step's panel) */
     if (kb > 0 && (k - NB) + Wr < Dp) { mbar_wait(bar0, ph0); ph0 ^= 1u; }
@@ -1565,7 +1570,7 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
     for (int j = 0; j < NBUF - 1 && j < nblk; j++) {
       const int kbj = nblk - 1 - j;
       mbar_expect_tx(&c.mbar[1 + (j % NBUF)], row_bytes);
-      tma_load_1d_stream(W + (j % NBUF) * bufsz, Lb + kbj * NB * ld, row_bytes, &c.mbar[1 + (j % NBUF)], pol);
+      tma_load_1d_stream(W + (j % NBUF) * bufsz, Lb + kbj * NB * ld, row_bytes, &c.mbar[1 + (j % NBUF)], polL);
     }
   }
   prof_mark(team, c, PF_BWD_INIT);
@@ -1580,7 +1585,7 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
       if (jn < nblk) {
         const int kbn = nblk - 1 - jn, bn = jn % NBUF;
         mbar_expect_tx(&c.mbar[1 + bn], row_bytes);
-        tma_load_1d_stream(W + bn * bufsz, Lb + kbn * NB * ld, row_bytes, &c.mbar[1 + bn], pol);
+        tma_load_1d_stream(W + bn * bufsz, Lb + kbn * NB * ld, row_bytes, &c.mbar[1 + bn], polL);
       }
     }
     const double *LR = W + buf * bufsz;

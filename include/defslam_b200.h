@@ -434,6 +434,52 @@ typedef struct defslam_newpoints_problem {
 int defslam_new_map_points(const defslam_newpoints_problem *p, uint8_t *action_out, float *world_xyz_out,
                            int32_t *n_new_out);
 
+/* Match production feeding the SfT solve: projection search of the last frame's template points.
+ * replaces: DefORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono)
+ *             Modules/Matching/DefORBmatcher.cc:296-451
+ *           Frame::GetFeaturesInArea / PosInGrid / AssignFeaturesToGrid
+ *             Thirdparty/ORBSLAM_2/src/Frame.cc:421-496,294-309
+ *           ORBmatcher::DescriptorDistance / ComputeThreeMaxima
+ *             Thirdparty/ORBSLAM_2/src/ORBmatcher.cc:1645-1707
+ * The reference loops over the last frame's keypoints in order and lets earlier assignments hide
+ * keypoints from later map points; here candidates and Hamming distances are computed in parallel
+ * (one thread per map point, every keypoint of the current frame tested against the reference's
+ * cell window) and one warp then replays the assignments in the reference's order, ties broken by
+ * the order GetFeaturesInArea would have listed the candidates (cell column, cell row, index).
+ *   last_state[i]: 1 = map point usable (non-null, not an outlier, not bad, has a facet), else 0
+ *   last_has_obs[i]: MapPoint::Observations() > 0 (a keypoint assigned to such a point is hidden from
+ *                    the points after it)
+ *   cur_taken[j]: CurrentFrame.mvpMapPoints[j] already holds a point with observations
+ *   match_out[j]: index i of the last-frame keypoint whose map point keypoint j received, or -1
+ *   *nmatches_out: the reference's return value */
+typedef struct defslam_projsearch_problem {
+  int32_t n_last, n_cur, n_levels;
+  const uint8_t *last_state;        /* [n_last]      */
+  const uint8_t *last_has_obs;      /* [n_last]      */
+  const float *last_world_xyz;      /* [n_last*3]  MapPoint::GetWorldPos()              */
+  const uint8_t *last_desc;         /* [n_last*32] MapPoint::GetDescriptor()            */
+  const int32_t *last_octave;       /* [n_last]    LastFrame.mvKeys[i].octave           */
+  const float *last_angle;          /* [n_last]    LastFrame.mvKeysUn[i].angle          */
+  const float *cur_xy;              /* [n_cur*2]   CurrentFrame.mvKeysUn[j].pt          */
+  const int32_t *cur_octave;        /* [n_cur]                                          */
+  const float *cur_angle;           /* [n_cur]                                          */
+  const uint8_t *cur_desc;          /* [n_cur*32]  CurrentFrame.mDescriptors            */
+  const float *cur_uright;          /* [n_cur]     mvuRight (negative: monocular)       */
+  const uint8_t *cur_taken;         /* [n_cur]                                          */
+  const float *scale_factors;       /* [n_levels]  mvScaleFactors                       */
+  float T_cw[16];                   /* CurrentFrame.mTcw, row-major                     */
+  float T_lw[16];                   /* LastFrame.mTcw                                   */
+  float fx, fy, cx, cy, mb, mbf;
+  float min_x, max_x, min_y, max_y; /* mnMinX ... mnMaxY                                */
+  float grid_width_inv, grid_height_inv; /* mfGridElementWidthInv / HeightInv (64 x 48 cells) */
+  float th;
+  int32_t mono;                     /* bMono                                            */
+  int32_t th_high;                  /* ORBmatcher::TH_HIGH (75)                         */
+  int32_t check_orientation;        /* mbCheckOrientation                               */
+} defslam_projsearch_problem;
+
+int defslam_search_by_projection(const defslam_projsearch_problem *p, int32_t *match_out, int32_t *nmatches_out);
+
 /* Surface -> template nodes.
  * replaces: Surface::getVertex  Modules/Mapping/Surface.cc:125-161
  * nodes_out: [xs*ys*3] fp32 (u d, v d, d), x-major outer loop */

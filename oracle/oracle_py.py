@@ -54,6 +54,8 @@ def load(native: bool = False):
     lib.oracle_mappoints_recalculate.restype = C.c_int
     lib.oracle_mappoints_recalculate.argtypes = [C.c_int32, P.c_double_p, C.c_int32, P.c_int32_p, P.c_double_p,
                                                  P.c_float_p]
+    lib.oracle_search_by_projection.restype = C.c_int
+    lib.oracle_search_by_projection.argtypes = _capi.PROTOTYPES["defslam_search_by_projection"][1]
     lib.oracle_new_map_points.restype = C.c_int
     lib.oracle_new_map_points.argtypes = _capi.PROTOTYPES["defslam_new_map_points"][1]
     lib.oracle_regular_triangulation.restype = C.c_int

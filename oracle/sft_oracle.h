@@ -56,6 +56,9 @@ int oracle_scale_min_median(int32_t n, const float *mono, const float *stereo, u
 int oracle_new_map_points(const defslam_newpoints_problem *p, uint8_t *action_out, float *world_xyz_out,
                           int32_t *n_new_out);
 
+/* ---- projection search (match_oracle.c) ---- */
+int oracle_search_by_projection(const defslam_projsearch_problem *p, int32_t *match_out, int32_t *nmatches_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,6 +10,7 @@
 #include "../../include/defslam_b200.h"
 #include "../../defslam_b200/csrc/mesh_core.h"
 #include "../../defslam_b200/csrc/newpts_core.h"
+#include "../../defslam_b200/csrc/match_core.h"
 
 using namespace ds;
 
@@ -114,6 +115,56 @@ int emu_new_map_points(const defslam_newpoints_problem *p, uint8_t *action, floa
     if (act == 2) cnt++;
   }
   *n_new = cnt;
+  return 0;
+}
+/* the kernels of match_cuda.cu in sequence: cells, candidates (count + ranked keys), in-order resolve */
+int emu_search_by_projection(const defslam_projsearch_problem *p, int32_t *match_out, int32_t *nmatches_out) {
+  ProjView V;
+  V.n_last = p->n_last; V.n_cur = p->n_cur; V.n_levels = p->n_levels;
+  V.last_state = p->last_state; V.last_has_obs = p->last_has_obs; V.last_desc = p->last_desc; V.cur_desc = p->cur_desc;
+  V.cur_taken = p->cur_taken; V.last_xyz = p->last_world_xyz; V.last_angle = p->last_angle; V.cur_xy = p->cur_xy;
+  V.cur_angle = p->cur_angle; V.cur_uright = p->cur_uright; V.scale = p->scale_factors; V.last_octave = p->last_octave;
+  V.cur_octave = p->cur_octave;
+  for (int k = 0; k < 16; k++) V.Tcw[k] = p->T_cw[k];
+  V.fx = p->fx; V.fy = p->fy; V.cx = p->cx; V.cy = p->cy; V.mbf = p->mbf;
+  V.min_x = p->min_x; V.max_x = p->max_x; V.min_y = p->min_y; V.max_y = p->max_y;
+  V.gwi = p->grid_width_inv; V.ghi = p->grid_height_inv; V.th = p->th; V.th_high = p->th_high;
+  V.check_orientation = p->check_orientation;
+  float twc[3];
+  for (int a = 0; a < 3; a++) twc[a] = -(p->T_cw[a] * p->T_cw[3] + p->T_cw[4 + a] * p->T_cw[7] + p->T_cw[8 + a] * p->T_cw[11]);
+  const float tlc2 = p->T_lw[8] * twc[0] + p->T_lw[9] * twc[1] + p->T_lw[10] * twc[2] + p->T_lw[11];
+  V.forward = tlc2 > p->mb && !p->mono; V.backward = -tlc2 > p->mb && !p->mono;
+  std::vector<int> cell(p->n_cur);
+  for (int j = 0; j < p->n_cur; j++) { cell[j] = keypoint_cell(V, j); match_out[j] = -1; }
+  std::vector<uint8_t> taken(p->cur_taken, p->cur_taken + p->n_cur);
+  std::vector<int> acc_i, acc_j;
+  int nmatches = 0;
+  for (int i = 0; i < p->n_last; i++) {
+    const Proj r = project_point(V, i);
+    if (!r.ok) continue;
+    uint64_t best = ~0ull;
+    for (int j = 0; j < p->n_cur; j++) {
+      if (!candidate_ok(V, r, j, cell[j]) || taken[j]) continue;
+      const uint64_t k = cand_key(hamming256(&p->last_desc[32 * (size_t)i], &p->cur_desc[32 * (size_t)j]), cell[j], j);
+      if (k < best) best = k;
+    }
+    if (best != ~0ull && key_dist(best) < 256 && key_dist(best) <= p->th_high) {
+      const int j = key_index(best);
+      match_out[j] = i; taken[j] = p->last_has_obs[i];
+      acc_i.push_back(i); acc_j.push_back(j);
+      nmatches++;
+    }
+  }
+  if (p->check_orientation) {
+    int hist[HISTO_LENGTH] = {0}, i1, i2, i3;
+    for (size_t a = 0; a < acc_i.size(); a++) hist[rotation_bin(p->last_angle[acc_i[a]], p->cur_angle[acc_j[a]])]++;
+    three_maxima(hist, HISTO_LENGTH, i1, i2, i3);
+    for (size_t a = 0; a < acc_i.size(); a++) {
+      const int bin = rotation_bin(p->last_angle[acc_i[a]], p->cur_angle[acc_j[a]]);
+      if (bin != i1 && bin != i2 && bin != i3) { match_out[acc_j[a]] = -1; nmatches--; }
+    }
+  }
+  *nmatches_out = nmatches;
   return 0;
 }
 }

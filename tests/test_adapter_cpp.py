@@ -60,3 +60,24 @@ def test_nrsfm_adapter_matches_oracle_on_gpu(oracle, cuda_lib):
     rc, out = _run(EXE2)
     assert rc == 0, out
     assert "nrsfm adapter ok" in out
+
+
+EXE3 = os.path.join(ROOT, "tests", "_emu", "test_adapter_matcher")
+
+
+def test_matcher_adapter_compiles_and_fails_loudly_without_a_device(oracle, cuda_lib):
+    """adapter/MatcherB200.h: DefORBmatcher::SearchByProjection against mock Frame / MapPoint types."""
+    _build(oracle, "test_adapter_matcher.cc", EXE3)
+    if cuda_lib.defslam_device_count() > 0:
+        pytest.skip("device present: covered by the gpu test")
+    rc, out = _run(EXE3)
+    assert rc == 0, out
+    assert "untouched" in out
+
+
+@pytest.mark.gpu
+def test_matcher_adapter_matches_oracle_on_gpu(oracle, cuda_lib):
+    _build(oracle, "test_adapter_matcher.cc", EXE3)
+    rc, out = _run(EXE3)
+    assert rc == 0, out
+    assert "0 mismatches" in out
