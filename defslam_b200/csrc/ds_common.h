@@ -33,7 +33,7 @@ namespace ds {
 
 constexpr int NB = 8;           /* panel width of the banded factorisation   */
 constexpr int TILE = 8;         /* tile edge of the trailing update (one DMMA m8n8k4 output) */
-constexpr int NFACC = 75;       /* per-facet accumulators (48 node + 27 cam) */
+constexpr int NFACC = 48;       /* per-facet accumulators (12 barycentric moments + 3 x 12 weighted Jacobian sums) */
 constexpr int NMSCR = 18;       /* per-match scratch doubles                 */
 
 /* 16-byte pair of doubles (LDS.128 / STS.128 on the device) */

@@ -419,8 +419,9 @@ DS_FN double curv_residual(const Ctx &c, const double *x, int i, double d[3], do
  * store=true additionally fills everything build_system() gathers from:
  * per-match scratch S, per-node A / centre / edge quantities (overlaid on the
  * window region of shared memory). */
-template <bool XS>
-DS_FN_NOINLINE double eval_state(const Team team, Ctx &cx, bool store) {
+template <bool XS, bool STORE>
+DS_FN_NOINLINE double eval_state(const Team team, Ctx &cx) {
+  constexpr bool store = STORE;
   Ctx &c = ctx_ref();
   (void)cx;
   const double *x = xvec<XS>(c), *ps = sm_base() + c.sl.pose;
@@ -439,6 +440,13 @@ DS_FN_NOINLINE double eval_state(const Team team, Ctx &cx, bool store) {
   double chi = 0.0;
   double R[9];
   if (store) quat_to_R(P.q, R);
+  /* camera block of J^T W J (upper triangle, 21) and J_c^T W e (6): no per-facet resolution is
+   * needed, so every thread sums its own matches here, where the Jacobian is in registers */
+  double cam[STORE ? 27 : 1];
+  if (store) {
+#pragma unroll
+    for (int k = 0; k < 27; k++) cam[k] = 0.0;
+  }
 
   /* reprojection edges, in facet-grouped order */
   DS_FOR(s, M) {
@@ -482,7 +490,35 @@ DS_FN_NOINLINE double eval_state(const Team team, Ctx &cx, bool store) {
       S[(15 + (code & 3)) * M + s] = b[0];
       S[(15 + ((code >> 2) & 3)) * M + s] = b[1];
       S[(15 + ((code >> 4) & 3)) * M + s] = b[2];
+      {
+        const double w = rho1 * info;
+        const double J[12] = {X * Y / Z2 * fx, -(1 + (X * X / Z2)) * fx, Y / Z * fx, -1. / Z * fx, 0, X / Z2 * fx,
+                              (1 + Y * Y / Z2) * fy, -X * Y / Z2 * fy, -X / Z * fy, 0, -1. / Z * fy, Y / Z2 * fy};
+        int k = 0;
+#pragma unroll
+        for (int r = 0; r < 6; r++)
+#pragma unroll
+          for (int q = r; q < 6; q++) cam[STORE ? k++ : 0] += w * (J[r] * J[q] + J[6 + r] * J[6 + q]);
+#pragma unroll
+        for (int r = 0; r < 6; r++) cam[STORE ? 21 + r : 0] += w * (J[r] * e[0] + J[6 + r] * e[1]);
+      }
     }
+  }
+  if (store) {
+    /* fixed-shape reduction: lanes by shuffle, then one partial per warp in the panel buffer
+     * (free outside factor_solve); build_system adds the warps in order */
+    double *part = sm_base() + c.sl.P;
+#if DS_CUDA
+    const int warp = team.tid >> 5, nwarp = team.nthr >> 5;
+#pragma unroll
+    for (int k = 0; k < 27; k++) {
+      double v = cam[STORE ? k : 0];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if ((team.tid & 31) == 0) part[k * nwarp + warp] = v;
+    }
+#else
+    for (int k = 0; k < 27; k++) part[k] = cam[STORE ? k : 0];
+#endif
   }
   /* temporal (EdgesReference sft_types.h:403-408), curvature, per-node A */
   DS_FOR(v, n) {
@@ -559,6 +595,29 @@ DS_FN_NOINLINE double build_system(const Team team, Ctx &cx) {
   DS_PROF_T0(bt0);
   DS_PROF_INC(PF_X_BUILDS, team.tid == 0);
 
+  /* (0) camera-camera block and b_c: the per-warp partial sums eval_state left in the panel
+   * buffer, added in warp order -- first, because the staging area of (1) covers that buffer */
+  {
+    const double *part = sm_base() + c.sl.P;
+#if DS_CUDA
+    const int nwarp = team.nthr >> 5;
+#else
+    const int nwarp = 1;
+#endif
+    DS_FOR(k, 27) {
+      double s = 0.0;
+      for (int w = 0; w < nwarp; w++) s += part[k * nwarp + w];
+      if (k < 21) {
+        int r = 0, rem = k;
+        while (rem >= 6 - r) { rem -= 6 - r; r++; }
+        const int q = r + rem;
+        Hcc[r * 6 + q] = s; Hcc[q * 6 + r] = s;
+      } else {
+        Hcc[36 + (k - 21)] = -s;
+      }
+    }
+  }
+
   /* (1) per-facet sums.  item = (facet, group).  The per-match scratch of a run of facets is
    * first staged into the shared memory that is idle during assembly (rest of the window, the
    * border rows, the panel buffer) by all threads -- coalesced, every load independent -- so the
@@ -608,7 +667,7 @@ DS_FN_NOINLINE double build_system(const Team team, Ctx &cx) {
       const int nfc = fe - fb;
       /* group-major: the lanes of a warp run the same group on consecutive facets (no divergence
        * between the four code paths, neighbouring rows of the scratch) */
-      DS_FOR(it, nfc * 6) {
+      DS_FOR(it, nfc * 4) {
         const int g = it / nfc, f = fb + (it - g * nfc);
         int sb, se;
         if (SS == stage) { sb = fps[f - fb]; se = fps[f - fb + 1]; }
@@ -636,7 +695,7 @@ DS_FN_NOINLINE double build_system(const Team team, Ctx &cx) {
       }
 #pragma unroll
       for (int k = 0; k < 12; k++) F[k * nf + f] = a[k];
-    } else if (g <= 3) {
+    } else {
       double a[12];
 #pragma unroll
       for (int k = 0; k < 12; k++) a[k] = 0.0;
@@ -652,55 +711,6 @@ DS_FN_NOINLINE double build_system(const Team team, Ctx &cx) {
       }
 #pragma unroll
       for (int k = 0; k < 12; k++) F[(12 * g + k) * nf + f] = a[k];
-    } else if (g == 4) {
-      /* camera block, rows 0-1 of the upper triangle of Jc^T w Jc (11 entries) */
-      double a[11];
-#pragma unroll
-      for (int k = 0; k < 11; k++) a[k] = 0.0;
-      for (int s0 = sb; s0 < se; s0 += 2) {
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-          const bool ok = s0 + u < se;
-          const int s = ok ? s0 + u : s0;
-          const double w = ok ? SS[2 * sst + s] : 0.0;
-          double J[12];
-#pragma unroll
-          for (int k = 0; k < 12; k++) J[k] = SS[(3 + k) * sst + s];
-#pragma unroll
-          for (int q = 0; q < 6; q++) a[q] += w * (J[0] * J[q] + J[6] * J[6 + q]);
-#pragma unroll
-          for (int q = 1; q < 6; q++) a[5 + q] += w * (J[1] * J[q] + J[7] * J[6 + q]);
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 11; k++) F[(48 + k) * nf + f] = a[k];
-    } else {
-      /* rows 2-5 (10 entries), then the 6 entries of Jc^T w e */
-      double a[16];
-#pragma unroll
-      for (int k = 0; k < 16; k++) a[k] = 0.0;
-      for (int s0 = sb; s0 < se; s0 += 2) {
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-          const bool ok = s0 + u < se;
-          const int s = ok ? s0 + u : s0;
-          const double w = ok ? SS[2 * sst + s] : 0.0, e0 = SS[s], e1 = SS[sst + s];
-          double J[12];
-#pragma unroll
-          for (int k = 0; k < 12; k++) J[k] = SS[(3 + k) * sst + s];
-#pragma unroll
-          for (int q = 2; q < 6; q++) a[q - 2] += w * (J[2] * J[q] + J[8] * J[6 + q]);
-#pragma unroll
-          for (int q = 3; q < 6; q++) a[4 + q - 3] += w * (J[3] * J[q] + J[9] * J[6 + q]);
-#pragma unroll
-          for (int q = 4; q < 6; q++) a[7 + q - 4] += w * (J[4] * J[q] + J[10] * J[6 + q]);
-          a[9] += w * (J[5] * J[5] + J[11] * J[11]);
-#pragma unroll
-          for (int r = 0; r < 6; r++) a[10 + r] += w * (J[r] * e0 + J[6 + r] * e1);
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 16; k++) F[(59 + k) * nf + f] = a[k];
     }
       }
       DS_PROF_LAP(fsacc, 3, fst);
@@ -711,35 +721,6 @@ DS_FN_NOINLINE double build_system(const Team team, Ctx &cx) {
   team.sync();
   DS_PROF_ADD(PF_X_BUILD + 0, bt0, team.tid == 0);
   DS_PROF_T0(bt1);
-
-  /* (2) camera-camera block and b_c: fixed two-level reduction over facets.
-   * 27 sums x NPART partial ranges, then the partials in order. */
-  {
-    constexpr int NPART = 8;
-    double *part = sm_base() + c.sl.P; /* 27*NPART doubles, free outside factor_solve */
-    const int chunk = (nf + NPART - 1) / NPART;
-    DS_FOR(it, 27 * NPART) {
-      const int k = it % 27, pt = it / 27;
-      const int f0 = pt * chunk, f1 = (f0 + chunk) < nf ? (f0 + chunk) : nf;
-      double s = 0.0;
-      const double *Fk = &F[(48 + k) * nf];
-      for (int f = f0; f < f1; f++) s += Fk[f];
-      part[it] = s;
-    }
-    team.sync();
-    DS_FOR(k, 27) {
-      double s = 0.0;
-      for (int pt = 0; pt < NPART; pt++) s += part[pt * 27 + k];
-      if (k < 21) {
-        int r = 0, rem = k;
-        while (rem >= 6 - r) { rem -= 6 - r; r++; }
-        const int q = r + rem;
-        Hcc[r * 6 + q] = s; Hcc[q * 6 + r] = s;
-      } else {
-        Hcc[36 + (k - 21)] = -s;
-      }
-    }
-  }
 
   DS_PROF_ADD(PF_X_BUILD + 1, bt1, team.tid == 0);
   DS_PROF_T0(bt2);
@@ -1792,7 +1773,7 @@ DS_FN_NOINLINE void sft_solve_one(const Team team, Ctx &cx) {
     return;
   }
   if (pb.mode == MODE_NORMAL_EQ) {
-    const double chi = eval_state<XS>(team, c, true);
+    const double chi = eval_state<XS, true>(team, c);
     build_system<XS>(team, c);
     expand_dense(team, c, chi);
     return;
@@ -1807,7 +1788,7 @@ DS_FN_NOINLINE void sft_solve_one(const Team team, Ctx &cx) {
   int nBad = 0, iterations = 0, trials = 0;
   bool last_rejected = false;
   for (int it = 0; it < max_it; it++) {
-    double currentChi = eval_state<XS>(team, c, true);
+    double currentChi = eval_state<XS, true>(team, c);
     prof_mark(team, c, PF_EVAL_STORE);
     double tempChi = currentChi;
     const double iniChi = currentChi;
@@ -1827,7 +1808,7 @@ DS_FN_NOINLINE void sft_solve_one(const Team team, Ctx &cx) {
       const bool ok2 = factor_solve<XS>(team, c, lambda);
       apply_update<XS>(team, c);
       prof_mark(team, c, PF_UPDATE);
-      tempChi = eval_state<XS>(team, c, false);
+      tempChi = eval_state<XS, false>(team, c);
       prof_mark(team, c, PF_EVAL_TRIAL);
       if (!ok2) tempChi = DBL_MAX;
       rho = currentChi - tempChi;

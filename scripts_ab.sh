@@ -1,8 +1,7 @@
 #!/bin/bash
 timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-echo "== timings (baseline a22bbe8: C2 52.0  C4 21.7  C3 108.6 ms)"
+echo "== timings (baseline a22bbe8: C2 52.0  C4 21.7  C3 108.6 ms; e23e16b: 36.4 16.6 67.1)"
 timeout 300 python tools/prof_run.py C2 2368 3 2>&1 | tail -1
 timeout 300 python tools/prof_run.py C4 2368 3 2>&1 | tail -1
 timeout 300 python tools/prof_run.py C3 1184 3 2>&1 | tail -1
-echo "== C5 (25x25, 2000 matches), 148 frames"
-timeout 300 python tools/prof_run.py C5 148 2 2>&1 | tail -1
+NPROBS=296 bash scripts_phase.sh 2>&1 | grep "cycles total\|per build\|facet sums per" | cut -c1-330
