@@ -58,6 +58,12 @@ struct PlanView {
   const int *blk_fac_ptr, *blk_fac; /* (facet<<4 | slot_p<<2 | slot_q)       */
   const int *blk_ctr_ptr, *blk_ctr; /* 3 ints: centre, cidx_p, cidx_q        */
   const int *blk_edge;          /* [n_blk] edge joining p,q (p != q) or -1   */
+  /* packed form of the same block plan, one dependent level shallower (diagonal blocks first):
+   * blk_hdr[8*bi] = p, q, edge, ctr_ptr, n_ctr, n_fac, (F index 0 | pointer into blk_fidx when n_fac > 2), F index 1;
+   * F index = pair_plane*n_facets + facet;  per centre entry: the centre and the two coefficients
+   * (1 for the centre itself, -w/W for a neighbour) */
+  const int *blk_hdr, *blk_fidx, *blk_ctr_i;
+  const double *blk_ctr_pq;     /* [2*entries] cp, cq */
 };
 
 }  // namespace ds
@@ -79,7 +85,8 @@ struct PlanHost {
   PlanView v;          /* offsets stored as pointers relative to NULL until bind() */
   size_t o_rest, o_kappa0, o_inv_len2, o_nbr_w, o_nbr_c, o_sum_w, o_edge_len0;
   size_t o_nbr_ptr, o_nbr_idx, o_edge_ab, o_facets, o_nf_ptr, o_nf_ent, o_ne_ptr, o_ne_ent, o_nc_ptr, o_nc_ent,
-      o_blk_pq, o_blk_fac_ptr, o_blk_fac, o_blk_ctr_ptr, o_blk_ctr, o_blk_edge;
+      o_blk_pq, o_blk_fac_ptr, o_blk_fac, o_blk_ctr_ptr, o_blk_ctr, o_blk_edge, o_blk_hdr, o_blk_fidx, o_blk_ctr_i,
+      o_blk_ctr_pq;
 
   /* returns DEFSLAM_OK or an error code */
   int build(const defslam_template_desc *d) {
@@ -191,7 +198,35 @@ struct PlanHost {
     }
     int bwn = 0;
     std::vector<int> blk_pq, blk_fac_ptr(1, 0), blk_fac, blk_ctr_ptr(1, 0), blk_ctr, blk_edge;
-    for (auto &kv : blocks) {
+    /* diagonal blocks first: they carry the longer dependent chain (stretch edges of the node), so
+     * they share warps with each other instead of stalling warps of off-diagonal blocks */
+    std::vector<std::pair<std::pair<int, int>, const Blk *>> order;
+    for (auto &kv : blocks) if (kv.first.first == kv.first.second) order.push_back({kv.first, &kv.second});
+    for (auto &kv : blocks) if (kv.first.first != kv.first.second) order.push_back({kv.first, &kv.second});
+    std::vector<int> blk_hdr, blk_fidx, blk_ctr_i;
+    std::vector<double> blk_ctr_pq;
+    for (auto &ov : order) {
+      struct { std::pair<int, int> first; const Blk &second; } kv = {ov.first, *ov.second};
+      {
+        int hdr[8] = {kv.first.first, kv.first.second, kv.second.edge, (int)blk_ctr_i.size(), (int)kv.second.ctr.size() / 3,
+                      (int)kv.second.fac.size(), -1, -1};
+        std::vector<int> fi;
+        for (int ent : kv.second.fac) {
+          const int f = ent >> 4, sp = (ent >> 2) & 3, sq = ent & 3;
+          const int lo = std::min(sp, sq), hi = std::max(sp, sq);
+          const int idx = lo == 0 ? hi : (lo == 1 ? 2 + hi : 5);
+          fi.push_back(idx * nf + f);
+        }
+        if (fi.size() <= 2) { for (size_t k = 0; k < fi.size(); k++) hdr[6 + k] = fi[k]; }
+        else { hdr[6] = (int)blk_fidx.size(); blk_fidx.insert(blk_fidx.end(), fi.begin(), fi.end()); }
+        blk_hdr.insert(blk_hdr.end(), hdr, hdr + 8);
+        for (size_t k = 0; k + 2 < kv.second.ctr.size() + 0; k += 3) {
+          const int ip = kv.second.ctr[k + 1], iq = kv.second.ctr[k + 2];
+          blk_ctr_i.push_back(kv.second.ctr[k]);
+          blk_ctr_pq.push_back(ip < 0 ? 1.0 : -nbrc[ip]);
+          blk_ctr_pq.push_back(iq < 0 ? 1.0 : -nbrc[iq]);
+        }
+      }
       blk_pq.push_back(kv.first.first);
       blk_pq.push_back(kv.first.second);
       bwn = std::max(bwn, kv.first.first - kv.first.second);
@@ -233,6 +268,12 @@ struct PlanHost {
     o_blk_fac_ptr = push_i(blk_fac_ptr); o_blk_fac = push_i(blk_fac);
     o_blk_ctr_ptr = push_i(blk_ctr_ptr); o_blk_ctr = push_i(blk_ctr);
     o_blk_edge = push_i(blk_edge);
+    if (blk_fidx.empty()) blk_fidx.push_back(0);
+    while (i32.size() & 3) i32.push_back(0);           /* headers are read as two 16-byte loads */
+    o_blk_hdr = push_i(blk_hdr);
+    o_blk_fidx = push_i(blk_fidx);
+    o_blk_ctr_i = push_i(blk_ctr_i);
+    o_blk_ctr_pq = push_d(blk_ctr_pq.data(), blk_ctr_pq.size());
     return DEFSLAM_OK;
   }
 
@@ -247,6 +288,8 @@ struct PlanHost {
     w.nc_ptr = I + o_nc_ptr; w.nc_ent = I + o_nc_ent;
     w.blk_pq = I + o_blk_pq; w.blk_fac_ptr = I + o_blk_fac_ptr; w.blk_fac = I + o_blk_fac;
     w.blk_ctr_ptr = I + o_blk_ctr_ptr; w.blk_ctr = I + o_blk_ctr; w.blk_edge = I + o_blk_edge;
+    w.blk_hdr = I + o_blk_hdr; w.blk_fidx = I + o_blk_fidx; w.blk_ctr_i = I + o_blk_ctr_i;
+    w.blk_ctr_pq = D + o_blk_ctr_pq;
     return w;
   }
   PlanView host_view() const { return bind(dbl.data(), i32.data(), u8.data()); }

@@ -727,39 +727,42 @@ DS_FN_NOINLINE double build_system(const Team team, Ctx &cx) {
   /* (3) node-node blocks: gather */
   double maxd = 0.0;
   DS_FOR(bi, pl.n_blk) {
-    const int p = pl.blk_pq[2 * bi], q = pl.blk_pq[2 * bi + 1];
+    /* packed plan record: everything the block needs from the plan in one 32-byte read */
+    const int *hd = &pl.blk_hdr[8 * bi];
+#if DS_CUDA
+    const int4 h0 = *(const int4 *)hd, h1 = *(const int4 *)(hd + 4);
+    const int p = h0.x, q = h0.y, edge = h0.z, c0 = h0.w, nctr = h1.x, nfac = h1.y, f0 = h1.z, f1 = h1.w;
+#else
+    const int p = hd[0], q = hd[1], edge = hd[2], c0 = hd[3], nctr = hd[4], nfac = hd[5], f0 = hd[6], f1 = hd[7];
+#endif
     double h[9];
     for (int k = 0; k < 9; k++) h[k] = 0.0;
     const bool fp = freev_ptr(c)[p], fq = freev_ptr(c)[q];
     if (fp && fq) {
       /* reprojection: (sum over shared facets of sum_m w b_p b_q) * A_p^T A_q */
       double beta = 0.0;
-      for (int k = pl.blk_fac_ptr[bi]; k < pl.blk_fac_ptr[bi + 1]; k++) {
-        const int ent = pl.blk_fac[k], f = ent >> 4, sp = (ent >> 2) & 3, sq = ent & 3;
-        const int lo = sp < sq ? sp : sq, hi = sp < sq ? sq : sp;
-        const int idx = lo == 0 ? hi : (lo == 1 ? 2 + hi : 5); /* (0,0)0 (0,1)1 (0,2)2 (1,1)3 (1,2)4 (2,2)5 */
-        beta += F[idx * nf + f];
+      if (nfac <= 2) {
+        if (nfac > 0) beta += F[f0];
+        if (nfac > 1) beta += F[f1];
+      } else {
+        for (int k = 0; k < nfac; k++) beta += F[pl.blk_fidx[f0 + k]];
       }
       const double *Ap = &A[6 * p], *Aq = &A[6 * q];
       for (int r = 0; r < 3; r++)
         for (int s = 0; s < 3; s++) h[3 * r + s] = beta * (Ap[r] * Aq[s] + Ap[3 + r] * Aq[3 + s]);
-      /* curvature: g_i c_ip c_iq d_i d_i^T.  Four centres at a time: the index loads and the
-       * coefficient loads of a batch are independent (one memory round trip each instead of
-       * one per centre); accumulation order unchanged. */
+      /* curvature: g_i c_ip c_iq d_i d_i^T.  Four centres at a time: the centre indices and the
+       * two coefficients of a batch are independent loads; accumulation order unchanged. */
       {
-        const int c0 = pl.blk_ctr_ptr[bi], c1 = pl.blk_ctr_ptr[bi + 1];
+        const int c1 = c0 + nctr;
         for (int kb4 = c0; kb4 < c1; kb4 += 4) {
-          int ci[4], cip[4], ciq[4];
-#pragma unroll
-          for (int u = 0; u < 4; u++) {
-            const int k = kb4 + u < c1 ? kb4 + u : c1 - 1;
-            ci[u] = pl.blk_ctr[3 * k]; cip[u] = pl.blk_ctr[3 * k + 1]; ciq[u] = pl.blk_ctr[3 * k + 2];
-          }
+          int ci[4];
           double cpv[4], cqv[4];
 #pragma unroll
           for (int u = 0; u < 4; u++) {
-            cpv[u] = cip[u] < 0 ? 1.0 : -pl.nbr_c[cip[u]];
-            cqv[u] = ciq[u] < 0 ? 1.0 : -pl.nbr_c[ciq[u]];
+            const int k = kb4 + u < c1 ? kb4 + u : c1 - 1;
+            ci[u] = pl.blk_ctr_i[k];
+            cpv[u] = pl.blk_ctr_pq[2 * k];
+            cqv[u] = pl.blk_ctr_pq[2 * k + 1];
           }
 #pragma unroll
           for (int u = 0; u < 4; u++) {
@@ -784,8 +787,8 @@ DS_FN_NOINLINE double build_system(const Team team, Ctx &cx) {
             for (int s = 0; s < 3; s++) h[3 * r + s] += w * u[r] * u[s];
         }
         if (viewed_ptr(c)[p]) { h[0] += c.info_ref; h[4] += c.info_ref; h[8] += c.info_ref; }
-      } else if (pl.blk_edge[bi] >= 0) {
-        const int e = pl.blk_edge[bi];
+      } else if (edge >= 0) {
+        const int e = edge;
         const double w = es[e];
         const double *u = &eu[3 * e];
         for (int r = 0; r < 3; r++)
