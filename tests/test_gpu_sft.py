@@ -88,3 +88,24 @@ def test_pipelined_host_path_equals_single_launch(cuda_lib, monkeypatch):
         assert a.r.lm_trials == b.r.lm_trials and a.r.n_inliers == b.r.n_inliers
         assert np.array_equal(a.outlier, b.outlier)
     T.close()
+
+
+def test_ragged_batch_of_different_templates(oracle, cuda_lib):
+    """one launch over frames of different meshes and match counts (the planner sizes shared memory and
+    the workspace for the largest; every CTA re-derives its layout per frame), plus a frame without matches"""
+    t9, t6, t13 = synthetic.make_template(9), synthetic.make_template(6), synthetic.make_template(13)
+    frames = [synthetic.make_frame(t9, 200, seed=41), synthetic.make_frame(t6, 60, seed=42),
+              synthetic.make_frame(t13, 700, seed=44), synthetic.make_frame(t9, 120, seed=43)]
+    empty = synthetic.make_frame(t9, 50, seed=45)
+    for name in ("match_nodes", "match_bary", "match_uv", "match_inv_sigma2"):
+        setattr(empty, name, np.ascontiguousarray(getattr(empty, name)[:0]))
+    frames.append(empty)
+    frames = frames * 3
+    outs = sft.solve_batched(frames)
+    for f, o in zip(frames, outs):
+        ref = oracle.sft_solve(f)
+        assert o.r.status == 0
+        assert o.r.lm_iterations == ref.r.lm_iterations and o.r.lm_trials == ref.r.lm_trials
+        assert _rel_nodes(o.nodes, ref.nodes) < NODE_TOL
+        assert o.r.n_inliers == ref.r.n_inliers
+    assert outs[4].r.n_inliers == 0 and np.array_equal(outs[4].nodes, outs[9].nodes)
