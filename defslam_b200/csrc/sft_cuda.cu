@@ -196,32 +196,34 @@ static int batch_load(defslam_sft_batch *B, int nprob, const defslam_sft_problem
   return 0;
 }
 
-static int batch_launch(defslam_sft_batch *B, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr) {
+static int batch_launch(defslam_sft_batch *B, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr,
+                        cudaStream_t st = nullptr) {
   DevCtx *ctx = B->ctx;
   if (!ev0) { ev0 = ctx->e0; ev1 = ctx->e1; }
+  if (!st) st = ctx->stream;
   const WorkspaceSizes z = B->bm.ws_sizes();
   long long *prof = nullptr;
   if (getenv("DEFSLAM_PROFILE")) { /* diagnostics: per-phase cycles of CTA 0 */
     int rc = B->d_prof.ensure(sizeof(long long) * PF_TOTAL);
     if (rc) return rc;
     prof = (long long *)B->d_prof.p;
-    DS_CUDA_TRY(cudaMemsetAsync(prof, 0, sizeof(long long) * PF_TOTAL, ctx->stream));
+    DS_CUDA_TRY(cudaMemsetAsync(prof, 0, sizeof(long long) * PF_TOTAL, st));
   }
   {
     int rc = B->d_counter.ensure(sizeof(int));
     if (rc) return rc;
-    DS_CUDA_TRY(cudaMemsetAsync(B->d_counter.p, 0, sizeof(int), ctx->stream));
+    DS_CUDA_TRY(cudaMemsetAsync(B->d_counter.p, 0, sizeof(int), st));
   }
-  DS_CUDA_TRY(cudaEventRecord(ev0, ctx->stream));
+  DS_CUDA_TRY(cudaEventRecord(ev0, st));
   if (!B->bm.any_x_global)
-    sft_lm_kernel<true><<<B->grid, SFT_THREADS, B->smem_bytes, ctx->stream>>>(
+    sft_lm_kernel<true><<<B->grid, SFT_THREADS, B->smem_bytes, st>>>(
         (const ProbView *)B->d_views.p, B->nprob, (uint8_t *)B->d_ws.p, B->ws_stride, z, prof, (int *)B->d_counter.p);
   else
-    sft_lm_kernel<false><<<B->grid, SFT_THREADS, B->smem_bytes, ctx->stream>>>(
+    sft_lm_kernel<false><<<B->grid, SFT_THREADS, B->smem_bytes, st>>>(
         (const ProbView *)B->d_views.p, B->nprob, (uint8_t *)B->d_ws.p, B->ws_stride, z, prof, (int *)B->d_counter.p);
   DS_CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1);
-  DS_CUDA_TRY(cudaEventRecord(ev1, ctx->stream));
+  DS_CUDA_TRY(cudaEventRecord(ev1, st));
   return 0;
 }
 
@@ -283,7 +285,7 @@ static defslam_sft_batch *tl_batch(DevCtx *ctx, int which = 0) {
  * them -- only the first marshal+upload and the last download+scatter are exposed. */
 static cudaStream_t tl_copy_stream(DevCtx *ctx, int which) {
   static thread_local std::map<int, cudaStream_t> tl;
-  const int key = ctx->device * 2 + which;
+  const int key = ctx->device * 4 + which;
   auto it = tl.find(key);
   if (it != tl.end()) return it->second;
   cudaStream_t s = nullptr;
@@ -294,7 +296,10 @@ static cudaStream_t tl_copy_stream(DevCtx *ctx, int which) {
 static int solve_pipelined(DevCtx *ctx, int nprob, const defslam_sft_problem *p, defslam_sft_result *r, int chunk) {
   defslam_sft_batch *Bs[2] = {tl_batch(ctx, 1), tl_batch(ctx, 2)};
   cudaStream_t cs = tl_copy_stream(ctx, 0), cs_down = tl_copy_stream(ctx, 1); /* uploads / downloads */
-  if (!cs || !cs_down) return DEFSLAM_ECUDA;
+  /* kernels of consecutive chunks go to two compute streams: the next chunk's CTAs move onto the SMs
+   * the current chunk's last frames leave idle (frames differ in LM trial count) */
+  cudaStream_t comp[2] = {ctx->stream, tl_copy_stream(ctx, 2)};
+  if (!cs || !cs_down || !comp[1]) return DEFSLAM_ECUDA;
   int rc;
   for (int k = 0; k < 2; k++)
     if ((rc = Bs[k]->ensure_events())) return rc;
@@ -317,8 +322,8 @@ static int solve_pipelined(DevCtx *ctx, int nprob, const defslam_sft_problem *p,
     const int off = c * chunk, cnt = nprob - off < chunk ? nprob - off : chunk;
     if ((rc = batch_load(B, cnt, p + off, MODE_SOLVE, cs))) return rc;
     DS_CUDA_TRY(cudaEventRecord(B->up, cs));
-    DS_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, B->up, 0));
-    if ((rc = batch_launch(B, B->k0, B->k1))) return rc;
+    DS_CUDA_TRY(cudaStreamWaitEvent(comp[c & 1], B->up, 0));
+    if ((rc = batch_launch(B, B->k0, B->k1, comp[c & 1]))) return rc;
     DS_CUDA_TRY(cudaStreamWaitEvent(cs_down, B->k1, 0));
     DS_CUDA_TRY(cudaMemcpyAsync(B->h_out.p, B->d_out.p, B->bm.out_bytes, cudaMemcpyDeviceToHost, cs_down));
     DS_CUDA_TRY(cudaEventRecord(B->done, cs_down));
