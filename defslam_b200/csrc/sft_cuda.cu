@@ -23,7 +23,10 @@ constexpr int SFT_THREADS = 256;
 /* XS: node positions and LM step in shared memory (every mesh up to ~21 x 21); the other variant
  * keeps them in the CTA's global workspace for meshes whose factorisation window fills the SM. */
 template <bool XS>
-__global__ void __launch_bounds__(SFT_THREADS, 2)
+#ifndef DS_MIN_CTAS
+#define DS_MIN_CTAS 2
+#endif
+__global__ void __launch_bounds__(SFT_THREADS, DS_MIN_CTAS)
 sft_lm_kernel(const ProbView *__restrict__ probs, int nprob, uint8_t *ws_base, size_t ws_stride, WorkspaceSizes z,
               long long *prof, int *work_counter) {
   extern __shared__ __align__(16) double smem[];
@@ -163,7 +166,11 @@ static int batch_load(defslam_sft_batch *B, int nprob, const defslam_sft_problem
     *dv = t->d_view;
     return 0;
   };
-  const int smem_limit = (ctx->smem_optin - 1024) / (int)sizeof(double);
+  int smem_limit = (ctx->smem_optin - 1024) / (int)sizeof(double);
+  if (const char *e = getenv("DEFSLAM_SMEM_LIMIT")) { /* experiments: force the planner's fallback placements */
+    const int lim = atoi(e) / (int)sizeof(double);
+    if (lim > 0 && lim < smem_limit) smem_limit = lim;
+  }
   int rc = B->bm.plan(nprob, p, mode, smem_limit, resolve);
   if (rc) return rc;
   if ((rc = B->h_in.ensure(B->bm.in_bytes)) || (rc = B->h_out.ensure(B->bm.out_bytes)) ||

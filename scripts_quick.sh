@@ -1,18 +1,10 @@
 #!/bin/bash
-timeout 600 python -m pytest tests/test_gpu_sft.py -x -q -m gpu 2>&1 | tail -2
-timeout 600 python - <<'PY'
-import time, numpy as np, os
+echo "== 2 CTAs/SM (product)"; timeout 300 python tools/prof_run.py C2 2368 3 2>&1 | tail -1
+echo "== forced global E/x, still 2 CTAs/SM (cost of the placement alone)"
+DEFSLAM_SMEM_LIMIT=75000 timeout 300 python tools/prof_run.py C2 2368 3 2>&1 | tail -1
+echo "== 3 CTAs/SM variant (85 regs, E and x/dx in global)"
+DEFSLAM_LIB=$PWD/defslam_b200/libdefslam_b200_c3.so DEFSLAM_SMEM_LIMIT=75000 timeout 300 python tools/prof_run.py C2 2664 3 2>&1 | tail -1
+DEFSLAM_LIB=$PWD/defslam_b200/libdefslam_b200_c3.so DEFSLAM_SMEM_LIMIT=75000 timeout 300 python -c "
 from defslam_b200 import sft, synthetic
-tmpl, base = synthetic.make_config_frames("C2", nframes=64)
-frames = [base[i % 64] for i in range(2368)]
-T = sft.Template(tmpl)
-hb = sft.HostBatch(frames, template=T)
-for _ in range(2): hb.solve()
-for tag in ("pipelined",):
-    ts = []
-    for _ in range(5):
-        t = time.perf_counter(); hb.solve(); ts.append(time.perf_counter() - t)
-    print(tag, "e2e ms", np.round(np.array(ts) * 1e3, 2), "solves/s %.0f" % (2368 / np.median(ts)))
-rb = sft.ResidentBatch(frames, template=T)
-print("resident ms", [round(rb.run(), 2) for _ in range(3)])
-PY
+tmpl, fr = synthetic.make_config_frames('C2', nframes=4)
+rb = sft.ResidentBatch([fr[i%4] for i in range(2664)], template=sft.Template(tmpl)); print(rb.info())"
