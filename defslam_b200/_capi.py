@@ -210,6 +210,17 @@ class ProjSearchProblem(C.Structure):
     ]
 
 
+class WarpSearchProblem(C.Structure):
+    _fields_ = [
+        ("bbs", Bbs), ("x", c_double_p), ("n1", C.c_int32), ("n2", C.c_int32),
+        ("kp1_norm", c_float_p), ("kp1_state", c_uint8_p), ("kp1_desc", c_uint8_p),
+        ("kp2_xy", c_float_p), ("kp2_has_mp", c_uint8_p), ("kp2_desc", c_uint8_p),
+        ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+        ("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float),
+        ("grid_width_inv", C.c_float), ("grid_height_inv", C.c_float), ("radius", C.c_float), ("th_low", C.c_int32),
+    ]
+
+
 NORMALS_ARGS = [C.POINTER(NormalsProblem), c_double_p, c_double_p, c_float_p, c_uint8_p, c_int32_p, c_float_p,
                 c_uint8_p]
 POLY_ARGS = [C.c_int32, c_float_p, c_float_p, c_float_p, c_float_p, c_double_p, c_double_p]
@@ -260,6 +271,7 @@ PROTOTYPES = {
     "defslam_scale_min_median": (C.c_int, [C.c_int32, c_float_p, c_float_p, C.c_uint64, c_float_p]),
     "defslam_new_map_points": (C.c_int, [C.POINTER(NewPointsProblem), c_uint8_p, c_float_p, c_int32_p]),
     "defslam_search_by_projection": (C.c_int, [C.POINTER(ProjSearchProblem), c_int32_p, c_int32_p]),
+    "defslam_search_by_schwarp": (C.c_int, [C.POINTER(WarpSearchProblem), c_int32_p, c_int32_p]),
     "defslam_surface_vertices": (C.c_int, [C.POINTER(Bbs), c_double_p, C.c_int32, C.c_int32, c_float_p]),
     "defslam_version": (C.c_char_p, []),
     "defslam_kernel_launch_count": (C.c_int64, []),

@@ -17,6 +17,7 @@
 #ifndef DS_MATCH_CORE_H_
 #define DS_MATCH_CORE_H_
 
+#include "bbs_core.h"
 #include "ds_common.h"
 #include "newpts_core.h" /* mul_rn / add_rn */
 
@@ -165,6 +166,62 @@ DS_FN void three_maxima(const int *size, int L, int &ind1, int &ind2, int &ind3)
   }
   if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
   else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+
+/* ---- warp-guided search (DefORBmatcher::searchBySchwarp, DefORBmatcher.cc:190-293) ---- */
+
+struct WarpView {
+  BbsView bbs;
+  const double *ctrl; /* interleaved [NC][2] like Warp::getEstimates builds it */
+  int n1, n2;
+  const float *kp1, *kp2;
+  const uint8_t *st1, *d1, *has2, *d2;
+  float fx, fy, cx, cy, min_x, max_x, min_y, max_y, gwi, ghi, radius;
+  int th_low;
+};
+
+DS_FN int cell_of_xy(float x, float y, float min_x, float min_y, float gwi, float ghi) {
+  const int px = (int)roundf(mul_rn(add_rn(x, -min_x), gwi));
+  const int py = (int)roundf(mul_rn(add_rn(y, -min_y), ghi));
+  if (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) return -1;
+  return px * GRID_ROWS + py;
+}
+
+/* best keypoint of keyframe 2 for keypoint i of keyframe 1, or -1 */
+DS_FN int warp_search_one(const WarpView &W, const int *cell2, int i) {
+  if (!W.st1[i]) return -1;
+  double val[2];
+  if (!bbs_eval_site(W.bbs, W.ctrl, (double)W.kp1[2 * i], (double)W.kp1[2 * i + 1], 0, 0, val)) return -1;
+  const float ex = (float)val[0], ey = (float)val[1]; /* cv::KeyPoint stores floats */
+  const float x = add_rn(mul_rn(ex, W.fx), W.cx), y = add_rn(mul_rn(ey, W.fy), W.cy);
+  if (!(x >= W.min_x && x < W.max_x && y >= W.min_y && y < W.max_y)) return -1; /* KeyFrame::IsInImage */
+  const float r = W.radius;
+  int a0 = floor_to_int(mul_rn(add_rn(add_rn(x, -W.min_x), -r), W.gwi));
+  if (a0 < 0) a0 = 0;
+  if (a0 >= GRID_COLS) return -1;
+  int a1 = ceil_to_int(mul_rn(add_rn(add_rn(x, -W.min_x), r), W.gwi));
+  if (a1 > GRID_COLS - 1) a1 = GRID_COLS - 1;
+  if (a1 < 0) return -1;
+  int b0 = floor_to_int(mul_rn(add_rn(add_rn(y, -W.min_y), -r), W.ghi));
+  if (b0 < 0) b0 = 0;
+  if (b0 >= GRID_ROWS) return -1;
+  int b1 = ceil_to_int(mul_rn(add_rn(add_rn(y, -W.min_y), r), W.ghi));
+  if (b1 > GRID_ROWS - 1) b1 = GRID_ROWS - 1;
+  if (b1 < 0) return -1;
+  uint64_t best = ~0ull;
+  for (int j = 0; j < W.n2; j++) {
+    const int cj = cell2[j];
+    if (cj < 0 || W.has2[j]) continue;
+    const int px = cj / GRID_ROWS, py = cj - px * GRID_ROWS;
+    if (px < a0 || px > a1 || py < b0 || py > b1) continue;
+    const float dx = add_rn(W.kp2[2 * j], -x), dy = add_rn(W.kp2[2 * j + 1], -y);
+    if (!(fabsf(dx) < r && fabsf(dy) < r)) continue;
+    const int dist = hamming256(&W.d1[32 * (size_t)i], &W.d2[32 * (size_t)j]);
+    if (dist >= W.th_low) continue;
+    const uint64_t k = cand_key(dist, cj, j);
+    if (k < best) best = k;
+  }
+  return best == ~0ull ? -1 : key_index(best);
 }
 
 }  // namespace ds

@@ -58,6 +58,22 @@ __global__ void candidates_kernel(ProjView P, const int *cell, Proj *proj, int *
   }
 }
 
+__global__ void warp_cell_kernel(WarpView W, int *cell2) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < W.n2; j += gridDim.x * blockDim.x)
+    cell2[j] = cell_of_xy(W.kp2[2 * j], W.kp2[2 * j + 1], W.min_x, W.min_y, W.gwi, W.ghi);
+}
+
+__global__ void warp_search_kernel(WarpView W, const int *cell2, int *match12, int *nmatches) {
+  int mine = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < W.n1; i += gridDim.x * blockDim.x) {
+    const int m = warp_search_one(W, cell2, i);
+    match12[i] = m;
+    mine += m >= 0;
+  }
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, o);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(nmatches, mine);
+}
+
 /* exclusive scan of cnt[0..n) by one CTA; total -> off[n] */
 __global__ void scan_kernel(const int *cnt, int *off, int n) {
   __shared__ int part[1024];
@@ -211,6 +227,52 @@ int defslam_search_by_projection(const defslam_projsearch_problem *p, int32_t *m
   DS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   memcpy(match_out, h, NC * 4);
   memcpy(nmatches_out, h + ((NC * 4 + 255) & ~(size_t)255), 4);
+  return DEFSLAM_OK;
+}
+
+int defslam_search_by_schwarp(const defslam_warpsearch_problem *p, int32_t *match12_out, int32_t *nmatches_out) {
+  if (!p || !match12_out || !nmatches_out || p->n1 < 0 || p->n2 < 0 || !p->x) return DEFSLAM_EBADARG;
+  if (p->bbs.nptsu < 4 || p->bbs.nptsv < 4 || p->bbs.valdim != 2 || !(p->bbs.umax > p->bbs.umin) || !(p->bbs.vmax > p->bbs.vmin))
+    return DEFSLAM_EBADARG;
+  if (p->n1 > 0 && (!p->kp1_norm || !p->kp1_state || !p->kp1_desc)) return DEFSLAM_EBADARG;
+  if (p->n2 > 0 && (!p->kp2_xy || !p->kp2_has_mp || !p->kp2_desc)) return DEFSLAM_EBADARG;
+  DevCtx *ctx = get_ctx(-1);
+  if (!ctx) return DEFSLAM_ECUDA;
+  *nmatches_out = 0;
+  const size_t N1 = (size_t)p->n1, N2 = (size_t)p->n2, NC = (size_t)p->bbs.nptsu * p->bbs.nptsv;
+  for (size_t i = 0; i < N1; i++) match12_out[i] = -1;
+  if (N1 == 0 || N2 == 0) return DEFSLAM_OK;
+  Packer in, wk;
+  const size_t o_c = in.add(NC * 16), o_k1 = in.add(N1 * 8), o_s1 = in.add(N1), o_d1 = in.add(N1 * 32), o_k2 = in.add(N2 * 8),
+               o_h2 = in.add(N2), o_d2 = in.add(N2 * 32);
+  const size_t w_cell = wk.add(N2 * 4), w_m = wk.add(N1 * 4), w_n = wk.add(4);
+  Scratch &S = tl_scratch(ctx->device);
+  int rc;
+  if ((rc = S.host.ensure(in.total > wk.total ? in.total : wk.total)) || (rc = S.dev.ensure(in.total + wk.total))) return rc;
+  uint8_t *h = (uint8_t *)S.host.p, *d = (uint8_t *)S.dev.p, *w = d + in.total;
+  double *ctrl = (double *)(h + o_c); /* Array[valdim*l + n] = ControlPoints(l, n), Schwarp.cc:185-193 */
+  for (size_t l = 0; l < NC; l++) { ctrl[2 * l] = p->x[l]; ctrl[2 * l + 1] = p->x[NC + l]; }
+  memcpy(h + o_k1, p->kp1_norm, N1 * 8); memcpy(h + o_s1, p->kp1_state, N1); memcpy(h + o_d1, p->kp1_desc, N1 * 32);
+  memcpy(h + o_k2, p->kp2_xy, N2 * 8); memcpy(h + o_h2, p->kp2_has_mp, N2); memcpy(h + o_d2, p->kp2_desc, N2 * 32);
+  DS_CUDA_TRY(cudaMemcpyAsync(d, h, in.total, cudaMemcpyHostToDevice, ctx->stream));
+  WarpView W;
+  W.bbs.umin = p->bbs.umin; W.bbs.umax = p->bbs.umax; W.bbs.vmin = p->bbs.vmin; W.bbs.vmax = p->bbs.vmax;
+  W.bbs.nptsu = p->bbs.nptsu; W.bbs.nptsv = p->bbs.nptsv; W.bbs.valdim = 2;
+  W.ctrl = (const double *)(d + o_c); W.n1 = p->n1; W.n2 = p->n2;
+  W.kp1 = (const float *)(d + o_k1); W.kp2 = (const float *)(d + o_k2); W.st1 = d + o_s1; W.d1 = d + o_d1; W.has2 = d + o_h2;
+  W.d2 = d + o_d2; W.fx = p->fx; W.fy = p->fy; W.cx = p->cx; W.cy = p->cy; W.min_x = p->min_x; W.max_x = p->max_x;
+  W.min_y = p->min_y; W.max_y = p->max_y; W.gwi = p->grid_width_inv; W.ghi = p->grid_height_inv; W.radius = p->radius;
+  W.th_low = p->th_low;
+  DS_CUDA_TRY(cudaMemsetAsync(w + w_n, 0, 4, ctx->stream));
+  warp_cell_kernel<<<grid_for(p->n2, ctx->sm_count), 128, 0, ctx->stream>>>(W, (int *)(w + w_cell));
+  warp_search_kernel<<<grid_for(p->n1, ctx->sm_count), 128, 0, ctx->stream>>>(W, (const int *)(w + w_cell), (int *)(w + w_m),
+                                                                              (int *)(w + w_n));
+  DS_CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(2);
+  DS_CUDA_TRY(cudaMemcpyAsync(h, w + w_m, (N1 * 4 + 255 & ~(size_t)255) + 4, cudaMemcpyDeviceToHost, ctx->stream));
+  DS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  memcpy(match12_out, h, N1 * 4);
+  memcpy(nmatches_out, h + ((N1 * 4 + 255) & ~(size_t)255), 4);
   return DEFSLAM_OK;
 }
 

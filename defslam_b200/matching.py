@@ -149,3 +149,102 @@ def make_case(seed: int, n_last: int = 1200, n_clutter: int = 400, flip_bits: in
         cur_angle=np.ascontiguousarray(cur_ang), cur_desc=np.ascontiguousarray(cur_desc), cur_uright=uright,
         cur_taken=taken, scale_factors=scale, T_cw=T_cw, T_lw=T_lw, fx=fx, fy=fy, cx=cx, cy=cy, mb=mb, mbf=mbf,
         width=W, height=H, mono=0 if stereo else 1, truth=truth)
+
+
+# ----------------------------------------------------------------------------- warp-guided search
+@dataclass
+class WarpSearchCase:
+    bbs: _capi.Bbs
+    x: np.ndarray            # f64 [2*NC], the reference's layout (NC u-coordinates, then NC v-coordinates)
+    kp1_norm: np.ndarray     # f32 [n1,2]
+    kp1_state: np.ndarray    # u8
+    kp1_desc: np.ndarray     # u8 [n1,32]
+    kp2_xy: np.ndarray       # f32 [n2,2]
+    kp2_has_mp: np.ndarray   # u8
+    kp2_desc: np.ndarray
+    fx: float = 435.2047
+    fy: float = 435.2047
+    cx: float = 367.4517
+    cy: float = 252.2009
+    width: int = 640
+    height: int = 480
+    radius: float = 2.0
+    th_low: int = 50
+    truth: np.ndarray = field(default=None)
+
+    def problem(self) -> _capi.WarpSearchProblem:
+        p = _capi.WarpSearchProblem()
+        p.bbs = self.bbs
+        p.x = _capi.as_ptr(self.x, C.c_double)
+        p.n1, p.n2 = len(self.kp1_state), len(self.kp2_has_mp)
+        for name, ct in (("kp1_norm", C.c_float), ("kp1_state", C.c_uint8), ("kp1_desc", C.c_uint8),
+                         ("kp2_xy", C.c_float), ("kp2_has_mp", C.c_uint8), ("kp2_desc", C.c_uint8)):
+            setattr(p, name, _capi.as_ptr(getattr(self, name), ct))
+        p.fx, p.fy, p.cx, p.cy = self.fx, self.fy, self.cx, self.cy
+        p.min_x, p.max_x, p.min_y, p.max_y = 0.0, float(self.width), 0.0, float(self.height)
+        p.grid_width_inv = float(np.float32(64) / np.float32(self.width))
+        p.grid_height_inv = float(np.float32(48) / np.float32(self.height))
+        p.radius, p.th_low = self.radius, self.th_low
+        return p
+
+
+def search_by_schwarp(case: WarpSearchCase, lib=None, prefix: str = "defslam_"):
+    """returns (match12[n1] -> keypoint of keyframe 2 or -1, nmatches)"""
+    lib = lib if lib is not None else _capi.load()
+    f = getattr(lib, prefix + "search_by_schwarp")
+    if prefix != "defslam_":
+        f.restype, f.argtypes = _capi.PROTOTYPES["defslam_search_by_schwarp"]
+    n1 = len(case.kp1_state)
+    match = np.full(max(n1, 1), -1, np.int32)
+    nm = C.c_int32(0)
+    p = case.problem()
+    rc = f(C.byref(p), _capi.as_ptr(match, C.c_int32), C.cast(C.byref(nm), _capi.c_int32_p))
+    if rc != 0:
+        raise DefslamError(prefix + "search_by_schwarp", rc)
+    return match[:n1], nm.value
+
+
+def make_warp_case(seed: int, n1: int = 1200, n_clutter: int = 500, nptsu: int = 13, nptsv: int = 15) -> WarpSearchCase:
+    """keyframe 1 keypoints, a smooth warp to keyframe 2 (control points = identity grid + a low-frequency
+    displacement), keyframe 2 keypoints = warped keypoints + sub-pixel noise + clutter + near-duplicates"""
+    from . import nrsfm
+    rng = np.random.default_rng(seed)
+    fx = fy = 435.2047
+    cx, cy = 367.4517, 252.2009
+    W, H = 640, 480
+    px = np.stack([rng.uniform(12, W - 12, n1), rng.uniform(12, H - 12, n1)], 1)
+    q1 = np.stack([(px[:, 0] - cx) / fx, (px[:, 1] - cy) / fy], 1).astype(np.float32)
+    umin, umax, vmin, vmax = nrsfm.keyframe_domain(q1)
+    bbs = nrsfm.make_bbs(umin, umax, vmin, vmax, nptsu, nptsv, 2)
+    NC = nptsu * nptsv
+    # a cubic B-spline reproduces linear functions from control values sampled at the Greville sites:
+    # uniform knots -> control point i sits at umin + (i - 1) * (umax - umin) / (nptsu - 3)
+    gu = umin + (np.arange(nptsu) - 1) * (umax - umin) / (nptsu - 3)
+    gv = vmin + (np.arange(nptsv) - 1) * (vmax - vmin) / (nptsv - 3)
+    GU, GV = np.meshgrid(gu, gv, indexing="ij")
+    ctrl_u = GU + 0.02 * np.sin(2.0 * GU) * np.cos(1.5 * GV) + 0.01
+    ctrl_v = GV + 0.015 * np.cos(1.7 * GU) - 0.005
+    x = np.concatenate([ctrl_u.reshape(-1), ctrl_v.reshape(-1)])
+    # warped positions through the library-independent formula are not needed: the test compares libraries;
+    # keyframe 2 keypoints are produced by the ORACLE-free closed form of the displacement (close enough to
+    # the spline for a 2 px window) plus noise
+    u, v = q1[:, 0].astype(float), q1[:, 1].astype(float)
+    wu = u + 0.02 * np.sin(2.0 * u) * np.cos(1.5 * v) + 0.01
+    wv = v + 0.015 * np.cos(1.7 * u) - 0.005
+    p2 = np.stack([wu * fx + cx, wv * fy + cy], 1) + rng.normal(0, 0.5, (n1, 2))
+    desc1 = rng.integers(0, 256, (n1, 32), dtype=np.uint8)
+    d2 = desc1.copy()
+    for r in range(n1):
+        for b in rng.choice(256, rng.integers(0, 40), replace=False):
+            d2[r, b >> 3] ^= np.uint8(1 << (b & 7))
+    dup = rng.choice(n1, n1 // 15, replace=False)
+    kp2 = np.concatenate([p2, p2[dup] + rng.normal(0, 0.6, (len(dup), 2)),
+                          np.stack([rng.uniform(0, W, n_clutter), rng.uniform(0, H, n_clutter)], 1)]).astype(np.float32)
+    desc2 = np.concatenate([d2, d2[dup], rng.integers(0, 256, (n_clutter, 32), dtype=np.uint8)])
+    truth = np.concatenate([np.arange(n1), dup, np.full(n_clutter, -1)]).astype(np.int32)
+    perm = rng.permutation(len(kp2))
+    kp2, desc2, truth = kp2[perm], desc2[perm], truth[perm]
+    return WarpSearchCase(bbs=bbs, x=np.ascontiguousarray(x), kp1_norm=np.ascontiguousarray(q1),
+                          kp1_state=(rng.uniform(size=n1) < 0.8).astype(np.uint8), kp1_desc=np.ascontiguousarray(desc1),
+                          kp2_xy=np.ascontiguousarray(kp2), kp2_has_mp=(rng.uniform(size=len(kp2)) < 0.1).astype(np.uint8),
+                          kp2_desc=np.ascontiguousarray(desc2), truth=truth)

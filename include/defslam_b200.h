@@ -480,6 +480,34 @@ typedef struct defslam_projsearch_problem {
 
 int defslam_search_by_projection(const defslam_projsearch_problem *p, int32_t *match_out, int32_t *nmatches_out);
 
+/* Warp-guided search of map points between two keyframes.
+ * replaces: DefORBmatcher::searchBySchwarp  Modules/Matching/DefORBmatcher.cc:190-293
+ *           (Warps::Warp::getEstimates  Modules/Mapping/Schwarp.cc:162-233, KeyFrame::GetFeaturesInArea / IsInImage
+ *            Thirdparty/ORBSLAM_2/src/KeyFrame.cc:618-668)
+ * Every keypoint of keyframe 1 that owns a usable map point not yet seen in keyframe 2 is sent through the
+ * bicubic B-spline warp x (the reference's layout: NC u-coordinates, then NC v-coordinates), converted to pixels
+ * of keyframe 2, and matched to the closest descriptor (< th_low) among the keypoints of keyframe 2 without a map
+ * point within `radius` pixels; first minimum in the grid order of GetFeaturesInArea.  No order dependence.
+ *   kp1_state[i]: 1 = candidate (map point non-null, not bad, not in keyframe 2), else 0
+ *   match12_out[i]: index of the keypoint of keyframe 2, or -1;  *nmatches_out = number of candidates matched */
+typedef struct defslam_warpsearch_problem {
+  defslam_bbs bbs;                  /* domain of keyframe 1, NCu x NCv, valdim 2          */
+  const double *x;                  /* [2*NC] warp control points                          */
+  int32_t n1, n2;
+  const float *kp1_norm;            /* [n1*2] DefKeyFrame::mpKeypointNorm[i].pt            */
+  const uint8_t *kp1_state;         /* [n1]                                                */
+  const uint8_t *kp1_desc;          /* [n1*32] mDescriptors of keyframe 1                  */
+  const float *kp2_xy;              /* [n2*2] mvKeysUn of keyframe 2 (pixels)              */
+  const uint8_t *kp2_has_mp;        /* [n2]   GetMapPoint(j) != NULL                       */
+  const uint8_t *kp2_desc;          /* [n2*32]                                             */
+  float fx, fy, cx, cy;             /* keyframe 2                                          */
+  float min_x, max_x, min_y, max_y, grid_width_inv, grid_height_inv;
+  float radius;                     /* th = 2                                              */
+  int32_t th_low;                   /* ORBmatcher::TH_LOW (50)                             */
+} defslam_warpsearch_problem;
+
+int defslam_search_by_schwarp(const defslam_warpsearch_problem *p, int32_t *match12_out, int32_t *nmatches_out);
+
 /* Surface -> template nodes.
  * replaces: Surface::getVertex  Modules/Mapping/Surface.cc:125-161
  * nodes_out: [xs*ys*3] fp32 (u d, v d, d), x-major outer loop */

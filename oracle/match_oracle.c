@@ -172,3 +172,80 @@ int oracle_search_by_projection(const defslam_projsearch_problem *p, int32_t *ma
   *nmatches_out = nmatches;
   return DEFSLAM_OK;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * DefORBmatcher::searchBySchwarp  (Modules/Matching/DefORBmatcher.cc:190-293), in the reference's own
+ * control flow: list of keypoints with a usable map point, Warp::getEstimates (one BBS evaluation of
+ * the warp, Schwarp.cc:162-233), pixel conversion, KeyFrame::IsInImage, KeyFrame::GetFeaturesInArea
+ * (KeyFrame.cc:618-663) over the 64 x 48 grid of keyframe 2, best descriptor below TH_LOW among the
+ * features without a map point.
+ * ---------------------------------------------------------------------------------------------- */
+int oracle_bbs_eval(const defslam_bbs *s, const double *ctrl, int32_t nsites, const double *u, const double *v,
+                    int32_t du, int32_t dv, double *val);
+
+int oracle_search_by_schwarp(const defslam_warpsearch_problem *p, int32_t *match12_out, int32_t *nmatches_out) {
+  const int N1 = p->n1, N2 = p->n2, NC = p->bbs.nptsu * p->bbs.nptsv;
+  cell_t *grid = (cell_t *)calloc(GRID_COLS * GRID_ROWS, sizeof(cell_t));
+  for (int j = 0; j < N2; j++) {       /* KeyFrame grid: built like Frame::AssignFeaturesToGrid */
+    const int posX = (int)roundf(fmul(fadd(p->kp2_xy[2 * j], -p->min_x), p->grid_width_inv));
+    const int posY = (int)roundf(fmul(fadd(p->kp2_xy[2 * j + 1], -p->min_y), p->grid_height_inv));
+    if (posX < 0 || posX >= GRID_COLS || posY < 0 || posY >= GRID_ROWS) continue;
+    cell_push(&grid[posX * GRID_ROWS + posY], j);
+  }
+  int *list = (int *)malloc(sizeof(int) * (N1 > 0 ? N1 : 1)), nl = 0;
+  double *u = (double *)malloc(sizeof(double) * (N1 > 0 ? N1 : 1)), *v = (double *)malloc(sizeof(double) * (N1 > 0 ? N1 : 1));
+  double *val = (double *)malloc(sizeof(double) * 2 * (N1 > 0 ? N1 : 1)), *Array = (double *)malloc(sizeof(double) * 2 * NC);
+  for (int i = 0; i < N1; i++) {
+    match12_out[i] = -1;
+    if (!p->kp1_state[i]) continue;
+    list[nl] = i; u[nl] = p->kp1_norm[2 * i]; v[nl] = p->kp1_norm[2 * i + 1]; nl++;
+  }
+  int nmatches = 0;
+  if (nl > 0) {
+    for (int n = 0; n < 2; n++)
+      for (int l = 0; l < NC; l++) Array[2 * l + n] = p->x[n * NC + l];
+    defslam_bbs b = p->bbs;
+    b.valdim = 2;
+    oracle_bbs_eval(&b, Array, nl, u, v, 0, 0, val);
+    for (int k = 0; k < nl; k++) {
+      const int i = list[k];
+      const float ex = (float)val[2 * k], ey = (float)val[2 * k + 1];
+      if (ex != ex || ey != ey) continue; /* outside the spline domain */
+      const float x = fadd(fmul(ex, p->fx), p->cx), y = fadd(fmul(ey, p->fy), p->cy);
+      if (!(x >= p->min_x && x < p->max_x && y >= p->min_y && y < p->max_y)) continue;
+      const float r = p->radius;
+      int bestDist = p->th_low, bestIdx2 = -1;
+      do {
+        int nMinCellX = (int)floorf(fmul(fadd(fadd(x, -p->min_x), -r), p->grid_width_inv));
+        if (nMinCellX < 0) nMinCellX = 0;
+        if (nMinCellX >= GRID_COLS) break;
+        int nMaxCellX = (int)ceilf(fmul(fadd(fadd(x, -p->min_x), r), p->grid_width_inv));
+        if (nMaxCellX > GRID_COLS - 1) nMaxCellX = GRID_COLS - 1;
+        if (nMaxCellX < 0) break;
+        int nMinCellY = (int)floorf(fmul(fadd(fadd(y, -p->min_y), -r), p->grid_height_inv));
+        if (nMinCellY < 0) nMinCellY = 0;
+        if (nMinCellY >= GRID_ROWS) break;
+        int nMaxCellY = (int)ceilf(fmul(fadd(fadd(y, -p->min_y), r), p->grid_height_inv));
+        if (nMaxCellY > GRID_ROWS - 1) nMaxCellY = GRID_ROWS - 1;
+        if (nMaxCellY < 0) break;
+        for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+          for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
+            const cell_t *vCell = &grid[ix * GRID_ROWS + iy];
+            for (int c = 0; c < vCell->n; c++) {
+              const int j = vCell->idx[c];
+              const float distx = fadd(p->kp2_xy[2 * j], -x), disty = fadd(p->kp2_xy[2 * j + 1], -y);
+              if (!(fabsf(distx) < r && fabsf(disty) < r)) continue;
+              if (p->kp2_has_mp[j]) continue;
+              const int dist = descriptor_distance(&p->kp1_desc[32 * (size_t)i], &p->kp2_desc[32 * (size_t)j]);
+              if (dist < p->th_low && dist < bestDist) { bestIdx2 = j; bestDist = dist; }
+            }
+          }
+      } while (0);
+      if (bestIdx2 >= 0) { match12_out[i] = bestIdx2; nmatches++; }
+    }
+  }
+  for (int k = 0; k < GRID_COLS * GRID_ROWS; k++) free(grid[k].idx);
+  free(grid); free(list); free(u); free(v); free(val); free(Array);
+  *nmatches_out = nmatches;
+  return DEFSLAM_OK;
+}

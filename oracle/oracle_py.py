@@ -56,6 +56,8 @@ def load(native: bool = False):
                                                  P.c_float_p]
     lib.oracle_search_by_projection.restype = C.c_int
     lib.oracle_search_by_projection.argtypes = _capi.PROTOTYPES["defslam_search_by_projection"][1]
+    lib.oracle_search_by_schwarp.restype = C.c_int
+    lib.oracle_search_by_schwarp.argtypes = _capi.PROTOTYPES["defslam_search_by_schwarp"][1]
     lib.oracle_new_map_points.restype = C.c_int
     lib.oracle_new_map_points.argtypes = _capi.PROTOTYPES["defslam_new_map_points"][1]
     lib.oracle_regular_triangulation.restype = C.c_int

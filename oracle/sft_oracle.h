@@ -58,6 +58,7 @@ int oracle_new_map_points(const defslam_newpoints_problem *p, uint8_t *action_ou
 
 /* ---- projection search (match_oracle.c) ---- */
 int oracle_search_by_projection(const defslam_projsearch_problem *p, int32_t *match_out, int32_t *nmatches_out);
+int oracle_search_by_schwarp(const defslam_warpsearch_problem *p, int32_t *match12_out, int32_t *nmatches_out);
 
 #ifdef __cplusplus
 }

@@ -167,4 +167,22 @@ int emu_search_by_projection(const defslam_projsearch_problem *p, int32_t *match
   *nmatches_out = nmatches;
   return 0;
 }
+int emu_search_by_schwarp(const defslam_warpsearch_problem *p, int32_t *match12_out, int32_t *nmatches_out) {
+  const size_t NC = (size_t)p->bbs.nptsu * p->bbs.nptsv;
+  std::vector<double> ctrl(2 * NC);
+  for (size_t l = 0; l < NC; l++) { ctrl[2 * l] = p->x[l]; ctrl[2 * l + 1] = p->x[NC + l]; }
+  WarpView W;
+  W.bbs.umin = p->bbs.umin; W.bbs.umax = p->bbs.umax; W.bbs.vmin = p->bbs.vmin; W.bbs.vmax = p->bbs.vmax;
+  W.bbs.nptsu = p->bbs.nptsu; W.bbs.nptsv = p->bbs.nptsv; W.bbs.valdim = 2;
+  W.ctrl = ctrl.data(); W.n1 = p->n1; W.n2 = p->n2; W.kp1 = p->kp1_norm; W.kp2 = p->kp2_xy; W.st1 = p->kp1_state;
+  W.d1 = p->kp1_desc; W.has2 = p->kp2_has_mp; W.d2 = p->kp2_desc; W.fx = p->fx; W.fy = p->fy; W.cx = p->cx; W.cy = p->cy;
+  W.min_x = p->min_x; W.max_x = p->max_x; W.min_y = p->min_y; W.max_y = p->max_y; W.gwi = p->grid_width_inv;
+  W.ghi = p->grid_height_inv; W.radius = p->radius; W.th_low = p->th_low;
+  std::vector<int> cell2(p->n2 > 0 ? p->n2 : 1);
+  for (int j = 0; j < p->n2; j++) cell2[j] = cell_of_xy(W.kp2[2 * j], W.kp2[2 * j + 1], W.min_x, W.min_y, W.gwi, W.ghi);
+  int n = 0;
+  for (int i = 0; i < p->n1; i++) { match12_out[i] = warp_search_one(W, cell2.data(), i); n += match12_out[i] >= 0; }
+  *nmatches_out = n;
+  return 0;
+}
 }

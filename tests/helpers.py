@@ -37,7 +37,7 @@ def emu_lib():
         lib.emu_plan_info.restype = C.c_int
         lib.emu_plan_info.argtypes = [C.c_void_p, P.c_int32_p]
         for nm in ("emu_mesh_laplacian", "emu_embed_points", "emu_mappoints_recalculate", "emu_new_map_points",
-                   "emu_search_by_projection"):
+                   "emu_search_by_projection", "emu_search_by_schwarp"):
             f = getattr(lib, nm)
             f.restype = C.c_int
             f.argtypes = P.PROTOTYPES["defslam_" + nm[4:]][1]

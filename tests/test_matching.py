@@ -60,3 +60,30 @@ def test_gpu_matches_oracle(cuda_lib, oracle):
     c.last_state[:] = 0
     m, n = matching.search_by_projection(c)
     assert n == 0 and (m == -1).all()
+
+
+# ----------------------------------------------------------------------------- warp-guided search
+def _check_warp(lib, prefix, oracle):
+    olib = oracle.load()
+    for seed, kw in ((1, {}), (2, dict(n1=300, n_clutter=3000)), (3, dict(nptsu=17, nptsv=17))):
+        c = matching.make_warp_case(seed, **kw)
+        mo, no = matching.search_by_schwarp(c, olib, "oracle_")
+        m, n = matching.search_by_schwarp(c, lib, prefix)
+        assert n == no and np.array_equal(m, mo)
+        good = mo >= 0
+        assert good.sum() > 0.3 * c.kp1_state.sum()
+        assert (c.truth[mo[good]] == np.flatnonzero(good)).mean() > 0.97
+        assert not c.kp2_has_mp[mo[good]].any() and c.kp1_state[good].all()
+
+
+def test_warp_search_kernel_code_matches_oracle(oracle):
+    _check_warp(emu_lib(), "emu_", oracle)
+
+
+@pytest.mark.gpu
+def test_warp_search_gpu_matches_oracle(cuda_lib, oracle):
+    _check_warp(cuda_lib, "defslam_", oracle)
+    c = matching.make_warp_case(4, n1=20, n_clutter=5)
+    c.kp1_state[:] = 0
+    m, n = matching.search_by_schwarp(c)
+    assert n == 0 and (m == -1).all()
