@@ -302,6 +302,38 @@ def stream_bench(lib, with_cpu: bool):
     return out
 
 
+def matching_bench(lib, with_cpu: bool):
+    """Match production that feeds the SfT solve: one call per frame through the C ABI on
+    host buffers (this is a latency path: 1200 map points x ~1400 keypoints), the oracle's literal loop beside it."""
+    from defslam_b200 import matching
+    out = {}
+    reps = 40
+    for name, case, fn in (("search_by_projection", matching.make_case(1), matching.search_by_projection),
+                           ("search_by_schwarp", matching.make_warp_case(1), matching.search_by_schwarp)):
+        for _ in range(3):
+            fn(case)
+        l0 = lib.defslam_kernel_launch_count()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            m, n = fn(case)
+        dt = (time.perf_counter() - t0) / reps
+        out[name] = {"value": 1.0 / dt, "unit": "frames/s", "ms_per_call": 1e3 * dt, "matches": int(n),
+                     "gpu_launches": int(lib.defslam_kernel_launch_count() - l0)}
+        if with_cpu:
+            from oracle import oracle_py
+            olib = oracle_py.load()
+            mo, no = fn(case, olib, "oracle_")
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn(case, olib, "oracle_")
+            dto = (time.perf_counter() - t0) / reps
+            out[name]["cpu_baseline"] = {"value": 1.0 / dto, "unit": "frames/s", "ms_per_call": 1e3 * dto, "cores": 1,
+                                         "kind": "port"}
+            out[name]["identical_to_oracle"] = bool(no == n and np.array_equal(mo, m))
+    out["workload"] = "1200 map points / keypoints of the previous (key)frame against ~1400-1800 keypoints, 256-bit ORB descriptors"
+    return out
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -344,6 +376,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-nrsfm", action="store_true", help="skip the NRSfM stage measurements")
     ap.add_argument("--no-stream", action="store_true", help="skip the C3 tracking+mapping stream")
+    ap.add_argument("--no-matching", action="store_true", help="skip the match-production measurements")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -433,6 +466,11 @@ def main():
     st_line = None
     if not args.no_stream and rank == 0:
         st_line = stream_bench(lib, not args.no_cpu_baseline)
+
+    # ---- match production (projection search, warp-guided search): per-frame calls on host buffers
+    mt_line = None
+    if not args.no_matching and rank == 0:
+        mt_line = matching_bench(lib, not args.no_cpu_baseline)
 
     # ---- parity spot check against the oracle (not timed) ----------------------------
     rel = None
@@ -524,6 +562,8 @@ def main():
                                                  "sample": "32 fits / 256 point sets / 16 keyframes, one unit per thread"}
         if st_line is not None:
             line["stream"] = st_line
+        if mt_line is not None:
+            line["matching"] = mt_line
         if not args.no_cpu_baseline and world >= 1:
             cores = os.cpu_count() or 1
             n_sample = max(cores, min(CPU_SAMPLE_FRAMES, 8 * cores))

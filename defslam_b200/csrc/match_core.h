@@ -187,29 +187,30 @@ DS_FN int cell_of_xy(float x, float y, float min_x, float min_y, float gwi, floa
   return px * GRID_ROWS + py;
 }
 
-/* best keypoint of keyframe 2 for keypoint i of keyframe 1, or -1 */
-DS_FN int warp_search_one(const WarpView &W, const int *cell2, int i) {
-  if (!W.st1[i]) return -1;
+/* best-ranked candidate key among the keypoints j = first, first+stride, ... of keyframe 2 for keypoint i
+ * of keyframe 1 (~0 when none): one thread scans everything with (0, 1), a warp splits the scan by lane */
+DS_FN uint64_t warp_search_lanes(const WarpView &W, const int *cell2, int i, int first, int stride) {
+  if (!W.st1[i]) return ~0ull;
   double val[2];
-  if (!bbs_eval_site(W.bbs, W.ctrl, (double)W.kp1[2 * i], (double)W.kp1[2 * i + 1], 0, 0, val)) return -1;
+  if (!bbs_eval_site(W.bbs, W.ctrl, (double)W.kp1[2 * i], (double)W.kp1[2 * i + 1], 0, 0, val)) return ~0ull;
   const float ex = (float)val[0], ey = (float)val[1]; /* cv::KeyPoint stores floats */
   const float x = add_rn(mul_rn(ex, W.fx), W.cx), y = add_rn(mul_rn(ey, W.fy), W.cy);
-  if (!(x >= W.min_x && x < W.max_x && y >= W.min_y && y < W.max_y)) return -1; /* KeyFrame::IsInImage */
+  if (!(x >= W.min_x && x < W.max_x && y >= W.min_y && y < W.max_y)) return ~0ull; /* KeyFrame::IsInImage */
   const float r = W.radius;
   int a0 = floor_to_int(mul_rn(add_rn(add_rn(x, -W.min_x), -r), W.gwi));
   if (a0 < 0) a0 = 0;
-  if (a0 >= GRID_COLS) return -1;
+  if (a0 >= GRID_COLS) return ~0ull;
   int a1 = ceil_to_int(mul_rn(add_rn(add_rn(x, -W.min_x), r), W.gwi));
   if (a1 > GRID_COLS - 1) a1 = GRID_COLS - 1;
-  if (a1 < 0) return -1;
+  if (a1 < 0) return ~0ull;
   int b0 = floor_to_int(mul_rn(add_rn(add_rn(y, -W.min_y), -r), W.ghi));
   if (b0 < 0) b0 = 0;
-  if (b0 >= GRID_ROWS) return -1;
+  if (b0 >= GRID_ROWS) return ~0ull;
   int b1 = ceil_to_int(mul_rn(add_rn(add_rn(y, -W.min_y), r), W.ghi));
   if (b1 > GRID_ROWS - 1) b1 = GRID_ROWS - 1;
-  if (b1 < 0) return -1;
+  if (b1 < 0) return ~0ull;
   uint64_t best = ~0ull;
-  for (int j = 0; j < W.n2; j++) {
+  for (int j = first; j < W.n2; j += stride) {
     const int cj = cell2[j];
     if (cj < 0 || W.has2[j]) continue;
     const int px = cj / GRID_ROWS, py = cj - px * GRID_ROWS;
@@ -221,6 +222,12 @@ DS_FN int warp_search_one(const WarpView &W, const int *cell2, int i) {
     const uint64_t k = cand_key(dist, cj, j);
     if (k < best) best = k;
   }
+  return best;
+}
+
+/* best keypoint of keyframe 2 for keypoint i of keyframe 1, or -1 */
+DS_FN int warp_search_one(const WarpView &W, const int *cell2, int i) {
+  const uint64_t best = warp_search_lanes(W, cell2, i, 0, 1);
   return best == ~0ull ? -1 : key_index(best);
 }
 

@@ -63,15 +63,125 @@ __global__ void warp_cell_kernel(WarpView W, int *cell2) {
     cell2[j] = cell_of_xy(W.kp2[2 * j], W.kp2[2 * j + 1], W.min_x, W.min_y, W.gwi, W.ghi);
 }
 
-__global__ void warp_search_kernel(WarpView W, const int *cell2, int *match12, int *nmatches) {
-  int mine = 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < W.n1; i += gridDim.x * blockDim.x) {
-    const int m = warp_search_one(W, cell2, i);
-    match12[i] = m;
-    mine += m >= 0;
+/* ---- low-latency path: one warp per map point, fixed-capacity candidate lists ------------------
+ * The lanes of a warp stride over the keypoints of the current frame; candidates take slots in
+ * keys[i*CAND_CAP ..) by ballot (their order does not matter: the resolve pass ranks by key).  A map
+ * point with more than CAND_CAP candidates raises `overflow` and the host repeats the search with the
+ * exact two-pass lists. */
+constexpr int CAND_CAP = 64;
+
+__global__ void candidates_warp_kernel(ProjView P, const int *cell, int *cnt, uint64_t *keys, int *overflow) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < P.n_last; i += gridDim.x * wpb) {
+    const Proj r = project_point(P, i);
+    int base = 0;
+    if (r.ok) {
+      const uint8_t *d = &P.last_desc[32 * (size_t)i];
+      uint64_t *out = keys + (size_t)i * CAND_CAP;
+      for (int j0 = 0; j0 < P.n_cur; j0 += 32) {
+        const int j = j0 + lane;
+        bool ok = false;
+        int cj = -1;
+        if (j < P.n_cur) { cj = cell[j]; ok = candidate_ok(P, r, j, cj); }
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+          const int pos = base + __popc(m & ((1u << lane) - 1u));
+          if (pos < CAND_CAP) out[pos] = cand_key(hamming256(d, &P.cur_desc[32 * (size_t)j]), cj, j);
+        }
+        base += __popc(m);
+      }
+    }
+    if (lane == 0) {
+      cnt[i] = base < CAND_CAP ? base : CAND_CAP;
+      if (base > CAND_CAP) atomicOr(overflow, 1);
+    }
   }
-  for (int o = 16; o > 0; o >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, o);
-  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(nmatches, mine);
+}
+
+/* resolve pass for the fixed-capacity lists: `taken` lives in shared memory, the first 32 keys of the
+ * next map point are in flight while the current one is reduced */
+__global__ void resolve_fixed_kernel(ProjView P, const int *cnt, const uint64_t *keys, const uint8_t *taken_in,
+                                     int *match, int *acc_i, int *acc_j, int *nmatches_out) {
+  extern __shared__ uint8_t taken[];
+  const int lane = threadIdx.x;
+  for (int j = lane; j < P.n_cur; j += 32) taken[j] = taken_in[j];
+  __syncwarp();
+  int nacc = 0, nmatches = 0;
+  uint64_t knext = keys[lane];
+  for (int i0 = 0; i0 < P.n_last; i0 += 32) {
+    const int my_cnt = i0 + lane < P.n_last ? cnt[i0 + lane] : 0;
+    const int tend = P.n_last - i0 < 32 ? P.n_last - i0 : 32;
+    for (int t = 0; t < tend; t++) {
+      const int i = i0 + t;
+      const int n = __shfl_sync(0xffffffffu, my_cnt, t);
+      uint64_t k = knext;
+      if (i + 1 < P.n_last) knext = keys[(size_t)(i + 1) * CAND_CAP + lane];
+      if (n == 0) continue;
+      if (lane >= n || taken[key_index(k)]) k = ~0ull;
+      uint64_t best = k;
+      if (n > 32) {
+        uint64_t k2 = ~0ull;
+        if (32 + lane < n) {
+          k2 = keys[(size_t)i * CAND_CAP + 32 + lane];
+          if (taken[key_index(k2)]) k2 = ~0ull;
+        }
+        best = k2 < best ? k2 : best;
+      }
+      {
+        /* 64-bit minimum by two hardware warp reductions: (distance, cell) first, then the index */
+        const unsigned hi = best == ~0ull ? 0xffffffffu : (unsigned)(best >> 32);
+        const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+        const unsigned lo = hi == mhi ? (unsigned)(best & 0xffffffffu) : 0xffffffffu;
+        const unsigned mlo = __reduce_min_sync(0xffffffffu, lo);
+        best = mhi == 0xffffffffu ? ~0ull : (((uint64_t)mhi << 32) | mlo);
+      }
+      if (best != ~0ull && key_dist(best) < 256 && key_dist(best) <= P.th_high) {
+        const int j = key_index(best);
+        if (lane == 0) {
+          match[j] = i;
+          taken[j] = P.last_has_obs[i];
+          acc_i[nacc] = i;
+          acc_j[nacc] = j;
+        }
+        nacc++;
+        nmatches++;
+      }
+      __syncwarp();
+    }
+  }
+  if (P.check_orientation) {
+    __shared__ int hist[HISTO_LENGTH];
+    if (lane < HISTO_LENGTH) hist[lane] = 0;
+    __syncwarp();
+    if (lane == 0) {
+      for (int a = 0; a < nacc; a++) hist[rotation_bin(P.last_angle[acc_i[a]], P.cur_angle[acc_j[a]])]++;
+      int i1, i2, i3;
+      three_maxima(hist, HISTO_LENGTH, i1, i2, i3);
+      for (int a = 0; a < nacc; a++) {
+        const int bin = rotation_bin(P.last_angle[acc_i[a]], P.cur_angle[acc_j[a]]);
+        if (bin != i1 && bin != i2 && bin != i3) { match[acc_j[a]] = -1; nmatches--; }
+      }
+    }
+  }
+  if (lane == 0) *nmatches_out = nmatches;
+}
+
+/* warp per keypoint of keyframe 1: lanes stride over the keypoints of keyframe 2 */
+__global__ void warp_search_warp_kernel(WarpView W, const int *cell2, int *match12, int *nmatches) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < W.n1; i += gridDim.x * wpb) {
+    const uint64_t best = warp_search_lanes(W, cell2, i, lane, 32);
+    uint64_t b = best;
+    for (int o = 16; o > 0; o >>= 1) {
+      const uint64_t other = __shfl_xor_sync(0xffffffffu, b, o);
+      b = other < b ? other : b;
+    }
+    if (lane == 0) {
+      match12[i] = b == ~0ull ? -1 : key_index(b);
+      if (b != ~0ull) atomicAdd(nmatches, 1);
+    }
+  }
 }
 
 /* exclusive scan of cnt[0..n) by one CTA; total -> off[n] */
@@ -172,7 +282,7 @@ int defslam_search_by_projection(const defslam_projsearch_problem *p, int32_t *m
                o_cd = in.add(NC * 32), o_cu = in.add(NC * 4), o_ct = in.add(NC), o_sc = in.add((size_t)p->n_levels * 4);
   const size_t w_cell = wk.add(NC * 4), w_proj = wk.add(NL * sizeof(Proj)), w_cnt = wk.add(NL * 4),
                w_off = wk.add((NL + 1) * 4), w_ai = wk.add(NL * 4), w_aj = wk.add(NL * 4), w_match = wk.add(NC * 4),
-               w_n = wk.add(4);
+               w_n = wk.add(8);
   Scratch &S = tl_scratch(ctx->device);
   int rc;
   if ((rc = S.host.ensure(in.total > wk.total ? in.total : wk.total)) || (rc = S.dev.ensure(in.total + wk.total))) return rc;
@@ -206,8 +316,31 @@ int defslam_search_by_projection(const defslam_projsearch_problem *p, int32_t *m
   }
   int *cell = (int *)(w + w_cell), *cnt = (int *)(w + w_cnt), *off = (int *)(w + w_off);
   Proj *proj = (Proj *)(w + w_proj);
-  DS_CUDA_TRY(cudaMemsetAsync(w + w_match, 0xff, NC * 4, ctx->stream));
+  const int wgrid = (p->n_last + 3) / 4 < ctx->sm_count * 16 ? (p->n_last + 3) / 4 : ctx->sm_count * 16;
+  bool exact = NC > 48 * 1024; /* the resolve pass keeps the taken flags in shared memory */
   cell_kernel<<<grid_for(p->n_cur, ctx->sm_count), 128, 0, ctx->stream>>>(V, cell);
+  if (!exact) {
+    /* low-latency path: three launches, one synchronisation */
+    if ((rc = S.keys.ensure(NL * CAND_CAP * 8))) return rc;
+    DS_CUDA_TRY(cudaMemsetAsync(w + w_match, 0xff, NC * 4, ctx->stream));
+    DS_CUDA_TRY(cudaMemsetAsync(w + w_n, 0, 8, ctx->stream));
+    candidates_warp_kernel<<<wgrid, 128, 0, ctx->stream>>>(V, cell, cnt, (uint64_t *)S.keys.p, (int *)(w + w_n) + 1);
+    resolve_fixed_kernel<<<1, 32, NC, ctx->stream>>>(V, cnt, (const uint64_t *)S.keys.p, d + o_ct, (int *)(w + w_match),
+                                                     (int *)(w + w_ai), (int *)(w + w_aj), (int *)(w + w_n));
+    DS_CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(3);
+    int tail[2] = {0, 0};
+    DS_CUDA_TRY(cudaMemcpyAsync(h, w + w_match, NC * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    DS_CUDA_TRY(cudaMemcpyAsync(tail, w + w_n, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    DS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (!tail[1]) {
+      memcpy(match_out, h, NC * 4);
+      *nmatches_out = tail[0];
+      return DEFSLAM_OK;
+    }
+    exact = true; /* a map point had more than CAND_CAP candidates: exact lists */
+  }
+  DS_CUDA_TRY(cudaMemsetAsync(w + w_match, 0xff, NC * 4, ctx->stream));
   candidates_kernel<false><<<grid_for(p->n_last, ctx->sm_count), 128, 0, ctx->stream>>>(V, cell, proj, cnt, nullptr, nullptr);
   scan_kernel<<<1, 1024, 0, ctx->stream>>>(cnt, off, p->n_last);
   DS_CUDA_TRY(cudaGetLastError());
@@ -265,8 +398,10 @@ int defslam_search_by_schwarp(const defslam_warpsearch_problem *p, int32_t *matc
   W.th_low = p->th_low;
   DS_CUDA_TRY(cudaMemsetAsync(w + w_n, 0, 4, ctx->stream));
   warp_cell_kernel<<<grid_for(p->n2, ctx->sm_count), 128, 0, ctx->stream>>>(W, (int *)(w + w_cell));
-  warp_search_kernel<<<grid_for(p->n1, ctx->sm_count), 128, 0, ctx->stream>>>(W, (const int *)(w + w_cell), (int *)(w + w_m),
-                                                                              (int *)(w + w_n));
+  {
+    const int wgrid = (p->n1 + 3) / 4 < ctx->sm_count * 16 ? (p->n1 + 3) / 4 : ctx->sm_count * 16;
+    warp_search_warp_kernel<<<wgrid, 128, 0, ctx->stream>>>(W, (const int *)(w + w_cell), (int *)(w + w_m), (int *)(w + w_n));
+  }
   DS_CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(2);
   DS_CUDA_TRY(cudaMemcpyAsync(h, w + w_m, (N1 * 4 + 255 & ~(size_t)255) + 4, cudaMemcpyDeviceToHost, ctx->stream));

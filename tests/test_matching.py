@@ -13,9 +13,13 @@ CASES = [dict(seed=1), dict(seed=2, n_last=300, n_clutter=2000), dict(seed=3, st
 
 def _check(lib, prefix, oracle):
     olib = oracle.load()
-    for kw in CASES:
+    for kw in CASES + [dict(seed=6, n_last=250, n_clutter=5000, th=45.0)]:   # last: > 64 candidates per point
         for orient in (1, 0):
+            kw = dict(kw)
+            th = kw.pop("th", None)
             c = matching.make_case(**kw)
+            if th is not None:
+                c.th = th
             c.check_orientation = orient
             mo, no = matching.search_by_projection(c, olib, "oracle_")
             m, n = matching.search_by_projection(c, lib, prefix)
