@@ -959,6 +959,8 @@ DS_FN void diag_factor(const Team team, double *W, int kslot, int Wr, int ld, in
     x[2] = (x[2] - x[0] * A11[3] - x[1] * A11[4]) * A11[5];
     x[3] = (x[3] - x[0] * A11[6] - x[1] * A11[7] - x[2] * A11[8]) * A11[9];
   }
+  /* every lane has read A11 / A21 before any lane overwrites them */
+  team.warp_sync();
   /* rows 0-3: every lane stores the same values (benign, one wavefront each) */
 #pragma unroll
   for (int a = 0; a < 4; a++)
@@ -976,6 +978,7 @@ DS_FN void diag_factor(const Team team, double *W, int kslot, int Wr, int ld, in
       A22[a * (a + 1) / 2 + b] = v;
     }
   bad = chol4(A22) || bad;
+  team.warp_sync(); /* every lane has read A22 */
 #pragma unroll
   for (int a = 0; a < 4; a++)
 #pragma unroll
@@ -1054,7 +1057,8 @@ DS_FN void panel_tile(const Team team, double *base, int rs, int o0, int og, int
   double d0 = 0.0, d1 = 0.0;
   dmma884(d0, d1, a0, invL[g * ILS + q]);
   dmma884(d0, d1, a1, invL[g * ILS + 4 + q]);
-  /* mma.sync is warp-synchronous: every lane has read its operands */
+  /* mma.sync is warp-synchronous: every lane has read its operands (the barrier states it) */
+  __syncwarp();
   if (o + 2 * q >= lo) base[g * rs + 2 * q] = d0;
   if (o + 2 * q + 1 >= lo) base[g * rs + 2 * q + 1] = d1;
   *(dbl2 *)&P[pidx(2 * q, r0 + g, HS)] = dbl2{d0, d1};
@@ -1518,8 +1522,8 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
   }
   /* all bulk stores of L must have landed before the TMA reads of the backward sweep */
   if (team.tid == tma_tid) tma_store_wait_all();
-  team.sync();
   if (team.tid == 0) c.ph[0] = ph0;
+  team.sync();
   prof_mark(team, c, PF_SCHUR);
   if (*flag != 0) { team.sync(); return false; }
 
