@@ -142,6 +142,20 @@ struct SmemLayout {
 
 DS_FN int asm_scratch_doubles(int n, int ne) { return 11 * n + 5 * ne; }
 
+/* panel buffer P[2][HS]: two halves (columns 0-3 / 4-7 of the panel) of PR = bwp + 8 rows x 4; the
+ * half stride HS = 4 PR + 8 is 8 (mod 16) doubles, so the 16-byte stores of a quarter-warp that
+ * straddle both halves fall on different banks */
+static inline
+#if DS_CUDA
+__host__ __device__
+#endif
+int panel_half_stride(int bwp) { return 4 * (bwp + 8) + 8; }
+static inline
+#if DS_CUDA
+__host__ __device__
+#endif
+int panel_doubles(int bwp) { const int d = 2 * panel_half_stride(bwp); return d > 216 ? d : 216; }
+
 static inline
 #if DS_CUDA
 __host__ __device__
@@ -157,11 +171,11 @@ SmemLayout smem_layout(int n_nodes, int n_edges, int Dn_pad, int bwp, int ld, in
   if (bsz > wsz) wsz = bsz;
   L.W = o;    o += wsz; o = (o + 1) & ~1;
   L.E = o;    o += e_in_smem ? 8 * ES : 0;
-  L.P = o;    o += (NB * (bwp + 8) > 216 ? NB * (bwp + 8) : 216); o = (o + 1) & ~1;
+  L.P = o;    o += panel_doubles(bwp); o = (o + 1) & ~1;
   L.x = o;    o += x_in_smem ? Dn_pad : 0;
   L.xb = o;   /* (backup lives in global memory) */
   L.dx = o;   o += x_in_smem ? Dn_pad + 8 : 0;
-  L.Lkk = o;  o += 64;
+  L.Lkk = o;  /* (unused) */
   L.invL = o; o += 192;  /* inv(L_kk), row stride 12; two buffers (step parity) */
   L.G = o;    o += 64;
   L.Hcc = o;  o += 48;   /* 36 Hcc + 6 bc + 6 dc(stale) */
@@ -625,7 +639,7 @@ DS_FN_NOINLINE double build_system(const Team team, Ctx &cx) {
   {
     const int asz = asm_scratch_doubles(n, ne);
     double *stage = sm_base() + c.sl.W + asz;
-    const int psz = NB * (pl.bwp + 8) > 216 ? NB * (pl.bwp + 8) : 216;
+    const int psz = panel_doubles(pl.bwp);
     /* the tail of the area holds the chunk's facet offsets (nf + 1 ints) */
     const int avail = (c.sl.P + psz) - (c.sl.W + asz) - (nf + 2) / 2 - 1;
     const int cap = avail > 0 ? avail / NMSCR : 0; /* matches per chunk */
@@ -1274,7 +1288,7 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
   (void)cx;
   const int bw = c.pl.bw, bwE = c.pl.bwE, ld = c.pl.ld, Dp = c.pl.Dn_pad, Wr = c.pl.Wr, bwp = c.pl.bwp,
             nblk = c.pl.nblk, ES = c.pl.ES;
-  const int PR = bwp + 8, HS = 4 * PR; /* panel rows: trailing rows, then the 8 border rows */
+  const int HS = panel_half_stride(bwp); /* panel rows: trailing rows, then the 8 border rows */
   double *const sm = sm_base();
   double *W = sm + c.sl.W, *P = sm + c.sl.P, *invL = sm + c.sl.invL;
   double *G = sm + c.sl.G, *Hcc = sm + c.sl.Hcc, *dx = dxvec<XS>(c);
