@@ -385,7 +385,7 @@ DS_FN_NOINLINE int prologue(const Team team, Ctx &cx) {
     c.info_str = n_str > 0 ? pb.reg_inex / (double)n_str : 0.0;
     const float deltaMono = (float)sqrt(5.991);
     c.hub_delta = (double)deltaMono;
-    c.hub_dsqr = c.hub_delta * c.hub_delta;
+    c.hub_dsqr = (double)(float)(c.hub_delta * c.hub_delta);  // RobustKernelHuber::dsqr is a float (robust_kernel_impl.h:84)
   }
   team.sync();
   return 0;

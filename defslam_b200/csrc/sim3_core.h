@@ -263,12 +263,8 @@ DS_FN int sim3_run_lm(const Team &team, const Sim3Prob &P, Sim3 &est, Sim3 &last
 
 /* Optimizer::OptimizeHorn for one keyframe.  red: sim3_red_doubles(nthr) doubles of shared memory. */
 DS_FN_NOINLINE void sim3_register_one(const Team team, const Sim3Prob &P, double *red) {
-#if DS_CUDA
-  const double delta = (double)sqrtf((float)P.huber);
-#else
-  const double delta = (double)(float)sqrt(P.huber);
-#endif
-  const double dsqr = delta * delta;
+  const double delta = (double)(float)sqrt(P.huber);  // const float deltaHuber = sqrt(huber)  DefOptimizer.cc:865
+  const double dsqr = (double)(float)(delta * delta);  // RobustKernelHuber::dsqr is a float (robust_kernel_impl.h:84)
   double *rs = red + 36 + 36 * ((team.nthr + 31) / 32);
   Sim3 est = P.init, last = P.init;
   const int it0 = sim3_run_lm(team, P, est, last, delta, dsqr, red);

@@ -71,6 +71,47 @@ def load(native: bool = False):
     return lib
 
 
+def load_g2o_ref():
+    """oracle/_ref/libg2o_sft_ref.so: the reference's OWN SfT code (sft_types.h, se3quat.h, base_*_edge.hpp,
+    the Levenberg driver...) behind g2o_ref_harness.cc.  Built only where /root/reference exists; returns None
+    when the prebuilt library is absent."""
+    global _ref
+    if _ref is not None:
+        return _ref
+    path = os.path.join(_DIR, "_ref", "libg2o_sft_ref.so")
+    if not os.path.exists(path):
+        return None
+    P = _capi
+    lib = C.CDLL(path)
+    lib.ref_sft_solve.restype = C.c_int
+    lib.ref_sft_solve.argtypes = [C.POINTER(P.SftProblem), C.POINTER(P.SftResult)]
+    lib.ref_sft_normal_equations.restype = C.c_int
+    lib.ref_sft_normal_equations.argtypes = [C.POINTER(P.SftProblem), P.c_double_p, P.c_double_p, P.c_double_p]
+    lib.ref_sft_residuals.restype = C.c_int
+    lib.ref_sft_residuals.argtypes = [C.POINTER(P.SftProblem), P.c_double_p, P.c_double_p, C.c_int]
+    lib.ref_se3_oplus.restype = None
+    lib.ref_se3_oplus.argtypes = [P.c_double_p] * 5
+    lib.ref_huber.restype = None
+    lib.ref_huber.argtypes = [C.c_float, C.c_double, P.c_double_p]
+    _ref = lib
+    return lib
+
+
+def sft_residuals(frame, lib=None, fn="oracle_sft_residuals", jac=True):
+    """(res, J) of oracle_sft_residuals / ref_sft_residuals: rows 2*n_rep, 3*n_ref, n_curv, n_str"""
+    lib = lib or load()
+    f = getattr(lib, fn)
+    D = 3 * frame.template.n_nodes + 6
+    p = frame.problem()
+    rows = f(C.byref(p), None, None, 0)
+    res = np.zeros(rows)
+    J = np.zeros((rows, D)) if jac else None
+    rc = f(C.byref(p), _capi.as_ptr(res, C.c_double), _capi.as_ptr(J, C.c_double) if jac else None, rows)
+    if rc != rows:
+        raise RuntimeError(f"{fn} rc={rc}")
+    return res, J
+
+
 class SftOutput:
     """numpy-side holder for a defslam_sft_result (works for oracle and product alike)."""
 
@@ -93,27 +134,27 @@ class SftOutput:
         return np.array(list(self.r.T_cw_out), dtype=np.float32).reshape(4, 4)
 
 
-def sft_solve(frame, lib=None):
+def sft_solve(frame, lib=None, fn="oracle_sft_solve"):
     lib = lib or load()
     out = SftOutput(frame.template.n_nodes, frame.n_matches)
     p = frame.problem()
-    rc = lib.oracle_sft_solve(C.byref(p), C.byref(out.r))
+    rc = getattr(lib, fn)(C.byref(p), C.byref(out.r))
     if rc != 0:
-        raise RuntimeError(f"oracle_sft_solve rc={rc}")
+        raise RuntimeError(f"{fn} rc={rc}")
     return out
 
 
-def sft_normal_equations(frame, lib=None):
+def sft_normal_equations(frame, lib=None, fn="oracle_sft_normal_equations"):
     lib = lib or load()
     D = 3 * frame.template.n_nodes + 6
     H = np.zeros((D, D))
     b = np.zeros(D)
     chi = C.c_double(0)
     p = frame.problem()
-    rc = lib.oracle_sft_normal_equations(C.byref(p), _capi.as_ptr(H, C.c_double), _capi.as_ptr(b, C.c_double),
-                                         C.cast(C.byref(chi), _capi.c_double_p))
+    rc = getattr(lib, fn)(C.byref(p), _capi.as_ptr(H, C.c_double), _capi.as_ptr(b, C.c_double),
+                          C.cast(C.byref(chi), _capi.c_double_p))
     if rc != 0:
-        raise RuntimeError(f"oracle_sft_normal_equations rc={rc}")
+        raise RuntimeError(f"{fn} rc={rc}")
     return H, b, chi.value
 
 

@@ -1,0 +1,2 @@
+// stand-in for Thirdparty/g2o/g2o/core/eigen_types.h: sft_types.h includes it by this path; everything is in g2o_shim.h
+#include "../../../inc/g2o_shim.h"

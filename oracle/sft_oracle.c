@@ -6,12 +6,21 @@
  * --impl reference legs may build or call it, and there only as the checker
  * or the timed CPU baseline.
  *
- * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures
- * for this path and cannot be compiled in this image (Eigen is absent; see
- * DESIGN.md).  This file is a line-by-line restatement of the reference
- * algorithm; it is pinned only by the self-consistency checks in tests/
- * (finite-difference Jacobians, an independent NumPy restatement,
- * fixed-point and recover-the-deformation properties).
+ * PARITY PINNED TO THE REFERENCE'S OWN CODE: the reference ships no tests or
+ * vectors for this path and cannot be built as a whole here (Eigen, OpenCV,
+ * Ceres are absent), but the files that hold the path's arithmetic compile
+ * against a minimal stand-in for Eigen (oracle/ref_shim/): sft_types.h,
+ * se3quat.h and core/base_{unary,binary,multi}_edge.hpp verbatim where they lie,
+ * the Levenberg driver (optimization_algorithm_levenberg.cpp:43-189), the Huber
+ * kernel (robust_kernel_impl.cpp:65-91), activeRobustChi2/update
+ * (sparse_optimizer.cpp:104-120,477-491) and the vertex oplus bodies by line
+ * range (oracle/Makefile target g2oref -> oracle/_ref/libg2o_sft_ref.so,
+ * harness g2o_ref_harness.cc).  tests/test_oracle_sft_ref.py checks this file
+ * against that library (per-edge errors and Jacobians to 1e-15, H/b/chi2 to
+ * 1e-13, identical LM iteration/trial pattern, lambda and chi2 traces, final
+ * nodes to 1e-9) live and through tests/golden/sft_ref.npz.  What remains a
+ * restatement: the graph construction of DefOptimizer.cc:251-513 (needs the
+ * Frame/Map/OpenCV types), BlockSolver bookkeeping, and Eigen's dense LDLT.
  *
  * What it follows (paths under the DefSLAM tree):
  *   graph construction      Modules/Tracking/DefOptimizer.cc:251-578
@@ -172,68 +181,9 @@ static void pose_to_Tcw(const double q[4], const double t[3], float T[16]) {
 
 /* ---------------------------------------------------------------- graph -- */
 
-typedef struct {
-  int m;          /* match index */
-  int v[3];       /* node ids */
-  double bary[3]; /* barycentrics */
-  double obs[2];
-  double info;    /* invSigma2 / N */
-  double err[2];
-  double Jc[12];    /* 2x6 */
-  double Jn[3][6];  /* 2x3 each */
-} EdgeReproj;
+#include "sft_oracle_graph.h"
 
-typedef struct {
-  int v;
-  double meas[3];
-  double err[3];
-} EdgeRef;
-
-typedef struct {
-  int nv;        /* 1 + #neighbours */
-  int *v;        /* v[0] centre, then neighbours */
-  double *w;     /* weights, same order as neighbours */
-  double len;    /* lenghtEdge_ */
-  double kappa0; /* measurement */
-  double err;
-  double mc[3], mcn, sumw; /* meanCurvature_, its norm, sumWeights_ */
-  double *J;     /* [nv*3] */
-} EdgeCurv;
-
-typedef struct {
-  int a, b;
-  double len0;
-  double err;
-  double Ja[3];
-} EdgeStretch;
-
-typedef struct {
-  /* sizes */
-  int n_nodes, n_matches;
-  /* state */
-  double q[4], t[3];
-  double *x; /* [n*3] */
-  /* camera */
-  double fx, fy, cx, cy;
-  /* free-variable map: idx[v] = first dense row of node v, -1 if fixed.
-   * camera occupies dense rows 0..5 (g2o: vertex id 0 first) */
-  int *idx;
-  int D;
-  /* edges */
-  int n_rep, n_ref, n_curv, n_str;
-  EdgeReproj *rep;
-  EdgeRef *ref;
-  EdgeCurv *curv;
-  EdgeStretch *str;
-  double info_ref, info_curv, info_str;
-  double huber_delta, huber_dsqr;
-  uint8_t *viewed, *optlap;
-  int n_optlap, n_viewed;
-  /* solver */
-  double *H, *b, *dx, *Hwork, *diag_backup;
-} Graph;
-
-static void graph_free(Graph *g) {
+void oracle_graph_free(Graph *g) {
   if (!g) return;
   for (int i = 0; i < g->n_curv; i++) {
     free(g->curv[i].v); free(g->curv[i].w); free(g->curv[i].J);
@@ -244,7 +194,7 @@ static void graph_free(Graph *g) {
 }
 
 /* DefOptimizer.cc:251-507: build the graph */
-static int graph_build(Graph *g, const defslam_sft_problem *p) {
+int oracle_graph_build(Graph *g, const defslam_sft_problem *p) {
   const defslam_template_desc *td = p->tmpl_desc;
   if (!td) return DEFSLAM_EBADARG;
   const int n = td->n_nodes;
@@ -262,7 +212,7 @@ static int graph_build(Graph *g, const defslam_sft_problem *p) {
   /* const float deltaMono = sqrt(5.991);  :286 (float!) */
   const float deltaMono = (float)sqrt(5.991);
   g->huber_delta = (double)deltaMono;
-  g->huber_dsqr = g->huber_delta * g->huber_delta; /* setDelta robust_kernel_impl.cpp:65-69 */
+  g->huber_dsqr = (double)(float)(g->huber_delta * g->huber_delta); /* setDelta robust_kernel_impl.cpp:65-69 into "float dsqr" (robust_kernel_impl.h:84) */
 
   /* ---- reprojection edges :293-361 */
   g->rep = (EdgeReproj *)calloc(p->n_matches > 0 ? p->n_matches : 1, sizeof(EdgeReproj));
@@ -614,7 +564,7 @@ static void build_system(Graph *g) {
  * full matrix, fail unless positive.  Eigen's LDLT pivots on the diagonal;
  * without pivoting the factors differ but the solution agrees to rounding.
  * Left-looking, row-major, contiguous dot products. */
-static int dense_ldlt_solve(int D, const double *H, double *L, const double *b, double *x) {
+int oracle_dense_ldlt_solve(int D, const double *H, double *L, const double *b, double *x) {
   /* L is D*D scratch: strictly-lower holds L, diagonal holds d */
   double *v = (double *)malloc(sizeof(double) * D);
   int ok = 1;
@@ -702,7 +652,7 @@ static void run_lm(Graph *g, int max_iterations, LMStats *st, double *trace, int
       memcpy(qb, g->q, sizeof(qb)); memcpy(tb, g->t, sizeof(tb));
       /* setLambda(lambda, backup=true)  block_solver.hpp:564-589 */
       for (int k = 0; k < D; k++) { g->diag_backup[k] = g->H[(size_t)k * D + k]; g->H[(size_t)k * D + k] += lambda; }
-      const int ok2 = dense_ldlt_solve(D, g->H, g->Hwork, g->b, g->dx);
+      const int ok2 = oracle_dense_ldlt_solve(D, g->H, g->Hwork, g->b, g->dx);
       apply_update(g, g->dx);
       /* restoreDiagonal */
       for (int k = 0; k < D; k++) g->H[(size_t)k * D + k] = g->diag_backup[k];
@@ -750,8 +700,8 @@ static void run_lm(Graph *g, int max_iterations, LMStats *st, double *trace, int
 int oracle_sft_solve(const defslam_sft_problem *p, defslam_sft_result *r) {
   if (!p || !r || !p->tmpl_desc || !p->node_xyz) return DEFSLAM_EBADARG;
   Graph g;
-  int rc = graph_build(&g, p);
-  if (rc) { graph_free(&g); return rc; }
+  int rc = oracle_graph_build(&g, p);
+  if (rc) { oracle_graph_free(&g); return rc; }
   const int n = g.n_nodes;
   /* e->computeError() at edge creation (:350) */
   compute_active_errors(&g);
@@ -793,7 +743,7 @@ int oracle_sft_solve(const defslam_sft_problem *p, defslam_sft_result *r) {
   r->lambda_final = st.lambda;
   r->status = 0;
   free(outl);
-  graph_free(&g);
+  oracle_graph_free(&g);
   return 0;
 }
 
@@ -803,8 +753,8 @@ int oracle_sft_solve(const defslam_sft_problem *p, defslam_sft_result *r) {
 int oracle_sft_normal_equations(const defslam_sft_problem *p, double *H_dense, double *b, double *chi2) {
   if (!p || !p->tmpl_desc) return DEFSLAM_EBADARG;
   Graph g;
-  int rc = graph_build(&g, p);
-  if (rc) { graph_free(&g); return rc; }
+  int rc = oracle_graph_build(&g, p);
+  if (rc) { oracle_graph_free(&g); return rc; }
   compute_active_errors(&g);
   if (chi2) *chi2 = active_robust_chi2(&g);
   build_system(&g);
@@ -824,7 +774,7 @@ int oracle_sft_normal_equations(const defslam_sft_problem *p, double *H_dense, d
       }
   }
   free(map);
-  graph_free(&g);
+  oracle_graph_free(&g);
   return 0;
 }
 
@@ -834,12 +784,12 @@ int oracle_sft_normal_equations(const defslam_sft_problem *p, double *H_dense, d
 int oracle_sft_residuals(const defslam_sft_problem *p, double *res, double *J, int max_rows) {
   if (!p || !p->tmpl_desc) return DEFSLAM_EBADARG;
   Graph g;
-  int rc = graph_build(&g, p);
-  if (rc) { graph_free(&g); return rc; }
+  int rc = oracle_graph_build(&g, p);
+  if (rc) { oracle_graph_free(&g); return rc; }
   compute_active_errors(&g);
   const int n = g.n_nodes, Dabi = 3 * n + 6;
   const int rows = 2 * g.n_rep + 3 * g.n_ref + g.n_curv + g.n_str;
-  if (rows > max_rows) { graph_free(&g); return rows; }
+  if (rows > max_rows) { oracle_graph_free(&g); return rows; }
   if (J) memset(J, 0, sizeof(double) * (size_t)rows * Dabi);
   int r0 = 0;
   for (int i = 0; i < g.n_rep; i++, r0 += 2) {
@@ -879,7 +829,7 @@ int oracle_sft_residuals(const defslam_sft_problem *p, double *res, double *J, i
       }
     }
   }
-  graph_free(&g);
+  oracle_graph_free(&g);
   return rows;
 }
 
@@ -903,19 +853,19 @@ int oracle_sft_apply_update(const defslam_sft_problem *p, const double *d, doubl
 int oracle_sft_residuals_pose(const defslam_sft_problem *p, const double *q, const double *t, const double *node_xyz,
                               double *res, int max_rows) {
   Graph g;
-  int rc = graph_build(&g, p);
-  if (rc) { graph_free(&g); return rc; }
+  int rc = oracle_graph_build(&g, p);
+  if (rc) { oracle_graph_free(&g); return rc; }
   memcpy(g.q, q, sizeof(g.q)); memcpy(g.t, t, sizeof(g.t));
   memcpy(g.x, node_xyz, sizeof(double) * 3 * g.n_nodes);
   compute_active_errors(&g);
   const int rows = 2 * g.n_rep + 3 * g.n_ref + g.n_curv + g.n_str;
-  if (rows > max_rows) { graph_free(&g); return rows; }
+  if (rows > max_rows) { oracle_graph_free(&g); return rows; }
   int r0 = 0;
   for (int i = 0; i < g.n_rep; i++) { res[r0++] = g.rep[i].err[0]; res[r0++] = g.rep[i].err[1]; }
   for (int i = 0; i < g.n_ref; i++) for (int c = 0; c < 3; c++) res[r0++] = g.ref[i].err[c];
   for (int i = 0; i < g.n_curv; i++) res[r0++] = g.curv[i].err;
   for (int i = 0; i < g.n_str; i++) res[r0++] = g.str[i].err;
-  graph_free(&g);
+  oracle_graph_free(&g);
   return rows;
 }
 

@@ -262,7 +262,7 @@ int oracle_sim3_register_batched(int32_t nprob, const defslam_sim3_problem *pp, 
     Reg g;
     g.n = p->n_points; g.p1 = p->pts1; g.p2 = p->pts2;
     g.delta = (double)(float)sqrt(p->huber); /* const float deltaHuber = sqrt(huber) */
-    g.dsqr = g.delta * g.delta;
+    g.dsqr = (double)(float)(g.delta * g.delta); /* float dsqr, robust_kernel_impl.h:84 */
     memcpy(g.est.q, p->rot, sizeof(g.est.q)); memcpy(g.est.t, p->trans, sizeof(g.est.t)); g.est.s = p->scale;
     g.err = (double *)malloc(sizeof(double) * 3 * (g.n + 1));
     compute_errors(&g, &g.est);

@@ -46,6 +46,28 @@ def test_solve_matches_oracle(cfg, nfr, oracle):
         _check(o, oracle.sft_solve(f), f)
 
 
+@pytest.mark.parametrize("name", ["tiny", "huber", "huber9", "C1_0", "C4_0"])
+def test_kernel_code_matches_reference_golden(name):
+    """the kernel sources against the outputs of the REFERENCE'S OWN code (tests/golden/sft_ref.npz,
+    see test_oracle_sft_ref.py); 'huber*' put gross outliers on the linear branch of the Huber kernel"""
+    from tests.golden.make_golden_sft import cases
+    g = golden("sft_ref.npz")
+    f = cases()[name]
+    rc, H, b, chi = emu_normal_equations(f)
+    assert rc == 0
+    assert abs(chi - float(g[f"{name}.chi2"])) <= 1e-12 * abs(chi)
+    assert np.abs(b - g[f"{name}.b"]).max() <= 1e-12 * np.abs(b).max()
+    assert np.abs(np.diag(H) - g[f"{name}.Hdiag"]).max() <= 1e-12 * np.abs(np.diag(H)).max()
+    rc, outs = emu_solve_batched([f])
+    assert rc == 0
+    o = outs[0]
+    its, trials, inl = (int(x) for x in g[f"{name}.scalars"][:3])
+    assert (o.r.lm_iterations, o.r.lm_trials, o.r.n_inliers) == (its, trials, inl)
+    assert rel_nodes(o.nodes, g[f"{name}.nodes"]) < 1e-8
+    assert np.array_equal(o.outlier[:f.n_matches], g[f"{name}.outlier"][:f.n_matches])
+    assert np.allclose(o.trace[:its], g[f"{name}.trace"], rtol=1e-8, atol=1e-12)
+
+
 def test_solve_matches_golden():
     g = golden("sft_oracle.npz")
     tmpl, frames = synthetic.make_config_frames("C1", nframes=3)
