@@ -31,10 +31,16 @@
 #include "ref_shim/inc/g2o_shim.h"
 #include <types/sft_types.h>  // the reference's own file (-I<ref>/Thirdparty/g2o/g2o)
 
+#include <types/sim3.h>       // the reference's own file (Sim3 exp / map / product)
+
 #include "sft_oracle_graph.h"
 
 namespace g2o {
 using namespace std;
+
+// ---- types_seven_dof_expmap.h:96-126 (VertexSim3ExpmapNoProj) and :159-188 (EdgeSim3Simple), whole classes ----
+#include "_ref/vertex_sim3_noproj.inc"
+#include "_ref/edge_sim3_simple.inc"
 
 // ---- robust_kernel_impl.cpp:65-91 (setDelta, setDeltaSqr, robustify of RobustKernelHuber) ----
 #include "_ref/robust_kernel_huber.inc"
@@ -577,6 +583,69 @@ void ref_se3_oplus(const double *q_in, const double *t_in, const double *update6
   const g2o::SE3Quat &e = v.estimate();
   q_out[0] = e.rotation().x(); q_out[1] = e.rotation().y(); q_out[2] = e.rotation().z(); q_out[3] = e.rotation().w();
   for (int i = 0; i < 3; i++) t_out[i] = e.translation()(i);
+}
+
+// Optimizer::OptimizeHorn (Modules/Tracking/DefOptimizer.cc:840-922) on the reference's own Sim3, EdgeSim3Simple,
+// VertexSim3ExpmapNoProj, numeric Jacobians (base_unary_edge.hpp:82-118), Huber kernel and Levenberg driver.
+// In/out as oracle_sim3_register_batched for one problem.
+int ref_sim3_optimize_horn(const defslam_sim3_problem *p, defslam_sim3_result *out) {
+  g2o::SparseOptimizer opt;
+  g2o::Solver solver(&opt);
+  g2o::OptimizationAlgorithmLevenberg lm(&solver);
+  lm.setOptimizer(&opt);
+  Eigen::Quaterniond q0(p->rot[3], p->rot[0], p->rot[1], p->rot[2]);
+  Eigen::Vector3d t0(p->trans[0], p->trans[1], p->trans[2]);
+  g2o::Sim3 g2oS12(q0, t0, p->scale);
+  g2o::VertexSim3ExpmapNoProj *vert0 = new g2o::VertexSim3ExpmapNoProj;
+  vert0->setEstimate(g2oS12);
+  vert0->setId(0);
+  vert0->setHessianIndex(0);
+  opt._ivMap.push_back(vert0);
+  const int N = p->n_points;
+  const float deltaHuber = sqrt(p->huber);
+  std::vector<g2o::EdgeSim3Simple *> edgesSimple;
+  std::vector<g2o::RobustKernelHuber *> kernels;
+  for (int i = 0; i < N; i++) {
+    g2o::EdgeSim3Simple *simple = new g2o::EdgeSim3Simple;
+    simple->setVertex(0, vert0);
+    Eigen::Matrix<double, 3, 1> v1;
+    v1 << p->pts1[3 * i], p->pts1[3 * i + 1], p->pts1[3 * i + 2];
+    Eigen::Matrix<double, 3, 1> v2;
+    v2 << p->pts2[3 * i], p->pts2[3 * i + 1], p->pts2[3 * i + 2];
+    simple->setPoints(v1, v2);
+    simple->setInformation(Eigen::Matrix3d::Identity());
+    g2o::RobustKernelHuber *rk = new g2o::RobustKernelHuber;
+    simple->setRobustKernel(rk);
+    rk->setDelta(deltaHuber);
+    kernels.push_back(rk);
+    edgesSimple.push_back(simple);
+    opt._activeEdges.push_back(simple);
+  }
+  for (int run = 0; run < 2; run++) {
+    int cj = 0;
+    bool ok = true;
+    for (int i = 0; i < p->max_iterations && ok; i++) {
+      ok = lm.solve(i, false) == g2o::OptimizationAlgorithm::OK;
+      ++cj;
+    }
+    out->iterations[run] = cj;
+    if (run == 0) {
+      const g2o::Sim3 &e = vert0->estimate();
+      out->rot[0] = e.rotation().x(); out->rot[1] = e.rotation().y(); out->rot[2] = e.rotation().z(); out->rot[3] = e.rotation().w();
+      for (int c = 0; c < 3; c++) out->trans[c] = e.translation()(c);
+      out->scale = e.scale();
+      int count = 0;
+      for (int i = 0; i < N; i++) if (!(edgesSimple[i]->chi2() > p->chi)) count++;
+      out->inliers = count;
+    }
+  }
+  double chi2 = 0.0;  // SparseOptimizer::chi2 = activeChi2 (sparse_optimizer.cpp:93-102)
+  for (int i = 0; i < N; i++) chi2 += edgesSimple[i]->chi2();
+  out->chi2 = chi2;
+  out->acceptable = std::isfinite(chi2) && (chi2 / out->inliers < p->chi);
+  for (int i = 0; i < N; i++) { delete edgesSimple[i]; delete kernels[i]; }
+  delete vert0;
+  return 0;
 }
 
 // RobustKernelHuber::setDelta + robustify (the reference's lines), delta passed as the reference passes it

@@ -91,10 +91,33 @@ def load_g2o_ref():
     lib.ref_sft_residuals.argtypes = [C.POINTER(P.SftProblem), P.c_double_p, P.c_double_p, C.c_int]
     lib.ref_se3_oplus.restype = None
     lib.ref_se3_oplus.argtypes = [P.c_double_p] * 5
+    lib.ref_sim3_optimize_horn.restype = C.c_int
+    lib.ref_sim3_optimize_horn.argtypes = [C.POINTER(P.Sim3Problem), C.POINTER(P.Sim3Result)]
+    lib.ref_mesh_laplacian.restype = C.c_int
+    lib.ref_mesh_laplacian.argtypes = [C.c_int32, P.c_double_p, C.c_int32, P.c_int32_p, C.c_int32, P.c_int32_p,
+                                       P.c_int32_p, P.c_double_p, P.c_uint8_p, P.c_double_p, P.c_int32_p]
     lib.ref_huber.restype = None
     lib.ref_huber.argtypes = [C.c_float, C.c_double, P.c_double_p]
     _ref = lib
     return lib
+
+
+def ref_mesh_laplacian(lib, nodes, facets, max_ring=8):
+    """LaplacianMesh::ExtractMeanCurvatures (the reference's own lines) -> dict like tests.helpers.mesh_laplacian_call"""
+    n, nf = len(nodes), len(facets)
+    nodes = np.ascontiguousarray(nodes, np.float64)
+    facets = np.ascontiguousarray(facets, np.int32)
+    cnt = np.zeros(n, np.int32)
+    idx = np.zeros((n, max_ring), np.int32)
+    w = np.zeros((n, max_ring))
+    bd = np.zeros(n, np.uint8)
+    k0 = np.zeros(n)
+    nb = C.c_int32(0)
+    rc = lib.ref_mesh_laplacian(n, _capi.as_ptr(nodes, C.c_double), nf, _capi.as_ptr(facets, C.c_int32), max_ring,
+                                _capi.as_ptr(cnt, C.c_int32), _capi.as_ptr(idx, C.c_int32), _capi.as_ptr(w, C.c_double),
+                                _capi.as_ptr(bd, C.c_uint8), _capi.as_ptr(k0, C.c_double),
+                                C.cast(C.byref(nb), _capi.c_int32_p))
+    return rc, dict(cnt=cnt, idx=idx, w=w, boundary=bd, kappa0=k0, n_bad=nb.value)
 
 
 def sft_residuals(frame, lib=None, fn="oracle_sft_residuals", jac=True):

@@ -108,7 +108,17 @@ template <typename Derived> class MatrixBase {
 
   Derived &noalias() { return derived(); }
   MatrixXd transpose() const;
-  MatrixXd inverse() const;  // 1x1 .. 3x3 (the reference inverts 1x1 only)
+  MatrixXd inverse() const;  // 1x1 only (all the reference inverts on this path)
+  // PartialPivLU stand-in: only Sim3::log() (sim3.h, not on the tested path) needs it to compile
+  struct LuSolver {
+    std::vector<double> a; int n;
+    template <typename O> Matrix<double, Dynamic, Dynamic> solve(const MatrixBase<O> &b) const;
+  };
+  LuSolver lu() const {
+    LuSolver l; l.n = rows(); l.a.resize((size_t)l.n * l.n);
+    for (int i = 0; i < l.n; i++) for (int j = 0; j < l.n; j++) l.a[(size_t)i * l.n + j] = (*this)(i, j);
+    return l;
+  }
   double squaredNorm() const {
     double s = 0;
     bool first = true;
@@ -330,6 +340,24 @@ template <typename Derived> MatrixXd MatrixBase<Derived>::inverse() const {
   assert(rows() == cols() && rows() == 1 && "mini_eigen: only the 1x1 inverse the reference uses");
   MatrixXd r(1, 1);
   r(0, 0) = 1.0 / (*this)(0, 0);
+  return r;
+}
+template <typename Derived> template <typename O>
+MatrixXd MatrixBase<Derived>::LuSolver::solve(const MatrixBase<O> &b) const {
+  std::vector<double> A(a), x(n);
+  for (int i = 0; i < n; i++) x[i] = b(i);
+  for (int k = 0; k < n; k++) {  // Gaussian elimination with partial pivoting
+    int p = k;
+    for (int i = k + 1; i < n; i++) if (std::fabs(A[(size_t)i * n + k]) > std::fabs(A[(size_t)p * n + k])) p = i;
+    if (p != k) { for (int j = 0; j < n; j++) std::swap(A[(size_t)k * n + j], A[(size_t)p * n + j]); std::swap(x[k], x[p]); }
+    for (int i = k + 1; i < n; i++) {
+      const double f = A[(size_t)i * n + k] / A[(size_t)k * n + k];
+      for (int j = k; j < n; j++) A[(size_t)i * n + j] -= f * A[(size_t)k * n + j];
+      x[i] -= f * x[k];
+    }
+  }
+  MatrixXd r(n, 1);
+  for (int i = n - 1; i >= 0; i--) { double s = x[i]; for (int j = i + 1; j < n; j++) s -= A[(size_t)i * n + j] * r(j, 0); r(i, 0) = s / A[(size_t)i * n + i]; }
   return r;
 }
 template <typename Derived> template <typename O> Vector3d MatrixBase<Derived>::cross(const MatrixBase<O> &o) const {

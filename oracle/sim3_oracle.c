@@ -2,10 +2,12 @@
  * sim3_oracle.c -- CPU restatement of the Sim(3) surface registration that ends DefLocalMapping::NRSfM.
  * TEST INFRASTRUCTURE ONLY (see sft_oracle.c header).
  *
- * PARITY UNPINNED BY THE REFERENCE: no tests/fixtures exist for this path, g2o/Eigen cannot be built
- * here, and scaleMinMedian draws from unseeded rand().  Pinned by: the analytic Jacobian against this
- * file's literal central differences (delta 1e-9, like the reference), exactness on noise-free
- * similarity transforms, committed regression vectors.
+ * PINNED TO THE REFERENCE'S OWN CODE for the registration: Optimizer::OptimizeHorn is re-run on the reference's
+ * own sim3.h (verbatim), EdgeSim3Simple / VertexSim3ExpmapNoProj (types_seven_dof_expmap.h:96-126,159-188), the
+ * numeric Jacobians of base_unary_edge.hpp (verbatim), Huber kernel and Levenberg driver (oracle/g2o_ref_harness.cc
+ * -> oracle/_ref/libg2o_sft_ref.so); tests/test_oracle_sft_ref.py compares this file with it live and through
+ * tests/golden/sft_ref.npz (estimate 1e-8, first-run iteration count, inliers, verdict).  scaleMinMedian draws
+ * from unseeded rand() in the reference (quirk C10) and stays a seeded restatement.
  *
  * Follows (paths under the DefSLAM tree):
  *   Optimizer::OptimizeHorn                Modules/Tracking/DefOptimizer.cc:840-922

@@ -1,7 +1,11 @@
 /*
  * template_oracle.c -- CPU restatement of the template (mesh) construction the
  * SfT solve depends on.  TEST INFRASTRUCTURE ONLY (see sft_oracle.c header).
- * PARITY UNPINNED (no reference tests/fixtures exist for this path).
+ * The Laplacian part (mean-value weights, boundary flags, kappa0) is PINNED TO THE REFERENCE'S OWN CODE:
+ * LaplacianMesh.cc:53-148,157-162 are compiled by oracle/Makefile behind oracle/template_ref_harness.cc and
+ * tests/test_oracle_sft_ref.py compares this file with them bit for bit (regular and Delaunay meshes, live and
+ * through tests/golden/sft_ref.npz).  Embedding (pointInTriangle) and triangulation remain restatements
+ * (they need OpenCV types); no reference tests/fixtures exist for them.
  *
  * Follows (paths under the DefSLAM tree):
  *   TriangularMesh::regularTriangulation     Modules/Template/TriangularMesh.cc:92-107

@@ -30,6 +30,27 @@ def cases():
     return out
 
 
+def sim3_cases():
+    from defslam_b200 import nrsfm
+    return [nrsfm.sim3_case(s) for s in range(4)] + [nrsfm.sim3_case(9, n=40, noise=1e-4, outlier_frac=0.0)]
+
+
+def mesh_cases():
+    """regular grids (perturbed so that no angle is degenerate) and an irregular Delaunay mesh"""
+    from scipy.spatial import Delaunay
+    out = {}
+    for G in (6, 9, 13):
+        t = synthetic.make_template(G)
+        rng = np.random.default_rng(G)
+        out[f"grid{G}"] = (t.nodes_rest + 0.01 * rng.normal(size=t.nodes_rest.shape), t.facets)
+    rng = np.random.default_rng(77)
+    uv = rng.uniform(-0.5, 0.5, (120, 2))
+    tri = Delaunay(uv)
+    xyz = np.column_stack([uv, 1.0 + 0.1 * np.sin(4 * uv[:, 0]) * np.cos(3 * uv[:, 1])])
+    out["delaunay"] = (xyz, tri.simplices.astype(np.int32))
+    return out
+
+
 def main():
     ref = oracle_py.load_g2o_ref()
     assert ref is not None, "build oracle/_ref first (make -C oracle ref)"
@@ -83,6 +104,20 @@ def main():
         ref.ref_huber(np.float32(np.sqrt(5.991)), float(e), _capi.as_ptr(r, C.c_double))
         rho[i] = r
     g["huber.e2"], g["huber.rho"] = e2, rho
+    # LaplacianMesh::ExtractMeanCurvatures, the reference's own lines (oracle/template_ref_harness.cc)
+    for name, (xyz, fac) in mesh_cases().items():
+        rc, r = oracle_py.ref_mesh_laplacian(ref, xyz, fac, max_ring=16)
+        assert rc == 0
+        for k in ("cnt", "idx", "w", "boundary", "kappa0"):
+            g[f"mesh.{name}.{k}"] = r[k]
+    # Optimizer::OptimizeHorn on the reference's own Sim3 / EdgeSim3Simple / numeric Jacobians / LM driver
+    rows = []
+    for c in sim3_cases():
+        p = c.problem()
+        r = _capi.Sim3Result()
+        ref.ref_sim3_optimize_horn(C.byref(p), C.byref(r))
+        rows.append(list(r.rot[:]) + list(r.trans[:]) + [r.scale, r.chi2, r.inliers, r.acceptable, r.iterations[0]])
+    g["sim3.out"] = np.array(rows)
     path = os.path.join(ROOT, "tests", "golden", "sft_ref.npz")
     np.savez_compressed(path, **g)
     print("wrote", path, os.path.getsize(path), "bytes")

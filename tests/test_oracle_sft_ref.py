@@ -131,6 +131,73 @@ def test_huber_kernel_equals_reference_golden(oracle, gold):
         assert abs(r0 - rho[0]) <= 1e-15 * max(1.0, abs(rho[0])) and abs(r1 - rho[1]) <= 1e-15
 
 
+def _check_mesh(o, r):
+    assert np.array_equal(o["cnt"], r["cnt"]) and np.array_equal(o["boundary"], r["boundary"])
+    for i in range(len(o["cnt"])):
+        a = dict(zip(o["idx"][i][:o["cnt"][i]], o["w"][i]))
+        b = dict(zip(r["idx"][i][:r["cnt"][i]], r["w"][i]))
+        assert a.keys() == b.keys()
+        for k in a:
+            assert abs(a[k] - b[k]) <= 1e-15 * abs(b[k])
+    assert np.abs(o["kappa0"] - r["kappa0"]).max() <= 1e-15 * np.abs(r["kappa0"]).max()
+
+
+@pytest.mark.parametrize("name", ["grid6", "grid9", "grid13", "delaunay"])
+def test_mesh_laplacian_equals_reference_golden(oracle, gold, name):
+    """oracle/template_oracle.c (mean-value weights, boundary flags, kappa0) against the reference's own
+    LaplacianMesh::ExtractMeanCurvatures lines (LaplacianMesh.cc:53-148,157-162)"""
+    from tests.golden.make_golden_sft import mesh_cases
+    from tests.helpers import mesh_laplacian_call
+    xyz, fac = mesh_cases()[name]
+    rc, o = mesh_laplacian_call(oracle.load().oracle_mesh_laplacian, xyz, fac, max_ring=16)
+    assert rc == 0
+    _check_mesh(o, {k: gold[f"mesh.{name}.{k}"] for k in ("cnt", "idx", "w", "boundary", "kappa0")})
+
+
+def test_live_mesh_laplacian(oracle, ref):
+    from tests.helpers import mesh_laplacian_call
+    for G in (10, 17, 25):
+        t = synthetic.make_template(G)
+        rng = np.random.default_rng(100 + G)
+        xyz = t.nodes_rest + 0.01 * rng.normal(size=t.nodes_rest.shape)
+        rc, o = mesh_laplacian_call(oracle.load().oracle_mesh_laplacian, xyz, t.facets)
+        rc2, r = oracle.ref_mesh_laplacian(ref, xyz, t.facets)
+        assert rc == 0 and rc2 == 0 and r["n_bad"] == 0
+        _check_mesh(o, r)
+
+
+def _check_sim3(o, row):
+    # numeric Jacobians (delta 1e-9) put ~1e-10 of noise on the estimate; the SECOND run starts at the optimum,
+    # where that noise decides how many iterations it takes -- not compared
+    assert o["iterations"][0] == int(row[11])
+    assert np.abs(o["rot"] - row[0:4]).max() < 1e-8 and np.abs(o["trans"] - row[4:7]).max() < 1e-8
+    assert abs(o["scale"] - row[7]) < 1e-8 * row[7]
+    assert abs(o["chi2"] - row[8]) < 1e-8 * row[8]
+    assert (o["inliers"], o["acceptable"]) == (int(row[9]), int(row[10]))
+
+
+def test_sim3_registration_equals_reference_golden(oracle, gold):
+    """oracle/sim3_oracle.c against Optimizer::OptimizeHorn run on the reference's own sim3.h, EdgeSim3Simple,
+    VertexSim3ExpmapNoProj (types_seven_dof_expmap.h:96-126,159-188), base_unary_edge.hpp numeric Jacobians,
+    Huber kernel and Levenberg driver"""
+    from defslam_b200 import nrsfm
+    from tests.golden.make_golden_sft import sim3_cases
+    orc = nrsfm.Api(oracle.load(), "oracle_")
+    for o, row in zip(orc.sim3_register(sim3_cases()), gold["sim3.out"]):
+        _check_sim3(o, row)
+
+
+def test_live_sim3_registration(oracle, ref):
+    from defslam_b200 import nrsfm
+    orc = nrsfm.Api(oracle.load(), "oracle_")
+    cases = [nrsfm.sim3_case(s, n=300) for s in range(20, 26)]
+    for c, o in zip(cases, orc.sim3_register(cases)):
+        p = c.problem()
+        r = _capi.Sim3Result()
+        assert ref.ref_sim3_optimize_horn(C.byref(p), C.byref(r)) == 0
+        _check_sim3(o, list(r.rot[:]) + list(r.trans[:]) + [r.scale, r.chi2, r.inliers, r.acceptable, r.iterations[0]])
+
+
 # ------------------------------------------------------------------ live tier (reference library present)
 LIVE = [("C1", 0), ("C1", 1), ("C2", 0), ("C2", 1), ("C4", 0), ("C4", 1), ("C3", 0)]
 
