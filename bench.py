@@ -40,6 +40,17 @@ FRAMES_PER_GPU = 2368    # 148 SMs x 2 resident CTAs x 8 waves
 CPU_SAMPLE_FRAMES = 64   # bounded CPU sample: ~64 x 0.25 s of CPU work
 
 
+METRIC = "SfT solves/sec (640x480, 1000 matches, 13x13 grid, 10 LM iterations)"
+
+
+def workload_string(cfg: str) -> str:
+    """the SAME string in both arms (the batch size lives in config.frames_per_step_per_gpu)"""
+    from defslam_b200 import synthetic
+    c = synthetic.CONFIGS[cfg]
+    return (f"{cfg}: G={c['G']} mesh (D={6 + 3 * c['G'] ** 2}), M={c['M']} matches, {c['max_iterations']} LM "
+            f"iterations, independent frames")
+
+
 def algorithmic_bytes_per_iteration(G: int, M: int) -> float:
     """B_iter = B_in + B_H(banded) + B_b + B_x per LM iteration per frame."""
     Nn = G * G
@@ -334,6 +345,153 @@ def matching_bench(lib, with_cpu: bool):
     return out
 
 
+def _median_ms(fn, reps, warm=2):
+    for _ in range(warm):
+        fn()
+    t = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        t.append(time.perf_counter() - t0)
+    return 1e3 * float(np.median(t))
+
+
+def _oracle_native():
+    from oracle import oracle_py
+    try:
+        return oracle_py.load(native=True)
+    except Exception:
+        return oracle_py.load()
+
+
+def configs_bench(lib, args, rank, world, dist, flush_fn, with_cpu: bool):
+    """Every BASELINE.json config as the survey shapes it; C2-batched is the headline above.
+      C1  G=9,  M=300,  B=1   the reference's own CPU-runnable case: oracle ms on ONE core (GPU latency beside it)
+      C2  G=13, M=1000, B=1   the call DefTracking makes every frame: defslam_sft_solve on host buffers vs one core
+      C4  G=10, M=400,  B=256 sharded 256/N per rank (shard.shard_range), STRONG scaling: batch latency + solves/s
+      C5  G=25, M=2000, B=64  stress mesh with its own roofline (fp64 and HBM views)
+    Called by every rank (C4 reduces over ranks); C1/C2/C5 run on rank 0."""
+    from defslam_b200 import sft, shard, synthetic
+    from oracle import oracle_py
+    out = {}
+    olib = _oracle_native() if (with_cpu and rank == 0) else None
+    import torch
+
+    # ---- C1 and C2 at B = 1 (latency)
+    if rank == 0:
+        for name, reps_cpu in (("C1", 20), ("C2", 5)):
+            c = synthetic.CONFIGS[name]
+            tmpl, frames = synthetic.make_config_frames(name, nframes=4)
+            T = sft.Template(tmpl)
+            f = frames[0]
+            gpu_ms = _median_ms(lambda: sft.solve(f, template=T), 30, warm=3)
+            kern_ms = float(lib.defslam_last_kernel_ms())
+            o = sft.solve(f, template=T)
+            ent = {"workload": workload_string(name), "frames": 1,
+                   "gpu_ms": gpu_ms, "gpu_kernel_ms": kern_ms,
+                   "how": "median of 30 defslam_sft_solve calls on host buffers (marshal + H2D + kernel + D2H inside)",
+                   "lm_iterations": int(o.r.lm_iterations), "lm_trials": int(o.r.lm_trials)}
+            if olib is not None:
+                cpu_ms = _median_ms(lambda: oracle_py.sft_solve(f, lib=olib), reps_cpu, warm=1)
+                ref = oracle_py.sft_solve(f, lib=olib)
+                ent["cpu_ms"] = cpu_ms
+                ent["cpu_baseline"] = {"value": 1e3 / cpu_ms, "unit": "solves/s", "cores": 1, "kind": "port",
+                                       "sample": f"median of {reps_cpu} oracle solves of the same frame on one core"}
+                ent["speedup_vs_1_core"] = cpu_ms / gpu_ms
+                ent["node_rel_err_vs_oracle"] = float(np.abs(o.nodes - ref.nodes).max() / np.sqrt((ref.nodes ** 2).sum(1).mean()))
+            out[name + "_b1"] = ent
+            T.close()
+
+    # ---- C4: 256 frames sharded over the ranks, strong scaling
+    c4 = synthetic.CONFIGS["C4"]
+    tmpl4, frames4 = synthetic.make_config_frames("C4", nframes=c4["B"])
+    lo, hi = shard.shard_range(c4["B"], rank, world)
+    mine = frames4[lo:hi]
+    T4 = sft.Template(tmpl4)
+    k_ms, e_ms = 0.0, 0.0
+    reps = 5
+    if mine:
+        rb4 = sft.ResidentBatch(mine, template=T4)
+        hb4 = sft.HostBatch(mine, template=T4)
+        for _ in range(2):
+            rb4.run(); hb4.solve()
+        ks, es = [], []
+        for _ in range(reps):
+            flush_fn()
+            ks.append(rb4.run())
+            flush_fn()
+            t0 = time.perf_counter()
+            hb4.solve()
+            es.append(1e3 * (time.perf_counter() - t0))
+        k_ms, e_ms = float(np.median(ks)), float(np.median(es))
+        rb4.close()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    d = dist if (world > 1) else None
+    k_job, solved = shard.reduce_job_stats(k_ms, len(mine), d, dev)
+    e_job, _ = shard.reduce_job_stats(e_ms, len(mine), d, dev)
+    if rank == 0:
+        ent = {"workload": workload_string("C4"), "frames": c4["B"], "frames_per_gpu": -(-c4["B"] // world),
+               "n_gpus": world, "scaling": "strong",
+               "batch_latency_ms": k_job, "value": solved / (k_job * 1e-3), "unit": "solves/s",
+               "e2e": {"batch_latency_ms": e_job, "value": solved / (e_job * 1e-3), "unit": "solves/s"},
+               "how": f"median of {reps} runs, max over ranks; resident launch (CUDA events) and one "
+                      "defslam_sft_solve_batched call on host buffers per rank"}
+        if olib is not None:
+            cores = os.cpu_count() or 1
+            rate, dt, build = cpu_solve_rate(frames4, cores)
+            ent["cpu_baseline"] = {"value": rate, "unit": "solves/s", "cores": cores, "kind": "port",
+                                   "sample": f"all {c4['B']} frames, one frame per thread, {dt:.1f} s wall, oracle {build}"}
+        out["C4"] = ent
+    T4.close()
+
+    # ---- C5: 64 frames of the 25x25 stress mesh
+    if rank == 0:
+        c5 = synthetic.CONFIGS["C5"]
+        tmpl5, base5 = synthetic.make_config_frames("C5", nframes=8)
+        frames5 = [base5[i % 8] for i in range(c5["B"])]
+        T5 = sft.Template(tmpl5)
+        rb5 = sft.ResidentBatch(frames5, template=T5)
+        hb5 = sft.HostBatch(frames5, template=T5)
+        for _ in range(2):
+            rb5.run(); hb5.solve()
+        ks, es = [], []
+        for _ in range(reps):
+            flush_fn()
+            ks.append(rb5.run())
+            flush_fn()
+            t0 = time.perf_counter()
+            hb5.solve()
+            es.append(1e3 * (time.perf_counter() - t0))
+        o5 = rb5.fetch()
+        info5 = rb5.info()
+        k5, e5 = float(np.median(ks)), float(np.median(es))
+        it5 = float(np.sum([o.r.lm_iterations for o in o5]))
+        tr5 = float(np.sum([o.r.lm_trials for o in o5]))
+        peaks, peak_kind = measured_peaks()
+        b_iter5 = algorithmic_bytes_per_iteration(c5["G"], c5["M"])
+        ach5 = it5 * b_iter5 / (k5 * 1e-3) / 1e9
+        ent = {"workload": workload_string("C5"), "frames": c5["B"], "distinct_frames": 8,
+               "batch_latency_ms": k5, "value": c5["B"] / (k5 * 1e-3), "unit": "solves/s",
+               "e2e": {"batch_latency_ms": e5, "value": c5["B"] / (e5 * 1e-3), "unit": "solves/s"},
+               "grid": info5["grid"], "threads": info5["threads"], "smem_bytes": info5["smem_bytes"],
+               "lm_iterations_per_frame": it5 / c5["B"], "lm_trials_per_frame": tr5 / c5["B"],
+               "roofline": {"bound": "hbm", "achieved": ach5, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                            "frac": ach5 / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind,
+                            "algorithmic_bytes_per_lm_iteration_per_frame": b_iter5,
+                            "fp64": fp64_roofline(c5["G"], tr5, it5, k5 * 1e-3, None),
+                            "note": "64 frames occupy 64 of 148 SMs (one CTA per frame, one CTA per SM at this size)"}}
+        if olib is not None:
+            cores = os.cpu_count() or 1
+            sample = [base5[i % 8] for i in range(min(cores, 16))]
+            rate, dt, build = cpu_solve_rate(sample, min(cores, 16))
+            ent["cpu_baseline"] = {"value": rate, "unit": "solves/s", "cores": min(cores, 16), "kind": "port",
+                                   "sample": f"{len(sample)} frames, one frame per thread, {dt:.1f} s wall, oracle {build}"}
+        out["C5"] = ent
+        rb5.close()
+        T5.close()
+    return out
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -350,12 +508,12 @@ def run_reference(args, rank, world):
         rates.append(r); secs.append(dt)
     value = len(sample) * args.steps / sum(secs)
     line = {
-        "impl": "reference", "metric": "SfT solves/sec (640x480, 1000 matches, 13x13 grid, 10 LM iterations)",
+        "impl": "reference", "metric": METRIC,
         "value": value, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * sum(secs) / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{CFG}: G={c['G']} mesh, M={c['M']} matches, {c['max_iterations']} LM iterations, "
-                               f"{n_sample} frames per step (bounded sample of the batch)"},
+        "config": {"workload": workload_string(CFG), "frames_per_step": n_sample,
+                   "sample": "bounded sample of the batch the GPU arm solves per step"},
         "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port",
                          "sample": f"{n_sample} frames/step x {args.steps} steps, one frame per thread, oracle {build}"},
         "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -377,6 +535,7 @@ def main():
     ap.add_argument("--no-nrsfm", action="store_true", help="skip the NRSfM stage measurements")
     ap.add_argument("--no-stream", action="store_true", help="skip the C3 tracking+mapping stream")
     ap.add_argument("--no-matching", action="store_true", help="skip the match-production measurements")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config measurements (C1, C2 B=1, C4, C5)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -462,6 +621,15 @@ def main():
         nrsfm_launches = lib.defslam_kernel_launch_count() - l0
         barrier()
 
+    # ---- every BASELINE.json config (C1, C2 at B=1, C4 sharded/strong, C5): all ranks take part in C4
+    cfg_line = None
+    if not args.no_configs:
+        def _flush2():
+            flush.fill_(1)
+            torch.cuda.synchronize()
+        cfg_line = configs_bench(lib, args, rank, world, dist, _flush2, not args.no_cpu_baseline)
+        barrier()
+
     # ---- C3: tracking + mapping loop over a 300-frame stream (rank 0; latency-bound: one frame at a time)
     st_line = None
     if not args.no_stream and rank == 0:
@@ -521,13 +689,12 @@ def main():
             if tj.get("frames") == args.frames and tj.get("workload") == CFG:
                 traffic = tj.get("dram_bytes_per_launch")
         line = {
-            "metric": "SfT solves/sec (640x480, 1000 matches, 13x13 grid, 10 LM iterations)",
+            "metric": METRIC,
             "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{CFG}: G={c['G']} mesh (D=513), M={c['M']} matches, {c['max_iterations']} LM "
-                                   f"iterations, {args.frames} independent frames per GPU per step "
-                                   f"({N_DISTINCT} distinct, tiled)",
+            "config": {"workload": workload_string(CFG), "frames_per_step_per_gpu": args.frames,
+                       "distinct_frames": N_DISTINCT,
                        "l2": "flushed between timed iterations (256 MB write)",
                        "grid": info["grid"], "threads": info["threads"], "smem_bytes": info["smem_bytes"],
                        "lm_iterations_per_frame": iters_all / n_frames_job,
@@ -560,6 +727,8 @@ def main():
                     line["nrsfm"]["stages"][k]["cpu_baseline"] = v
                 line["nrsfm"]["cpu_baseline"] = {"cores": os.cpu_count() or 1, "kind": "port",
                                                  "sample": "32 fits / 256 point sets / 16 keyframes, one unit per thread"}
+        if cfg_line:
+            line["configs"] = cfg_line
         if st_line is not None:
             line["stream"] = st_line
         if mt_line is not None:

@@ -31,6 +31,7 @@ struct BatchMarshal {
   size_t ws_band = 0, ws_dinv = 0, ws_cg = 0, ws_F = 0, ws_S = 0, ws_M = 0, ws_nf = 0, ws_dp = 0;
   int smem_doubles = 0;
   bool any_e_global = false;
+  int row_mode = 1;          /* 0: never use the row-owner factorisation (DEFSLAM_ROW_MODE=0, A/B runs) */
   bool any_x_global = false; /* then EVERY problem of the batch keeps x/dx in the workspace (one kernel variant per launch) */
 
   WorkspaceSizes ws_sizes() const {
@@ -95,10 +96,24 @@ struct BatchMarshal {
       for (int k = 0; k < 16; k++) v.Tcw[k] = p[i].T_cw[k];
 
       /* shared-memory placement, most resident first: border rows and x/dx in smem; border rows in
-       * the global workspace; x/dx there too (large meshes: the window alone fills the SM) */
+       * the global workspace; x/dx there too (large meshes: the window alone fills the SM).  Meshes whose
+       * band has a supported tile count and whose ring fits take the row-owner factorisation (sft_rows.h). */
       SmemLayout L = smem_layout(hv->n_nodes, hv->n_edges, hv->Dn_pad, hv->bwp, hv->ld, hv->Wr, hv->ES, true, true);
       v.e_in_smem = 1;
       v.x_in_smem = 1;
+      v.row_nt = 0;
+      {
+        const int nt = hv->bwp / NB + 1;
+        if (row_mode != 0 && mode == MODE_SOLVE && row_mode_nt_supported(nt)) {
+          const SmemLayout Lr = smem_layout(hv->n_nodes, hv->n_edges, hv->Dn_pad, hv->bwp, hv->ld, hv->Wr, hv->ES, false, true, nt);
+          if (Lr.total + CTX_DOUBLES <= smem_limit_doubles) {
+            L = Lr;
+            v.row_nt = nt;
+            v.e_in_smem = 0;
+            ws_band = std::max(ws_band, row_mode_factor_doubles(hv->nblk, nt));
+          }
+        }
+      }
       if (L.total + CTX_DOUBLES > smem_limit_doubles) {
         L = smem_layout(hv->n_nodes, hv->n_edges, hv->Dn_pad, hv->bwp, hv->ld, hv->Wr, hv->ES, false, true);
         v.e_in_smem = 0;
@@ -125,6 +140,7 @@ struct BatchMarshal {
       for (int i = 0; i < nprob; i++) {
         const PlanView *hv = hvs[i];
         views[i].x_in_smem = 0;
+        views[i].row_nt = 0;
         const SmemLayout L = smem_layout(hv->n_nodes, hv->n_edges, hv->Dn_pad, hv->bwp, hv->ld, hv->Wr, hv->ES,
                                          views[i].e_in_smem != 0, false);
         if (L.total + CTX_DOUBLES > smem_doubles) smem_doubles = L.total + CTX_DOUBLES;

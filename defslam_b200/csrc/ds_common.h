@@ -9,6 +9,12 @@
  * that tests can exercise the kernel source on a box without a GPU
  * (tests/emu/, never shipped, never loaded by the package).
  */
+#ifndef DS_ISO
+#define DS_ISO 0
+#endif
+#ifndef DS_FAST_RSQRT
+#define DS_FAST_RSQRT 0
+#endif
 #ifndef DS_COMMON_H_
 #define DS_COMMON_H_
 

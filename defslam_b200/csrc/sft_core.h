@@ -60,7 +60,7 @@ struct ProbView {
   int trace_cap;
   int e_in_smem;
   int x_in_smem;           /* node positions / LM step in shared memory (else in the global workspace) */
-  int pad_;
+  int row_nt;              /* > 0: row-owner factorisation (sft_rows.h) with this many tiles per block row; 0: sliding window */
   double fx, fy, cx, cy;
   double reg_lap, reg_inex, reg_temp;
   float Tcw[16];
@@ -138,7 +138,13 @@ Workspace carve_workspace(uint8_t *base, const WorkspaceSizes &z) {
  * and device (pointers) */
 struct SmemLayout {
   int W, E, P, x, xb, dx, Lkk, invL, G, Hcc, red, pose, tiles, flags, total;
+  int er, db, sy; /* row-owner factorisation: border-tile ring, diagonal hand-off buffers, progress counters */
 };
+
+/* row-owner factorisation (sft_rows.h): ring slots and sizes */
+constexpr int ROWS_OWNERS_ = 5;
+constexpr int ROWS_LT_STRIDE_ = 72;
+constexpr int ROWS_BWD_BUFS_ = 4; /* row blocks of the factor in flight during the backward sweep */
 
 DS_FN int asm_scratch_doubles(int n, int ne) { return 11 * n + 5 * ne; }
 
@@ -161,17 +167,35 @@ static inline
 __host__ __device__
 #endif
 SmemLayout smem_layout(int n_nodes, int n_edges, int Dn_pad, int bwp, int ld, int Wr, int ES, bool e_in_smem,
-                       bool x_in_smem = true) {
+                       bool x_in_smem = true, int row_nt = 0) {
   SmemLayout L;
   int o = 0;
+  const int asz = 11 * n_nodes + 5 * n_edges; /* assembly scratch */
+  L.er = L.db = L.sy = 0;
+  if (row_nt > 0) {
+    /* ring of (NT-1 + owners) block rows of NT tiles; backward sweep: 4 x (row block + inverse) + the solution */
+    const int nblk = Dn_pad / NB;
+    int wsz = (row_nt - 1 + ROWS_OWNERS_) * row_nt * 64;
+    const int bsz = ROWS_BWD_BUFS_ * (row_nt * ROWS_LT_STRIDE_ + 64) + Dn_pad, esz = nblk * 64;
+    if (asz > wsz) wsz = asz;
+    if (bsz > wsz) wsz = bsz;
+    if (esz > wsz) wsz = esz; /* (emulation keeps the border tiles there) */
+    L.W = o;  o += wsz; o = (o + 1) & ~1;
+    L.E = o;
+    L.P = o;
+    L.er = o; o += row_nt * 64;
+    L.db = o; o += 128;
+    L.sy = o; o += (3 * nblk + 2 + 16 + 1) / 2 + 1; o = (o + 1) & ~1; /* counters + the warps' sub-partitions */
+  } else {
   int wsz = Wr * ld;
-  /* assembly scratch; backward sweep: ring of 4 row blocks + the solution vector */
-  const int asz = 11 * n_nodes + 5 * n_edges, bsz = 4 * (NB * ld) + Dn_pad;
+  /* backward sweep: ring of 4 row blocks + the solution vector */
+  const int bsz = 4 * (NB * ld) + Dn_pad;
   if (asz > wsz) wsz = asz;
   if (bsz > wsz) wsz = bsz;
   L.W = o;    o += wsz; o = (o + 1) & ~1;
   L.E = o;    o += e_in_smem ? 8 * ES : 0;
   L.P = o;    o += panel_doubles(bwp); o = (o + 1) & ~1;
+  }
   L.x = o;    o += x_in_smem ? Dn_pad : 0;
   L.xb = o;   /* (backup lives in global memory) */
   L.dx = o;   o += x_in_smem ? Dn_pad + 8 : 0;
@@ -183,7 +207,8 @@ SmemLayout smem_layout(int n_nodes, int n_edges, int Dn_pad, int bwp, int ld, in
   L.pose = o; o += 16;   /* pose (7) + backup (7) */
   {
     const int nrow = bwp / NB + 1;
-    L.tiles = o; o += 2 * (nrow * (nrow + 1) / 2) + 10; /* one int4 per trailing-update tile + per-warp ranges */
+    L.tiles = o; /* one int4 per trailing-update tile + per-warp ranges (sliding-window path only) */
+    if (row_nt == 0) o += 2 * (nrow * (nrow + 1) / 2) + 10;
   }
   L.flags = o; o += (2 * n_nodes + 7) / 8 + 1;
   L.total = o;
@@ -201,8 +226,8 @@ struct Ctx {
   double inv_n;
   long long *prof;  /* optional per-phase cycle counters (global), CTA 0 only */
   long long prof_last;
-  uint32_t ph[8];  /* phase parity of each mbarrier */
-  uint64_t mbar[8]; /* 0: forward window, 1..4: backward ring (fixed address for the whole launch) */
+  uint32_t ph[16];  /* phase parity of each mbarrier */
+  uint64_t mbar[16]; /* 0: forward window, 1..: backward ring (fixed address for the whole launch) */
 };
 
 /* doubles reserved at the head of shared memory for the CTA-wide context */
@@ -885,7 +910,23 @@ DS_FN_NOINLINE double build_system(const Team team, Ctx &cx) {
  * round trip on it; lanes only split the stores. */
 DS_FN double ds_rsqrt(double d) {
 #if DS_CUDA
+#if DS_FAST_RSQRT
+  /* branch-free: hardware seed (MUFU.RSQ64H, ~2^-22) and one third-order step
+   * y1 = y0 (1 + e/2 + 3 e^2/8), e = 1 - d y0^2  (relative error ~ e^3 -> below 2^-60).
+   * The library rsqrt() carries a slow-path call per use, which ends the basic block and stops the
+   * scheduler from overlapping the 62-cycle latency with the independent updates of the block.
+   * Pivots here are > 0 and far from the denormal range (lambda is added to every diagonal entry);
+   * a non-positive pivot is caught by the caller before the value is used. */
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
+  const double h = y0 * y0;
+  const double e = fma(-d, h, 1.0);
+  const double p = fma(0.375, e, 0.5);
+  const double t = y0 * e;
+  return fma(t, p, y0);
+#else
   return rsqrt(d);
+#endif
 #else
   return 1.0 / sqrt(d);
 #endif
@@ -1143,12 +1184,17 @@ DS_FN void build_tile_table(const Team team, TileDesc *tt, int *wstart, int nwar
   }
   /* warp 0's fixed load per step: its panel tile, tile 0 and the look-ahead factorisation; the other
    * warps share nt8 panel tiles and the remaining trailing tiles */
-  int n0 = ((ntiles - 1) + nt8 - (LOOKAHEAD_TILES + 2) * (nwarp - 1)) / nwarp;
+  /* DS_ISO: warp 4 shares its scheduler (SM sub-partition = warp id mod 4) and FP64 pipe with warp 0, whose
+   * diagonal factorisation is the latency chain of the step; it takes the TMA duty and no tensor-core work, so the
+   * chain's DFMAs do not queue behind 16-cycle DMMAs */
+  const int idle_w = (DS_ISO && nwarp == 8) ? 4 : -1;
+  const int nwork = nwarp - 1 - (idle_w >= 0 ? 1 : 0); /* warps that run S2/S3 next to warp 0 */
+  int n0 = ((ntiles - 1) + nt8 - (LOOKAHEAD_TILES + 2) * nwork) / (nwork + 1);
   if (n0 < 0) n0 = 0;
   const int nshared = ntiles - n0;
   team.sync();
-  /* Contiguous ranges of equal COST for warps 1..: a panel tile the warp solves before the update
-   * (S2, row tiles w, w + nwarp-1, ...) counts 1.4 tiles, a tile that needs per-entry checks
+  /* Contiguous ranges of equal COST for the worker warps: a panel tile the warp solves before the update
+   * (S2, row tiles 1 + wi, 1 + wi + nwork, ...) counts 1.4 tiles, a tile that needs per-entry checks
    * (diagonal, corner) 1.5 -- ratios from the per-warp cycle counters of the profile build. */
   if (team.tid == 0) {
     wstart[0] = nshared;
@@ -1156,13 +1202,14 @@ DS_FN void build_tile_table(const Team team, TileDesc *tt, int *wstart, int nwar
       int total = 0;
       for (int t = 1; t < nshared; t++) total += (tt[t].kind == 2 || tt[t].kind == 4) ? 15 : 10;
       for (int rt = 1; rt <= nt8; rt++) total += 14;
-      int cur = 1;
+      int cur = 1, wi = 0;
       for (int w = 1; w < nwarp; w++) {
         wstart[w] = cur;
+        if (w == idle_w) continue; /* empty range: wstart[w+1] = cur as well */
         int acc = 0;
-        for (int rt = w; rt <= nt8; rt += nwarp - 1) acc += 14;
-        const int budget = total / (nwarp - w);
-        if (w == nwarp - 1) cur = nshared;
+        for (int rt = 1 + wi; rt <= nt8; rt += nwork) acc += 14;
+        const int budget = total / (nwork - wi);
+        if (wi == nwork - 1) cur = nshared;
         while (cur < nshared) {
           const int cst = (tt[cur].kind == 2 || tt[cur].kind == 4) ? 15 : 10;
           if (acc + cst / 2 >= budget) break;
@@ -1170,6 +1217,7 @@ DS_FN void build_tile_table(const Team team, TileDesc *tt, int *wstart, int nwar
           cur++;
         }
         total -= acc;
+        wi++;
       }
       wstart[nwarp] = nshared;
     } else {
@@ -1278,6 +1326,10 @@ DS_FN void named_arrive(int id, int count) {
 DS_FN void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 #endif
 
+}  // namespace ds
+#include "sft_rows.h"
+namespace ds {
+
 /* Solve (H + lambda I) dx = b.  dx -> sm[sl.dx] (nodes, then camera at Dn_pad).
  * Returns false if a pivot is not positive (LinearSolverDense::solve returning
  * false, linear_solver_dense.h:107-112); dx is then left untouched (stale), as
@@ -1361,7 +1413,10 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
    * barrier per step.  inv(L_kk) is double-buffered: warp 0 writes the next one while the
    * others may still read the current one. */
 #if DS_CUDA
-  const int tma_tid = 32; /* TMA duty (bulk store of finished rows, refill of the freed slot): warp 1 */
+  /* TMA duty (bulk store of finished rows, refill of the freed slot): warp 1, or the warp kept free of
+   * tensor-core work (DS_ISO) */
+  const int iso_w = (DS_ISO && nwarp == 8) ? 4 : -1;
+  const int tma_tid = iso_w >= 0 ? 32 * iso_w : 32;
 #else
   const int tma_tid = 0;
 #endif
@@ -1386,7 +1441,10 @@ DS_FN_NOINLINE bool factor_solve(const Team team, Ctx &cx, double lambda) {
     const int lo = bwE - bw;
     DS_PROF_T0(s2t0);
 #if DS_CUDA
-    const int rt_first = warp == 0 ? 0 : warp, rt_step = warp == 0 ? nt8 + 1 : nwarp - 1;
+    /* warp 0: the tile under the diagonal block; worker wi: row tiles 1 + wi, 1 + wi + nwork, ... */
+    const int nwork = nwarp - 1 - (iso_w >= 0 ? 1 : 0);
+    const int wi = warp - 1 - (iso_w >= 0 && warp > iso_w ? 1 : 0);
+    const int rt_first = warp == 0 ? 0 : (warp == iso_w ? nt8 + 1 : 1 + wi), rt_step = warp == 0 ? nt8 + 1 : nwork;
 #else
     const int rt_first = 0, rt_step = 1;
 #endif
@@ -1777,7 +1835,7 @@ DS_FN_NOINLINE void sft_solve_one(const Team team, Ctx &cx) {
   const int Dp = pl.Dn_pad;
 
   const int rc = prologue<XS>(team, c);
-  {
+  if (pb.row_nt == 0) {
     TileDesc *tt = (TileDesc *)(sm_base() + c.sl.tiles);
     const int nt8 = pl.bwp / NB;
 #if DS_CUDA
@@ -1826,7 +1884,19 @@ DS_FN_NOINLINE void sft_solve_one(const Team team, Ctx &cx) {
       DS_FOR(i, pl.Dn) xb[i] = x[i];
       if (team.tid == 0) for (int k = 0; k < 7; k++) psb[k] = ps[k];
       prof_mark(team, c, PF_LM_SCALAR);
-      const bool ok2 = factor_solve<XS>(team, c, lambda);
+      bool ok2;
+      if (XS && pb.row_nt > 0) {
+        switch (pb.row_nt) { /* tiles per block row: 9x9 .. 17x17 regular meshes (and the small test meshes) */
+          case 5: ok2 = factor_rows<5>(team, lambda); break;
+          case 6: ok2 = factor_rows<6>(team, lambda); break;
+          case 8: ok2 = factor_rows<8>(team, lambda); break;
+          case 9: ok2 = factor_rows<9>(team, lambda); break;
+          case 11: ok2 = factor_rows<11>(team, lambda); break;
+          default: ok2 = factor_rows<14>(team, lambda); break;
+        }
+      } else {
+        ok2 = factor_solve<XS>(team, c, lambda);
+      }
       apply_update<XS>(team, c);
       prof_mark(team, c, PF_UPDATE);
       tempChi = eval_state<XS, false>(team, c);
@@ -1893,7 +1963,7 @@ DS_FN void sft_run_problem(const Team &team, const ProbView &pv, double *smem, u
   team.sync();
   if (team.tid == 0) {
     if (first_of_launch) {
-      for (int i = 0; i < 8; i++) { mbar_init(&c.mbar[i], 1); c.ph[i] = 0; }
+      for (int i = 0; i < 16; i++) { mbar_init(&c.mbar[i], 1); c.ph[i] = 0; }
       fence_mbar_init();
     }
     c.prof = prof;
@@ -1904,7 +1974,7 @@ DS_FN void sft_run_problem(const Team &team, const ProbView &pv, double *smem, u
     c.pl = *pv.plan;
     c.ws = carve_workspace(ws_base, z);
     c.sl = smem_layout(c.pl.n_nodes, c.pl.n_edges, c.pl.Dn_pad, c.pl.bwp, c.pl.ld, c.pl.Wr, c.pl.ES, pv.e_in_smem != 0,
-                       pv.x_in_smem != 0);
+                       pv.x_in_smem != 0, pv.row_nt);
   }
   team.sync();
   sft_solve_one<XS>(team, c);

@@ -171,6 +171,7 @@ static int batch_load(defslam_sft_batch *B, int nprob, const defslam_sft_problem
     const int lim = atoi(e) / (int)sizeof(double);
     if (lim > 0 && lim < smem_limit) smem_limit = lim;
   }
+  if (const char *e = getenv("DEFSLAM_ROW_MODE")) B->bm.row_mode = atoi(e); /* 0: sliding-window factorisation only */
   int rc = B->bm.plan(nprob, p, mode, smem_limit, resolve);
   if (rc) return rc;
   if ((rc = B->h_in.ensure(B->bm.in_bytes)) || (rc = B->h_out.ensure(B->bm.out_bytes)) ||
@@ -258,6 +259,12 @@ static int batch_wait_kernel(defslam_sft_batch *B) {
     fprintf(stderr, "; S2 phase %.0f busy per warp:", (double)h[PF_S2] / steps);
     for (int w = 0; w < 16; w++) if (h[PF_X_S2W + w]) fprintf(stderr, " %.0f", (double)h[PF_X_S2W + w] / steps);
     fprintf(stderr, "\n");
+    if (h[PF_X_STEPS] == 0 && h[PF_X_WARP + 1]) { /* row-owner factorisation: chain warp and owners, per block row */
+      fprintf(stderr, "[defslam profile] row owner path, cycles summed over the launch: chain warp waiting %lld, factoring %lld; "
+                      "owners (everything before the last step, last step):", h[PF_X_WARP], h[PF_X_WARP + 1]);
+      for (int w = 0; w < 5; w++) fprintf(stderr, " %lld/%lld", h[PF_X_WARP + 2 + 2 * w], h[PF_X_WARP + 3 + 2 * w]);
+      fprintf(stderr, "\n");
+    }
     const double nb = (double)(h[PF_X_BUILDS] ? h[PF_X_BUILDS] : 1);
     fprintf(stderr, "[defslam profile] per build (%lld builds): phase %.0f; facet sums %.0f, camera reduce %.0f, block gather %.0f, "
             "per-node %.0f, max-diag reduce %.0f (thread 0)\n", h[PF_X_BUILDS], (double)h[PF_BUILD] / nb,

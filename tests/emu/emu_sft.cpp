@@ -49,6 +49,7 @@ int run(int nprob, const defslam_sft_problem *p, defslam_sft_result *r, int mode
   /* DEFSLAM_EMU_SMEM_LIMIT (doubles) lets a test force the placements the planner falls back to on
    * the device: border rows, then x/dx, in the global workspace */
   const char *lim = getenv("DEFSLAM_EMU_SMEM_LIMIT");
+  if (const char *e = getenv("DEFSLAM_ROW_MODE")) bm.row_mode = atoi(e);
   int rc = bm.plan(nprob, p, mode, lim ? atoi(lim) : 1 << 28, resolve);
   if (rc) return rc;
   std::vector<uint8_t> in(bm.in_bytes + 16), out(bm.out_bytes + 16, 0);

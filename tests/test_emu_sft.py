@@ -159,11 +159,19 @@ def test_plan_bandwidth_of_the_regular_grid():
 
 
 def test_fallback_placements_give_identical_results(monkeypatch):
-    """The planner's fallbacks for large meshes (border rows, then x/dx, in the global workspace
-    instead of shared memory) run the same arithmetic: bitwise identical solutions."""
+    """The planner's fallbacks of the sliding-window factorisation for large meshes (border rows, then
+    x/dx, in the global workspace instead of shared memory) run the same arithmetic: bitwise identical
+    solutions.  The row-owner factorisation (the default where it fits) sums in a different order:
+    same LM trajectory, nodes equal to rounding."""
     tmpl, frames = synthetic.make_config_frames("C1", nframes=2)
+    rc, rows = emu_solve_batched(frames)
+    assert rc == 0
+    monkeypatch.setenv("DEFSLAM_ROW_MODE", "0")
     rc, base = emu_solve_batched(frames)
     assert rc == 0
+    for a, b in zip(rows, base):
+        assert rel_nodes(a.nodes, b.nodes) < 1e-10
+        assert a.r.lm_trials == b.r.lm_trials and a.r.n_inliers == b.r.n_inliers
     import ctypes as C
     lib = emu_lib()
     h = C.c_void_p()
@@ -183,6 +191,17 @@ def test_fallback_placements_give_identical_results(monkeypatch):
     monkeypatch.setenv("DEFSLAM_EMU_SMEM_LIMIT", "1000")
     rc, _ = emu_solve_batched(frames)
     assert rc == -4  # DEFSLAM_ETOOLARGE
+
+
+@pytest.mark.parametrize("cfg,nfr", [("C1", 2), ("C2", 1), ("C4", 2), ("C3", 1)])
+def test_sliding_window_factorisation_still_matches_oracle(cfg, nfr, oracle, monkeypatch):
+    """the sliding-window path stays the fallback for meshes the row-owner ring does not fit (25x25)"""
+    monkeypatch.setenv("DEFSLAM_ROW_MODE", "0")
+    tmpl, frames = synthetic.make_config_frames(cfg, nframes=nfr)
+    rc, outs = emu_solve_batched(frames)
+    assert rc == 0
+    for f, o in zip(frames, outs):
+        _check(o, oracle.sft_solve(f), f)
 
 
 def test_stress_mesh_25x25_matches_oracle(oracle):
