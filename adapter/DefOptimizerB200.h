@@ -113,21 +113,97 @@ int extract_template(TemplateT *tmpl, TemplateArrays &A, std::vector<NodeT *> &n
   return 0;
 }
 
-/* The drop-in.  FrameT/MapT/... are the reference's types (or the test mocks). */
-template <class FrameT, class MapT, class TemplateT, class NodeT, class DefMapPointT>
-int DefPoseOptimization(FrameT *pFrame, MapT *mMap, PlanCache<TemplateT, NodeT> &cache, double RegLap = 5000,
-                        double RegInex = 5000, double RegTemp = 0, unsigned int NeighboursLayers = 1) {
+/* updateNodes (DefOptimizer.cc:955-968) after the roles the graph construction set on the nodes
+ * (setViewed :332, setLocal :433): the reference calls Node::update(), which latches the role into the
+ * viewed/local flags the drawers read (Node.cc:142-165), then resetRole(), then setXYZ. */
+template <class TemplateT, class NodeT>
+void write_back_nodes(PlanCache<TemplateT, NodeT> &cache, const std::vector<double> &node_out,
+                      const std::vector<uint8_t> &role) {
+  for (size_t i = 0; i < cache.nodes.size(); i++) {
+    NodeT *nd = cache.nodes[i];
+    nd->resetRole();
+    if (role[i] & 1) nd->setViewed();
+    else if (role[i] & 2) nd->setLocal();
+    nd->update();
+    nd->resetRole();
+    nd->setXYZ(node_out[3 * i], node_out[3 * i + 1], node_out[3 * i + 2]);
+  }
+}
+
+/* plan of the map's current template (rebuilt when DefMap swapped the template) */
+template <class MapT, class TemplateT, class NodeT>
+bool ensure_plan(MapT *mMap, PlanCache<TemplateT, NodeT> &cache) {
   TemplateT *tmpl = mMap->GetTemplate();
-  if (!tmpl) return 0;
-  if (cache.owner != tmpl || !cache.plan) { /* the template was swapped by DefMap::createTemplate */
+  if (!tmpl) return false;
+  if (cache.owner != tmpl || !cache.plan) {
     defslam_template_destroy(cache.plan);
     cache.plan = nullptr;
     TemplateArrays A;
     extract_template<TemplateT, NodeT>(tmpl, A, cache.nodes, cache.index);
     const defslam_template_desc d = A.desc();
-    if (defslam_template_create(&d, -1, &cache.plan) != DEFSLAM_OK) return 0;
+    if (defslam_template_create(&d, -1, &cache.plan) != DEFSLAM_OK) return false;
     cache.owner = tmpl;
   }
+  return true;
+}
+
+/* The second overload,
+ *   int DefPoseOptimization(const std::vector<std::vector<double>> &matches, Frame *pFrame, Map *mMap,
+ *                           std::vector<bool> &outlier, double RegLap, double RegInex, double RegTemp)
+ *   (Modules/Tracking/DefOptimizer.h:58-61, body DefOptimizer.cc:582-837).
+ * matches[i] = {n0, n1, n2, b0, b1, b2, u, v} with n* positions in Template::nodeArray_ (:631-650).
+ * The reference leaves EdgeMeanCurvature::lenghtEdge_ uninitialised in this overload (quirk C8); the
+ * caller states the value here (curvEdgeLen; the median edge length is the natural choice).  Like the
+ * reference: outlier[] is APPENDED to (:806-818), the pose is not written back, the return value is 0. */
+template <class FrameT, class MapT, class TemplateT, class NodeT>
+int DefPoseOptimization(const std::vector<std::vector<double>> &matches, FrameT *pFrame, MapT *mMap,
+                        PlanCache<TemplateT, NodeT> &cache, std::vector<bool> &outlier, double RegLap,
+                        double RegInex, double RegTemp, double curvEdgeLen) {
+  if (!ensure_plan(mMap, cache)) return 0;
+  TemplateT *tmpl = mMap->GetTemplate();
+  const int n_nodes = (int)cache.nodes.size();
+  std::vector<double> node_xyz(3 * (size_t)n_nodes), node_out(3 * (size_t)n_nodes);
+  for (int i = 0; i < n_nodes; i++) {
+    double x, y, z;
+    cache.nodes[i]->getXYZ(x, y, z);
+    node_xyz[3 * i] = x; node_xyz[3 * i + 1] = y; node_xyz[3 * i + 2] = z;
+  }
+  const int M = (int)matches.size();
+  std::vector<int32_t> mnodes(3 * (size_t)M); std::vector<double> mbary(3 * (size_t)M); std::vector<float> muv(2 * (size_t)M);
+  for (int i = 0; i < M; i++) {
+    for (int k = 0; k < 3; k++) {
+      mnodes[3 * i + k] = cache.index.at(tmpl->nodeArray_[(size_t)matches[i][k]]);   /* Nodes[matches[i][ui-1]] :640 */
+      mbary[3 * i + k] = matches[i][3 + k];
+    }
+    muv[2 * i] = (float)matches[i][6]; muv[2 * i + 1] = (float)matches[i][7];
+  }
+  defslam_sft_problem p = {};
+  p.tmpl = cache.plan;
+  p.node_xyz = node_xyz.data();
+  p.n_matches = M;
+  p.match_nodes = mnodes.data(); p.match_bary = mbary.data(); p.match_uv = muv.data();
+  p.fx = pFrame->fx; p.fy = pFrame->fy; p.cx = pFrame->cx; p.cy = pFrame->cy;
+  pFrame->getPoseRowMajor(p.T_cw);
+  p.reg_lap = RegLap; p.reg_inex = RegInex; p.reg_temp = RegTemp;
+  p.max_iterations = 50;
+  p.matches_given = 1;
+  p.curv_edge_len = curvEdgeLen;
+  std::vector<uint8_t> outl((size_t)std::max(M, 1)), role((size_t)n_nodes);
+  defslam_sft_result r = {};
+  r.node_xyz_out = node_out.data(); r.outlier_out = outl.data(); r.node_role_out = role.data();
+  if (defslam_sft_solve(&p, &r) != DEFSLAM_OK) return 0;
+  for (int m = 0; m < M; m++) outlier.push_back(outl[m] != 0);                   /* :806-818 */
+  /* roles: every matched node was setViewed (:647), the curvature centres setLocal afterwards (:711) */
+  for (int i = 0; i < n_nodes; i++) role[i] = (role[i] & 1) ? ((cache.nodes[i]->isBoundary()) ? 1 : 2) : 0;
+  write_back_nodes(cache, node_out, role);                                       /* :822 */
+  return 0;
+}
+
+/* The drop-in.  FrameT/MapT/... are the reference's types (or the test mocks). */
+template <class FrameT, class MapT, class TemplateT, class NodeT, class DefMapPointT>
+int DefPoseOptimization(FrameT *pFrame, MapT *mMap, PlanCache<TemplateT, NodeT> &cache, double RegLap = 5000,
+                        double RegInex = 5000, double RegTemp = 0, unsigned int NeighboursLayers = 1) {
+  if (!ensure_plan(mMap, cache)) return 0; /* (re)built when DefMap::createTemplate swapped the template */
   const int n_nodes = (int)cache.nodes.size();
   std::vector<double> node_xyz(3 * (size_t)n_nodes), node_out(3 * (size_t)n_nodes);
   for (int i = 0; i < n_nodes; i++) {
@@ -170,13 +246,7 @@ int DefPoseOptimization(FrameT *pFrame, MapT *mMap, PlanCache<TemplateT, NodeT> 
   for (int m = 0; m < M; m++) pFrame->mvbOutlier[midx[m]] = outl[m] != 0;        /* :515-537 */
   pFrame->repError = r.rep_error;                                              /* :559 */
   pFrame->SetPoseRowMajor(r.T_cw_out);                                         /* :562-566 */
-  for (int i = 0; i < n_nodes; i++) {                                          /* updateNodes :955-968 */
-    NodeT *nd = cache.nodes[i];
-    nd->setXYZ(node_out[3 * i], node_out[3 * i + 1], node_out[3 * i + 2]);
-    nd->resetRole();
-    if (role[i] & 1) nd->setViewed();
-    else if (role[i] & 2) nd->setLocal();
-  }
+  write_back_nodes(cache, node_out, role);                                     /* updateNodes :955-968 */
   for (auto *pMP : mMap->GetAllMapPoints())                                    /* :570-576 */
     if (static_cast<DefMapPointT *>(pMP)->getFacet()) static_cast<DefMapPointT *>(pMP)->RecalculatePosition();
   return r.n_inliers;                                                          /* :577 */

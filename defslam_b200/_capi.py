@@ -58,6 +58,8 @@ class SftProblem(C.Structure):
         ("reg_temp", C.c_double),
         ("neighbour_layers", C.c_int32),
         ("max_iterations", C.c_int32),
+        ("matches_given", C.c_int32),
+        ("curv_edge_len", C.c_double),
     ]
 
 
@@ -261,6 +263,7 @@ PROTOTYPES = {
     "defslam_schwarp_fit_batched": (
         C.c_int, [C.c_int32, C.POINTER(SchwarpProblem), C.POINTER(DiffProp), C.c_int32]),
     "defslam_schwarp_evaluate": (C.c_int, [C.POINTER(SchwarpProblem), c_double_p, c_double_p]),
+    "defslam_schwarp_initial": (C.c_int, [C.POINTER(SchwarpProblem), c_uint8_p, c_double_p]),
     "defslam_normals_batched": (C.c_int, NORMALS_ARGS),
     "defslam_polysolver_coefficients": (C.c_int, POLY_ARGS),
     "defslam_sfn_solve": (C.c_int, [C.POINTER(SfnProblem)]),

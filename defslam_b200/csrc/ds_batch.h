@@ -58,8 +58,9 @@ struct BatchMarshal {
       const int rc = resolve(p[i], &hv, &dv);
       if (rc != 0) return rc;
       hvs[i] = hv;
-      if (!p[i].node_xyz || p[i].n_matches < 0 || p[i].n_frame_keypoints <= 0) return DEFSLAM_EBADARG;
-      if (p[i].n_matches > 0 && (!p[i].match_nodes || !p[i].match_bary || !p[i].match_uv || !p[i].match_inv_sigma2))
+      if (!p[i].node_xyz || p[i].n_matches < 0 || (p[i].n_frame_keypoints <= 0 && !p[i].matches_given)) return DEFSLAM_EBADARG;
+      if (p[i].n_matches > 0 && (!p[i].match_nodes || !p[i].match_bary || !p[i].match_uv ||
+                                 (!p[i].match_inv_sigma2 && !p[i].matches_given)))
         return DEFSLAM_EBADARG;
       ProbSlot &s = slots[i];
       const size_t n = hv->n_nodes, M = p[i].n_matches;
@@ -90,6 +91,9 @@ struct BatchMarshal {
       v.n_kp = p[i].n_frame_keypoints;
       v.max_it = p[i].max_iterations;
       v.layers = p[i].neighbour_layers;
+      v.variant = p[i].matches_given ? 1 : 0;
+      v.curv_len = p[i].curv_edge_len;
+      if (v.variant == 1 && !(p[i].curv_edge_len > 0.0)) return DEFSLAM_EBADARG;
       v.trace_cap = s.trace_cap;
       v.fx = p[i].fx; v.fy = p[i].fy; v.cx = p[i].cx; v.cy = p[i].cy;
       v.reg_lap = p[i].reg_lap; v.reg_inex = p[i].reg_inex; v.reg_temp = p[i].reg_temp;
@@ -159,7 +163,8 @@ struct BatchMarshal {
         memcpy(b + s.o_bary, p[i].match_bary, 3 * M * sizeof(double));
         memcpy(b + s.o_mnodes, p[i].match_nodes, 3 * M * sizeof(int));
         memcpy(b + s.o_uv, p[i].match_uv, 2 * M * sizeof(float));
-        memcpy(b + s.o_isig, p[i].match_inv_sigma2, M * sizeof(float));
+        if (p[i].match_inv_sigma2) memcpy(b + s.o_isig, p[i].match_inv_sigma2, M * sizeof(float));
+        else memset(b + s.o_isig, 0, M * sizeof(float));
       }
     }
   }

@@ -58,6 +58,14 @@ struct DevCtx {
   ~DevCtx();
 };
 
+/* Entry points that take a device ordinal switch to it (get_ctx) for their CUDA calls; this guard puts the
+ * caller's current device back when the entry point returns. */
+struct DeviceGuard {
+  int prev = -1;
+  DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; } }
+  ~DeviceGuard() { if (prev >= 0) { int cur = -1; if (cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev); } }
+};
+
 /* context of the calling thread on `device` (-1: current device); nullptr when
  * no usable CUDA device exists -- callers return DEFSLAM_ECUDA, there is no
  * CPU fallback. */

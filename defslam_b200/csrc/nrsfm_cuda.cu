@@ -81,6 +81,34 @@ __global__ void schwarp_rows_kernel(SchwarpProb P, int nrows, double *r, double 
     schwarp_row(P, row, r, J);
 }
 
+/* NaN scrub of the first nscrub control coordinates (DefORBmatcher.cc:149-154) */
+__global__ void schwarp_scrub_kernel(double *x, int nscrub) {
+  for (int i = threadIdx.x; i < nscrub; i += blockDim.x)
+    if (isnan(x[i])) x[i] = 0.0;
+}
+
+/* ceres::Problem::Evaluate residuals of the one Warp block under HuberLoss(5.77) (Corrector: scale sqrt(rho')),
+ * then the reference's test residuals[2i]^2 + residuals[2i+1]^2 > 20 (DefORBmatcher.cc:166-180).  One CTA; the
+ * block's squared norm is summed in a fixed order. */
+__global__ void schwarp_initial_filter_kernel(const double *r, int n, uint8_t *keep, double *err) {
+  __shared__ double part[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) s += r[i] * r[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+    __syncthreads();
+  }
+  const double sq = part[0], delta = 5.77;
+  const double rho1 = sq <= delta * delta ? 1.0 : delta / sqrt(sq);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double e = rho1 * (r[2 * i] * r[2 * i] + r[2 * i + 1] * r[2 * i + 1]);
+    err[i] = e;
+    keep[i] = e > 20.0 ? 0 : 1;
+  }
+}
+
 __global__ void normals_kernel(NormalsProb P) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n_points; i += gridDim.x * blockDim.x) normals_point(P, i);
 }
@@ -176,6 +204,7 @@ int defslam_schwarp_fit_batched(int32_t nprob, const defslam_schwarp_problem *p,
     if (p[i].bbs.nptsv > nv) nv = p[i].bbs.nptsv;
     if (p[i].n_matches > nmax) nmax = p[i].n_matches;
   }
+  DeviceGuard device_guard_;
   DevCtx *ctx = get_ctx(device);
   if (!ctx) return DEFSLAM_ECUDA;
   if (nprob == 0) return DEFSLAM_OK;
@@ -226,7 +255,7 @@ int defslam_schwarp_fit_batched(int32_t nprob, const defslam_schwarp_problem *p,
   }
   *(int *)(h + o_counter) = 0;
   DS_CUDA_TRY(cudaMemcpyAsync(d_in, h, in.total + x_total, cudaMemcpyHostToDevice, ctx->stream));
-  DS_CUDA_TRY(cudaFuncSetAttribute(schwarp_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DS_CUDA_TRY(cudaFuncSetAttribute(schwarp_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
   DS_CUDA_TRY(cudaEventRecord(ctx->e0, ctx->stream));
   schwarp_fit_kernel<<<grid, NRSFM_THREADS, smem, ctx->stream>>>((const SchwarpProb *)(d_in + o_probs), nprob,
                                                                  (uint8_t *)S.ws.p, ws_stride, nu, nv, nmax,
@@ -299,6 +328,54 @@ int defslam_schwarp_evaluate(const defslam_schwarp_problem *p, double *r, double
   DS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   memcpy(r, h + o_r, 8 * NR);
   if (J) memcpy(J, h + o_J, 8 * NR * NP);
+  return DEFSLAM_OK;
+}
+
+/* DefORBmatcher::CalculateInitialSchwarp (DefORBmatcher.cc:111-187): Warp::initialize on the device (the fit
+ * kernel with zero trust-region steps), then NaN scrub, data residuals, loss corrector and the > 20 filter in two
+ * more launches. */
+int defslam_schwarp_initial(const defslam_schwarp_problem *p, uint8_t *keep_out, double *err_out) {
+  if (!p || !keep_out || !bbs_ok(&p->bbs, 2) || p->n_matches <= 0 || !p->kp1 || !p->kp2 || !p->inv_sigma || !p->x)
+    return DEFSLAM_EBADARG;
+  defslam_schwarp_problem q = *p;
+  q.initialize = 1;
+  q.max_iterations = 0;
+  defslam_diffprop dp;
+  memset(&dp, 0, sizeof(dp));
+  int rc = defslam_schwarp_fit_batched(1, &q, &dp, -1); /* x <- (C'C + lambda B)^-1 C' q2 */
+  if (rc) return rc;
+  DevCtx *ctx = get_ctx(-1);
+  if (!ctx) return DEFSLAM_ECUDA;
+  const size_t n = p->n_matches, NC = (size_t)p->bbs.nptsu * p->bbs.nptsv, NP = 2 * NC;
+  Packer in, outp;
+  const size_t o_kp1 = in.add(8 * n + 8), o_kp2 = in.add(8 * n + 8), o_sig = in.add(4 * n + 8);
+  const size_t o_x = outp.add(8 * NP), o_keep = outp.add(n + 8), o_err = outp.add(8 * n), o_r = outp.add(16 * n);
+  Scratch &S = tl_scratch(ctx->device);
+  if ((rc = S.host.ensure(in.total + outp.total)) || (rc = S.dev.ensure(in.total + outp.total))) return rc;
+  uint8_t *h = (uint8_t *)S.host.p, *d_in = (uint8_t *)S.dev.p, *d_out = d_in + in.total, *h_out = h + in.total;
+  memcpy(h + o_kp1, p->kp1, 8 * n); memcpy(h + o_kp2, p->kp2, 8 * n); memcpy(h + o_sig, p->inv_sigma, 4 * n);
+  memcpy(h_out + o_x, p->x, 8 * NP);
+  DS_CUDA_TRY(cudaMemcpyAsync(d_in, h, in.total + o_keep, cudaMemcpyHostToDevice, ctx->stream));
+  SchwarpProb P;
+  memset(&P, 0, sizeof(P));
+  P.bbs = to_view(&p->bbs);
+  P.n = p->n_matches;
+  P.kp1 = (const float *)(d_in + o_kp1); P.kp2 = (const float *)(d_in + o_kp2); P.isig = (const float *)(d_in + o_sig);
+  P.lambda = p->lambda; P.fx = p->fx; P.fy = p->fy;
+  P.x = (double *)(d_out + o_x);
+  int nscrub = 2 * p->bbs.nptsu * p->bbs.nptsu; /* quirk C9: NCu*NCu*2, not NCu*NCv*2 */
+  if (nscrub > (int)NP) nscrub = (int)NP;
+  schwarp_scrub_kernel<<<1, 256, 0, ctx->stream>>>(P.x, nscrub);
+  schwarp_rows_kernel<<<grid_for((int)(2 * n), ctx->sm_count), 256, 0, ctx->stream>>>(P, (int)(2 * n), (double *)(d_out + o_r), nullptr);
+  schwarp_initial_filter_kernel<<<1, 256, 0, ctx->stream>>>((const double *)(d_out + o_r), (int)n, d_out + o_keep,
+                                                            (double *)(d_out + o_err));
+  DS_CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(3);
+  DS_CUDA_TRY(cudaMemcpyAsync(h_out, d_out, o_r, cudaMemcpyDeviceToHost, ctx->stream));
+  DS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  memcpy(p->x, h_out + o_x, 8 * NP);
+  memcpy(keep_out, h_out + o_keep, n);
+  if (err_out) memcpy(err_out, h_out + o_err, 8 * n);
   return DEFSLAM_OK;
 }
 
@@ -431,6 +508,7 @@ int defslam_sfn_solve_batched(int32_t nprob, const defslam_sfn_problem *p, int32
     if (p[i].bbs.nptsv > nv) nv = p[i].bbs.nptsv;
     if (p[i].n_normals > nmax) nmax = p[i].n_normals;
   }
+  DeviceGuard device_guard_;
   DevCtx *ctx = get_ctx(device);
   if (!ctx) return DEFSLAM_ECUDA;
   if (nprob == 0) return DEFSLAM_OK;
@@ -472,7 +550,7 @@ int defslam_sfn_solve_batched(int32_t nprob, const defslam_sfn_problem *p, int32
   *(int *)(h + o_counter) = 0;
   DS_CUDA_TRY(cudaMemcpyAsync(d_in, h, in.total, cudaMemcpyHostToDevice, ctx->stream));
   DS_CUDA_TRY(cudaMemsetAsync(d_out, 0xff, outp.total, ctx->stream));
-  DS_CUDA_TRY(cudaFuncSetAttribute(sfn_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DS_CUDA_TRY(cudaFuncSetAttribute(sfn_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
   DS_CUDA_TRY(cudaEventRecord(ctx->e0, ctx->stream));
   sfn_solve_kernel<<<grid, NRSFM_THREADS, smem, ctx->stream>>>((const SfnProb *)(d_in + o_probs), nprob,
                                                                (uint8_t *)S.ws.p, ws_stride, nu, nv, nmax, n_in_smem,
@@ -542,6 +620,7 @@ int defslam_sim3_register_batched(int32_t nprob, const defslam_sim3_problem *p, 
   if (nprob < 0 || (nprob > 0 && (!p || !out))) return DEFSLAM_EBADARG;
   for (int i = 0; i < nprob; i++)
     if (p[i].n_points <= 0 || !p[i].pts1 || !p[i].pts2 || p[i].max_iterations < 0 || !(p[i].huber > 0)) return DEFSLAM_EBADARG;
+  DeviceGuard device_guard_;
   DevCtx *ctx = get_ctx(device);
   if (!ctx) return DEFSLAM_ECUDA;
   if (nprob == 0) return DEFSLAM_OK;
@@ -612,7 +691,7 @@ int defslam_scale_min_median(int32_t n, const float *mono_xyz, const float *ster
   DS_CUDA_TRY(cudaMemcpyAsync(d_in, h, in.total, cudaMemcpyHostToDevice, ctx->stream));
   const size_t smem = 4 * (size_t)n;
   if (smem > 48 * 1024)
-    DS_CUDA_TRY(cudaFuncSetAttribute(scale_min_median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DS_CUDA_TRY(cudaFuncSetAttribute(scale_min_median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
   scale_min_median_kernel<<<1, 512, smem, ctx->stream>>>(n, (const float *)(d_in + om), (const float *)(d_in + os), seed,
                                                          (float *)(d_out + oo));
   DS_CUDA_TRY(cudaGetLastError());

@@ -60,6 +60,8 @@ struct ProbView {
   int trace_cap;
   int e_in_smem;
   int x_in_smem;           /* node positions / LM step in shared memory (else in the global workspace) */
+  int variant;             /* 1: the matches-given overload (DefOptimizer.cc:582-837) */
+  double curv_len;         /* variant 1: EdgeMeanCurvature::lenghtEdge_ (quirk C8) */
   int row_nt;              /* > 0: row-owner factorisation (sft_rows.h) with this many tiles per block row; 0: sliding window */
   double fx, fy, cx, cy;
   double reg_lap, reg_inex, reg_temp;
@@ -224,6 +226,7 @@ struct Ctx {
   double info_ref, info_curv, info_str;
   double hub_delta, hub_dsqr;
   double inv_n;
+  double info_uniform;     /* > 0: every reprojection edge has this information (matches-given overload) */
   long long *prof;  /* optional per-phase cycle counters (global), CTA 0 only */
   long long prof_last;
   uint32_t ph[16];  /* phase parity of each mbarrier */
@@ -367,7 +370,8 @@ DS_FN_NOINLINE int prologue(const Team team, Ctx &cx) {
   /* OptLap = Viewed U ring1(Viewed)  (DefOptimizer.cc:384-406, quirk C3) */
   DS_FOR(v, n) {
     int fr = viewed_ptr(c)[v];
-    if (!fr && pb.layers >= 1)
+    if (pb.variant == 1) fr = 1; /* every node is free (DefOptimizer.cc:615-620) */
+    else if (!fr && pb.layers >= 1)
       for (int k = pl.nbr_ptr[v]; k < pl.nbr_ptr[v + 1]; k++) fr |= viewed_ptr(c)[pl.nbr_idx[k]];
     freev_ptr(c)[v] = (uint8_t)fr;
   }
@@ -408,7 +412,14 @@ DS_FN_NOINLINE int prologue(const Team team, Ctx &cx) {
     c.info_ref = pb.reg_temp / pow(pl.median_len, 2);
     c.info_curv = n_optlap > 0 ? pb.reg_lap / (double)n_optlap : 0.0;
     c.info_str = n_str > 0 ? pb.reg_inex / (double)n_str : 0.0;
-    const float deltaMono = (float)sqrt(5.991);
+    c.info_uniform = 0.0;
+    float deltaMono = (float)sqrt(5.991);
+    if (pb.variant == 1) { /* DefOptimizer.cc:582-837 */
+      c.info_ref = 0.0;                                              /* temporal edges never added (:688) */
+      c.info_curv = n_viewed > 0 ? pb.reg_lap / (double)n_viewed : 0.0; /* OptLap = ViewedNodes (:693,:755) */
+      c.info_uniform = 1.0 / (double)(M > 0 ? M : 1);                              /* Identity / double(matches.size()) (:655) */
+      deltaMono = 0.5f;                                              /* :625 */
+    }
     c.hub_delta = (double)deltaMono;
     c.hub_dsqr = (double)(float)(c.hub_delta * c.hub_delta);  // RobustKernelHuber::dsqr is a float (robust_kernel_impl.h:84)
   }
@@ -437,7 +448,9 @@ DS_FN void reproj_error(const Ctx &c, const double *x, const Pose &P, int m, dou
   e[1] = (double)pb.match_uv[2 * m + 1] - v;
 }
 
-DS_FN double match_info(const Ctx &c, int m) { return (double)c.pb.match_isig[m] / (double)c.pb.n_kp; }
+DS_FN double match_info(const Ctx &c, int m) {
+  return c.info_uniform > 0.0 ? c.info_uniform : (double)c.pb.match_isig[m] / (double)c.pb.n_kp;
+}
 
 /* curvature residual of centre i: delta = x_i - sum(w x_j)/W  (sft_types.h:257-291) */
 DS_FN double curv_residual(const Ctx &c, const double *x, int i, double d[3], double &nrm) {
@@ -566,11 +579,15 @@ DS_FN_NOINLINE double eval_state(const Team team, Ctx &cx) {
                    e2 = x[3 * v + 2] - pl.rest[3 * v + 2];
       chi += (e0 * e0 + e1 * e1 + e2 * e2) * c.info_ref;
     }
-    const bool active = freev_ptr(c)[v] && !pl.boundary[v] && (pl.nbr_ptr[v + 1] > pl.nbr_ptr[v]);
+    /* curvature centres: OptLap, which is the free set -- or the viewed nodes in the matches-given overload */
+    const bool in_lap = pb.variant == 1 ? viewed_ptr(c)[v] != 0 : freev_ptr(c)[v] != 0;
+    const bool active = in_lap && !pl.boundary[v] && (pl.nbr_ptr[v + 1] > pl.nbr_ptr[v]);
     if (active) {
       double d[3], nrm;
       const double r = curv_residual(c, x, v, d, nrm);
-      const double g = c.info_curv * pl.inv_len2[v];
+      /* deg(v) copies of the residual, each divided by its edge length -- or all by the caller's lenghtEdge_ (C8) */
+      const double g = c.info_curv * (pb.variant == 1 ? (double)(pl.nbr_ptr[v + 1] - pl.nbr_ptr[v]) / (pb.curv_len * pb.curv_len)
+                                                       : pl.inv_len2[v]);
       chi += r * r * g;
       if (store) {
         const double inv = nrm < 1E-15 ? 0.0 : 1.0 / nrm;
@@ -1792,7 +1809,8 @@ DS_FN_NOINLINE void finalize(const Team team, Ctx &cx, bool last_rejected, int i
     reproj_error(c, xl, Pl, m, e, Pc);
     const double info = match_info(c, m);
     const float chi2 = (float)(e[0] * info * e[0] + e[1] * info * e[1]);
-    const bool out = chi2 > 5.991;
+    /* matches-given overload: outlier <=> deltaMono < |e| (DefOptimizer.cc:806-818) */
+    const bool out = pb.variant == 1 ? c.hub_delta < sqrt(pow(e[0], 2) + pow(e[1], 2)) : chi2 > 5.991;
     if (pb.out_outlier) pb.out_outlier[m] = out ? 1 : 0;
     if (out) nbad++;
     else {

@@ -185,10 +185,10 @@ static int batch_load(defslam_sft_batch *B, int nprob, const defslam_sft_problem
   const bool xs = !B->bm.any_x_global;
   int occ = 0;
   if (xs) {
-    DS_CUDA_TRY(cudaFuncSetAttribute(sft_lm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, B->smem_bytes));
+    DS_CUDA_TRY(cudaFuncSetAttribute(sft_lm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin)); /* per-device attribute: always the maximum, so concurrent batches of different sizes cannot undercut each other */
     DS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sft_lm_kernel<true>, SFT_THREADS, B->smem_bytes));
   } else {
-    DS_CUDA_TRY(cudaFuncSetAttribute(sft_lm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B->smem_bytes));
+    DS_CUDA_TRY(cudaFuncSetAttribute(sft_lm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
     DS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sft_lm_kernel<false>, SFT_THREADS, B->smem_bytes));
   }
   if (occ < 1) return DEFSLAM_ETOOLARGE;
@@ -287,10 +287,12 @@ static int batch_download(defslam_sft_batch *B) {
 }
 
 static defslam_sft_batch *tl_batch(DevCtx *ctx, int which = 0) {
-  static thread_local std::map<int, std::unique_ptr<defslam_sft_batch>> tl;
-  auto &b = tl[ctx->device * 4 + which];
-  if (!b) { b.reset(new defslam_sft_batch); b->ctx = ctx; }
-  return b.get();
+  /* raw pointers, never deleted: a thread_local destructor would call cudaFree / cudaFreeHost at thread or
+   * process exit, possibly after the CUDA runtime shut down (same reason as DevCtx::~DevCtx) */
+  static thread_local std::map<int, defslam_sft_batch *> tl;
+  defslam_sft_batch *&b = tl[ctx->device * 4 + which];
+  if (!b) { b = new defslam_sft_batch; b->ctx = ctx; }
+  return b;
 }
 
 /* Large host batches are cut into chunks that ping-pong between two batch objects: while the
@@ -355,6 +357,7 @@ extern "C" {
 int defslam_template_create(const defslam_template_desc *desc, int device, defslam_template **out) {
   if (!desc || !out) return DEFSLAM_EBADARG;
   *out = nullptr;
+  DeviceGuard device_guard_;
   DevCtx *ctx = get_ctx(device);
   if (!ctx) return DEFSLAM_ECUDA;
   return template_make(desc, ctx, out);
@@ -378,6 +381,7 @@ int defslam_template_info(const defslam_template *t, int32_t *bandwidth, int32_t
 
 int defslam_sft_solve_batched(int32_t nprob, const defslam_sft_problem *p, defslam_sft_result *r, int device) {
   if (nprob < 0 || (nprob > 0 && (!p || !r))) return DEFSLAM_EBADARG;
+  DeviceGuard device_guard_;
   DevCtx *ctx = get_ctx(device);
   if (!ctx) return DEFSLAM_ECUDA;
   if (nprob == 0) return DEFSLAM_OK;
@@ -427,6 +431,7 @@ int defslam_sft_normal_equations(const defslam_sft_problem *p, double *H_dense, 
 int defslam_sft_batch_create(int32_t nprob, const defslam_sft_problem *p, int device, defslam_sft_batch **out) {
   if (!out || nprob <= 0 || !p) return DEFSLAM_EBADARG;
   *out = nullptr;
+  DeviceGuard device_guard_;
   DevCtx *ctx = get_ctx(device);
   if (!ctx) return DEFSLAM_ECUDA;
   std::unique_ptr<defslam_sft_batch> B(new defslam_sft_batch);

@@ -230,7 +230,7 @@ class Api:
         self.prefix = prefix
         if prefix != "defslam_":
             P = _capi.PROTOTYPES
-            for name in ("schwarp_fit", "schwarp_evaluate", "normals_batched", "polysolver_coefficients",
+            for name in ("schwarp_fit", "schwarp_evaluate", "schwarp_initial", "normals_batched", "polysolver_coefficients",
                          "sfn_solve", "sfn_system", "schwarp_fit_batched", "sfn_solve_batched",
                          "sim3_register_batched", "scale_min_median", "new_map_points"):
                 if hasattr(self.lib, prefix + name):
@@ -263,6 +263,16 @@ class Api:
         p = case.problem(x)
         self._check("schwarp_init", self._f("schwarp_init")(C.byref(p), _capi.as_ptr(x, C.c_double)))
         return x
+
+    def schwarp_initial(self, case: SchwarpCase):
+        """DefORBmatcher::CalculateInitialSchwarp (DefORBmatcher.cc:111-187): (x0, keep[n], err[n])"""
+        x = np.zeros(2 * case.NC)
+        keep = np.zeros(case.n, np.uint8)
+        err = np.zeros(case.n)
+        p = case.problem(x)
+        self._check("schwarp_initial", self._f("schwarp_initial")(
+            C.byref(p), _capi.as_ptr(keep, C.c_uint8), _capi.as_ptr(err, C.c_double)))
+        return x, keep, err
 
     def schwarp_fit(self, case: SchwarpCase) -> DiffPropOut:
         out = DiffPropOut(case.n)

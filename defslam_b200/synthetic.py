@@ -252,6 +252,8 @@ class SftFrame:
     reg_temp: float = 0.05
     neighbour_layers: int = 2
     max_iterations: int = 50
+    matches_given: int = 0        # 1: the matches-given overload (DefOptimizer.h:58-61)
+    curv_edge_len: float = 0.0    # its lenghtEdge_ (quirk C8)
     gt_nodes: np.ndarray | None = None
     gt_T_cw: np.ndarray | None = None
     is_gross_outlier: np.ndarray | None = None
@@ -277,6 +279,8 @@ class SftFrame:
         p.reg_lap, p.reg_inex, p.reg_temp = self.reg_lap, self.reg_inex, self.reg_temp
         p.neighbour_layers = self.neighbour_layers
         p.max_iterations = self.max_iterations
+        p.matches_given = self.matches_given
+        p.curv_edge_len = self.curv_edge_len
         return p
 
 

@@ -132,6 +132,19 @@ typedef struct defslam_sft_problem {
   double reg_temp;                /* RegTemp                                    */
   int32_t neighbour_layers;       /* NeighboursLayers (>=1 behaves as 1, C3)    */
   int32_t max_iterations;         /* optimizer.optimize(50) (:513); <=0 -> 50   */
+  /* matches_given = 1 selects the second overload,
+   *   DefPoseOptimization(const vector<vector<double>> &matches, Frame*, Map*, vector<bool> &outlier,
+   *                       RegLap, RegInex, RegTemp)      DefOptimizer.h:58-61, DefOptimizer.cc:582-837
+   * whose graph differs: every node is free (:615-620); Omega = I / #matches (:655) and the Huber width
+   * is 0.5 (:625); the temporal edges are built but never added (:676-689); curvature edges exist for the
+   * non-boundary VIEWED nodes only, one per neighbour, information RegLap / #viewed (:693-758); stretch
+   * edges for ALL mesh edges, information RegInex / #edges (:764-797); outlier <=> |e| > 0.5 px (:806-818).
+   * match_inv_sigma2 / n_frame_keypoints / neighbour_layers are ignored.  The reference leaves
+   * EdgeMeanCurvature::lenghtEdge_ uninitialised there (no setDistanceEdges, quirk C8): the caller says
+   * what value it stands for in curv_edge_len (> 0).  The reference does not write the pose back in this
+   * overload (only updateNodes, :822); T_cw_out holds the optimised pose all the same. */
+  int32_t matches_given;
+  double curv_edge_len;
 } defslam_sft_problem;
 
 typedef struct defslam_sft_result {
@@ -288,6 +301,21 @@ int defslam_schwarp_fit(const defslam_schwarp_problem *p, defslam_diffprop *out)
 /* nprob independent keyframe pairs, one CTA each. device: CUDA ordinal, -1 = current */
 int defslam_schwarp_fit_batched(int32_t nprob, const defslam_schwarp_problem *p,
                                 defslam_diffprop *out, int32_t device);
+
+/* Initial warp between two keyframes and the match filter that goes with it.
+ * replaces: DefORBmatcher::CalculateInitialSchwarp  Modules/Matching/DefORBmatcher.cc:111-187
+ *           (the first half of DefORBmatcher::findbyWarp :47-71; the second half is defslam_search_by_schwarp)
+ *   x <- Warps::Warp::initialize (:146-147), NaN entries among the first 2*NCu*NCu of them set to 0 (:149-154;
+ *   the reference scrubs NCu*NCu*2 = 338 of its 390 entries, quirk C9);
+ *   residuals of the Warp cost at x as ceres::Problem::Evaluate returns them with HuberLoss(5.77) on the block
+ *   (:156-169; default EvaluateOptions apply the loss: every residual is scaled by sqrt(rho'), rho' = 1 if the
+ *   block's squared norm s <= 5.77^2 else 5.77/sqrt(s));
+ *   match i is dropped when residuals[2i]^2 + residuals[2i+1]^2 > 20 (:171-186).  Kept bug-compatible: the
+ *   residual vector is laid out [all x residuals; all y residuals] (Schwarp.cc:275-280), so entries 2i, 2i+1 are
+ *   the x (i < n/2) or y residuals of matches 2i, 2i+1 (mod n), not the two residuals of match i.
+ * p->fx, p->fy: as handed to Warps::Warp here, (KF->fx, KF->fy) (:159-160).  p->initialize / max_iterations are
+ * ignored.  p->x: out [2*NC].  keep_out: [n] 1 = match kept.  err_out: [n] the tested quantity, or NULL. */
+int defslam_schwarp_initial(const defslam_schwarp_problem *p, uint8_t *keep_out, double *err_out);
 
 /* Residuals / Jacobian of the Schwarp cost at p->x, before the loss corrector (parity hook).
  * replaces: Warp::Evaluate Schwarp.cc:235-303 + Schwarzian::Evaluate :368-543

@@ -347,7 +347,7 @@ void build_ref_graph(RefGraph &R, const Graph &g, const defslam_sft_problem *p) 
   for (int v = 0; v < n; v++)
     if (g.optlap[v]) { R.nodes[v]->setHessianIndex(hi++); R.opt._ivMap.push_back(R.nodes[v]); }
 
-  const float deltaMono = sqrt(5.991);  // :286
+  const float deltaMono = g.variant ? 0.5 : sqrt(5.991);  // :286 ; :625 in the matches-given overload
   for (int i = 0; i < g.n_rep; i++) {   // :305-357
     const EdgeReproj &o = g.rep[i];
     Eigen::Matrix<double, 2, 1> obs;
@@ -360,9 +360,10 @@ void build_ref_graph(RefGraph &R, const Graph &g, const defslam_sft_problem *p) 
     for (int k = 0; k < 3; k++) e->setVertex(k + 1, R.nodes[o.v[k]]);
     e->setBarycentric(bary);
     e->setMeasurement(obs);
-    const float invSigma2 = p->match_inv_sigma2[o.m];
+    const float invSigma2 = g.variant ? 0.f : p->match_inv_sigma2[o.m];
     const int N = p->n_frame_keypoints;
-    e->setInformation(Eigen::Matrix2d::Identity() * invSigma2 / N);
+    if (g.variant) e->setInformation(Eigen::Matrix2d::Identity() / double(p->n_matches));  // :655
+    else e->setInformation(Eigen::Matrix2d::Identity() * invSigma2 / N);
     g2o::RobustKernelHuber *rk = new g2o::RobustKernelHuber;
     R.kernels.push_back(rk);
     e->setRobustKernel(rk);
@@ -398,7 +399,7 @@ void build_ref_graph(RefGraph &R, const Graph &g, const defslam_sft_problem *p) 
     InitialMeanCurvature << o.kappa0;
     e->setMeasurement(InitialMeanCurvature);
     e->computeError();
-    e->setInformation(p->reg_lap * Eigen::Vector1D::Identity() / (double)(size_t)g.n_optlap);
+    e->setInformation(p->reg_lap * Eigen::Vector1D::Identity() / (double)(size_t)g.n_curv_den);
     R.curv.push_back(e);
     R.opt._activeEdges.push_back(e);
   }
@@ -534,12 +535,15 @@ int ref_sft_solve(const defslam_sft_problem *p, defslam_sft_result *r) {
     lam_prev = lm.currentLambda();
     ++cjIterations;
   }
+  const float deltaMonoV = 0.5;
   // outliers, reprojection error: DefOptimizer.cc:515-559
   int nBad = 0;
   std::vector<uint8_t> outl(g.n_rep > 0 ? g.n_rep : 1, 0);
   for (int i = 0; i < g.n_rep; i++) {
     const float chi2 = R.rep[i]->chi2();
-    if (chi2 > 5.991) { outl[i] = 1; nBad++; }
+    const double *a = R.rep[i]->errorData();
+    const bool out = g.variant ? (deltaMonoV < sqrt(pow(a[0], 2) + pow(a[1], 2))) : (chi2 > 5.991);  // :806-818
+    if (out) { outl[i] = 1; nBad++; }
   }
   double sumError = 0.0;
   unsigned cnt = 0;

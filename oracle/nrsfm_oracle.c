@@ -251,6 +251,37 @@ typedef struct {
 #define LM_MIN_REL_DECREASE 1e-3
 #define LM_MAX_INVALID 5
 
+/* DefORBmatcher::CalculateInitialSchwarp  Modules/Matching/DefORBmatcher.cc:111-187 */
+int oracle_schwarp_initial(const defslam_schwarp_problem *p, uint8_t *keep_out, double *err_out) {
+  const defslam_bbs *s = &p->bbs;
+  const int NC = s->nptsu * s->nptsv, n = p->n_matches, NP = 2 * NC, NR = 2 * n + 4 * NC;
+  if (s->valdim != 2 || n <= 0 || !p->x || !keep_out) return DEFSLAM_EBADARG;
+  /* x[i] = 0 for the first NCu*NCu*2 entries (:138-142) is overwritten by initialize (:146-147) */
+  int rc = oracle_schwarp_init(p, p->x);
+  if (rc) return rc;
+  int nscrub = s->nptsu * s->nptsu * 2; /* :149 -- NCu*NCu, quirk C9 */
+  if (nscrub > NP) nscrub = NP;
+  for (int i = 0; i < nscrub; i++)
+    if (isnan(p->x[i])) p->x[i] = 0.0;
+  double *r = (double *)malloc(sizeof(double) * NR);
+  rc = oracle_schwarp_evaluate(p, r, NULL);
+  if (rc) { free(r); return rc; }
+  /* problem.Evaluate with default options applies HuberLoss(5.77) to the block: Ceres' Corrector scales the
+   * residuals by sqrt(rho'(s)), s = squared norm of the block (rho'' <= 0 for Huber: no alpha correction) */
+  double sq = 0.0;
+  for (int i = 0; i < 2 * n; i++) sq += r[i] * r[i];
+  const double delta = 5.77;
+  const double rho1 = sq <= delta * delta ? 1.0 : delta / sqrt(sq);
+  for (int i = 0; i < n; i++) {
+    /* residuals[2*i]^2 + residuals[2*i+1]^2 on the [x block; y block] layout (:171-176) */
+    const double e = rho1 * (r[2 * i] * r[2 * i] + r[2 * i + 1] * r[2 * i + 1]);
+    if (err_out) err_out[i] = e;
+    keep_out[i] = e > 20 ? 0 : 1;
+  }
+  free(r);
+  return 0;
+}
+
 int oracle_schwarp_fit(const defslam_schwarp_problem *p, defslam_diffprop *out) {
   const defslam_bbs *s = &p->bbs;
   const int NC = s->nptsu * s->nptsv, n = p->n_matches, NP = 2 * NC, NR = 2 * n + 4 * NC;

@@ -209,8 +209,10 @@ int oracle_graph_build(Graph *g, const defslam_sft_problem *p) {
   g->optlap = (uint8_t *)calloc(n, 1);
   g->idx = (int *)malloc(sizeof(int) * n);
 
-  /* const float deltaMono = sqrt(5.991);  :286 (float!) */
-  const float deltaMono = (float)sqrt(5.991);
+  g->variant = p->matches_given ? 1 : 0;
+  if (g->variant && !(p->curv_edge_len > 0.0)) return DEFSLAM_EBADARG;
+  /* const float deltaMono = sqrt(5.991);  :286 (float!) ; const float deltaMono = 0.5 in the overload :625 */
+  const float deltaMono = g->variant ? 0.5f : (float)sqrt(5.991);
   g->huber_delta = (double)deltaMono;
   g->huber_dsqr = (double)(float)(g->huber_delta * g->huber_delta); /* setDelta robust_kernel_impl.cpp:65-69 into "float dsqr" (robust_kernel_impl.h:84) */
 
@@ -229,8 +231,8 @@ int oracle_graph_build(Graph *g, const defslam_sft_problem *p) {
     }
     e->obs[0] = (double)p->match_uv[2 * m];
     e->obs[1] = (double)p->match_uv[2 * m + 1];
-    /* Identity * invSigma2 / N with float invSigma2, int N  :339-340 */
-    e->info = (double)p->match_inv_sigma2[m] / (double)N;
+    /* Identity * invSigma2 / N with float invSigma2, int N  :339-340 ; Identity / double(matches.size()) :655 */
+    e->info = g->variant ? 1.0 / (double)p->n_matches : (double)p->match_inv_sigma2[m] / (double)N;
   }
 
   /* ---- temporal edges for viewed nodes :363-382 */
@@ -239,6 +241,8 @@ int oracle_graph_build(Graph *g, const defslam_sft_problem *p) {
   g->ref = (EdgeRef *)calloc(n, sizeof(EdgeRef));
   for (int v = 0; v < n; v++)
     if (g->viewed[v]) {
+      g->n_viewed += g->variant; /* (counted below for the first overload) */
+      if (g->variant) continue;  /* the overload builds these edges but never adds them (:676-689) */
       EdgeRef *e = &g->ref[g->n_ref++];
       e->v = v;
       for (int c = 0; c < 3; c++) e->meas[c] = td->node_rest_xyz[3 * v + c];
@@ -247,7 +251,8 @@ int oracle_graph_build(Graph *g, const defslam_sft_problem *p) {
 
   /* ---- OptLap = Viewed U ring1(Viewed) :384-406 (layers>1 == 1, quirk C3) */
   memcpy(g->optlap, g->viewed, n);
-  if (p->neighbour_layers >= 1)
+  if (g->variant) memset(g->optlap, 1, n); /* every node is free (:615-620); g->optlap = the free set */
+  else if (p->neighbour_layers >= 1)
     for (int v = 0; v < n; v++)
       if (g->viewed[v])
         for (int k = td->nbr_ptr[v]; k < td->nbr_ptr[v + 1]; k++) g->optlap[td->nbr_idx[k]] = 1;
@@ -276,12 +281,15 @@ int oracle_graph_build(Graph *g, const defslam_sft_problem *p) {
   /* ---- curvature edges :411-463, one per incident edge of every
    *      non-boundary OptLap node (quirk C2) */
   int ncurv = 0;
+  /* curvature centres: OptLap -- in the overload OptLap = ViewedNodes (:693) although every node is free */
+  const uint8_t *lap = g->variant ? g->viewed : g->optlap;
+  g->n_curv_den = g->variant ? g->n_viewed : g->n_optlap;
   for (int v = 0; v < n; v++)
-    if (g->optlap[v] && !td->node_boundary[v]) ncurv += deg[v + 1] - deg[v];
+    if (lap[v] && !td->node_boundary[v]) ncurv += deg[v + 1] - deg[v];
   g->curv = (EdgeCurv *)calloc(ncurv > 0 ? ncurv : 1, sizeof(EdgeCurv));
-  g->info_curv = g->n_optlap > 0 ? p->reg_lap / (double)g->n_optlap : 0.0; /* :458 */
+  g->info_curv = g->n_curv_den > 0 ? p->reg_lap / (double)g->n_curv_den : 0.0; /* :458, :755 */
   for (int v = 0; v < n; v++) {
-    if (!(g->optlap[v] && !td->node_boundary[v])) continue;
+    if (!(lap[v] && !td->node_boundary[v])) continue;
     const int nn = td->nbr_ptr[v + 1] - td->nbr_ptr[v];
     for (int ie = deg[v]; ie < deg[v + 1]; ie++) {
       EdgeCurv *e = &g->curv[g->n_curv++];
@@ -294,7 +302,8 @@ int oracle_graph_build(Graph *g, const defslam_sft_problem *p) {
         e->v[k + 1] = td->nbr_idx[td->nbr_ptr[v] + k];
         e->w[k] = td->nbr_w[td->nbr_ptr[v] + k];
       }
-      e->len = td->edge_len0[inc[ie]]; /* setDistanceEdges((*ite)->getDist()) :446 */
+      /* setDistanceEdges((*ite)->getDist()) :446 ; never set in the overload (quirk C8): the caller's value */
+      e->len = g->variant ? p->curv_edge_len : td->edge_len0[inc[ie]];
       e->kappa0 = td->node_kappa0[v];  /* GetMeanCurvatureInitial :449-453 */
     }
   }
@@ -717,7 +726,9 @@ int oracle_sft_solve(const defslam_sft_problem *p, defslam_sft_result *r) {
   for (int i = 0; i < g.n_rep; i++) {
     const EdgeReproj *e = &g.rep[i];
     const float chi2 = (float)(e->err[0] * e->info * e->err[0] + e->err[1] * e->info * e->err[1]);
-    if (chi2 > 5.991) { outl[i] = 1; nBad++; }
+    /* overload: deltaMono < sqrt(a0^2 + a1^2)  :806-818 */
+    const int out = g.variant ? (g.huber_delta < sqrt(pow(e->err[0], 2) + pow(e->err[1], 2))) : (chi2 > 5.991);
+    if (out) { outl[i] = 1; nBad++; }
   }
   /* mean reprojection error over inliers, errors recomputed at the final
    * estimate :538-559 */

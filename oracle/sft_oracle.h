@@ -39,6 +39,7 @@ int oracle_surface_vertices(const defslam_bbs *s, const double *ctrl, int32_t xs
 int oracle_schwarp_evaluate(const defslam_schwarp_problem *p, double *r, double *J);
 int oracle_schwarp_init(const defslam_schwarp_problem *p, double *x0);
 int oracle_schwarp_fit(const defslam_schwarp_problem *p, defslam_diffprop *out);
+int oracle_schwarp_initial(const defslam_schwarp_problem *p, uint8_t *keep_out, double *err_out);
 int oracle_polysolver_coefficients(int32_t npairs, const float *J12, const float *H12, const float *I1,
                                    const float *I2, double *eq1, double *eq2);
 int oracle_normals_batched(const defslam_normals_problem *p, double *k_out, double *cov_out, float *normal_out,

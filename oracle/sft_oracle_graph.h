@@ -67,6 +67,8 @@ typedef struct {
   double huber_delta, huber_dsqr;
   uint8_t *viewed, *optlap;
   int n_optlap, n_viewed;
+  int variant;    /* 1: the matches-given overload (DefOptimizer.cc:582-837) */
+  int n_curv_den; /* denominator of the curvature information: |OptLap| (= |Viewed| in the overload) */
   /* solver */
   double *H, *b, *dx, *Hwork, *diag_backup;
 } Graph;

@@ -13,11 +13,17 @@ def pytest_configure(config):
 
 
 def _has_gpu() -> bool:
+    """gpu-marked tests are skipped only when the product library LOADS and reports no device (or the box has no
+    nvidia-smi at all).  A library that is missing or does not load on a GPU box is a failure, not a skip."""
+    import shutil
+    from defslam_b200 import _capi
     try:
-        from defslam_b200 import _capi
-        return _capi.load().defslam_device_count() > 0
+        lib = _capi.load()
     except Exception:
-        return False
+        if shutil.which("nvidia-smi") is None:
+            return False       # build container without the library built yet: the CPU tier still runs
+        raise
+    return lib.defslam_device_count() > 0
 
 
 def pytest_collection_modifyitems(config, items):

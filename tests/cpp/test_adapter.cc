@@ -15,7 +15,8 @@
 #include "../../oracle/sft_oracle.h"
 
 struct Node {
-  int idx; double x, y, z, xO, yO, zO; bool boundary = false; int role = 0;
+  int idx; double x, y, z, xO, yO, zO; bool boundary = false; int role = 0; bool viewed = false, local = false;
+  void update() { viewed = role == 1; local = role == 2; }  // Node.cc:142-153: latch the role into the flags the drawers read
   std::set<Node *> nbrs; std::map<Node *, double> weights;
   int getIndex() const { return idx; }
   std::vector<double> getInitialPose() const { return {xO, yO, zO}; }
@@ -31,6 +32,7 @@ struct Edge { Node *a, *b; double d; std::pair<Node *, Node *> get_pair_nodes() 
 struct Facet { std::set<Node *> nodes; std::set<Node *> getNodes() const { return nodes; } };
 struct Template {
   std::set<Node *> nodes; std::set<Edge *> edges; std::set<Facet *> facets; std::map<Node *, double> kappa; double median;
+  std::vector<Node *> nodeArray_;
   std::set<Node *> get_nodes() const { return nodes; }
   std::set<Edge *> get_edges() const { return edges; }
   std::set<Facet *> get_facets() const { return facets; }
@@ -140,5 +142,34 @@ int main() {
   DefMapPoint chk = mps[7]; chk.RecalculatePosition();
   const bool mp_ok = memcmp(chk.pos, mps[7].pos, sizeof(chk.pos)) == 0;
   printf("adapter: inliers %d (oracle %d), max node err %.3g, pose err %.3g, outlier diff %d, repError %.4f (oracle %.4f)\n", inl, r.n_inliers, err, terr, outl_diff, fr.repError, r.rep_error);
-  return (inl == r.n_inliers && err < 1e-8 && terr < 1e-6 && outl_diff == 0 && mp_ok && std::fabs(fr.repError - r.rep_error) < 1e-4) ? 0 : 5;
+  // updateNodes: Node::update() latched the roles (viewed / local flags the drawers read), role left at NONOBS
+  int flag_bad = 0, n_viewed_flag = 0;
+  std::vector<uint8_t> orole(n); defslam_sft_result r2 = {}; r2.node_role_out = orole.data();
+  for (int i = 0; i < n; i++) { X[3 * i] = nodes[i].xO; X[3 * i + 1] = nodes[i].yO; X[3 * i + 2] = nodes[i].zO; }
+  if (oracle_sft_solve(&p, &r2)) return 3;
+  for (int i = 0; i < n; i++) {
+    flag_bad += nodes[i].viewed != ((orole[i] & 1) != 0);
+    flag_bad += nodes[i].local != (!(orole[i] & 1) && (orole[i] & 2));
+    flag_bad += nodes[i].role != 0;
+    n_viewed_flag += nodes[i].viewed;
+  }
+  printf("adapter: %d nodes flagged viewed, %d role/flag mismatches\n", n_viewed_flag, flag_bad);
+  if (!(inl == r.n_inliers && err < 1e-8 && terr < 1e-6 && outl_diff == 0 && mp_ok && std::fabs(fr.repError - r.rep_error) < 1e-4 && flag_bad == 0)) return 5;
+
+  // ---- the matches-given overload (DefOptimizer.h:58-61) from the same state
+  for (int i = 0; i < n; i++) { nodes[i].x = nodes[i].xO; nodes[i].y = nodes[i].yO; nodes[i].z = nodes[i].zO; T.nodeArray_.push_back(&nodes[i]); }
+  memcpy(fr.Tcw, I4, sizeof(I4));
+  std::vector<std::vector<double>> matches;
+  for (int m = 0; m < M; m++)
+    matches.push_back({(double)mn[3 * m], (double)mn[3 * m + 1], (double)mn[3 * m + 2], mb[3 * m], mb[3 * m + 1], mb[3 * m + 2], uv[2 * m], uv[2 * m + 1]});
+  p.matches_given = 1; p.curv_edge_len = med; p.match_inv_sigma2 = nullptr; p.n_frame_keypoints = 0;
+  std::vector<double> onodes2(3 * n); std::vector<uint8_t> ooutl2(M); defslam_sft_result r3 = {}; r3.node_xyz_out = onodes2.data(); r3.outlier_out = ooutl2.data();
+  if (oracle_sft_solve(&p, &r3)) return 6;
+  std::vector<bool> outlier;
+  const int rc2 = defslam_b200::DefPoseOptimization<Frame, DefMap, Template, Node>(matches, &fr, &map, cache, outlier, 700, 12000, 0.05, med);
+  double err2 = 0; int od2 = 0;
+  for (int i = 0; i < n; i++) { err2 = std::max(err2, std::fabs(nodes[i].x - onodes2[3 * i])); err2 = std::max(err2, std::fabs(nodes[i].y - onodes2[3 * i + 1])); err2 = std::max(err2, std::fabs(nodes[i].z - onodes2[3 * i + 2])); }
+  for (int m = 0; m < M; m++) od2 += (bool)outlier[m] != (ooutl2[m] != 0);
+  printf("adapter (matches given): rc %d, max node err %.3g, outlier diff %d of %zu, pose untouched %d\n", rc2, err2, od2, outlier.size(), memcmp(fr.Tcw, I4, sizeof(I4)) == 0);
+  return (rc2 == 0 && err2 < 1e-8 && od2 == 0 && (int)outlier.size() == M && memcmp(fr.Tcw, I4, sizeof(I4)) == 0) ? 0 : 7;
 }

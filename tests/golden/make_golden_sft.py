@@ -27,6 +27,12 @@ def cases():
     out["huber"] = synthetic.make_frame(t6, 60, seed=11, n_frame_keypoints=6, outlier_frac=0.2)
     t9 = synthetic.make_template(9)
     out["huber9"] = synthetic.make_frame(t9, 300, seed=12, n_frame_keypoints=30, outlier_frac=0.1)
+    # the matches-given overload (DefOptimizer.cc:582-837): every node free, Omega = I/#matches, Huber 0.5,
+    # no temporal term, curvature on the viewed nodes with the caller's lenghtEdge_ (quirk C8)
+    for name, tm, M, seed in (("mg_tiny", t6, 40, 21), ("mg_9", t9, 300, 22)):
+        f = synthetic.make_frame(tm, M, seed=seed, noise_px=0.2)
+        f.matches_given, f.curv_edge_len = 1, float(tm.desc().edge_median_len)
+        out[name] = f
     return out
 
 
@@ -56,7 +62,7 @@ def main():
     assert ref is not None, "build oracle/_ref first (make -C oracle ref)"
     g = {}
     for name, f in cases().items():
-        small = name in ("tiny", "huber")
+        small = name in ("tiny", "huber", "mg_tiny")
         res, J = oracle_py.sft_residuals(f, ref, "ref_sft_residuals", jac=small)
         H, b, chi = oracle_py.sft_normal_equations(f, ref, "ref_sft_normal_equations")
         o = oracle_py.sft_solve(f, ref, "ref_sft_solve")

@@ -81,3 +81,47 @@ def test_matcher_adapter_matches_oracle_on_gpu(oracle, cuda_lib):
     rc, out = _run(EXE3)
     assert rc == 0, out
     assert "0 mismatches" in out
+
+
+EXE4 = os.path.join(ROOT, "tests", "_emu", "test_adapter_findbywarp")
+
+
+def test_findbywarp_adapter_compiles_and_fails_loudly_without_a_device(oracle, cuda_lib):
+    """adapter/MatcherB200.h: DefORBmatcher::findbyWarp / CalculateInitialSchwarp / searchBySchwarp against mock
+    DefKeyFrame / MapPoint types."""
+    _build(oracle, "test_adapter_findbywarp.cc", EXE4)
+    if cuda_lib.defslam_device_count() > 0:
+        pytest.skip("device present: covered by the gpu test")
+    rc, out = _run(EXE4)
+    assert rc == 0, out
+    assert "untouched" in out
+
+
+@pytest.mark.gpu
+def test_findbywarp_adapter_matches_oracle_on_gpu(oracle, cuda_lib):
+    _build(oracle, "test_adapter_findbywarp.cc", EXE4)
+    rc, out = _run(EXE4)
+    assert rc == 0, out
+    assert "identical" in out
+
+
+EXE5 = os.path.join(ROOT, "tests", "_emu", "test_adapter_template")
+
+
+def test_template_adapter_compiles_and_fails_loudly_without_a_device(oracle, cuda_lib):
+    """adapter/TemplateB200.h: TemplateGenerator::LaplacianMeshCreate (LaplacianMesh / TriangularMesh constructors)
+    against mock Surface / KeyFrame / Template / Node / Facet / DefMapPoint types."""
+    _build(oracle, "test_adapter_template.cc", EXE5)
+    if cuda_lib.defslam_device_count() > 0:
+        pytest.skip("device present: covered by the gpu test")
+    rc, out = _run(EXE5)
+    assert rc == 0, out
+    assert "untouched" in out
+
+
+@pytest.mark.gpu
+def test_template_adapter_matches_oracle_on_gpu(oracle, cuda_lib):
+    _build(oracle, "test_adapter_template.cc", EXE5)
+    rc, out = _run(EXE5)
+    assert rc == 0, out
+    assert "map point diff 0" in out

@@ -46,7 +46,7 @@ def test_solve_matches_oracle(cfg, nfr, oracle):
         _check(o, oracle.sft_solve(f), f)
 
 
-@pytest.mark.parametrize("name", ["tiny", "huber", "huber9", "C1_0", "C4_0"])
+@pytest.mark.parametrize("name", ["tiny", "huber", "huber9", "C1_0", "C4_0", "mg_tiny", "mg_9"])
 def test_kernel_code_matches_reference_golden(name):
     """the kernel sources against the outputs of the REFERENCE'S OWN code (tests/golden/sft_ref.npz,
     see test_oracle_sft_ref.py); 'huber*' put gross outliers on the linear branch of the Huber kernel"""

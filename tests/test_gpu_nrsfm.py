@@ -136,3 +136,19 @@ def test_sim3_registration_and_min_median_scale(apis):
     for c in cases[:3]:
         a, o = api.scale_min_median(c.pts1, c.pts2, seed=7), orc.scale_min_median(c.pts1, c.pts2, seed=7)
         assert abs(a - o) <= 1e-6 * abs(o)
+
+
+def test_schwarp_initial_matches_oracle(apis):
+    """DefORBmatcher::CalculateInitialSchwarp (DefORBmatcher.cc:111-187): Warp::initialize, the loss-corrected
+    residuals of the Warp block and the > 20 filter, CUDA vs oracle; a few wrong matches so that the filter acts"""
+    api, orc = apis
+    for seed in (5, 6):
+        w = nrsfm.make_window(seed, n_keypoints=400, n_views=2)
+        c = nrsfm.schwarp_cases(w)[0]
+        c.kp2 = c.kp2.copy()
+        c.kp2[:8] += 0.3
+        xa, ka, ea = api.schwarp_initial(c)
+        xo, ko, eo = orc.schwarp_initial(c)
+        assert np.abs(xa - xo).max() < 1e-9
+        assert np.allclose(ea, eo, rtol=1e-8, atol=1e-12)
+        assert np.array_equal(ka, ko) and 0 < ka.sum() < c.n

@@ -40,13 +40,13 @@ def ref(oracle):
     return lib
 
 
-NAMES = ["C1_0", "C1_1", "C2_0", "C4_0", "C3_0", "tiny", "huber", "huber9"]
+NAMES = ["C1_0", "C1_1", "C2_0", "C4_0", "C3_0", "tiny", "huber", "huber9", "mg_tiny", "mg_9"]
 
 
 @pytest.mark.parametrize("name", NAMES)
 def test_edge_errors_and_normal_equations_equal_reference_golden(oracle, gold, frames, name):
     f = frames[name]
-    small = name in ("tiny", "huber")
+    small = name in ("tiny", "huber", "mg_tiny")
     res, J = oracle.sft_residuals(f, jac=small)
     assert res.shape == gold[f"{name}.res"].shape
     assert _rel(res, gold[f"{name}.res"]) < 1e-15
@@ -200,6 +200,26 @@ def test_live_sim3_registration(oracle, ref):
 
 # ------------------------------------------------------------------ live tier (reference library present)
 LIVE = [("C1", 0), ("C1", 1), ("C2", 0), ("C2", 1), ("C4", 0), ("C4", 1), ("C3", 0)]
+
+
+@pytest.mark.parametrize("cfg", ["C1", "C4", "C2"])
+def test_live_matches_given_overload(oracle, ref, cfg):
+    """DefPoseOptimization(matches, ...) (DefOptimizer.cc:582-837) on the reference's own edges and LM driver"""
+    tmpl, fr = synthetic.make_config_frames(cfg, nframes=1)
+    f = fr[0]
+    f.matches_given, f.curv_edge_len = 1, float(tmpl.desc().edge_median_len)
+    res, J = oracle.sft_residuals(f)
+    res_r, J_r = oracle.sft_residuals(f, ref, "ref_sft_residuals")
+    assert _rel(res, res_r) < 1e-15 and _rel(J, J_r) < 1e-15
+    H, b, chi = oracle.sft_normal_equations(f)
+    Hr, br, chir = oracle.sft_normal_equations(f, ref, "ref_sft_normal_equations")
+    assert _rel(H, Hr) < 1e-13 and _rel(b, br) < 1e-13 and abs(chi - chir) < 1e-13 * chir
+    o = oracle.sft_solve(f)
+    r = oracle.sft_solve(f, ref, "ref_sft_solve")
+    assert (o.r.lm_iterations, o.r.lm_trials, o.r.n_inliers) == (r.r.lm_iterations, r.r.lm_trials, r.r.n_inliers)
+    scale = np.sqrt((r.nodes ** 2).sum(1).mean())
+    assert np.abs(o.nodes - r.nodes).max() / scale < 1e-9
+    assert np.array_equal(o.outlier, r.outlier)
 
 
 @pytest.mark.parametrize("cfg,idx", LIVE + [("C5", 0)])
