@@ -66,6 +66,11 @@ struct DeviceGuard {
   ~DeviceGuard() { if (prev >= 0) { int cur = -1; if (cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev); } }
 };
 
+/* cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute of the function, not of the calling thread
+ * or stream: it is only ever RAISED, under a lock, so that two host threads launching batches of different sizes
+ * cannot undercut each other between set and launch. */
+cudaError_t raise_dynamic_smem(const void *func, int device, int bytes);
+
 /* context of the calling thread on `device` (-1: current device); nullptr when
  * no usable CUDA device exists -- callers return DEFSLAM_ECUDA, there is no
  * CPU fallback. */

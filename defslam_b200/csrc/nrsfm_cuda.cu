@@ -255,7 +255,7 @@ int defslam_schwarp_fit_batched(int32_t nprob, const defslam_schwarp_problem *p,
   }
   *(int *)(h + o_counter) = 0;
   DS_CUDA_TRY(cudaMemcpyAsync(d_in, h, in.total + x_total, cudaMemcpyHostToDevice, ctx->stream));
-  DS_CUDA_TRY(cudaFuncSetAttribute(schwarp_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
+  DS_CUDA_TRY(raise_dynamic_smem((const void *)schwarp_fit_kernel, ctx->device, (int)smem));
   DS_CUDA_TRY(cudaEventRecord(ctx->e0, ctx->stream));
   schwarp_fit_kernel<<<grid, NRSFM_THREADS, smem, ctx->stream>>>((const SchwarpProb *)(d_in + o_probs), nprob,
                                                                  (uint8_t *)S.ws.p, ws_stride, nu, nv, nmax,
@@ -550,7 +550,7 @@ int defslam_sfn_solve_batched(int32_t nprob, const defslam_sfn_problem *p, int32
   *(int *)(h + o_counter) = 0;
   DS_CUDA_TRY(cudaMemcpyAsync(d_in, h, in.total, cudaMemcpyHostToDevice, ctx->stream));
   DS_CUDA_TRY(cudaMemsetAsync(d_out, 0xff, outp.total, ctx->stream));
-  DS_CUDA_TRY(cudaFuncSetAttribute(sfn_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
+  DS_CUDA_TRY(raise_dynamic_smem((const void *)sfn_solve_kernel, ctx->device, (int)smem));
   DS_CUDA_TRY(cudaEventRecord(ctx->e0, ctx->stream));
   sfn_solve_kernel<<<grid, NRSFM_THREADS, smem, ctx->stream>>>((const SfnProb *)(d_in + o_probs), nprob,
                                                                (uint8_t *)S.ws.p, ws_stride, nu, nv, nmax, n_in_smem,
@@ -691,7 +691,7 @@ int defslam_scale_min_median(int32_t n, const float *mono_xyz, const float *ster
   DS_CUDA_TRY(cudaMemcpyAsync(d_in, h, in.total, cudaMemcpyHostToDevice, ctx->stream));
   const size_t smem = 4 * (size_t)n;
   if (smem > 48 * 1024)
-    DS_CUDA_TRY(cudaFuncSetAttribute(scale_min_median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
+    DS_CUDA_TRY(raise_dynamic_smem((const void *)scale_min_median_kernel, ctx->device, (int)smem));
   scale_min_median_kernel<<<1, 512, smem, ctx->stream>>>(n, (const float *)(d_in + om), (const float *)(d_in + os), seed,
                                                          (float *)(d_out + oo));
   DS_CUDA_TRY(cudaGetLastError());

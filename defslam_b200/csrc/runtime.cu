@@ -4,6 +4,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <mutex>
+#include <utility>
+
 #include "ds_runtime.h"
 
 namespace ds {
@@ -15,6 +18,17 @@ void note_cuda_error(cudaError_t e, const char *what, const char *file, int line
   if (getenv("DEFSLAM_QUIET") == nullptr)
     fprintf(stderr, "defslam_b200: CUDA error %d (%s) at %s:%d: %s\n", (int)e, cudaGetErrorString(e), file, line, what);
   cudaGetLastError(); /* clear the sticky-free error state */
+}
+
+cudaError_t raise_dynamic_smem(const void *func, int device, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void *, int>, int> cur;
+  std::lock_guard<std::mutex> lock(mu);
+  int &have = cur[std::make_pair(func, device)];
+  if (bytes <= have) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) have = bytes;
+  return e;
 }
 
 DevCtx::~DevCtx() {

@@ -185,10 +185,10 @@ static int batch_load(defslam_sft_batch *B, int nprob, const defslam_sft_problem
   const bool xs = !B->bm.any_x_global;
   int occ = 0;
   if (xs) {
-    DS_CUDA_TRY(cudaFuncSetAttribute(sft_lm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin)); /* per-device attribute: always the maximum, so concurrent batches of different sizes cannot undercut each other */
+    DS_CUDA_TRY(raise_dynamic_smem((const void *)sft_lm_kernel<true>, ctx->device, B->smem_bytes));
     DS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sft_lm_kernel<true>, SFT_THREADS, B->smem_bytes));
   } else {
-    DS_CUDA_TRY(cudaFuncSetAttribute(sft_lm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
+    DS_CUDA_TRY(raise_dynamic_smem((const void *)sft_lm_kernel<false>, ctx->device, B->smem_bytes));
     DS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sft_lm_kernel<false>, SFT_THREADS, B->smem_bytes));
   }
   if (occ < 1) return DEFSLAM_ETOOLARGE;
