@@ -717,6 +717,28 @@ def main():
             units = {"schwarp_fit": "keyframe-pair fits/s", "normals": "map-point normals/s", "sfn": "keyframe solves/s"}
             for k in nr_line:
                 nr_line[k]["unit"] = units[k]
+            # per-stage rooflines (resident rate x algorithmic work per unit)
+            mhz = float((clocks or {}).get("sm_mhz") or 1965.0)
+            fp64_peak = 64 * 2 * 148 * mhz * 1e6 / 1e12
+            NPs, bws = 2 * 13 * 15, 3 * 30 + 29      # Schwarp unknowns; half bandwidth of the block-banded normal matrix
+            fl_fit = 4 * (NPs * bws * bws + 4 * NPs * bws)   # Warp::initialize solve + 3 LM steps, factor + two sweeps each
+            a = nr_line["schwarp_fit"]["value"] / world * fl_fit / 1e12
+            nr_line["schwarp_fit"]["roofline"] = {"bound": "fp64", "achieved": a, "peak": fp64_peak, "unit": "TFLOP/s",
+                                                  "frac": a / fp64_peak, "flops_per_fit": fl_fit,
+                                                  "kernel": "schwarp_fit_kernel (block-banded Cholesky, 390 unknowns)"}
+            nb = wl["normals"]
+            by_pt = (86.0 * nb.npairs + 89.0 * nb.n) / nb.n   # 73 B in + 13 B out per pair, 24 B in + 65 B out per point
+            a = nr_line["normals"]["value"] / world * by_pt / 1e9
+            nr_line["normals"]["roofline"] = {"bound": "hbm", "achieved": a, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                              "frac": a / peaks["hbm_gbs"], "bytes_per_point": by_pt,
+                                              "kernel": "normals_kernel (thread per map point)"}
+            NCs = 13 * 15
+            n_nrm = float(np.mean([len(k.uv) for k in wl["keyframes_base"]]))
+            fl_kf = NCs ** 3 / 3.0 + 2 * 2 * n_nrm * 256 + 5 * 2 * NCs * NCs   # packed Cholesky + M'M gather + solves/residual sweeps
+            a = nr_line["sfn"]["value"] / world * fl_kf / 1e12
+            nr_line["sfn"]["roofline"] = {"bound": "fp64", "achieved": a, "peak": fp64_peak, "unit": "TFLOP/s",
+                                          "frac": a / fp64_peak, "flops_per_keyframe": fl_kf,
+                                          "kernel": "sfn_solve_kernel (packed Cholesky, 195 unknowns)"}
             line["nrsfm"] = {"stages": nr_line, "gpu_launches": int(nrsfm_launches),
                              "workload": f"{NRSFM_WINDOWS} distinct synthetic keyframe windows (1200 keypoints, 4 views, "
                                          "13x15 control grid) tiled; value = units / device time of the stage kernel "

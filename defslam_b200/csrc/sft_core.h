@@ -146,7 +146,10 @@ struct SmemLayout {
 /* row-owner factorisation (sft_rows.h): ring slots and sizes */
 constexpr int ROWS_OWNERS_ = 5;
 constexpr int ROWS_LT_STRIDE_ = 72;
-constexpr int ROWS_BWD_BUFS_ = 4; /* row blocks of the factor in flight during the backward sweep */
+#ifndef DS_BWD_BUFS
+#define DS_BWD_BUFS 4
+#endif
+constexpr int ROWS_BWD_BUFS_ = DS_BWD_BUFS; /* row blocks of the factor in flight during the backward sweep */
 
 DS_FN int asm_scratch_doubles(int n, int ne) { return 11 * n + 5 * ne; }
 

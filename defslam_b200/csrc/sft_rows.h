@@ -110,6 +110,9 @@ DS_FN void spin_ge(const int *p, int need) {
 #ifndef DS_ROWS_PREFETCH
 #define DS_ROWS_PREFETCH 0
 #endif
+#ifndef DS_ROWS_BORDER_ON_CHAIN_SP
+#define DS_ROWS_BORDER_ON_CHAIN_SP 0
+#endif
 DS_FN void publish(int *p, int v, int lane) {
   __syncwarp();
 #if DS_ROWS_FENCE_LIGHT
@@ -419,7 +422,14 @@ DS_FN_NOINLINE bool factor_rows(const Team team, double lambda) {
     int chain_w = 0;
     for (int w = nwarp - 1; w >= 0; w--) if (wsp[w] == 0) chain_w = w;
     const int chain_sp = wsp[chain_w];
-    /* workers: every warp off the chain's sub-partition; the first is the border warp, up to ROW_OWNERS own rows */
+    /* the border warp (24 DMMAs per block row, a sixth of an owner's load) shares the chain's sub-partition when a
+     * second warp sits there only with DS_ROWS_BORDER_ON_CHAIN_SP (measured: C2 1 % faster, C1/C3/C4 5-9 % slower --
+     * the chain loses more than the sixth owner gains; default off); every other warp on that sub-partition idles */
+    int border_w = -1;
+#if DS_ROWS_BORDER_ON_CHAIN_SP
+    for (int w = nwarp - 1; w >= 0; w--) if (w != chain_w && wsp[w] == chain_sp) border_w = w;
+#endif
+    /* workers: every warp off the chain's sub-partition; without a border warp yet the first one takes that role */
     int my = -1, nworkers = 0;
     for (int w = 0; w < nwarp; w++) {
       if (w == chain_w || wsp[w] == chain_sp) continue;
@@ -429,7 +439,9 @@ DS_FN_NOINLINE bool factor_rows(const Team team, double lambda) {
     if (nworkers < 2) { /* degenerate slot assignment: fall back to logical roles */
       my = warp == chain_w ? -1 : (warp > chain_w ? warp - 1 : warp);
       nworkers = nwarp - 1;
+      border_w = -1;
     }
+    if (border_w >= 0) { if (warp == border_w) my = 0; else if (my >= 0) my += 1; nworkers += 1; }
     const int nown = nworkers - 1 < ROW_OWNERS ? nworkers - 1 : ROW_OWNERS;
     RowShared S;
     S.ring = smem_u32(W);
@@ -623,10 +635,27 @@ DS_FN_NOINLINE bool factor_rows(const Team team, double lambda) {
       if (b == buf) { mbar_wait(&c.mbar[1 + b], phb[b]); phb[b] ^= 1u; }
     const int t0 = kb < NBK ? NBK - kb : 0; /* first tile of the row that exists */
     const int nupd = NB * (NBK - t0);
-    const bool active = team.tid < (nupd > NB ? nupd : NB);
+    const bool active = team.tid < (((nupd > NB ? nupd : NB) + 31) & ~31); /* whole warps (the broadcast below) */
     if (active) {
-      /* d[a] = sum_{m >= a} Y[m][a] y[m]: eight independent dot products (Y = inv(L_kk), row-major) */
-      double y[NB], d[NB];
+      /* d[a] = sum_{m >= a} Y[m][a] y[m] (Y = inv(L_kk), row-major) */
+      double d[NB];
+#if DS_CUDA
+      /* lane a of every active warp forms d[a] (one 8-term dot product), then the eight values are broadcast:
+       * 32 instructions per warp instead of 72 when every thread forms all eight */
+      {
+        const int la = team.tid & 7;
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int m = 0; m < NB; m += 2) {
+          s0 = fma(m >= la ? Y[m * 8 + la] : 0.0, dx[k + m], s0);
+          s1 = fma(m + 1 >= la ? Y[(m + 1) * 8 + la] : 0.0, dx[k + m + 1], s1);
+        }
+        const double mine = s0 + s1;
+#pragma unroll
+        for (int a = 0; a < NB; a++) d[a] = __shfl_sync(0xffffffffu, mine, a);
+      }
+#else
+      double y[NB];
 #pragma unroll
       for (int a = 0; a < NB; a++) y[a] = dx[k + a];
 #pragma unroll
@@ -636,6 +665,7 @@ DS_FN_NOINLINE bool factor_rows(const Team team, double lambda) {
         for (int m = a + 1; m < NB; m++) s += Y[m * 8 + a] * y[m];
         d[a] = s;
       }
+#endif
       if (team.tid == 0) {
 #pragma unroll
         for (int a = 0; a < NB; a++) sol[k + a] = d[a];

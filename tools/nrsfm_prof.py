@@ -1,12 +1,14 @@
-"""One launch of each NRSfM stage kernel on a bench-shaped workload (for ncu)."""
+"""One launch of each NRSfM stage kernel on the bench-shaped workload (for ncu): 592 Schwarp fits, ~480 k map-point
+normals, 296 shape-from-normals keyframes -- the same units bench.py times."""
+import os
 import sys
-sys.path.insert(0, ".")
-from defslam_b200 import nrsfm
-api = nrsfm.Api()
-wins = [nrsfm.make_window(100 + i, n_keypoints=1200, n_views=4) for i in range(4)]
-cases = [c for w in wins for c in nrsfm.schwarp_cases(w)]
-fits = api.schwarp_fit_batched(cases * 37)   # 592 pairs
-ncs = [nrsfm.normals_case(w, fits[4 * i:4 * i + 4]) for i, w in enumerate(wins)]
-nouts = [api.normals(nc) for nc in ncs]
-scs = [nrsfm.sfn_case(w, no) for w, no in zip(wins, nouts)]
-api.sfn_solve_batched(scs * 74)              # 296 keyframes
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+
+wl = bench.nrsfm_workload()
+api = wl["api"]
+api.schwarp_prepare(wl["pairs"])()
+api.normals_prepare(wl["normals"])()
+api.sfn_prepare(wl["keyframes"])()
+print("pairs", len(wl["pairs"]), "points", wl["normals"].n, "keyframes", len(wl["keyframes"]))
