@@ -12,6 +12,7 @@
 
 #include <vector>
 
+#include "ds_host.h"
 #include "sft_core.h"
 
 namespace ds {
@@ -154,7 +155,10 @@ struct BatchMarshal {
   }
 
   void pack_inputs(const defslam_sft_problem *p, uint8_t *host_in) const {
-    for (size_t i = 0; i < slots.size(); i++) {
+    /* ~52 KB per C2 frame: threads once the batch is a few MB */
+    const size_t per_frame = slots.empty() ? 1 : std::max<size_t>(1, in_bytes / slots.size());
+    host_parallel_for(slots.size(), std::max<size_t>(1, ((size_t)4 << 20) / per_frame), [&](size_t lo_, size_t hi_) {
+    for (size_t i = lo_; i < hi_; i++) {
       const ProbSlot &s = slots[i];
       uint8_t *b = host_in + s.in_off;
       const size_t n = s.n_nodes, M = s.M;
@@ -167,6 +171,7 @@ struct BatchMarshal {
         else memset(b + s.o_isig, 0, M * sizeof(float));
       }
     }
+    });
   }
 
   /* resolve the arena-relative pointers of every view */

@@ -12,6 +12,7 @@
 
 #include <vector>
 
+#include "ds_host.h"
 #include "ds_runtime.h"
 #include "nrsfm_core.h"
 #include "sim3_core.h"
@@ -407,15 +408,18 @@ int defslam_normals_batched(const defslam_normals_problem *p, double *k_out, dou
       (rc = S.dev.ensure(in.total + outp.total)) || (rc = S.ws.ensure(scr.total)))
     return rc;
   uint8_t *h = (uint8_t *)S.host.p, *d_in = (uint8_t *)S.dev.p, *d_out = d_in + in.total;
-  memcpy(h + o_ptr, p->pair_ptr, 4 * (n + 1));
+  /* the caller's arrays go into the pinned arena as they are (one H2D for all of them); large batches are copied
+   * by several host threads */
+  host_big_memcpy(h + o_ptr, p->pair_ptr, 4 * (n + 1));
   if (np) {
-    memcpy(h + o_j12, p->J12, 16 * np); memcpy(h + o_j21, p->J21, 16 * np); memcpy(h + o_h12, p->H12, 24 * np);
-    memcpy(h + o_i1, p->I1, 8 * np); memcpy(h + o_i2, p->I2, 8 * np);
-    if (p->pair_from_ref) memcpy(h + o_fr, p->pair_from_ref, np);
-    if (p->k_first) memcpy(h + o_kf, p->k_first, 8 * np);
+    host_big_memcpy(h + o_j12, p->J12, 16 * np); host_big_memcpy(h + o_j21, p->J21, 16 * np);
+    host_big_memcpy(h + o_h12, p->H12, 24 * np);
+    host_big_memcpy(h + o_i1, p->I1, 8 * np); host_big_memcpy(h + o_i2, p->I2, 8 * np);
+    if (p->pair_from_ref) host_big_memcpy(h + o_fr, p->pair_from_ref, np);
+    if (p->k_first) host_big_memcpy(h + o_kf, p->k_first, 8 * np);
   }
-  if (p->k_init) memcpy(h + o_ki, p->k_init, 16 * n);
-  memcpy(h + o_uv, p->ref_uv, 8 * n);
+  if (p->k_init) host_big_memcpy(h + o_ki, p->k_init, 16 * n);
+  host_big_memcpy(h + o_uv, p->ref_uv, 8 * n);
   DS_CUDA_TRY(cudaMemcpyAsync(d_in, h, in.total, cudaMemcpyHostToDevice, ctx->stream));
   NormalsProb P;
   P.n_points = (int)n; P.npairs = (int)np;
@@ -443,21 +447,25 @@ int defslam_normals_batched(const defslam_normals_problem *p, double *k_out, dou
   float ms = 0.f;
   cudaEventElapsedTime(&ms, ctx->e0, ctx->e1);
   g_last_kernel_ms = ms;
-  if (k_out) memcpy(k_out, h + o_k, 16 * n);
-  if (status_out) memcpy(status_out, h + o_st, n);
-  if (iters_out) memcpy(iters_out, h + o_it, 4 * n);
+  if (k_out) host_big_memcpy(k_out, h + o_k, 16 * n);
+  if (status_out) host_big_memcpy(status_out, h + o_st, n);
+  if (iters_out) host_big_memcpy(iters_out, h + o_it, 4 * n);
   const uint8_t *st = h + o_st;
   /* covariance / normal only where estimated (the reference leaves the rest untouched) */
-  for (size_t i = 0; i < n; i++) {
-    if (st[i] != 1) continue;
-    if (cov_out) memcpy(cov_out + 4 * i, h + o_cov + 32 * i, 32);
-    if (normal_out) memcpy(normal_out + 3 * i, h + o_nrm + 12 * i, 12);
-  }
+  host_parallel_for(n, 65536, [&](size_t lo_, size_t hi_) {
+    for (size_t i = lo_; i < hi_; i++) {
+      if (st[i] != 1) continue;
+      if (cov_out) memcpy(cov_out + 4 * i, h + o_cov + 32 * i, 32);
+      if (normal_out) memcpy(normal_out + 3 * i, h + o_nrm + 12 * i, 12);
+    }
+  });
   const uint8_t *pv = h + o_pv;
-  if (pair_valid_out && np) memcpy(pair_valid_out, pv, np);
+  if (pair_valid_out && np) host_big_memcpy(pair_valid_out, pv, np);
   if (pair_normal_out)
-    for (size_t j = 0; j < np; j++)
-      if (pv[j]) memcpy(pair_normal_out + 3 * j, h + o_pn + 12 * j, 12);
+    host_parallel_for(np, 65536, [&](size_t lo_, size_t hi_) {
+      for (size_t j = lo_; j < hi_; j++)
+        if (pv[j]) memcpy(pair_normal_out + 3 * j, h + o_pn + 12 * j, 12);
+    });
   return DEFSLAM_OK;
 }
 
