@@ -3,6 +3,8 @@
  * solve).  Device arithmetic lives in match_core.h; see include/defslam_b200.h for what the entry
  * point replaces in the reference.
  */
+#include <stdlib.h>
+
 #include <vector>
 
 #include "ds_runtime.h"
@@ -167,6 +169,130 @@ __global__ void resolve_fixed_kernel(ProjView P, const int *cnt, const uint64_t 
   if (lane == 0) *nmatches_out = nmatches;
 }
 
+
+/* ---- fused path: ONE launch (one CTA of 1024 threads) for cells, projections, candidate lists and the resolve.
+ * The reference loop is order dependent only through the taken flags: point i takes its best-ranked candidate that no
+ * EARLIER point with observations took.  That is the unique fixed point of
+ *     choice[i] = best candidate j of i with owner[j] >= i,   owner[j] = min { i : has_obs[i], choice[i] = j }
+ * (induction on i: choice[i] depends on the choices of smaller indices only), so instead of replaying 1200 points
+ * one after the other the CTA iterates the two maps in parallel until nothing changes -- as many rounds as the
+ * longest chain of displaced points (a handful), not as many as there are points.  What the loop leaves in match[]
+ * is reproduced exactly: the last writer of match[j] is the taker if there is one, else the largest chooser without
+ * observations; nmatches counts every point that chose, and the rotation filter clears match[j] as soon as ANY point
+ * that chose j falls outside the three dominant bins (DefORBmatcher.cc:424-446). */
+constexpr int FUSED_THREADS = 1024;
+__global__ void __launch_bounds__(FUSED_THREADS, 1)
+search_fused_kernel(ProjView P, uint64_t *keys, int *cnt, int *choice, int *match,
+                    int *tail /* nmatches, overflow, CTAs done */) {
+  extern __shared__ int sm_i[];
+  const int NC = P.n_cur, NL = P.n_last;
+  int *cell = sm_i, *owner = cell + NC, *owner_new = owner + NC, *lastw = owner_new + NC;
+  uint8_t *kill = (uint8_t *)(lastw + NC);
+  __shared__ int hist[HISTO_LENGTH];
+  __shared__ int s_flag, s_nm, s_keep[3], s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = FUSED_THREADS / 32;
+  for (int j = tid; j < NC; j += FUSED_THREADS) cell[j] = keypoint_cell(P, j);
+  __syncthreads();
+  /* candidate lists, all CTAs: warp per map point, lanes stride over the keypoints (slots by ballot) */
+  for (int i = blockIdx.x * nwarp + warp; i < NL; i += gridDim.x * nwarp) {
+    const Proj r = project_point(P, i);
+    int base = 0;
+    if (r.ok) {
+      const uint8_t *d = &P.last_desc[32 * (size_t)i];
+      uint64_t *out = keys + (size_t)i * CAND_CAP;
+      for (int j0 = 0; j0 < NC; j0 += 32) {
+        const int j = j0 + lane;
+        bool ok = false;
+        int cj = -1;
+        if (j < NC) { cj = cell[j]; ok = candidate_ok(P, r, j, cj); }
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+          const int pos = base + __popc(m & ((1u << lane) - 1u));
+          if (pos < CAND_CAP) out[pos] = cand_key(hamming256(d, &P.cur_desc[32 * (size_t)j]), cj, j);
+        }
+        base += __popc(m);
+      }
+    }
+    if (lane == 0) {
+      cnt[i] = base < CAND_CAP ? base : CAND_CAP;
+      if (base > CAND_CAP) atomicOr(&tail[1], 1);
+    }
+  }
+  /* the CTA that finishes last resolves (its loads of the other CTAs' lists come after the fence + atomic) */
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(&tail[2], 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (*(volatile int *)&tail[1]) return; /* overflow: the host repeats the search with exact lists */
+  for (int j = tid; j < NC; j += FUSED_THREADS) {
+    owner[j] = P.cur_taken[j] ? -1 : 0x7fffffff; /* -1: taken before the search started, blocks every point */
+    lastw[j] = -1;
+    kill[j] = 0;
+  }
+  if (tid < HISTO_LENGTH) hist[tid] = 0;
+  if (tid == 0) { s_flag = 0; s_nm = 0; }
+  __syncthreads();
+  for (int i = tid; i < NL; i += FUSED_THREADS) choice[i] = -2; /* not evaluated yet */
+  /* fixed-point rounds */
+  for (int round = 0; round < NL + 2; round++) {
+    for (int j = tid; j < NC; j += FUSED_THREADS) owner_new[j] = P.cur_taken[j] ? -1 : 0x7fffffff;
+    __syncthreads();
+    if (tid == 0) s_flag = 0;
+    __syncthreads();
+    bool changed = false;
+    for (int i = tid; i < NL; i += FUSED_THREADS) {
+      const int n = __ldcg(&cnt[i]);
+      uint64_t best = ~0ull;
+      const uint64_t *k = keys + (size_t)i * CAND_CAP;
+      for (int c = 0; c < n; c++) {
+        const uint64_t key = __ldcg((const unsigned long long *)&k[c]);
+        if (owner[key_index(key)] >= i && key < best) best = key;
+      }
+      int ch = -1;
+      if (best != ~0ull && key_dist(best) < 256 && key_dist(best) <= P.th_high) ch = key_index(best);
+      if (ch != choice[i]) { choice[i] = ch; changed = true; }
+      if (ch >= 0 && P.last_has_obs[i]) atomicMin(&owner_new[ch], i);
+    }
+    if (changed) s_flag = 1;
+    __syncthreads();
+    const bool again = s_flag != 0;
+    for (int j = tid; j < NC; j += FUSED_THREADS) owner[j] = owner_new[j];
+    __syncthreads();
+    if (!again) break;
+  }
+  /* what the sequential loop leaves behind */
+  int mine = 0;
+  for (int i = tid; i < NL; i += FUSED_THREADS) {
+    const int j = choice[i];
+    if (j < 0) continue;
+    mine++;
+    if (owner[j] == 0x7fffffff) atomicMax(&lastw[j], i); /* no taker: the largest chooser wrote last */
+    if (P.check_orientation) atomicAdd(&hist[rotation_bin(P.last_angle[i], P.cur_angle[j])], 1);
+  }
+  if (mine) atomicAdd(&s_nm, mine);
+  __syncthreads();
+  if (P.check_orientation) {
+    if (tid == 0) { int i1, i2, i3; three_maxima(hist, HISTO_LENGTH, i1, i2, i3); s_keep[0] = i1; s_keep[1] = i2; s_keep[2] = i3; }
+    __syncthreads();
+    int dropped = 0;
+    for (int i = tid; i < NL; i += FUSED_THREADS) {
+      const int j = choice[i];
+      if (j < 0) continue;
+      const int bin = rotation_bin(P.last_angle[i], P.cur_angle[j]);
+      if (bin != s_keep[0] && bin != s_keep[1] && bin != s_keep[2]) { kill[j] = 1; dropped++; }
+    }
+    if (dropped) atomicSub(&s_nm, dropped);
+    __syncthreads();
+  }
+  for (int j = tid; j < NC; j += FUSED_THREADS) {
+    const int o = owner[j];
+    match[j] = kill[j] ? -1 : (o != 0x7fffffff && o >= 0 ? o : lastw[j]);
+  }
+  if (tid == 0) tail[0] = s_nm;
+}
+
 /* warp per keypoint of keyframe 1: lanes stride over the keypoints of keyframe 2 */
 __global__ void warp_search_warp_kernel(WarpView W, const int *cell2, int *match12, int *nmatches) {
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -282,7 +408,7 @@ int defslam_search_by_projection(const defslam_projsearch_problem *p, int32_t *m
                o_cd = in.add(NC * 32), o_cu = in.add(NC * 4), o_ct = in.add(NC), o_sc = in.add((size_t)p->n_levels * 4);
   const size_t w_cell = wk.add(NC * 4), w_proj = wk.add(NL * sizeof(Proj)), w_cnt = wk.add(NL * 4),
                w_off = wk.add((NL + 1) * 4), w_ai = wk.add(NL * 4), w_aj = wk.add(NL * 4), w_match = wk.add(NC * 4),
-               w_n = wk.add(8);
+               w_n = wk.add(16);
   Scratch &S = tl_scratch(ctx->device);
   int rc;
   if ((rc = S.host.ensure(in.total > wk.total ? in.total : wk.total)) || (rc = S.dev.ensure(in.total + wk.total))) return rc;
@@ -318,6 +444,29 @@ int defslam_search_by_projection(const defslam_projsearch_problem *p, int32_t *m
   Proj *proj = (Proj *)(w + w_proj);
   const int wgrid = (p->n_last + 3) / 4 < ctx->sm_count * 16 ? (p->n_last + 3) / 4 : ctx->sm_count * 16;
   bool exact = NC > 48 * 1024; /* the resolve pass keeps the taken flags in shared memory */
+  /* fused path: one launch, one synchronisation (cells, owners and flags of the current frame in shared memory) */
+  const size_t fused_smem = NC * 17;
+  if (!exact && fused_smem <= (size_t)ctx->smem_optin - 2048 && getenv("DEFSLAM_MATCH_UNFUSED") == nullptr) {
+    if ((rc = S.keys.ensure(NL * CAND_CAP * 8))) return rc;
+    DS_CUDA_TRY(raise_dynamic_smem((const void *)search_fused_kernel, ctx->device, (int)fused_smem));
+    DS_CUDA_TRY(cudaMemsetAsync(w + w_n, 0, 16, ctx->stream));
+    int fgrid = (p->n_last + 31) / 32;
+    if (fgrid > ctx->sm_count) fgrid = ctx->sm_count;
+    search_fused_kernel<<<fgrid, FUSED_THREADS, fused_smem, ctx->stream>>>(V, (uint64_t *)S.keys.p, cnt, (int *)(w + w_ai),
+                                                                           (int *)(w + w_match), (int *)(w + w_n));
+    DS_CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1);
+    /* matches and the two tail words in one copy (w_match and w_n are adjacent arena slots) */
+    DS_CUDA_TRY(cudaMemcpyAsync(h, w + w_match, (w_n - w_match) + 16, cudaMemcpyDeviceToHost, ctx->stream));
+    DS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    const int *tail = (const int *)(h + (w_n - w_match));
+    if (!tail[1]) {
+      memcpy(match_out, h, NC * 4);
+      *nmatches_out = tail[0];
+      return DEFSLAM_OK;
+    }
+    exact = true; /* a map point had more than CAND_CAP candidates: exact lists */
+  }
   cell_kernel<<<grid_for(p->n_cur, ctx->sm_count), 128, 0, ctx->stream>>>(V, cell);
   if (!exact) {
     /* low-latency path: three launches, one synchronisation */
