@@ -1907,12 +1907,16 @@ DS_FN_NOINLINE void sft_solve_one(const Team team, Ctx &cx) {
       prof_mark(team, c, PF_LM_SCALAR);
       bool ok2;
       if (XS && pb.row_nt > 0) {
-        switch (pb.row_nt) { /* tiles per block row: 9x9 .. 17x17 regular meshes (and the small test meshes) */
+        switch (pb.row_nt) { /* tiles per block row = bwp/8 + 1: 5 (4x4 mesh) .. 14 (17x17) */
           case 5: ok2 = factor_rows<5>(team, lambda); break;
           case 6: ok2 = factor_rows<6>(team, lambda); break;
+          case 7: ok2 = factor_rows<7>(team, lambda); break;
           case 8: ok2 = factor_rows<8>(team, lambda); break;
           case 9: ok2 = factor_rows<9>(team, lambda); break;
+          case 10: ok2 = factor_rows<10>(team, lambda); break;
           case 11: ok2 = factor_rows<11>(team, lambda); break;
+          case 12: ok2 = factor_rows<12>(team, lambda); break;
+          case 13: ok2 = factor_rows<13>(team, lambda); break;
           default: ok2 = factor_rows<14>(team, lambda); break;
         }
       } else {

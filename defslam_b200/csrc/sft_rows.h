@@ -42,7 +42,7 @@ static inline
 #if DS_CUDA
 __host__ __device__
 #endif
-bool row_mode_nt_supported(int nt) { return nt == 5 || nt == 6 || nt == 8 || nt == 9 || nt == 11 || nt == 14; }
+bool row_mode_nt_supported(int nt) { return nt >= 5 && nt <= 14; } /* 4x4 .. 17x17 regular meshes: one instantiation each */
 
 /* global workspace of the tile-form factor: nblk rows of nt tiles */
 static inline

@@ -216,3 +216,13 @@ def test_stress_mesh_25x25_matches_oracle(oracle):
         del os.environ["DEFSLAM_EMU_SMEM_LIMIT"]
     assert rc == 0
     _check(outs[0], oracle.sft_solve(frames[0]), frames[0])
+
+
+@pytest.mark.parametrize("G", [7, 11, 12, 14, 15, 16])
+def test_row_owner_factorisation_on_every_mesh_size(G, oracle):
+    """every tile count NT = 5..14 has its own instantiation of the row-owner factorisation"""
+    tmpl = synthetic.make_template(G)
+    f = synthetic.make_frame(tmpl, 25 * G, seed=100 + G)
+    rc, outs = emu_solve_batched([f])
+    assert rc == 0
+    _check(outs[0], oracle.sft_solve(f), f)
