@@ -114,6 +114,20 @@ DS_FN void mbar_wait(uint64_t *bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+/* one poll, no loop: 1 when the phase with this parity is complete */
+DS_FN uint32_t mbar_try(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
 #else
 DS_FN void mbar_init(uint64_t *, int) {}
 DS_FN void fence_mbar_init() {}

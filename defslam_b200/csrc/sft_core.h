@@ -147,7 +147,7 @@ struct SmemLayout {
 constexpr int ROWS_OWNERS_ = 5;
 constexpr int ROWS_LT_STRIDE_ = 72;
 #ifndef DS_BWD_BUFS
-#define DS_BWD_BUFS 4
+#define DS_BWD_BUFS 8
 #endif
 constexpr int ROWS_BWD_BUFS_ = DS_BWD_BUFS; /* row blocks of the factor in flight during the backward sweep */
 

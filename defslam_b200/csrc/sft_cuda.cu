@@ -272,7 +272,7 @@ static int batch_wait_kernel(defslam_sft_batch *B) {
             (double)h[PF_X_BUILD + 3] / nb, (double)h[PF_X_BUILD + 4] / nb);
     fprintf(stderr, "[defslam profile] facet sums per build (thread 0): chunk setup+barrier %.0f, staging copy %.0f, barrier %.0f, sums %.0f\n",
             (double)h[PF_X_FS] / nb, (double)h[PF_X_FS + 1] / nb, (double)h[PF_X_FS + 2] / nb, (double)h[PF_X_FS + 3] / nb);
-    fprintf(stderr, "[defslam profile] backward sweep per step (thread 0): phase %.0f; TMA wait %.0f, block solve %.0f, update %.0f, barrier %.0f\n",
+    fprintf(stderr, "[defslam profile] backward sweep (thread 0; sliding window: per step, row owners: summed): phase %.0f; sliding window: TMA wait / row owners: copy issue %.0f, block solve / row arithmetic %.0f, update / late copy %.0f, barrier %.0f\n",
             (double)h[PF_BWD] / steps, (double)h[PF_X_BWD] / steps, (double)h[PF_X_BWD + 1] / steps,
             (double)h[PF_X_BWD + 2] / steps, (double)h[PF_X_BWD + 3] / steps);
   }

@@ -97,10 +97,27 @@ DS_FN int ld_vol_s32(const int *p) {
   asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
   return v;
 }
+DS_FN dbl2 ldcg_dbl2(const dbl2 *p) {
+  dbl2 v;
+  asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
 DS_FN void st_vol_s32(int *p, int v) { asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory"); }
 /* every lane polls (broadcast read); the data guarded by the counter is read after it in program order */
 DS_FN void spin_ge(const int *p, int need) {
   while (ld_vol_s32(p) < need) {
+  }
+}
+/* waits that are not on the critical path (border rows, producers of the backward sweep) back off between polls:
+ * a spinning warp takes issue slots and shared-memory cycles from the SM's other CTA */
+#ifndef DS_SPIN_SLEEP_NS
+#define DS_SPIN_SLEEP_NS 0
+#endif
+DS_FN void spin_ge_relaxed(const int *p, int need) {
+  while (ld_vol_s32(p) < need) {
+#if DS_SPIN_SLEEP_NS > 0
+    __nanosleep(DS_SPIN_SLEEP_NS);
+#endif
   }
 }
 /* publish: the warp's shared-memory stores first, then the counter */
@@ -290,7 +307,11 @@ DS_FN void rows_owner_warp(const RowShared &S, int widx, int nown, int nblk, int
       const int k = I - NBK + t;
       if (k < 0) continue; /* rows at the top: the tile does not exist */
       /* row I-1 has finished its tile of column k (=> so has every row above it, and inv(L_kk) exists) */
+#if defined(DS_SPIN_SLEEP_OWNERS)
+      spin_ge_relaxed(&S.prog[I - 1], t + 2);
+#else
       spin_ge(&S.prog[I - 1], t + 2);
+#endif
       const uint32_t tile = slot + 512u * (uint32_t)t;
       const uint32_t inv = S.ring + 512u * (uint32_t)((k % R) * NT + NBK);
       /* X = C inv(L_kk)^T: C goes through the tile's own ring location to change from accumulator to operand order */
@@ -342,7 +363,7 @@ DS_FN void rows_border_warp(const RowShared &S, int nblk, int R, const double *C
     /* border block of H (rows: camera border 0-5, rhs 6, pad 7; columns 8J..8J+7) */
     const dbl2 h = *(const dbl2 *)(Cg + (size_t)g * ES + NB * J + 2 * q);
     double e0 = h.x, e1 = h.y, f0 = 0.0, f1 = 0.0;
-    spin_ge(&S.ddone[J], 1); /* row J is final (its tiles and inv(L_JJ) are in the ring) */
+    spin_ge_relaxed(&S.ddone[J], 1); /* row J is final (its tiles and inv(L_JJ) are in the ring) */
     const uint32_t slot = S.ring + 512u * (uint32_t)((J % R) * NT);
 #pragma unroll
     for (int t = 0; t < NBK; t++) {
@@ -594,8 +615,9 @@ DS_FN_NOINLINE bool factor_rows(const Team team, double lambda) {
     for (int e = 0; e < 6; e++) s -= Eg[e * (size_t)ES + i] * dx[Dp + e];
     dx[i] = s;
   }
-  /* tiles written with plain stores by the row owners are read back through the async proxy */
-  fence_proxy_async();
+#if DS_CUDA
+  DS_FOR(i, nblk + 1) sy[i] = 0; /* ready flag of every block row + the sweep's progress */
+#endif
   team.sync();
 
   /* backward sweep L^T dn = v by block rows, bottom up: d = inv(L_kk)^T y, then dx[J] -= L(kb,J)^T d.
@@ -603,89 +625,142 @@ DS_FN_NOINLINE bool factor_rows(const Team team, double lambda) {
   constexpr int NBUF = ROWS_BWD_BUFS_;
   constexpr int BUFD = NT * LT_STRIDE + 64;
   double *sol = W + NBUF * BUFD;
-  const uint32_t row_bytes = (uint32_t)(NT * LT_STRIDE * sizeof(double)), inv_bytes = 64u * (uint32_t)sizeof(double);
-  const uint64_t polL = l2_policy_evict_first();
-  uint32_t phb[NBUF];
+  prof_mark(team, c, PF_BWD_INIT);
+#if DS_CUDA
+  /* ONE warp runs the sweep: the chain d_k -> y_{k-1} -> d_{k-1} has no parallelism across block rows, and a
+   * CTA-wide barrier per block row cost more than the 8 x NBK columns of a row give back when they are spread over
+   * eight warps (1.2 k cycles per block row).  As a single warp a row is: its columns of the row block, its entries
+   * of inv(L_kk) and y_k requested from shared memory up front, d by lanes + broadcast, <= 4 independent 8-term
+   * chains per lane, one warp barrier.  The other warps are the producers: warp w copies block rows w-1, w-1+P, ...
+   * of the factor from the workspace (L2) into the ring with plain 16-byte loads and raises the row's flag; they
+   * follow the sweep's progress counter NBUF rows ahead.  (Bulk copies issued by the sweeping warp itself cost it
+   * 320 cycles per row for the issue and 90 for each mbarrier poll -- measured -- on a row that needs about 300.)
+   * Same operations in the same order per entry as before: bit-identical. */
+  {
+    int *ready = sy, *done = sy + nblk;
+    const int P = nwarp - 1;
+    if (warp > 0) {
+      constexpr int NV = (BUFD / 2 + 31) / 32; /* 16-byte pieces of a row block per lane */
+      for (int j = warp - 1; j < nblk; j += P) {
+        const int kbj = nblk - 1 - j;
+        const dbl2 *srcL = (const dbl2 *)(Lt + (size_t)kbj * NT * LT_STRIDE), *srcY = (const dbl2 *)(Dinv + kbj * 64);
+        if (j >= NBUF) spin_ge_relaxed(done, j - NBUF + 1); /* the buffer's previous tenant has been consumed */
+        dbl2 *dst = (dbl2 *)(W + (j % NBUF) * BUFD);
 #pragma unroll
-  for (int b = 0; b < NBUF; b++) phb[b] = c.ph[1 + b];
-  if (team.tid == 0) {
-    for (int j = 0; j < NBUF - 1 && j < nblk; j++) {
-      const int kbj = nblk - 1 - j;
-      mbar_expect_tx(&c.mbar[1 + j], row_bytes + inv_bytes);
-      tma_load_1d_stream(W + j * BUFD, Lt + (size_t)kbj * NT * LT_STRIDE, row_bytes, &c.mbar[1 + j], polL);
-      tma_load_1d_stream(W + j * BUFD + NT * LT_STRIDE, Dinv + kbj * 64, inv_bytes, &c.mbar[1 + j], polL);
+        for (int i0 = 0; i0 < NV; i0 += 8) { /* eight loads in flight per lane */
+          dbl2 v[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const int e = lane + 32 * (i0 + i);
+            if (i0 + i < NV) {
+              if (e < NT * LT_STRIDE / 2) v[i] = ldcg_dbl2(srcL + e);
+              else if (e < BUFD / 2) v[i] = ldcg_dbl2(srcY + (e - NT * LT_STRIDE / 2));
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const int e = lane + 32 * (i0 + i);
+            if (i0 + i < NV && e < BUFD / 2) dst[e] = v[i];
+          }
+        }
+        publish(&ready[j], 1, lane);
+      }
+    } else {
+      constexpr int RN = (NB * NBK + 31) / 32; /* columns of a block row per lane */
+      DS_PROF_LOCALS(bwacc, 4);
+      DS_PROF_T0M(bwt);
+      spin_ge(&ready[0], 1);
+      DS_PROF_LAP(bwacc, 2, bwt);
+      for (int kb = nblk - 1; kb >= 0; kb--) {
+        const int k = kb * NB;
+        const int j = nblk - 1 - kb, buf = j % NBUF;
+        const double *LR = W + buf * BUFD, *Y = LR + NT * LT_STRIDE;
+        const int t0 = kb < NBK ? NBK - kb : 0; /* first tile of the row that exists */
+        const int nupd = NB * (NBK - t0);
+        /* the block next to the diagonal first: the next row's d depends on it alone */
+        double lv[RN][NB], yv[RN];
+        int jcs[RN];
+        bool valid[RN];
+#pragma unroll
+        for (int r = 0; r < RN; r++) {
+          /* lanes past the row's last column load from a valid address and do not store */
+          const int jj = lane + 32 * r;
+          const int tt = NBK - 1 - (jj >> 3), t = tt > 0 ? tt : 0, cc = jj & 7;
+          valid[r] = jj < nupd;
+          jcs[r] = valid[r] ? NB * (kb - NBK + t) + cc : 0;
+          const double *Lc = LR + t * LT_STRIDE + cc; /* Lc[a*8] = L[k+a][jc] */
+#pragma unroll
+          for (int a = 0; a < NB; a++) lv[r][a] = Lc[a * 8];
+          yv[r] = dx[jcs[r]];
+        }
+        const int la = lane & 7;
+        double ya[NB], xk[NB];
+        /* (the entries of inv(L_kk) above the diagonal are stored zeros) */
+#pragma unroll
+        for (int m = 0; m < NB; m++) { ya[m] = Y[m * 8 + la]; xk[m] = dx[k + m]; }
+        /* the next row's flag is read now and looked at after this row's arithmetic */
+        const int next_ready = kb > 0 ? ld_vol_s32(&ready[j + 1]) : 1;
+        /* d[a] = sum_{m >= a} Y[m][a] y[m] (Y = inv(L_kk), row-major): lane a (mod 8) forms d[a], then broadcast */
+        double d[NB];
+        {
+          double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+          for (int m = 0; m < NB; m += 2) {
+            s0 = fma(ya[m], xk[m], s0);
+            s1 = fma(ya[m + 1], xk[m + 1], s1);
+          }
+          const double mine = s0 + s1;
+          if (lane < NB) sol[k + lane] = mine;
+#pragma unroll
+          for (int a = 0; a < NB; a++) d[a] = __shfl_sync(0xffffffffu, mine, a);
+        }
+#pragma unroll
+        for (int a = 0; a < NB; a++)
+#pragma unroll
+          for (int r = 0; r < RN; r++) yv[r] -= lv[r][a] * d[a];
+#pragma unroll
+        for (int r = 0; r < RN; r++)
+          if (valid[r]) dx[jcs[r]] = yv[r];
+        __syncwarp();
+        if (lane == 0) st_vol_s32(done, j + 1);
+        DS_PROF_LAP(bwacc, 1, bwt); /* loads, d, update, stores */
+        if (next_ready < 1) {
+          spin_ge(&ready[j + 1], 1);
+          DS_PROF_LAP(bwacc, 2, bwt); /* the copy had not landed */
+        }
+      }
+      DS_PROF_FLUSH(bwacc, 4, PF_X_BWD, lane == 0);
     }
   }
-  prof_mark(team, c, PF_BWD_INIT);
+  team.sync();
+#else
   for (int kb = nblk - 1; kb >= 0; kb--) {
     const int k = kb * NB;
-    const int j = nblk - 1 - kb, buf = j % NBUF;
-    if (team.tid == 0) {
-      const int jn = j + NBUF - 1;
-      if (jn < nblk) { /* its buffer was last read at step j-1, before the barrier that ended that step */
-        const int kbn = nblk - 1 - jn, bn = jn % NBUF;
-        mbar_expect_tx(&c.mbar[1 + bn], row_bytes + inv_bytes);
-        tma_load_1d_stream(W + bn * BUFD, Lt + (size_t)kbn * NT * LT_STRIDE, row_bytes, &c.mbar[1 + bn], polL);
-        tma_load_1d_stream(W + bn * BUFD + NT * LT_STRIDE, Dinv + kbn * 64, inv_bytes, &c.mbar[1 + bn], polL);
-      }
-    }
-    const double *LR = W + buf * BUFD, *Y = LR + NT * LT_STRIDE;
-#pragma unroll
-    for (int b = 0; b < NBUF; b++)
-      if (b == buf) { mbar_wait(&c.mbar[1 + b], phb[b]); phb[b] ^= 1u; }
     const int t0 = kb < NBK ? NBK - kb : 0; /* first tile of the row that exists */
     const int nupd = NB * (NBK - t0);
-    const bool active = team.tid < (((nupd > NB ? nupd : NB) + 31) & ~31); /* whole warps (the broadcast below) */
-    if (active) {
-      /* d[a] = sum_{m >= a} Y[m][a] y[m] (Y = inv(L_kk), row-major) */
-      double d[NB];
-#if DS_CUDA
-      /* lane a of every active warp forms d[a] (one 8-term dot product), then the eight values are broadcast:
-       * 32 instructions per warp instead of 72 when every thread forms all eight */
-      {
-        const int la = team.tid & 7;
-        double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-        for (int m = 0; m < NB; m += 2) {
-          s0 = fma(m >= la ? Y[m * 8 + la] : 0.0, dx[k + m], s0);
-          s1 = fma(m + 1 >= la ? Y[(m + 1) * 8 + la] : 0.0, dx[k + m + 1], s1);
-        }
-        const double mine = s0 + s1;
-#pragma unroll
-        for (int a = 0; a < NB; a++) d[a] = __shfl_sync(0xffffffffu, mine, a);
+    const double *LR = Lt + (size_t)kb * NT * LT_STRIDE, *Y = Dinv + kb * 64;
+    double d[NB], y[NB];
+    for (int a = 0; a < NB; a++) y[a] = dx[k + a];
+    for (int a = 0; a < NB; a++) {
+      /* the device's summation order: two interleaved partial sums over m, zero terms above the diagonal */
+      double s0 = 0.0, s1 = 0.0;
+      for (int m = 0; m < NB; m += 2) {
+        s0 = fma(m >= a ? Y[m * 8 + a] : 0.0, y[m], s0);
+        s1 = fma(m + 1 >= a ? Y[(m + 1) * 8 + a] : 0.0, y[m + 1], s1);
       }
-#else
-      double y[NB];
-#pragma unroll
-      for (int a = 0; a < NB; a++) y[a] = dx[k + a];
-#pragma unroll
-      for (int a = 0; a < NB; a++) {
-        double s = Y[a * 8 + a] * y[a];
-#pragma unroll
-        for (int m = a + 1; m < NB; m++) s += Y[m * 8 + a] * y[m];
-        d[a] = s;
-      }
-#endif
-      if (team.tid == 0) {
-#pragma unroll
-        for (int a = 0; a < NB; a++) sol[k + a] = d[a];
-      }
-      DS_FOR(jj, nupd) {
-        const int t = t0 + (jj >> 3), cc = jj & 7;
-        const int jc = NB * (kb - NBK + t) + cc;
-        const double *Lc = LR + t * LT_STRIDE + cc; /* Lc[a*8] = L[k+a][jc] */
-        double s = dx[jc];
-#pragma unroll
-        for (int a = 0; a < NB; a++) s -= Lc[a * 8] * d[a];
-        dx[jc] = s;
-      }
+      d[a] = s0 + s1;
     }
-    team.sync();
+    for (int a = 0; a < NB; a++) sol[k + a] = d[a];
+    for (int jj = 0; jj < nupd; jj++) {
+      const int t = t0 + (jj >> 3), cc = jj & 7;
+      const int jc = NB * (kb - NBK + t) + cc;
+      const double *Lc = LR + t * LT_STRIDE + cc;
+      double s = dx[jc];
+      for (int a = 0; a < NB; a++) s -= Lc[a * 8] * d[a];
+      dx[jc] = s;
+    }
   }
-  if (team.tid == 0) {
-#pragma unroll
-    for (int b = 0; b < NBUF; b++) c.ph[1 + b] = phb[b];
-  }
+#endif
   DS_FOR(i, Dp) dx[i] = sol[i];
   team.sync();
   prof_mark(team, c, PF_BWD);

@@ -43,6 +43,48 @@ template <int RS> __device__ __forceinline__ void chol8(double *a) {
       for (int j = k + 1; j <= i; j++) a[i * (i + 1) / 2 + j] -= a[i * (i + 1) / 2 + k] * a[j * (j + 1) / 2 + k];
   }
 }
+// third-order reciprocal from the hardware seed (MUFU.RCP64H, ~2^-20): y1 = y0 (1 + e + e^2), e = 1 - d y0
+__device__ __forceinline__ double rcp_fast(double d) {
+  double y0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
+  const double e = fma(-d, y0, 1.0);
+  const double t = y0 * e;
+  const double q = 1.0 + e;
+  return fma(t, q, y0);
+}
+// 2x2 block pivots (block LDL^T turned into the Cholesky factor off the chain): per pair of columns the only
+// dependent sequence is det -> 1/det -> one fma per entry of the next pivot block; the reciprocal square roots that
+// scale the columns of L are not on the path to the next pivot
+__device__ __forceinline__ void chol8_blk2(double *a) {
+#define A_(i, j) a[(i) * ((i) + 1) / 2 + (j)]
+#pragma unroll
+  for (int k = 0; k < 8; k += 2) {
+    const double p = A_(k, k), b = A_(k + 1, k), c = A_(k + 1, k + 1);
+    const double det = fma(p, c, -b * b);
+    const double rdet = rcp_fast(det);
+    double na[8], nb[8];
+#pragma unroll
+    for (int i = k + 2; i < 8; i++) {
+      const double u = A_(i, k), v = A_(i, k + 1);
+      na[i] = fma(u, c, -v * b);
+      nb[i] = fma(v, p, -u * b);
+    }
+#pragma unroll
+    for (int i = k + 2; i < 8; i++)
+#pragma unroll
+      for (int j = k + 2; j <= i; j++) {
+        const double w = fma(na[i], A_(j, k), nb[i] * A_(j, k + 1));
+        A_(i, j) = fma(-w, rdet, A_(i, j));
+      }
+    const double r1 = rsq_fast(p), r2 = rsq_fast(p * det);
+    A_(k, k) = r1;
+    A_(k + 1, k) = b * r1;
+    A_(k + 1, k + 1) = p * r2;
+#pragma unroll
+    for (int i = k + 2; i < 8; i++) { A_(i, k) *= r1; A_(i, k + 1) = nb[i] * r2; }
+  }
+#undef A_
+}
 // column j of the inverse
 __device__ __forceinline__ void invcol8(const double *a, int j, double *col) {
   double s[8];
@@ -89,7 +131,7 @@ __global__ void chain(double *gm, long long *cyc, int n, int busy_warps) {
 #pragma unroll
         for (int j = 0; j <= i; j++) a[i * (i + 1) / 2 + j] = LOAD ? Dv[i * 8 + j] : (gm[i * 8 + j] + acc);
       a[0] += acc; /* dependency between iterations: the chain */
-      chol8<RS>(a);
+      if (RS == 3) chol8_blk2(a); else chol8<RS>(a);
       double col[8];
       if (INV == 1) {
         invcol8(a, lane & 7, col);
@@ -138,6 +180,17 @@ template <int RS, int INV, bool LOAD> void run(const char *name, double *gm, lon
   printf("%-46s busy warps %d: %7.1f cycles / block\n", name, busy, (double)h / n);
 }
 
+__global__ void cmp_kernel(const double *gm, double *out) {
+  double a[36], b[36];
+  for (int i = 0; i < 8; i++)
+    for (int j = 0; j <= i; j++) a[i * (i + 1) / 2 + j] = b[i * (i + 1) / 2 + j] = gm[i * 8 + j];
+  chol8<0>(a);
+  chol8_blk2(b);
+  double m = 0.0;
+  for (int i = 0; i < 36; i++) m = fmax(m, fabs(a[i] - b[i]) / fabs(a[i]));
+  out[0] = m;
+}
+
 int main() {
   double h[64];
   for (int i = 0; i < 8; i++)
@@ -152,6 +205,14 @@ int main() {
     run<0, 1, true>("chol8 lib rsqrt + inverse (runtime column)", gm, cyc, busy);
     run<1, 1, true>("chol8 fast rsqrt + inverse (runtime column)", gm, cyc, busy);
     run<1, 2, true>("chol8 fast rsqrt + inverse (switch column)", gm, cyc, busy);
+    run<3, 0, true>("2x2 block pivots, no inverse", gm, cyc, busy);
+    run<3, 1, true>("2x2 block pivots + inverse (runtime column)", gm, cyc, busy);
+  }
+  {
+    double *out; cudaMalloc(&out, 8);
+    cmp_kernel<<<1, 1>>>(gm, out);
+    double m; cudaMemcpy(&m, out, 8, cudaMemcpyDeviceToHost);
+    printf("2x2 block pivots vs library-rsqrt Cholesky: max relative difference of the factor %.3g\n", m);
   }
   printf("err %s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;
