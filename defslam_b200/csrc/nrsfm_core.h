@@ -26,6 +26,7 @@
 #define DS_NRSFM_CORE_H_
 #include "../../include/defslam_b200.h"
 #include "bbs_core.h"
+#include "ds_rowchol.h"
 
 #if DS_CUDA
 #define DS_HD __host__ __device__ __forceinline__
@@ -216,6 +217,154 @@ DS_FN_NOINLINE bool bband_solve(const Team team, const BandDims bd, const double
 }
 
 /* ===================================================================== *
+ *  The same solve on the FP64 tensor cores: row-owner banded Cholesky of
+ *  ds_rowchol.h (the machinery of the SfT step).  The block band is read as a
+ *  scalar band of half-bandwidth (kb+1)*bs - 1 in tiles of 8x8; n is padded to
+ *  a multiple of 8 with identity rows; the right-hand sides are the border rows.
+ * ===================================================================== */
+constexpr int ROWS_SWEEP_BUFS = 8;
+
+struct RowPlan {
+  int nt;      /* tiles per block row (0: not available, use bband_solve) */
+  int owners;  /* row-owner warps the ring has room for */
+  int nblk, Dp;
+  int smem;    /* doubles of shared memory */
+  int ws;      /* doubles of global workspace (tile-form factor, inverses of the diagonal blocks, border rows) */
+};
+
+/* instantiated tile counts (a band narrower than NT-1 tiles carries zero tiles on its left) */
+static inline
+#if DS_CUDA
+__host__ __device__
+#endif
+int rows_nt_for(int nbk) {
+  const int need = nbk + 1;
+  const int have[] = {6, 8, 10, 12, 14, 16, 18};
+  for (int i = 0; i < 7; i++) if (have[i] >= need) return have[i];
+  return 0;
+}
+
+static inline
+#if DS_CUDA
+__host__ __device__
+#endif
+RowPlan rows_plan(int n, int bw, int avail_doubles, int nthreads) {
+  RowPlan p{0, 0, 0, 0, 0, 0};
+#if DS_CUDA
+  const int nt = rows_nt_for((bw + 7) / 8);
+  if (nt == 0 || nthreads < 128) return p;
+  const int Dp = round_up(n, 8), nblk = Dp / 8;
+  const int fixed = nt * 64 + 128 + (3 * nblk + 2 + 32 + 2) / 2 + 2 + 2 * (Dp + 8);
+  const int bsz = ROWS_SWEEP_BUFS * (nt * LT_STRIDE + 64);
+  for (int own = 5; own >= 2; own--) {
+    int w = (nt - 1 + own) * nt * 64;
+    if (w < bsz) w = bsz;
+    if (fixed + w <= avail_doubles) {
+      p.nt = nt; p.owners = own; p.nblk = nblk; p.Dp = Dp; p.smem = fixed + w;
+      p.ws = nblk * nt * LT_STRIDE + nblk * 64 + 16 * Dp;
+      return p;
+    }
+  }
+#else
+  (void)n; (void)bw; (void)avail_doubles; (void)nthreads;
+#endif
+  return p;
+}
+
+#if DS_CUDA
+/* entry (i, c) of diag(sc) H diag(sc) + diag(add), padded with the identity */
+struct BBandLoader {
+  const double *Hb;
+  BandDims bd;
+  const double *sc, *add;
+  int n;
+  DS_FN double entry(int i, int Ib, int ir, double si, int c, int Jb, int cr) const {
+    if (c > i) return 0.0;
+    if (i >= n) return i == c ? 1.0 : 0.0;
+    const int d = Ib - Jb;
+    if (d > bd.kb) return 0.0;
+    double v = Hb[bd.blk(Ib, d) + (size_t)ir * bd.bs + cr];
+    if (sc) v *= si * sc[c];
+    if (add && i == c) v += add[i];
+    return v;
+  }
+  template <int NT>
+  DS_FN void load(int I, int g, int q, double *a0, double *a1) const {
+    constexpr int NBK = NT - 1;
+    const int bs = bd.bs;
+    const int i = NB * I + g;
+    const int Ib = i < n ? i / bs : 0, ir = i - Ib * bs;
+    const double si = (sc && i < n) ? sc[i] : 1.0;
+    int Jb = 0, cr = 0; /* block and offset of column c, advanced from tile to tile */
+#pragma unroll
+    for (int t = 0; t < NT; t++) {
+      const int J = I - NBK + t;
+      if (J < 0) { a0[t] = 0.0; a1[t] = 0.0; continue; }
+      const int c = NB * J + 2 * q;
+      if (J == 0 || t == 0) { Jb = c / bs; cr = c - Jb * bs; }
+      else { cr += NB; while (cr >= bs) { cr -= bs; Jb++; } }
+      int Jb1 = Jb, cr1 = cr + 1;
+      if (cr1 >= bs) { cr1 = 0; Jb1++; }
+      a0[t] = entry(i, Ib, ir, si, c, Jb, cr);
+      a1[t] = entry(i, Ib, ir, si, c + 1, Jb1, cr1);
+    }
+  }
+};
+
+/* Same contract as bband_solve(); ws: plan.ws doubles of global workspace; sh: plan.smem doubles. */
+template <int NT>
+DS_FN_NOINLINE bool bband_solve_rows(const Team team, const BandDims bd, const RowPlan plan, const double *Hb, double *wsg,
+                                     const double *sc, const double *add, double *sh, double *rhs, int nrhs, int ldr) {
+  const int n = bd.nb * bd.bs, Dp = plan.Dp, nblk = plan.nblk;
+  const int R = NT - 1 + plan.owners;
+  int wsz = R * NT * 64;
+  { const int bsz = ROWS_SWEEP_BUFS * (NT * LT_STRIDE + 64); if (wsz < bsz) wsz = bsz; }
+  double *W = sh, *er = W + wsz, *db = er + NT * 64, *dx = db + 128, *sol = dx + Dp + 8;
+  int *sy = (int *)(sol + Dp + 8), *flag = sy + 3 * nblk + 2 + 32 + 1;
+  double *Lt = wsg, *Dinv = Lt + (size_t)nblk * NT * LT_STRIDE, *Cg = Dinv + (size_t)nblk * 64, *Eg = Cg + 8 * (size_t)Dp;
+  /* the right-hand sides as border rows (the other rows of the border tile are zero) */
+  DS_FOR(idx, 8 * Dp) {
+    const int r = idx / Dp, i = idx - r * Dp;
+    Cg[idx] = (r < nrhs && i < n) ? rhs[r * ldr + i] : 0.0;
+  }
+  team.sync();
+  rows_factor<NT>(team.tid, team.nthr, nblk, plan.owners, BBandLoader{Hb, bd, sc, add, n}, W, er, db, sy, flag, Cg, Eg, Dp,
+                  (double *)nullptr, (const double *)nullptr, 0.0, Lt, Dinv);
+  if (*flag != 0) { team.sync(); return false; }
+  for (int r = 0; r < nrhs; r++) {
+    DS_FOR(i, Dp) dx[i] = Eg[(size_t)r * Dp + i];
+    DS_FOR(i, nblk + 1) sy[i] = 0;
+    team.sync();
+    rows_backward<NT, ROWS_SWEEP_BUFS>(team.tid, team.nthr, nblk, W, sy, Lt, Dinv, dx, sol);
+    team.sync();
+    DS_FOR(i, n) rhs[r * ldr + i] = sol[i];
+    team.sync();
+  }
+  return true;
+}
+#endif
+
+/* dispatch: tensor-core row form where the plan has one, the scalar window otherwise */
+DS_FN bool bband_solve_any(const Team team, const BandDims bd, const RowPlan plan, const double *Hb, double *Lb,
+                           const double *sc, const double *add, double *sh, double *rhs, int nrhs, int ldr) {
+#if DS_CUDA
+  switch (plan.nt) {
+    case 6: return bband_solve_rows<6>(team, bd, plan, Hb, Lb, sc, add, sh, rhs, nrhs, ldr);
+    case 8: return bband_solve_rows<8>(team, bd, plan, Hb, Lb, sc, add, sh, rhs, nrhs, ldr);
+    case 10: return bband_solve_rows<10>(team, bd, plan, Hb, Lb, sc, add, sh, rhs, nrhs, ldr);
+    case 12: return bband_solve_rows<12>(team, bd, plan, Hb, Lb, sc, add, sh, rhs, nrhs, ldr);
+    case 14: return bband_solve_rows<14>(team, bd, plan, Hb, Lb, sc, add, sh, rhs, nrhs, ldr);
+    case 16: return bband_solve_rows<16>(team, bd, plan, Hb, Lb, sc, add, sh, rhs, nrhs, ldr);
+    case 18: return bband_solve_rows<18>(team, bd, plan, Hb, Lb, sc, add, sh, rhs, nrhs, ldr);
+    default: break;
+  }
+#else
+  (void)plan;
+#endif
+  return bband_solve(team, bd, Hb, Lb, sc, add, sh, rhs, nrhs, ldr);
+}
+
+/* ===================================================================== *
  *  Sites sorted by knot cell (shared by the Schwarp data term and SfN)
  * ===================================================================== */
 struct CellSort {
@@ -322,6 +471,67 @@ struct SchwarpSizes {
   size_t cell, cstart, perm, taps, CtC, Hb, Lb, Js, rdata, sdv, total;
 };
 
+/* shared-memory carve-up (doubles); sdv < 0: site arrays live in the global workspace */
+struct SchwarpSmem {
+  int x, xc, g, scale, add, step, sdv, rs, ci, red, su, ints, solver, total;
+  RowPlan p1, p2; /* tensor-core row form of the initialisation solve (bs = nptsv) and of the LM solve (bs = 2 nptsv) */
+};
+constexpr int SCHWARP_SMEM_LIMIT_DOUBLES = 227 * 1024 / 8 - 64;
+#ifndef NRSFM_THREADS_
+#define NRSFM_THREADS_ 512
+#endif
+static inline
+#if DS_CUDA
+__host__ __device__
+#endif
+SchwarpSmem schwarp_smem(int nptsu, int nptsv) {
+  SchwarpSmem m;
+  const int NC = nptsu * nptsv, NP = 2 * NC;
+  BandDims b1{nptsv, nptsu, 3}, b2{2 * nptsv, nptsu, 3};
+  const int nints = (3 * (nptsu + nptsv) + 1) / 2 + 2;
+  const int base = 6 * NP + 48 + 40 + nints + 1;
+  /* the solver region: the row form of the LM solve if its ring fits (with the site arrays in shared memory if
+   * that fits too, else with them in the global workspace), else the scalar window */
+  bool sites_in_smem = false;
+  m.p1 = m.p2 = RowPlan{0, 0, 0, 0, 0, 0};
+  int solver = 0;
+  for (int pass = 0; pass < 2 && m.p2.nt == 0; pass++) {
+    const int avail = SCHWARP_SMEM_LIMIT_DOUBLES - base - (pass == 0 ? 14 * NC : 0);
+    const RowPlan p2 = rows_plan(NP, 4 * b2.bs - 1, avail, NRSFM_THREADS_);
+    if (p2.nt == 0) continue;
+    m.p2 = p2;
+    sites_in_smem = pass == 0;
+    solver = p2.smem;
+    const RowPlan p1 = rows_plan(NC, 4 * b1.bs - 1, avail, NRSFM_THREADS_);
+    if (p1.nt > 0) { m.p1 = p1; if (p1.smem > solver) solver = p1.smem; }
+    else if ((int)b1.smem_doubles(2) <= avail) { if ((int)b1.smem_doubles(2) > solver) solver = (int)b1.smem_doubles(2); }
+    else { m.p2 = RowPlan{0, 0, 0, 0, 0, 0}; } /* (cannot happen for grids the scalar path accepts) */
+  }
+  if (m.p2.nt == 0) {
+    solver = (int)b2.smem_doubles(2);
+    sites_in_smem = base + 14 * NC + solver <= SCHWARP_SMEM_LIMIT_DOUBLES;
+  }
+  int o = 0;
+  m.x = o; o += NP;
+  m.xc = o; o += NP;
+  m.g = o; o += NP;      /* gradient, block order */
+  m.scale = o; o += NP;  /* Jacobi scaling, block order */
+  m.add = o; o += NP;
+  m.step = o; o += NP;   /* rhs / solution (2 columns for the initialisation: NP >= 2*NC) */
+  m.sdv = sites_in_smem ? o : -1; /* per site: xu yu xv yv xuu yuu xvv yvv xuv yuv */
+  if (sites_in_smem) o += 10 * NC;
+  m.rs = sites_in_smem ? o : -1;
+  if (sites_in_smem) o += 4 * NC;
+  m.ci = o; o += 48;
+  m.red = o; o += 40;
+  m.su = o; o += 0;
+  m.ints = o; o += nints; /* site intervals + lo/hi site ranges (ints) */
+  o = (o + 1) & ~1;       /* the solver region holds 16-byte tiles */
+  m.solver = o; o += solver;
+  m.total = o;
+  return m;
+}
+
 static inline
 #if DS_CUDA
 __host__ __device__
@@ -337,47 +547,18 @@ SchwarpSizes schwarp_ws_sizes(int nptsu, int nptsv, int nmax) {
   z.taps = o; o += al(sizeof(double) * 8 * nmax);
   z.CtC = o; o += al(sizeof(double) * nptsu * 4 * nptsv * nptsv);
   z.Hb = o; o += al(sizeof(double) * nptsu * 4 * 4 * nptsv * nptsv);
-  z.Lb = o; o += al(sizeof(double) * nptsu * 4 * 4 * nptsv * nptsv);
+  {
+    const SchwarpSmem m = schwarp_smem(nptsu, nptsv);
+    size_t lb = (size_t)nptsu * 4 * 4 * nptsv * nptsv;
+    if ((size_t)m.p1.ws > lb) lb = (size_t)m.p1.ws;
+    if ((size_t)m.p2.ws > lb) lb = (size_t)m.p2.ws;
+    z.Lb = o; o += al(sizeof(double) * lb);
+  }
   z.Js = o; o += al(sizeof(double) * NC * 128);
   z.rdata = o; o += al(sizeof(double) * 2 * nmax);
   z.sdv = o; o += al(sizeof(double) * 14 * NC);
   z.total = o;
   return z;
-}
-
-/* shared-memory carve-up (doubles); sdv < 0: site arrays live in the global workspace */
-struct SchwarpSmem {
-  int x, xc, g, scale, add, step, sdv, rs, ci, red, su, ints, solver, total;
-};
-constexpr int SCHWARP_SMEM_LIMIT_DOUBLES = 227 * 1024 / 8 - 64;
-static inline
-#if DS_CUDA
-__host__ __device__
-#endif
-SchwarpSmem schwarp_smem(int nptsu, int nptsv) {
-  SchwarpSmem m;
-  const int NC = nptsu * nptsv, NP = 2 * NC;
-  int o = 0;
-  m.x = o; o += NP;
-  m.xc = o; o += NP;
-  m.g = o; o += NP;      /* gradient, block order */
-  m.scale = o; o += NP;  /* Jacobi scaling, block order */
-  m.add = o; o += NP;
-  m.step = o; o += NP;   /* rhs / solution (2 columns for the initialisation: NP >= 2*NC) */
-  BandDims b2{2 * nptsv, nptsu, 3};
-  const bool sites_in_smem = 6 * NP + 14 * NC + 48 + 40 + (3 * (nptsu + nptsv) + 1) / 2 + 2 + (int)b2.smem_doubles(2) <=
-                             SCHWARP_SMEM_LIMIT_DOUBLES;
-  m.sdv = sites_in_smem ? o : -1; /* per site: xu yu xv yv xuu yuu xvv yvv xuv yuv */
-  if (sites_in_smem) o += 10 * NC;
-  m.rs = sites_in_smem ? o : -1;
-  if (sites_in_smem) o += 4 * NC;
-  m.ci = o; o += 48;
-  m.red = o; o += 40;
-  m.su = o; o += 0;
-  m.ints = o; o += (3 * (nptsu + nptsv) + 1) / 2 + 2; /* site intervals + lo/hi site ranges (ints) */
-  m.solver = o; o += (int)b2.smem_doubles(2);
-  m.total = o;
-  return m;
 }
 
 DS_FN double *site_derivs(const SchwarpWs &ws, double *sh, const SchwarpSmem &m) { return m.sdv >= 0 ? sh + m.sdv : ws.sdv; }
@@ -751,7 +932,7 @@ DS_FN_NOINLINE void schwarp_fit_one(const Team team, const SchwarpProb &P, const
       step[NC + p] = ay;
     }
     team.sync();
-    const bool ok = bband_solve(team, b1, ws.Hb, ws.Lb, nullptr, nullptr, sh + m.solver, step, 2, NC);
+    const bool ok = bband_solve_any(team, b1, m.p1, ws.Hb, ws.Lb, nullptr, nullptr, sh + m.solver, step, 2, NC);
     team.sync();
     if (ok) {
       DS_FOR(i, NP) x[i] = step[i];
@@ -792,7 +973,7 @@ DS_FN_NOINLINE void schwarp_fit_one(const Team team, const SchwarpProb &P, const
       step[i] = g[i] * scale[i];
     }
     team.sync();
-    bool valid = bband_solve(team, b2, ws.Hb, ws.Lb, scale, add, sh + m.solver, step, 1, NP);
+    bool valid = bband_solve_any(team, b2, m.p2, ws.Hb, ws.Lb, scale, add, sh + m.solver, step, 1, NP);
     team.sync();
     double model_change = 0.0;
     if (valid) {

@@ -37,7 +37,7 @@ struct Packer {
   size_t add(size_t bytes) { size_t o = total; total += (bytes + 255) & ~(size_t)255; return o; }
 };
 
-constexpr int NRSFM_THREADS = 512;
+constexpr int NRSFM_THREADS = NRSFM_THREADS_;
 
 BbsView to_view(const defslam_bbs *b) {
   BbsView s;

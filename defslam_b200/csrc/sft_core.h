@@ -1071,7 +1071,8 @@ DS_FN void diag_factor(const Team team, double *W, int kslot, int Wr, int ld, in
 #endif
 }
 
-#if DS_CUDA
+#if DS_CUDA && !defined(DS_DMMA884_DEFINED)
+#define DS_DMMA884_DEFINED
 /* D(8x8) += A(8x4) B(4x8) on the FP64 tensor cores.  Lane T holds a = A[T/4][T%4],
  * b = B[T%4][T/4], and d0,d1 = D[T/4][2*(T%4)], D[T/4][2*(T%4)+1]. */
 DS_FN void dmma884(double &d0, double &d1, double a, double b) {
