@@ -246,6 +246,7 @@ DS_FN void rows_owner_warp(const RowShared &S, int widx, int nown, int nblk, int
     /* ---- the row's band of H into accumulator registers (lane (g,q): row g, columns 2q, 2q+1 of each tile) */
     double a0[NT], a1[NT];
     ldr.template load<NT>(I, g, q, a0, a1);
+    DS_PROF_LAP(oacc, 0, ot); /* the row's band read */
     /* the slot's previous tenant (row I-R) was last read by the border warp */
     if (I >= R) spin_ge(S.edone, I - R + 1);
     const uint32_t slot = S.ring + 512u * (uint32_t)((I % R) * NT);

@@ -26,6 +26,16 @@
 #define DS_NRSFM_CORE_H_
 #include "../../include/defslam_b200.h"
 #include "bbs_core.h"
+#if defined(DS_NRSFM_PROF) && defined(__CUDACC__)
+#include <stdio.h>
+/* diagnostic build: the lap counters of ds_rowchol.h summed into a device array (block 0 prints them) */
+__device__ long long g_rowprof[40];
+enum { PF_X_WARP = 0, PF_X_BWD = 20 };
+#define DS_PROF_LOCALS(name, n) long long name[n] = {}
+#define DS_PROF_LAP(name, i, t) do { const long long now_ = clock64(); name[i] += now_ - t; t = now_; } while (0)
+#define DS_PROF_T0M(var) long long var = clock64()
+#define DS_PROF_FLUSH(name, n, idx, cond) do { if (blockIdx.x == 0 && (cond)) for (int i_ = 0; i_ < n; i_++) g_rowprof[idx + i_] += name[i_]; } while (0)
+#endif
 #include "ds_rowchol.h"
 
 #if DS_CUDA
@@ -254,7 +264,7 @@ RowPlan rows_plan(int n, int bw, int avail_doubles, int nthreads) {
   const int nt = rows_nt_for((bw + 7) / 8);
   if (nt == 0 || nthreads < 128) return p;
   const int Dp = round_up(n, 8), nblk = Dp / 8;
-  const int fixed = nt * 64 + 128 + (3 * nblk + 2 + 32 + 2) / 2 + 2 + 2 * (Dp + 8);
+  const int fixed = nt * 64 + 128 + (3 * nblk + 2 + 32 + 2 + Dp + 2) / 2 + 2 + 2 * (Dp + 8);
   const int bsz = ROWS_SWEEP_BUFS * (nt * LT_STRIDE + 64);
   for (int own = 5; own >= 2; own--) {
     int w = (nt - 1 + own) * nt * 64;
@@ -272,42 +282,72 @@ RowPlan rows_plan(int n, int bw, int avail_doubles, int nthreads) {
 }
 
 #if DS_CUDA
-/* entry (i, c) of diag(sc) H diag(sc) + diag(add), padded with the identity */
+/* entry (i, c) of diag(sc) H diag(sc) + diag(add), padded with the identity.  Straight-line code: ctab[c] holds the
+ * block and the offset inside the block of column c ((c / bs) << 16 | c % bs, one table per solve in shared memory);
+ * the addresses of a lane's entries are formed first, then all loads of a batch are issued (clamped to a valid
+ * address where the entry is a structural zero), then scaled.  With a branch per entry the loads went out one L2
+ * round trip after the other, with the division-free walk over the columns the lanes of a warp diverged. */
 struct BBandLoader {
   const double *Hb;
   BandDims bd;
   const double *sc, *add;
   int n;
-  DS_FN double entry(int i, int Ib, int ir, double si, int c, int Jb, int cr) const {
-    if (c > i) return 0.0;
-    if (i >= n) return i == c ? 1.0 : 0.0;
-    const int d = Ib - Jb;
-    if (d > bd.kb) return 0.0;
-    double v = Hb[bd.blk(Ib, d) + (size_t)ir * bd.bs + cr];
-    if (sc) v *= si * sc[c];
-    if (add && i == c) v += add[i];
-    return v;
-  }
+  const int *ctab;
   template <int NT>
   DS_FN void load(int I, int g, int q, double *a0, double *a1) const {
     constexpr int NBK = NT - 1;
-    const int bs = bd.bs;
+    const int bs = bd.bs, kb = bd.kb;
     const int i = NB * I + g;
-    const int Ib = i < n ? i / bs : 0, ir = i - Ib * bs;
-    const double si = (sc && i < n) ? sc[i] : 1.0;
-    int Jb = 0, cr = 0; /* block and offset of column c, advanced from tile to tile */
+    const bool rowok = i < n;
+    const int ti = ctab[rowok ? i : 0];
+    const int Ib = ti >> 16, ir = ti & 0xffff;
+    const double si = (sc && rowok) ? sc[i] : 1.0;
+    const int blk_doubles = bs * bs;
+    const double *rowp = Hb + (size_t)Ib * (kb + 1) * blk_doubles + (size_t)ir * bs; /* row ir of block (Ib, 0) */
+    constexpr int HT = (NT + 1) / 2; /* two batches of loads: the addresses of one batch fit the register budget */
 #pragma unroll
-    for (int t = 0; t < NT; t++) {
-      const int J = I - NBK + t;
-      if (J < 0) { a0[t] = 0.0; a1[t] = 0.0; continue; }
-      const int c = NB * J + 2 * q;
-      if (J == 0 || t == 0) { Jb = c / bs; cr = c - Jb * bs; }
-      else { cr += NB; while (cr >= bs) { cr -= bs; Jb++; } }
-      int Jb1 = Jb, cr1 = cr + 1;
-      if (cr1 >= bs) { cr1 = 0; Jb1++; }
-      a0[t] = entry(i, Ib, ir, si, c, Jb, cr);
-      a1[t] = entry(i, Ib, ir, si, c + 1, Jb1, cr1);
+    for (int h = 0; h < 2; h++) {
+      int off0[HT], off1[HT]; /* offset of the entry from rowp, -1: structural zero */
+#pragma unroll
+      for (int tt = 0; tt < HT; tt++) {
+        const int t = h * HT + tt;
+        if (t >= NT) continue;
+        const int c = NB * (I - NBK + t) + 2 * q; /* c + 1 <= 8 J + 7 < Dp */
+        const int cc = c >= 0 ? c : 0;
+        const int t0 = ctab[cc], t1 = ctab[cc + 1];
+        const int d0 = Ib - (t0 >> 16), d1 = Ib - (t1 >> 16);
+        const bool v0 = rowok && c >= 0 && c <= i && d0 <= kb;
+        const bool v1 = rowok && c >= 0 && c + 1 <= i && d1 <= kb;
+        off0[tt] = v0 ? d0 * blk_doubles + (t0 & 0xffff) : -1;
+        off1[tt] = v1 ? d1 * blk_doubles + (t1 & 0xffff) : -1;
+      }
+#pragma unroll
+      for (int tt = 0; tt < HT; tt++) {
+        const int t = h * HT + tt;
+        if (t >= NT) continue;
+#if defined(DS_LOADER_NOMEM) /* experiment: no global loads (timing only, wrong results) */
+        a0[t] = (NB * (I - NBK + t) + 2 * q == i) ? 1e6 : 1e-9 * off0[tt];
+        a1[t] = (NB * (I - NBK + t) + 2 * q + 1 == i) ? 1e6 : 1e-9 * off1[tt];
+#else
+        a0[t] = rowp[off0[tt] >= 0 ? off0[tt] : 0];
+        a1[t] = rowp[off1[tt] >= 0 ? off1[tt] : 0];
+#endif
+      }
+#pragma unroll
+      for (int tt = 0; tt < HT; tt++) {
+        const int t = h * HT + tt;
+        if (t >= NT) continue;
+        const int c = NB * (I - NBK + t) + 2 * q;
+        double s0 = 1.0, s1 = 1.0;
+        if (sc) { s0 = si * sc[off0[tt] >= 0 ? c : 0]; s1 = si * sc[off1[tt] >= 0 ? c + 1 : 0]; }
+        a0[t] = off0[tt] >= 0 ? a0[t] * s0 : 0.0;
+        a1[t] = off1[tt] >= 0 ? a1[t] * s1 : 0.0;
+      }
     }
+    /* the diagonal entry: + add, or 1 on the padding rows */
+    const double dadd = rowok ? (add ? add[i] : 0.0) : 1.0;
+    if (2 * q == g) a0[NT - 1] += dadd;
+    if (2 * q + 1 == g) a1[NT - 1] += dadd;
   }
 };
 
@@ -320,16 +360,26 @@ DS_FN_NOINLINE bool bband_solve_rows(const Team team, const BandDims bd, const R
   int wsz = R * NT * 64;
   { const int bsz = ROWS_SWEEP_BUFS * (NT * LT_STRIDE + 64); if (wsz < bsz) wsz = bsz; }
   double *W = sh, *er = W + wsz, *db = er + NT * 64, *dx = db + 128, *sol = dx + Dp + 8;
-  int *sy = (int *)(sol + Dp + 8), *flag = sy + 3 * nblk + 2 + 32 + 1;
+  int *sy = (int *)(sol + Dp + 8), *flag = sy + 3 * nblk + 2 + 32 + 1, *ctab = flag + 1;
   double *Lt = wsg, *Dinv = Lt + (size_t)nblk * NT * LT_STRIDE, *Cg = Dinv + (size_t)nblk * 64, *Eg = Cg + 8 * (size_t)Dp;
   /* the right-hand sides as border rows (the other rows of the border tile are zero) */
+#if defined(DS_NRSFM_PROF)
+  const long long q0 = clock64();
+#endif
   DS_FOR(idx, 8 * Dp) {
     const int r = idx / Dp, i = idx - r * Dp;
     Cg[idx] = (r < nrhs && i < n) ? rhs[r * ldr + i] : 0.0;
   }
+  DS_FOR(c, Dp + 1) { const int J = c / bd.bs; ctab[c] = c < n ? (J << 16) | (c - J * bd.bs) : (0x7fff << 16); }
   team.sync();
-  rows_factor<NT>(team.tid, team.nthr, nblk, plan.owners, BBandLoader{Hb, bd, sc, add, n}, W, er, db, sy, flag, Cg, Eg, Dp,
+#if defined(DS_NRSFM_PROF)
+  const long long q1 = clock64();
+#endif
+  rows_factor<NT>(team.tid, team.nthr, nblk, plan.owners, BBandLoader{Hb, bd, sc, add, n, ctab}, W, er, db, sy, flag, Cg, Eg, Dp,
                   (double *)nullptr, (const double *)nullptr, 0.0, Lt, Dinv);
+#if defined(DS_NRSFM_PROF)
+  const long long q2 = clock64();
+#endif
   if (*flag != 0) { team.sync(); return false; }
   for (int r = 0; r < nrhs; r++) {
     DS_FOR(i, Dp) dx[i] = Eg[(size_t)r * Dp + i];
@@ -340,6 +390,16 @@ DS_FN_NOINLINE bool bband_solve_rows(const Team team, const BandDims bd, const R
     DS_FOR(i, n) rhs[r * ldr + i] = sol[i];
     team.sync();
   }
+#if defined(DS_NRSFM_PROF)
+  if (team.tid == 0 && blockIdx.x == 0)
+  {
+    printf("[nrsfm prof] NT %d nblk %d owners %d: staging %lld, factorisation %lld, backward sweeps %lld cycles; chain wait %lld busy %lld; owners (load / steps):"
+           " %lld/%lld %lld/%lld %lld/%lld %lld/%lld %lld/%lld\n", NT, nblk,
+           plan.owners, q1 - q0, q2 - q1, clock64() - q2, g_rowprof[0], g_rowprof[1], g_rowprof[2], g_rowprof[3], g_rowprof[4],
+           g_rowprof[5], g_rowprof[6], g_rowprof[7], g_rowprof[8], g_rowprof[9], g_rowprof[10], g_rowprof[11]);
+    for (int i = 0; i < 40; i++) g_rowprof[i] = 0;
+  }
+#endif
   return true;
 }
 #endif
@@ -552,6 +612,8 @@ SchwarpSizes schwarp_ws_sizes(int nptsu, int nptsv, int nmax) {
     size_t lb = (size_t)nptsu * 4 * 4 * nptsv * nptsv;
     if ((size_t)m.p1.ws > lb) lb = (size_t)m.p1.ws;
     if ((size_t)m.p2.ws > lb) lb = (size_t)m.p2.ws;
+    const size_t gram = (size_t)(nptsu - 3) * (nptsv - 3) * 256; /* per-cell Gram matrices of the C'C build */
+    if (gram > lb) lb = gram;
     z.Lb = o; o += al(sizeof(double) * lb);
   }
   z.Js = o; o += al(sizeof(double) * NC * 128);
@@ -755,33 +817,40 @@ DS_FN_NOINLINE void schwarp_build(const Team team, const SchwarpProb &P, const S
     }
     g[Pi] = acc;
   }
-  /* band of H */
+  /* band of H.  One work item per coupled pair of control points ((pu, pv), (qu, qv)), qu = pu - d, |pv - qv| <= 3:
+   * its 2 x 2 entries (x/y of either point) share the sites and the taps, so the site Jacobians are read as 16-byte
+   * pairs once for four sums; every other entry of the band is a structural zero (filled first). */
   const BandDims b2{2 * nv, nu, 3}, b1{nv, nu, 3};
   const int bs = b2.bs;
   const double wdata = 2.0 * P.fx * P.fx * rho1;
-  DS_FOR(idx, nu * 4 * bs * bs) {
-    const int c = idx % bs, r = (idx / bs) % bs, d = (idx / (bs * bs)) & 3, I = idx / (4 * bs * bs);
+  DS_FOR(idx, nu * 4 * bs * bs) ws.Hb[idx] = 0.0;
+  team.sync();
+  DS_FOR(item, nu * 4 * nv * 7) {
+    const int e = item % (nv * 7), Id = item / (nv * 7), d = Id & 3, I = Id >> 2;
+    const int pv = e / 7, qv = pv - 3 + (e - pv * 7);
     const int pu = I, qu = I - d;
-    double acc = 0.0;
-    if (qu >= 0) {
-      const int pv = r >> 1, cp = r & 1, qv = c >> 1, cq = c & 1;
-      const int dv = pv > qv ? pv - qv : qv - pv;
-      if (dv <= 3) {
-        const int i0 = sm.lou[pu] > sm.lou[qu] ? sm.lou[pu] : sm.lou[qu];
-        const int i1 = sm.hiu[pu] < sm.hiu[qu] ? sm.hiu[pu] : sm.hiu[qu];
-        const int j0 = sm.lov[pv] > sm.lov[qv] ? sm.lov[pv] : sm.lov[qv];
-        const int j1 = sm.hiv[pv] < sm.hiv[qv] ? sm.hiv[pv] : sm.hiv[qv];
-        for (int i = i0; i <= i1; i++)
-          for (int j = j0; j <= j1; j++) {
-            const int k = i * nv + j;
-            const int tp = (pu - sm.Su[i]) * 4 + (pv - sm.Sv[j]), tq = (qu - sm.Su[i]) * 4 + (qv - sm.Sv[j]);
-            const double *Jp = ws.Js + (size_t)k * 128 + 2 * tp + cp, *Jq = ws.Js + (size_t)k * 128 + 2 * tq + cq;
-            acc += Jp[0] * Jq[0] + Jp[32] * Jq[32] + Jp[64] * Jq[64] + Jp[96] * Jq[96];
-          }
-        if (cp == 0 && cq == 0) acc += wdata * ws.CtC[b1.blk(I, d) + (size_t)pv * nv + qv];
+    if (qu < 0 || qv < 0 || qv >= nv) continue;
+    const int i0 = sm.lou[pu] > sm.lou[qu] ? sm.lou[pu] : sm.lou[qu];
+    const int i1 = sm.hiu[pu] < sm.hiu[qu] ? sm.hiu[pu] : sm.hiu[qu];
+    const int j0 = sm.lov[pv] > sm.lov[qv] ? sm.lov[pv] : sm.lov[qv];
+    const int j1 = sm.hiv[pv] < sm.hiv[qv] ? sm.hiv[pv] : sm.hiv[qv];
+    double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0; /* a[cp][cq] */
+    for (int i = i0; i <= i1; i++)
+      for (int j = j0; j <= j1; j++) {
+        const int k = i * nv + j;
+        const int tp = (pu - sm.Su[i]) * 4 + (pv - sm.Sv[j]), tq = (qu - sm.Su[i]) * 4 + (qv - sm.Sv[j]);
+        const dbl2 *Jp = (const dbl2 *)(ws.Js + (size_t)k * 128 + 2 * tp), *Jq = (const dbl2 *)(ws.Js + (size_t)k * 128 + 2 * tq);
+        const dbl2 p0 = Jp[0], p1 = Jp[16], p2 = Jp[32], p3 = Jp[48];
+        const dbl2 q0 = Jq[0], q1 = Jq[16], q2 = Jq[32], q3 = Jq[48];
+        a00 += p0.x * q0.x + p1.x * q1.x + p2.x * q2.x + p3.x * q3.x;
+        a01 += p0.x * q0.y + p1.x * q1.y + p2.x * q2.y + p3.x * q3.y;
+        a10 += p0.y * q0.x + p1.y * q1.x + p2.y * q2.x + p3.y * q3.x;
+        a11 += p0.y * q0.y + p1.y * q1.y + p2.y * q2.y + p3.y * q3.y;
       }
-    }
-    ws.Hb[idx] = acc;
+    a00 += wdata * ws.CtC[b1.blk(I, d) + (size_t)pv * nv + qv];
+    double *out = ws.Hb + b2.blk(I, d) + (size_t)(2 * pv) * bs + 2 * qv;
+    out[0] = a00; out[1] = a01;
+    out[bs] = a10; out[bs + 1] = a11;
   }
   team.sync();
 }
@@ -880,32 +949,51 @@ DS_FN_NOINLINE void schwarp_fit_one(const Team team, const SchwarpProb &P, const
   }
   DS_FOR(i, NP) x[i] = P.x[i];
   team.sync();
+#if defined(DS_NRSFM_PROF) && DS_CUDA
+  long long pfp[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pft = clock64();
+#define PF_LAP(i) do { const long long n_ = clock64(); pfp[i] += n_ - pft; pft = n_; } while (0)
+#else
+#define PF_LAP(i) do {} while (0)
+#endif
   CellSort cs{P.n, nu - 3, nv - 3, ws.cell, ws.cstart, ws.perm, ws.taps};
   const int bad = cell_sort(team, s, P.kp1, cs, sh + m.red);
   if (bad) {
     if (team.tid == 0) { P.scalars[0] = P.scalars[1] = 0.0; P.scalars[2] = P.scalars[3] = 0.0; P.scalars[4] = SCHWARP_OUT_OF_DOMAIN; }
     return;
   }
-  /* C'C in band form (bs = nptsv): entry = sum over the matches of the cells that cover both */
-  DS_FOR(idx, nu * 4 * nv * nv) {
-    const int qv = idx % nv, pv = (idx / nv) % nv, d = (idx / (nv * nv)) & 3, pu = idx / (4 * nv * nv), qu = pu - d;
-    double acc = 0.0;
-    const int dv = pv > qv ? pv - qv : qv - pv;
-    if (qu >= 0 && dv <= 3) {
-      const int u0 = pu - 3 > 0 ? pu - 3 : 0, u1 = qu < nu - 4 ? qu : nu - 4;
-      const int vhi = pv < qv ? pv : qv, vlo = (pv > qv ? pv : qv) - 3;
-      for (int Iu = u0; Iu <= u1; Iu++)
-        for (int Iv = (vlo > 0 ? vlo : 0); Iv <= vhi && Iv <= nv - 4; Iv++) {
-          const int c = Iu * (nv - 3) + Iv;
-          for (int q = ws.cstart[c]; q < ws.cstart[c + 1]; q++) {
-            const double *tp = ws.taps + 8 * (size_t)ws.perm[q];
-            acc += tp[pu - Iu] * tp[4 + pv - Iv] * tp[qu - Iu] * tp[4 + qv - Iv];
-          }
-        }
+  PF_LAP(0);
+  /* C'C in band form (bs = nptsv).  Per knot cell the 16 x 16 Gram matrix of its matches' tap products first
+   * (fixed order over the cell's matches; scratch: the factor workspace, not in use yet), then every band entry
+   * sums the <= 16 cells that cover both control points. */
+  {
+    const int ncv = nv - 3, ncells = (nu - 3) * ncv;
+    double *G = ws.Lb;
+    DS_FOR(item, ncells * 256) {
+      const int c = item >> 8, ab = item & 255, ta = ab >> 4, tb = ab & 15;
+      double acc = 0.0;
+      for (int q = ws.cstart[c]; q < ws.cstart[c + 1]; q++) {
+        const double *tp = ws.taps + 8 * (size_t)ws.perm[q];
+        acc += tp[ta >> 2] * tp[4 + (ta & 3)] * tp[tb >> 2] * tp[4 + (tb & 3)];
+      }
+      G[item] = acc;
     }
-    ws.CtC[idx] = acc;
+    team.sync();
+    DS_FOR(idx, nu * 4 * nv * nv) {
+      const int qv = idx % nv, pv = (idx / nv) % nv, d = (idx / (nv * nv)) & 3, pu = idx / (4 * nv * nv), qu = pu - d;
+      double acc = 0.0;
+      const int dv = pv > qv ? pv - qv : qv - pv;
+      if (qu >= 0 && dv <= 3) {
+        const int u0 = pu - 3 > 0 ? pu - 3 : 0, u1 = qu < nu - 4 ? qu : nu - 4;
+        const int vhi = pv < qv ? pv : qv, vlo = (pv > qv ? pv : qv) - 3;
+        for (int Iu = u0; Iu <= u1; Iu++)
+          for (int Iv = (vlo > 0 ? vlo : 0); Iv <= vhi && Iv <= nv - 4; Iv++)
+            acc += G[(size_t)(Iu * ncv + Iv) * 256 + ((pu - Iu) * 4 + (pv - Iv)) * 16 + (qu - Iu) * 4 + (qv - Iv)];
+      }
+      ws.CtC[idx] = acc;
+    }
   }
   team.sync();
+  PF_LAP(1);
   int status = SCHWARP_OK;
   if (P.initialize) {
     /* Warp::initialize (Schwarp.cc:99-160): (C'C + lambda B) x0 = C' q2, two right-hand sides.
@@ -941,17 +1029,26 @@ DS_FN_NOINLINE void schwarp_fit_one(const Team team, const SchwarpProb &P, const
     }
     team.sync();
   }
+  PF_LAP(2);
+#if defined(DS_NRSFM_PROF) && DS_CUDA
+  long long pf_solve = 0;
+  const long long pf_lm0 = clock64();
+#endif
   /* ---- Ceres-style Levenberg-Marquardt */
   double radius = LM_INITIAL_RADIUS, decrease = 2.0, cost = 0.0, rho1 = 1.0, cost_initial = 0.0;
   int iters = 0, accepted = 0, invalid = 0;
   bool have_scale = false, need_eval = true;
   while (status == SCHWARP_OK) {
     if (need_eval) {
+      PF_LAP(7);
       cost = schwarp_eval(team, P, ws, sh, m, x, true, &rho1);
       if (iters == 0) cost_initial = cost;
       team.sync();
+      PF_LAP(3);
       schwarp_site_jacobians(team, P, ws, sh, m);
+      PF_LAP(4);
       schwarp_build(team, P, ws, sh, m, rho1);
+      PF_LAP(5);
       double gmax = 0.0;
       DS_FOR(i, NP) gmax = fmax(gmax, fabs(g[i]));
       gmax = team_max(team, gmax, sh + m.red);
@@ -973,8 +1070,14 @@ DS_FN_NOINLINE void schwarp_fit_one(const Team team, const SchwarpProb &P, const
       step[i] = g[i] * scale[i];
     }
     team.sync();
+#if defined(DS_NRSFM_PROF) && DS_CUDA
+    const long long pf0 = clock64();
+#endif
     bool valid = bband_solve_any(team, b2, m.p2, ws.Hb, ws.Lb, scale, add, sh + m.solver, step, 1, NP);
     team.sync();
+#if defined(DS_NRSFM_PROF) && DS_CUDA
+    pf_solve += clock64() - pf0;
+#endif
     double model_change = 0.0;
     if (valid) {
       /* -(J s).(r + J s/2) with s = -y: (y'Sg + y'D y)/2 from the solved system */
@@ -1030,16 +1133,27 @@ DS_FN_NOINLINE void schwarp_fit_one(const Team team, const SchwarpProb &P, const
     }
   }
   team.sync();
+  PF_LAP(7);
   if (status == SCHWARP_OK) {
     DS_FOR(i, NP) P.x[i] = x[i];
     schwarp_diffprop(team, P, ws, x);
   }
+  PF_LAP(6);
+#if defined(DS_NRSFM_PROF) && DS_CUDA
+  if (team.tid == 0 && blockIdx.x == 0)
+    printf("[nrsfm prof] fit: cell sort %lld, C'C %lld, initialisation %lld, eval %lld, site Jacobians %lld, build %lld, DiffProp %lld, LM loop rest (solves, candidate evals) %lld\n",
+           pfp[0], pfp[1], pfp[2], pfp[3], pfp[4], pfp[5], pfp[6], pfp[7]);
+#endif
   if (team.tid == 0) {
     P.scalars[0] = cost_initial;
     P.scalars[1] = cost;
     P.scalars[2] = iters;
     P.scalars[3] = accepted;
     P.scalars[4] = status;
+#if defined(DS_NRSFM_PROF) && DS_CUDA
+    P.scalars[0] = (double)pf_solve;              /* cycles inside the LM solves */
+    P.scalars[1] = (double)(clock64() - pf_lm0);  /* cycles of the LM loop + DiffProp */
+#endif
   }
 }
 
