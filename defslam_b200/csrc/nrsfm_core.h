@@ -36,6 +36,11 @@ enum { PF_X_WARP = 0, PF_X_BWD = 20 };
 #define DS_PROF_T0M(var) long long var = clock64()
 #define DS_PROF_FLUSH(name, n, idx, cond) do { if (blockIdx.x == 0 && (cond)) for (int i_ = 0; i_ < n; i_++) g_rowprof[idx + i_] += name[i_]; } while (0)
 #endif
+/* release fence of the progress counters: fence.acq_rel.cta instead of __threadfence_block() (fence.sc.cta).  The
+ * initialisation solve is bound by the chain warp, which publishes twice per block row: 250 k -> 197 k cycles. */
+#ifndef DS_ROWS_FENCE_LIGHT
+#define DS_ROWS_FENCE_LIGHT 1
+#endif
 #include "ds_rowchol.h"
 
 #if DS_CUDA
@@ -238,6 +243,7 @@ struct RowPlan {
   int nt;      /* tiles per block row (0: not available, use bband_solve) */
   int owners;  /* row-owner warps the ring has room for */
   int nblk, Dp;
+  int bw;      /* scalar half-bandwidth; the row-band copy has bwE = bw rounded up to even, row stride bwE + 1 */
   int smem;    /* doubles of shared memory */
   int ws;      /* doubles of global workspace (tile-form factor, inverses of the diagonal blocks, border rows) */
 };
@@ -259,19 +265,19 @@ static inline
 __host__ __device__
 #endif
 RowPlan rows_plan(int n, int bw, int avail_doubles, int nthreads) {
-  RowPlan p{0, 0, 0, 0, 0, 0};
+  RowPlan p{0, 0, 0, 0, 0, 0, 0};
 #if DS_CUDA
   const int nt = rows_nt_for((bw + 7) / 8);
   if (nt == 0 || nthreads < 128) return p;
   const int Dp = round_up(n, 8), nblk = Dp / 8;
-  const int fixed = nt * 64 + 128 + (3 * nblk + 2 + 32 + 2 + Dp + 2) / 2 + 2 + 2 * (Dp + 8);
+  const int fixed = nt * 64 + 128 + (3 * nblk + 2 + 32 + 2) / 2 + 2 + 2 * (Dp + 8);
   const int bsz = ROWS_SWEEP_BUFS * (nt * LT_STRIDE + 64);
   for (int own = 5; own >= 2; own--) {
     int w = (nt - 1 + own) * nt * 64;
     if (w < bsz) w = bsz;
     if (fixed + w <= avail_doubles) {
-      p.nt = nt; p.owners = own; p.nblk = nblk; p.Dp = Dp; p.smem = fixed + w;
-      p.ws = nblk * nt * LT_STRIDE + nblk * 64 + 16 * Dp;
+      p.nt = nt; p.owners = own; p.nblk = nblk; p.Dp = Dp; p.bw = bw; p.smem = fixed + w;
+      p.ws = nblk * nt * LT_STRIDE + nblk * 64 + 16 * Dp + Dp * ((bw | 1) + 2);
       return p;
     }
   }
@@ -282,101 +288,87 @@ RowPlan rows_plan(int n, int bw, int avail_doubles, int nthreads) {
 }
 
 #if DS_CUDA
-/* entry (i, c) of diag(sc) H diag(sc) + diag(add), padded with the identity.  Straight-line code: ctab[c] holds the
- * block and the offset inside the block of column c ((c / bs) << 16 | c % bs, one table per solve in shared memory);
- * the addresses of a lane's entries are formed first, then all loads of a batch are issued (clamped to a valid
- * address where the entry is a structural zero), then scaled.  With a branch per entry the loads went out one L2
- * round trip after the other, with the division-free walk over the columns the lanes of a warp diverged. */
-struct BBandLoader {
-  const double *Hb;
-  BandDims bd;
-  const double *sc, *add;
+/* The row owners read their block row from a row-band copy of diag(sc) H diag(sc) (row i holds columns i-bw..i at
+ * offset c - i + bwE, stride ld = bwE + 1: the layout of the SfT band, 16-byte pairs), padded with identity rows.
+ * It is written once per build of H -- not per solve: reading the block band directly cost the owners a table
+ * look-up, a scaling product and an 8-byte load per entry, 9 k cycles per block row, a third of the factorisation. */
+DS_FN double *rows_hr(const RowPlan &plan, double *wsg) {
+  return wsg + (size_t)plan.nblk * plan.nt * LT_STRIDE + (size_t)plan.nblk * 64 + 16 * (size_t)plan.Dp;
+}
+DS_FN_NOINLINE void band_to_rows(const Team team, const BandDims bd, const RowPlan plan, const double *Hb, const double *sc,
+                                 double *wsg) {
+  const int n = bd.nb * bd.bs, bs = bd.bs, bw = plan.bw, bwE = (bw + 1) & ~1, ld = bwE + 1, W1 = bw + 1;
+  double *Hr = rows_hr(plan, wsg);
+  DS_FOR(idx, plan.Dp * W1) {
+    const int i = idx / W1, c = i - bw + (idx - i * W1);
+    double v = 0.0;
+    if (i >= n) v = c == i ? 1.0 : 0.0;
+    else if (c >= 0) {
+      const int Ib = i / bs, Jb = c / bs;
+      if (Ib - Jb <= bd.kb) {
+        v = Hb[bd.blk(Ib, Ib - Jb) + (size_t)(i - Ib * bs) * bs + (c - Jb * bs)];
+        if (sc) v *= sc[i] * sc[c];
+      }
+    }
+    Hr[(size_t)i * ld + (c - i + bwE)] = v;
+  }
+  team.sync();
+}
+
+struct RowBandLoader {
+  const double *Hr;
+  int ld, bwE, bw;
+  const double *add; /* added to the diagonal of rows < n (may be null) */
   int n;
-  const int *ctab;
   template <int NT>
   DS_FN void load(int I, int g, int q, double *a0, double *a1) const {
     constexpr int NBK = NT - 1;
-    const int bs = bd.bs, kb = bd.kb;
+    const int lo = bwE - bw;
     const int i = NB * I + g;
-    const bool rowok = i < n;
-    const int ti = ctab[rowok ? i : 0];
-    const int Ib = ti >> 16, ir = ti & 0xffff;
-    const double si = (sc && rowok) ? sc[i] : 1.0;
-    const int blk_doubles = bs * bs;
-    const double *rowp = Hb + (size_t)Ib * (kb + 1) * blk_doubles + (size_t)ir * bs; /* row ir of block (Ib, 0) */
-    constexpr int HT = (NT + 1) / 2; /* two batches of loads: the addresses of one batch fit the register budget */
+    const double *rowp = Hr + (size_t)i * ld;
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-      int off0[HT], off1[HT]; /* offset of the entry from rowp, -1: structural zero */
-#pragma unroll
-      for (int tt = 0; tt < HT; tt++) {
-        const int t = h * HT + tt;
-        if (t >= NT) continue;
-        const int c = NB * (I - NBK + t) + 2 * q; /* c + 1 <= 8 J + 7 < Dp */
-        const int cc = c >= 0 ? c : 0;
-        const int t0 = ctab[cc], t1 = ctab[cc + 1];
-        const int d0 = Ib - (t0 >> 16), d1 = Ib - (t1 >> 16);
-        const bool v0 = rowok && c >= 0 && c <= i && d0 <= kb;
-        const bool v1 = rowok && c >= 0 && c + 1 <= i && d1 <= kb;
-        off0[tt] = v0 ? d0 * blk_doubles + (t0 & 0xffff) : -1;
-        off1[tt] = v1 ? d1 * blk_doubles + (t1 & 0xffff) : -1;
-      }
-#pragma unroll
-      for (int tt = 0; tt < HT; tt++) {
-        const int t = h * HT + tt;
-        if (t >= NT) continue;
-#if defined(DS_LOADER_NOMEM) /* experiment: no global loads (timing only, wrong results) */
-        a0[t] = (NB * (I - NBK + t) + 2 * q == i) ? 1e6 : 1e-9 * off0[tt];
-        a1[t] = (NB * (I - NBK + t) + 2 * q + 1 == i) ? 1e6 : 1e-9 * off1[tt];
-#else
-        a0[t] = rowp[off0[tt] >= 0 ? off0[tt] : 0];
-        a1[t] = rowp[off1[tt] >= 0 ? off1[tt] : 0];
-#endif
-      }
-#pragma unroll
-      for (int tt = 0; tt < HT; tt++) {
-        const int t = h * HT + tt;
-        if (t >= NT) continue;
-        const int c = NB * (I - NBK + t) + 2 * q;
-        double s0 = 1.0, s1 = 1.0;
-        if (sc) { s0 = si * sc[off0[tt] >= 0 ? c : 0]; s1 = si * sc[off1[tt] >= 0 ? c + 1 : 0]; }
-        a0[t] = off0[tt] >= 0 ? a0[t] * s0 : 0.0;
-        a1[t] = off1[tt] >= 0 ? a1[t] * s1 : 0.0;
-      }
+    for (int t = 0; t < NT; t++) {
+      const int J = I - NBK + t;
+      const int off = NB * J + 2 * q - i + bwE;
+      const bool v0 = J >= 0 && off >= lo && off <= bwE, v1 = J >= 0 && off + 1 >= lo && off + 1 <= bwE;
+      double x0 = 0.0, x1 = 0.0;
+      if (v0 && v1) { const dbl2 v = *(const dbl2 *)(rowp + off); x0 = v.x; x1 = v.y; }
+      else { if (v0) x0 = rowp[off]; if (v1) x1 = rowp[off + 1]; }
+      a0[t] = x0; a1[t] = x1;
     }
-    /* the diagonal entry: + add, or 1 on the padding rows */
-    const double dadd = rowok ? (add ? add[i] : 0.0) : 1.0;
+    const double dadd = (add && i < n) ? add[i] : 0.0;
     if (2 * q == g) a0[NT - 1] += dadd;
     if (2 * q + 1 == g) a1[NT - 1] += dadd;
   }
 };
 
-/* Same contract as bband_solve(); ws: plan.ws doubles of global workspace; sh: plan.smem doubles. */
+/* Same contract as bband_solve() with the matrix taken from the row-band copy (band_to_rows); wsg: plan.ws doubles
+ * of global workspace; sh: plan.smem doubles. */
 template <int NT>
-DS_FN_NOINLINE bool bband_solve_rows(const Team team, const BandDims bd, const RowPlan plan, const double *Hb, double *wsg,
-                                     const double *sc, const double *add, double *sh, double *rhs, int nrhs, int ldr) {
+DS_FN_NOINLINE bool bband_solve_rows(const Team team, const BandDims bd, const RowPlan plan, double *wsg, const double *add,
+                                     double *sh, double *rhs, int nrhs, int ldr) {
   const int n = bd.nb * bd.bs, Dp = plan.Dp, nblk = plan.nblk;
   const int R = NT - 1 + plan.owners;
   int wsz = R * NT * 64;
   { const int bsz = ROWS_SWEEP_BUFS * (NT * LT_STRIDE + 64); if (wsz < bsz) wsz = bsz; }
   double *W = sh, *er = W + wsz, *db = er + NT * 64, *dx = db + 128, *sol = dx + Dp + 8;
-  int *sy = (int *)(sol + Dp + 8), *flag = sy + 3 * nblk + 2 + 32 + 1, *ctab = flag + 1;
+  int *sy = (int *)(sol + Dp + 8), *flag = sy + 3 * nblk + 2 + 32 + 1;
   double *Lt = wsg, *Dinv = Lt + (size_t)nblk * NT * LT_STRIDE, *Cg = Dinv + (size_t)nblk * 64, *Eg = Cg + 8 * (size_t)Dp;
-  /* the right-hand sides as border rows (the other rows of the border tile are zero) */
+  const int bwE = (plan.bw + 1) & ~1;
 #if defined(DS_NRSFM_PROF)
   const long long q0 = clock64();
 #endif
+  /* the right-hand sides as border rows (the other rows of the border tile are zero) */
   DS_FOR(idx, 8 * Dp) {
     const int r = idx / Dp, i = idx - r * Dp;
     Cg[idx] = (r < nrhs && i < n) ? rhs[r * ldr + i] : 0.0;
   }
-  DS_FOR(c, Dp + 1) { const int J = c / bd.bs; ctab[c] = c < n ? (J << 16) | (c - J * bd.bs) : (0x7fff << 16); }
   team.sync();
 #if defined(DS_NRSFM_PROF)
   const long long q1 = clock64();
 #endif
-  rows_factor<NT>(team.tid, team.nthr, nblk, plan.owners, BBandLoader{Hb, bd, sc, add, n, ctab}, W, er, db, sy, flag, Cg, Eg, Dp,
-                  (double *)nullptr, (const double *)nullptr, 0.0, Lt, Dinv);
+  rows_factor<NT>(team.tid, team.nthr, nblk, plan.owners, RowBandLoader{rows_hr(plan, wsg), bwE + 1, bwE, plan.bw, add, n}, W, er,
+                  db, sy, flag, Cg, Eg, Dp, (double *)nullptr, (const double *)nullptr, 0.0, Lt, Dinv);
 #if defined(DS_NRSFM_PROF)
   const long long q2 = clock64();
 #endif
@@ -391,8 +383,7 @@ DS_FN_NOINLINE bool bband_solve_rows(const Team team, const BandDims bd, const R
     team.sync();
   }
 #if defined(DS_NRSFM_PROF)
-  if (team.tid == 0 && blockIdx.x == 0)
-  {
+  if (team.tid == 0 && blockIdx.x == 0) {
     printf("[nrsfm prof] NT %d nblk %d owners %d: staging %lld, factorisation %lld, backward sweeps %lld cycles; chain wait %lld busy %lld; owners (load / steps):"
            " %lld/%lld %lld/%lld %lld/%lld %lld/%lld %lld/%lld\n", NT, nblk,
            plan.owners, q1 - q0, q2 - q1, clock64() - q2, g_rowprof[0], g_rowprof[1], g_rowprof[2], g_rowprof[3], g_rowprof[4],
@@ -404,18 +395,19 @@ DS_FN_NOINLINE bool bband_solve_rows(const Team team, const BandDims bd, const R
 }
 #endif
 
-/* dispatch: tensor-core row form where the plan has one, the scalar window otherwise */
+/* dispatch: tensor-core row form where the plan has one (the caller has run band_to_rows since H or sc last
+ * changed), the scalar window otherwise */
 DS_FN bool bband_solve_any(const Team team, const BandDims bd, const RowPlan plan, const double *Hb, double *Lb,
                            const double *sc, const double *add, double *sh, double *rhs, int nrhs, int ldr) {
 #if DS_CUDA
   switch (plan.nt) {
-    case 6: return bband_solve_rows<6>(team, bd, plan, Hb, Lb, sc, add, sh, rhs, nrhs, ldr);
-    case 8: return bband_solve_rows<8>(team, bd, plan, Hb, Lb, sc, add, sh, rhs, nrhs, ldr);
-    case 10: return bband_solve_rows<10>(team, bd, plan, Hb, Lb, sc, add, sh, rhs, nrhs, ldr);
-    case 12: return bband_solve_rows<12>(team, bd, plan, Hb, Lb, sc, add, sh, rhs, nrhs, ldr);
-    case 14: return bband_solve_rows<14>(team, bd, plan, Hb, Lb, sc, add, sh, rhs, nrhs, ldr);
-    case 16: return bband_solve_rows<16>(team, bd, plan, Hb, Lb, sc, add, sh, rhs, nrhs, ldr);
-    case 18: return bband_solve_rows<18>(team, bd, plan, Hb, Lb, sc, add, sh, rhs, nrhs, ldr);
+    case 6: return bband_solve_rows<6>(team, bd, plan, Lb, add, sh, rhs, nrhs, ldr);
+    case 8: return bband_solve_rows<8>(team, bd, plan, Lb, add, sh, rhs, nrhs, ldr);
+    case 10: return bband_solve_rows<10>(team, bd, plan, Lb, add, sh, rhs, nrhs, ldr);
+    case 12: return bband_solve_rows<12>(team, bd, plan, Lb, add, sh, rhs, nrhs, ldr);
+    case 14: return bband_solve_rows<14>(team, bd, plan, Lb, add, sh, rhs, nrhs, ldr);
+    case 16: return bband_solve_rows<16>(team, bd, plan, Lb, add, sh, rhs, nrhs, ldr);
+    case 18: return bband_solve_rows<18>(team, bd, plan, Lb, add, sh, rhs, nrhs, ldr);
     default: break;
   }
 #else
@@ -451,22 +443,48 @@ DS_FN_NOINLINE int cell_sort(const Team team, const BbsView &s, const float *xy,
   }
   bad = team_sum_int(team, bad, red);
   const int nc = cs.ncu * cs.ncv;
+#if DS_CUDA
+  /* one warp per cell, 32 sites per trip: count by ballot, place by the prefix of the ballot (original order kept) */
+  const int warp = team.tid >> 5, lane = team.tid & 31, nwarp = team.nthr >> 5;
+  for (int c = warp; c < nc; c += nwarp) {
+    int cnt = 0;
+    for (int m0 = 0; m0 < cs.n; m0 += 32) {
+      const int m = m0 + lane;
+      cnt += __popc(__ballot_sync(0xffffffffu, m < cs.n && cs.cell[m] == c));
+    }
+    if (lane == 0) cs.start[c + 1] = cnt;
+  }
+#else
   DS_FOR(c, nc) {
     int cnt = 0;
     for (int m = 0; m < cs.n; m++) cnt += cs.cell[m] == c;
     cs.start[c + 1] = cnt;
   }
+#endif
   team.sync();
   if (team.tid == 0) {
     cs.start[0] = 0;
     for (int c = 0; c < nc; c++) cs.start[c + 1] += cs.start[c];
   }
   team.sync();
+#if DS_CUDA
+  for (int c = warp; c < nc; c += nwarp) {
+    int o = cs.start[c];
+    for (int m0 = 0; m0 < cs.n; m0 += 32) {
+      const int m = m0 + lane;
+      const bool mine = m < cs.n && cs.cell[m] == c;
+      const unsigned bal = __ballot_sync(0xffffffffu, mine);
+      if (mine) cs.perm[o + __popc(bal & ((1u << lane) - 1u))] = m;
+      o += __popc(bal);
+    }
+  }
+#else
   DS_FOR(c, nc) {
     int o = cs.start[c];
     for (int m = 0; m < cs.n; m++)
       if (cs.cell[m] == c) cs.perm[o++] = m;
   }
+#endif
   team.sync();
   return bad;
 }
@@ -553,7 +571,7 @@ SchwarpSmem schwarp_smem(int nptsu, int nptsv) {
   /* the solver region: the row form of the LM solve if its ring fits (with the site arrays in shared memory if
    * that fits too, else with them in the global workspace), else the scalar window */
   bool sites_in_smem = false;
-  m.p1 = m.p2 = RowPlan{0, 0, 0, 0, 0, 0};
+  m.p1 = m.p2 = RowPlan{0, 0, 0, 0, 0, 0, 0};
   int solver = 0;
   for (int pass = 0; pass < 2 && m.p2.nt == 0; pass++) {
     const int avail = SCHWARP_SMEM_LIMIT_DOUBLES - base - (pass == 0 ? 14 * NC : 0);
@@ -565,7 +583,7 @@ SchwarpSmem schwarp_smem(int nptsu, int nptsv) {
     const RowPlan p1 = rows_plan(NC, 4 * b1.bs - 1, avail, NRSFM_THREADS_);
     if (p1.nt > 0) { m.p1 = p1; if (p1.smem > solver) solver = p1.smem; }
     else if ((int)b1.smem_doubles(2) <= avail) { if ((int)b1.smem_doubles(2) > solver) solver = (int)b1.smem_doubles(2); }
-    else { m.p2 = RowPlan{0, 0, 0, 0, 0, 0}; } /* (cannot happen for grids the scalar path accepts) */
+    else { m.p2 = RowPlan{0, 0, 0, 0, 0, 0, 0}; } /* (cannot happen for grids the scalar path accepts) */
   }
   if (m.p2.nt == 0) {
     solver = (int)b2.smem_doubles(2);
@@ -1020,6 +1038,9 @@ DS_FN_NOINLINE void schwarp_fit_one(const Team team, const SchwarpProb &P, const
       step[NC + p] = ay;
     }
     team.sync();
+#if DS_CUDA
+    if (m.p1.nt > 0) band_to_rows(team, b1, m.p1, ws.Hb, nullptr, ws.Lb);
+#endif
     const bool ok = bband_solve_any(team, b1, m.p1, ws.Hb, ws.Lb, nullptr, nullptr, sh + m.solver, step, 2, NC);
     team.sync();
     if (ok) {
@@ -1057,6 +1078,9 @@ DS_FN_NOINLINE void schwarp_fit_one(const Team team, const SchwarpProb &P, const
         have_scale = true;
         team.sync();
       }
+#if DS_CUDA
+      if (m.p2.nt > 0) band_to_rows(team, b2, m.p2, ws.Hb, scale, ws.Lb);
+#endif
       need_eval = false;
       if (gmax <= 1e-10) break;
     }
