@@ -23,7 +23,22 @@ namespace {
 
 struct Scratch {
   DevBuf dev, host, ws;
+  /* two side streams + events for calls that pipeline their batch in chunks (normals) */
+  cudaStream_t side[2] = {nullptr, nullptr};
+  cudaEvent_t ev_done[16] = {}, ev_k0[16] = {}, ev_k1[16] = {};
+  bool side_ok = false;
   Scratch() { host.pinned = true; }
+  int ensure_side() {
+    if (side_ok) return 0;
+    for (int i = 0; i < 2; i++) DS_CUDA_TRY(cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking));
+    for (int i = 0; i < 16; i++) {
+      DS_CUDA_TRY(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
+      DS_CUDA_TRY(cudaEventCreate(&ev_k0[i]));
+      DS_CUDA_TRY(cudaEventCreate(&ev_k1[i]));
+    }
+    side_ok = true;
+    return 0;
+  }
 };
 Scratch &tl_scratch(int device) {
   static thread_local std::map<int, std::unique_ptr<Scratch>> tl;
@@ -110,8 +125,9 @@ __global__ void schwarp_initial_filter_kernel(const double *r, int n, uint8_t *k
   }
 }
 
-__global__ void normals_kernel(NormalsProb P) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n_points; i += gridDim.x * blockDim.x) normals_point(P, i);
+/* map points [point0, point1) of the problem */
+__global__ void normals_kernel(NormalsProb P, int point0, int point1) {
+  for (int i = point0 + blockIdx.x * blockDim.x + threadIdx.x; i < point1; i += gridDim.x * blockDim.x) normals_point(P, i);
 }
 
 __global__ void poly_kernel(int npairs, const float *J12, const float *H12, const float *I1, const float *I2,
@@ -408,19 +424,8 @@ int defslam_normals_batched(const defslam_normals_problem *p, double *k_out, dou
       (rc = S.dev.ensure(in.total + outp.total)) || (rc = S.ws.ensure(scr.total)))
     return rc;
   uint8_t *h = (uint8_t *)S.host.p, *d_in = (uint8_t *)S.dev.p, *d_out = d_in + in.total;
-  /* the caller's arrays go into the pinned arena as they are (one H2D for all of them); large batches are copied
-   * by several host threads */
-  host_big_memcpy(h + o_ptr, p->pair_ptr, 4 * (n + 1));
-  if (np) {
-    host_big_memcpy(h + o_j12, p->J12, 16 * np); host_big_memcpy(h + o_j21, p->J21, 16 * np);
-    host_big_memcpy(h + o_h12, p->H12, 24 * np);
-    host_big_memcpy(h + o_i1, p->I1, 8 * np); host_big_memcpy(h + o_i2, p->I2, 8 * np);
-    if (p->pair_from_ref) host_big_memcpy(h + o_fr, p->pair_from_ref, np);
-    if (p->k_first) host_big_memcpy(h + o_kf, p->k_first, 8 * np);
-  }
-  if (p->k_init) host_big_memcpy(h + o_ki, p->k_init, 16 * n);
-  host_big_memcpy(h + o_uv, p->ref_uv, 8 * n);
-  DS_CUDA_TRY(cudaMemcpyAsync(d_in, h, in.total, cudaMemcpyHostToDevice, ctx->stream));
+  /* The pinned arena holds the inputs first and is reused for the outputs (in.total vs outp.total: separate halves
+   * when the batch is pipelined). */
   NormalsProb P;
   P.n_points = (int)n; P.npairs = (int)np;
   P.pair_ptr = (const int *)(d_in + o_ptr);
@@ -435,37 +440,146 @@ int defslam_normals_batched(const defslam_normals_problem *p, double *k_out, dou
   P.k_out = (double *)(d_out + o_k); P.cov_out = (double *)(d_out + o_cov); P.normal_out = (float *)(d_out + o_nrm);
   P.status_out = d_out + o_st; P.iters_out = (int *)(d_out + o_it);
   P.pair_normal_out = (float *)(d_out + o_pn); P.pair_valid_out = d_out + o_pv;
-  DS_CUDA_TRY(cudaMemsetAsync(d_out, 0, outp.total, ctx->stream));
-  DS_CUDA_TRY(cudaEventRecord(ctx->e0, ctx->stream));
-  int g = (int)((n + 127) / 128);
-  normals_kernel<<<g < 1 ? 1 : g, 128, 0, ctx->stream>>>(P);
-  DS_CUDA_TRY(cudaGetLastError());
-  g_launches.fetch_add(1);
-  DS_CUDA_TRY(cudaEventRecord(ctx->e1, ctx->stream));
-  DS_CUDA_TRY(cudaMemcpyAsync(h, d_out, outp.total, cudaMemcpyDeviceToHost, ctx->stream));
-  DS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  float ms = 0.f;
-  cudaEventElapsedTime(&ms, ctx->e0, ctx->e1);
-  g_last_kernel_ms = ms;
-  if (k_out) host_big_memcpy(k_out, h + o_k, 16 * n);
-  if (status_out) host_big_memcpy(status_out, h + o_st, n);
-  if (iters_out) host_big_memcpy(iters_out, h + o_it, 4 * n);
-  const uint8_t *st = h + o_st;
-  /* covariance / normal only where estimated (the reference leaves the rest untouched) */
-  host_parallel_for(n, 65536, [&](size_t lo_, size_t hi_) {
-    for (size_t i = lo_; i < hi_; i++) {
-      if (st[i] != 1) continue;
-      if (cov_out) memcpy(cov_out + 4 * i, h + o_cov + 32 * i, 32);
-      if (normal_out) memcpy(normal_out + 3 * i, h + o_nrm + 12 * i, 12);
+
+  /* Large batches run as a pipeline of chunks of map points (their pairs are contiguous: CSR) over two side streams:
+   * while the device works on chunk c (upload, kernel, download), the host packs chunk c+1 into the pinned arena and
+   * unpacks chunk c-1 from it, both on several threads.  Serially the call was 13x slower than its kernel (pack 82 MB,
+   * upload, 1.5 ms of kernel, download 44 MB, unpack). */
+  /* (chunks stay large: a chunk's kernel lasts as long as its slowest point, up to max_iterations trips) */
+  size_t nchunk = n >= 65536 ? std::max<size_t>(2, std::min<size_t>(6, n / 98304)) : 1;
+  if (const char *e = getenv("DEFSLAM_NORMALS_CHUNKS")) { /* 1: one pass (the kernel timed alone), 2..16: forced */
+    const int v = atoi(e);
+    if (v >= 1) nchunk = std::min<size_t>((size_t)std::min(v, 16), std::max<size_t>(1, n / 128));
+  }
+  uint8_t *h_in = h, *h_out = h;
+  if (nchunk > 1) {
+    if ((rc = S.host.ensure(in.total + outp.total)) || (rc = S.ensure_side())) return rc;
+    h = (uint8_t *)S.host.p; h_in = h; h_out = h + in.total;
+  }
+  struct Slice { size_t i0, i1, p0, p1; };
+  auto slice_of = [&](size_t c) {
+    Slice sl;
+    sl.i0 = n * c / nchunk; sl.i1 = n * (c + 1) / nchunk;
+    sl.p0 = (size_t)p->pair_ptr[sl.i0]; sl.p1 = (size_t)p->pair_ptr[sl.i1];
+    return sl;
+  };
+  /* byte ranges of the arrays of one slice: {arena offset, caller pointer, element bytes, first, count} */
+  struct Seg { size_t off; const void *src; size_t eb, first, count; };
+  auto in_segs = [&](const Slice &sl, Seg *sg) {
+    int k = 0;
+    const size_t ni = sl.i1 - sl.i0, nq = sl.p1 - sl.p0;
+    sg[k++] = Seg{o_ptr, p->pair_ptr, 4, sl.i0, ni + 1}; /* the kernel reads pair_ptr[i1] as well */
+    if (nq) {
+      sg[k++] = Seg{o_j12, p->J12, 16, sl.p0, nq}; sg[k++] = Seg{o_j21, p->J21, 16, sl.p0, nq};
+      sg[k++] = Seg{o_h12, p->H12, 24, sl.p0, nq};
+      sg[k++] = Seg{o_i1, p->I1, 8, sl.p0, nq}; sg[k++] = Seg{o_i2, p->I2, 8, sl.p0, nq};
+      if (p->pair_from_ref) sg[k++] = Seg{o_fr, p->pair_from_ref, 1, sl.p0, nq};
+      if (p->k_first) sg[k++] = Seg{o_kf, p->k_first, 8, sl.p0, nq};
     }
-  });
-  const uint8_t *pv = h + o_pv;
-  if (pair_valid_out && np) host_big_memcpy(pair_valid_out, pv, np);
-  if (pair_normal_out)
-    host_parallel_for(np, 65536, [&](size_t lo_, size_t hi_) {
-      for (size_t j = lo_; j < hi_; j++)
-        if (pv[j]) memcpy(pair_normal_out + 3 * j, h + o_pn + 12 * j, 12);
+    if (p->k_init) sg[k++] = Seg{o_ki, p->k_init, 16, sl.i0, ni};
+    sg[k++] = Seg{o_uv, p->ref_uv, 8, sl.i0, ni};
+    return k;
+  };
+  auto out_segs = [&](const Slice &sl, Seg *sg) {
+    int k = 0;
+    const size_t ni = sl.i1 - sl.i0, nq = sl.p1 - sl.p0;
+    sg[k++] = Seg{o_k, nullptr, 16, sl.i0, ni}; sg[k++] = Seg{o_cov, nullptr, 32, sl.i0, ni};
+    sg[k++] = Seg{o_nrm, nullptr, 12, sl.i0, ni}; sg[k++] = Seg{o_st, nullptr, 1, sl.i0, ni};
+    sg[k++] = Seg{o_it, nullptr, 4, sl.i0, ni};
+    if (nq) { sg[k++] = Seg{o_pn, nullptr, 12, sl.p0, nq}; sg[k++] = Seg{o_pv, nullptr, 1, sl.p0, nq}; }
+    return k;
+  };
+  auto pack = [&](const Slice &sl) {
+    Seg sg[12];
+    const int k = in_segs(sl, sg);
+    size_t bytes = 0;
+    for (int a = 0; a < k; a++) bytes += sg[a].eb * sg[a].count;
+    /* every thread copies its share of every array */
+    host_parallel_for(bytes, (size_t)2 << 20, [&](size_t b, size_t e) {
+      const double f0 = (double)b / (double)bytes, f1 = (double)e / (double)bytes;
+      for (int a = 0; a < k; a++) {
+        const size_t len = sg[a].eb * sg[a].count;
+        const size_t lo = e == bytes && b == 0 ? 0 : (size_t)(f0 * (double)len) & ~(size_t)15;
+        const size_t hi = e == bytes ? len : (size_t)(f1 * (double)len) & ~(size_t)15;
+        if (hi > lo) memcpy(h_in + sg[a].off + sg[a].eb * sg[a].first + lo, (const uint8_t *)sg[a].src + sg[a].eb * sg[a].first + lo, hi - lo);
+      }
     });
+  };
+  auto unpack = [&](const Slice &sl) {
+    const uint8_t *st = h_out + o_st, *pv = h_out + o_pv;
+    const size_t ni = sl.i1 - sl.i0, nq = sl.p1 - sl.p0;
+    host_parallel_for(ni + nq, 65536, [&](size_t b, size_t e) {
+      /* points [i0 + b', ...) and pairs, split proportionally */
+      const size_t ib = sl.i0 + (size_t)((double)b / (double)(ni + nq) * (double)ni);
+      const size_t ie = e == ni + nq ? sl.i1 : sl.i0 + (size_t)((double)e / (double)(ni + nq) * (double)ni);
+      const size_t qb = sl.p0 + (size_t)((double)b / (double)(ni + nq) * (double)nq);
+      const size_t qe = e == ni + nq ? sl.p1 : sl.p0 + (size_t)((double)e / (double)(ni + nq) * (double)nq);
+      if (k_out) memcpy(k_out + 2 * ib, h_out + o_k + 16 * ib, 16 * (ie - ib));
+      if (status_out) memcpy(status_out + ib, st + ib, ie - ib);
+      if (iters_out) memcpy(iters_out + ib, h_out + o_it + 4 * ib, 4 * (ie - ib));
+      /* covariance / normal only where estimated (the reference leaves the rest untouched) */
+      for (size_t i = ib; i < ie; i++) {
+        if (st[i] != 1) continue;
+        if (cov_out) memcpy(cov_out + 4 * i, h_out + o_cov + 32 * i, 32);
+        if (normal_out) memcpy(normal_out + 3 * i, h_out + o_nrm + 12 * i, 12);
+      }
+      if (pair_valid_out && qe > qb) memcpy(pair_valid_out + qb, pv + qb, qe - qb);
+      if (pair_normal_out)
+        for (size_t j = qb; j < qe; j++)
+          if (pv[j]) memcpy(pair_normal_out + 3 * j, h_out + o_pn + 12 * j, 12);
+    });
+  };
+  auto enqueue = [&](const Slice &sl, cudaStream_t st, cudaEvent_t k0, cudaEvent_t k1) -> int {
+    Seg sg[12];
+    int k = in_segs(sl, sg);
+    for (int a = 0; a < k; a++) {
+      const size_t off = sg[a].off + sg[a].eb * sg[a].first, len = sg[a].eb * sg[a].count;
+      if (len) DS_CUDA_TRY(cudaMemcpyAsync(d_in + off, h_in + off, len, cudaMemcpyHostToDevice, st));
+    }
+    DS_CUDA_TRY(cudaEventRecord(k0, st));
+    const size_t ni = sl.i1 - sl.i0;
+    if (ni) {
+      const int g = (int)((ni + 127) / 128);
+      normals_kernel<<<g, 128, 0, st>>>(P, (int)sl.i0, (int)sl.i1);
+      DS_CUDA_TRY(cudaGetLastError());
+      g_launches.fetch_add(1);
+    }
+    DS_CUDA_TRY(cudaEventRecord(k1, st));
+    k = out_segs(sl, sg);
+    for (int a = 0; a < k; a++) {
+      const size_t off = sg[a].off + sg[a].eb * sg[a].first, len = sg[a].eb * sg[a].count;
+      if (len) DS_CUDA_TRY(cudaMemcpyAsync(h_out + off, d_out + off, len, cudaMemcpyDeviceToHost, st));
+    }
+    return DEFSLAM_OK;
+  };
+  float ms_total = 0.f;
+  if (nchunk == 1) {
+    const Slice sl = slice_of(0);
+    pack(sl);
+    if ((rc = enqueue(sl, ctx->stream, ctx->e0, ctx->e1))) return rc;
+    DS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ms_total, ctx->e0, ctx->e1);
+    unpack(sl);
+  } else {
+    for (size_t c = 0; c < nchunk; c++) {
+      const Slice sl = slice_of(c);
+      pack(sl);
+      if ((rc = enqueue(sl, S.side[c & 1], S.ev_k0[c], S.ev_k1[c]))) return rc;
+      DS_CUDA_TRY(cudaEventRecord(S.ev_done[c], S.side[c & 1]));
+      if (c >= 1) {
+        DS_CUDA_TRY(cudaEventSynchronize(S.ev_done[c - 1]));
+        unpack(slice_of(c - 1));
+      }
+    }
+    DS_CUDA_TRY(cudaEventSynchronize(S.ev_done[nchunk - 1]));
+    unpack(slice_of(nchunk - 1));
+    for (size_t c = 0; c < nchunk; c++) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, S.ev_k0[c], S.ev_k1[c]);
+      ms_total += ms;
+    }
+  }
+  g_last_kernel_ms = ms_total;
   return DEFSLAM_OK;
 }
 

@@ -79,6 +79,39 @@ def test_normals_large_batch_and_mixed_pairs(apis):
     ck.check_normals(api, orc, nc2)
 
 
+def test_normals_pipelined_batch_equals_single_pass(apis):
+    """batches of >= 64 k map points run as a pipeline of chunks over two streams: same results, point for point,
+    as the tile they are made of solved in one pass (untouched outputs stay untouched)"""
+    api, orc = apis
+    win = nrsfm.make_window(21, n_keypoints=1500, n_views=4, match_frac=0.8)
+    fits = [orc.schwarp_fit(c) for c in nrsfm.schwarp_cases(win)]
+    nc = nrsfm.normals_case(win, fits)
+    rng = np.random.default_rng(1)
+    nc.pair_from_ref = (rng.uniform(size=nc.npairs) > 0.2).astype(np.uint8)
+    nc.k_first = rng.normal(size=(nc.npairs, 2)).astype(np.float32) * 0.1
+    one = api.normals(nc)
+    reps = 70000 // nc.n + 1
+    ptr = [0]
+    for _ in range(reps):
+        ptr.extend((nc.pair_ptr[1:] + ptr[-1]).tolist())
+    tile = lambda a: np.ascontiguousarray(np.concatenate([a] * reps))
+    big = nrsfm.NormalsCase(pair_ptr=np.array(ptr, np.int32), J12=tile(nc.J12[:nc.npairs]), J21=tile(nc.J21[:nc.npairs]),
+                            H12=tile(nc.H12[:nc.npairs]), I1=tile(nc.I1[:nc.npairs]), I2=tile(nc.I2[:nc.npairs]),
+                            pair_from_ref=tile(nc.pair_from_ref[:nc.npairs]), k_first=tile(nc.k_first[:nc.npairs]),
+                            k_init=tile(nc.k_init), ref_uv=tile(nc.ref_uv))
+    assert big.n >= 65536
+    out = api.normals(big)
+    n, q = nc.n, nc.npairs
+    for r in (0, 1, reps // 2, reps - 1):
+        assert np.array_equal(out.status[r * n:(r + 1) * n], one.status[:n])
+        assert np.array_equal(out.iters[r * n:(r + 1) * n], one.iters[:n])
+        assert np.array_equal(out.k[r * n:(r + 1) * n], one.k, equal_nan=True)
+        assert np.array_equal(out.cov[r * n:(r + 1) * n], one.cov, equal_nan=True)
+        assert np.array_equal(out.normal[r * n:(r + 1) * n], one.normal, equal_nan=True)
+        assert np.array_equal(out.pair_valid[r * q:(r + 1) * q], one.pair_valid[:q])
+        assert np.array_equal(out.pair_normal[r * q:(r + 1) * q], one.pair_normal[:q], equal_nan=True)
+
+
 def test_polysolver_coefficients_match_oracle(apis):
     api, orc = apis
     rng = np.random.default_rng(1)
