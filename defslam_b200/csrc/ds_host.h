@@ -48,6 +48,8 @@ class HostPool {
  private:
   HostPool() {
     unsigned t = std::thread::hardware_concurrency() / 2;
+    /* one process per GPU on a shared host (torchrun exports LOCAL_WORLD_SIZE): the ranks share the cores */
+    if (const char *e = getenv("LOCAL_WORLD_SIZE")) { const int w = atoi(e); if (w > 1) t /= (unsigned)w; }
     if (const char *e = getenv("DEFSLAM_HOST_THREADS")) t = (unsigned)atoi(e);
     nmax_ = std::max(1u, std::min(8u, t));
   }

@@ -253,7 +253,9 @@ int defslam_schwarp_fit_batched(int32_t nprob, const defslam_schwarp_problem *p,
     return rc;
   uint8_t *h = (uint8_t *)S.host.p, *d_in = (uint8_t *)S.dev.p, *d_out = d_in + in.total, *h_out = h + in.total;
   SchwarpProb *hp = (SchwarpProb *)(h + o_probs);
-  for (int i = 0; i < nprob; i++) {
+  /* (large batches: several host threads, a share of the problems each) */
+  host_parallel_for((size_t)nprob, 32, [&](size_t i_lo, size_t i_hi) {
+  for (size_t i = i_lo; i < i_hi; i++) {
     const size_t n = p[i].n_matches, NC = (size_t)p[i].bbs.nptsu * p[i].bbs.nptsv;
     memcpy(h + o_kp1[i], p[i].kp1, 8 * n);
     memcpy(h + o_kp2[i], p[i].kp2, 8 * n);
@@ -270,6 +272,7 @@ int defslam_schwarp_fit_batched(int32_t nprob, const defslam_schwarp_problem *p,
     P.warp_uv = (float *)(d_out + o_uv[i]); P.J12 = (float *)(d_out + o_j12[i]); P.J21 = (float *)(d_out + o_j21[i]);
     P.H12 = (float *)(d_out + o_h12[i]); P.keep = d_out + o_keep[i]; P.scalars = (double *)(d_out + o_sc[i]);
   }
+  });
   *(int *)(h + o_counter) = 0;
   DS_CUDA_TRY(cudaMemcpyAsync(d_in, h, in.total + x_total, cudaMemcpyHostToDevice, ctx->stream));
   DS_CUDA_TRY(raise_dynamic_smem((const void *)schwarp_fit_kernel, ctx->device, (int)smem));
@@ -287,24 +290,25 @@ int defslam_schwarp_fit_batched(int32_t nprob, const defslam_schwarp_problem *p,
   g_last_kernel_ms = ms;
   int worst = DEFSLAM_OK;
   for (int i = 0; i < nprob; i++) {
-    const size_t n = p[i].n_matches, NC = (size_t)p[i].bbs.nptsu * p[i].bbs.nptsv;
     const double *sc = (const double *)(h_out + o_sc[i]);
     const int st = (int)sc[4];
     out[i].cost_initial = sc[0]; out[i].cost_final = sc[1];
     out[i].iterations = (int)sc[2]; out[i].accepted = (int)sc[3];
-    if (st != SCHWARP_OK) {
-      /* outputs untouched, like the reference keeping its previous estimate */
-      const int e = st == SCHWARP_OUT_OF_DOMAIN ? DEFSLAM_EBADARG : DEFSLAM_ENUMERIC;
-      if (worst == DEFSLAM_OK) worst = e;
-      continue;
-    }
-    memcpy(p[i].x, h_out + o_x[i], 16 * NC);
-    if (out[i].warp_uv) memcpy(out[i].warp_uv, h_out + o_uv[i], 8 * n);
-    if (out[i].J12) memcpy(out[i].J12, h_out + o_j12[i], 16 * n);
-    if (out[i].J21) memcpy(out[i].J21, h_out + o_j21[i], 16 * n);
-    if (out[i].H12) memcpy(out[i].H12, h_out + o_h12[i], 24 * n);
-    if (out[i].keep) memcpy(out[i].keep, h_out + o_keep[i], n);
+    if (st != SCHWARP_OK && worst == DEFSLAM_OK) worst = st == SCHWARP_OUT_OF_DOMAIN ? DEFSLAM_EBADARG : DEFSLAM_ENUMERIC;
   }
+  host_parallel_for((size_t)nprob, 32, [&](size_t i_lo, size_t i_hi) {
+    for (size_t i = i_lo; i < i_hi; i++) {
+      const size_t n = p[i].n_matches, NC = (size_t)p[i].bbs.nptsu * p[i].bbs.nptsv;
+      /* a failed fit leaves its outputs untouched, like the reference keeping its previous estimate */
+      if ((int)((const double *)(h_out + o_sc[i]))[4] != SCHWARP_OK) continue;
+      memcpy(p[i].x, h_out + o_x[i], 16 * NC);
+      if (out[i].warp_uv) memcpy(out[i].warp_uv, h_out + o_uv[i], 8 * n);
+      if (out[i].J12) memcpy(out[i].J12, h_out + o_j12[i], 16 * n);
+      if (out[i].J21) memcpy(out[i].J21, h_out + o_j21[i], 16 * n);
+      if (out[i].H12) memcpy(out[i].H12, h_out + o_h12[i], 24 * n);
+      if (out[i].keep) memcpy(out[i].keep, h_out + o_keep[i], n);
+    }
+  });
   return worst;
 }
 
