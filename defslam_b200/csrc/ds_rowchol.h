@@ -77,6 +77,9 @@ DS_FN void spin_ge_relaxed(const int *p, int need) {
 #ifndef DS_ROWS_BORDER_ON_CHAIN_SP
 #define DS_ROWS_BORDER_ON_CHAIN_SP 0
 #endif
+#ifndef DS_ROWS_SPLIT_CHAINS
+#define DS_ROWS_SPLIT_CHAINS 0
+#endif
 DS_FN void publish(int *p, int v, int lane) {
   __syncwarp();
 #if DS_ROWS_FENCE_LIGHT
@@ -219,18 +222,40 @@ struct SftBandLoader {
     const int lo = bwE - bw;
     const int i = NB * I + g;
     const double *rowp = Hb + (size_t)i * ld;
+    /* Straight-line for the tiles left of the diagonal: every pair is requested (from a clamped, valid address where
+     * it lies outside the band) before any is used.  With a branch per tile the loads went out one memory round trip
+     * after the other: 4 k cycles per block row of an owner, a quarter of its time, with the chain warp waiting. */
 #pragma unroll
-    for (int t = 0; t < NT; t++) {
+    for (int t = 0; t < NBK; t++) {
+      const int off = NB * (I - NBK + t) + 2 * q - i + bwE; /* even, <= bwE - 2 */
+      /* a row is 16-byte aligned at offsets of its own parity; off = -1 (odd row, its first column the second of the
+       * pair) reads the last slot of the row above with it */
+      const dbl2 w = *(const dbl2 *)(rowp + (off >= -1 ? off : (i & 1)));
+      a0[t] = w.x; a1[t] = w.y;
+    }
+    {
+      /* the diagonal tile: columns up to the diagonal (offset bwE) only */
+      const int off = NB * I + 2 * q - i + bwE;
+      double x0 = 0.0, x1 = 0.0;
+      if (off + 1 <= bwE) { const dbl2 w = *(const dbl2 *)(rowp + off); x0 = w.x; x1 = w.y; }
+      else if (off == bwE) x0 = rowp[off];
+      a0[NBK] = x0; a1[NBK] = x1;
+    }
+#pragma unroll
+    for (int t = 0; t < NBK; t++) {
       const int J = I - NBK + t;
       const int off = NB * J + 2 * q - i + bwE;
-      const bool v0 = J >= 0 && off >= lo && off <= bwE, v1 = J >= 0 && off + 1 >= lo && off + 1 <= bwE;
-      double x0 = 0.0, x1 = 0.0;
-      if (v0 && v1) { const dbl2 v = *(const dbl2 *)(rowp + off); x0 = v.x; x1 = v.y; }
-      else { if (v0) x0 = rowp[off]; if (v1) x1 = rowp[off + 1]; }
-      a0[t] = x0; a1[t] = x1;
+      a0[t] = (J >= 0 && off >= lo) ? a0[t] : 0.0;
+      a1[t] = (J >= 0 && off + 1 >= lo) ? a1[t] : 0.0;
     }
     if (2 * q == g) a0[NT - 1] += lambda;
     if (2 * q + 1 == g) a1[NT - 1] += lambda;
+  }
+  /* L2 prefetch of block row I: 4 lanes per row, one 128-byte line each per trip */
+  DS_FN void prefetch(int I, int lane) const {
+    const char *seg = (const char *)(Hb + (size_t)(NB * I + (lane >> 2)) * ld + (bwE - bw));
+    const int nline = ((bw + 1) * 8 + 127) / 128 + 1;
+    for (int l = (lane & 3); l < nline; l += 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(seg + 128 * l));
   }
 };
 
@@ -247,6 +272,10 @@ DS_FN void rows_owner_warp(const RowShared &S, int widx, int nown, int nblk, int
     double a0[NT], a1[NT];
     ldr.template load<NT>(I, g, q, a0, a1);
     DS_PROF_LAP(oacc, 0, ot); /* the row's band read */
+#if DS_ROWS_PREFETCH
+    /* experiment (not kept: C2 batch 3 % slower): L2 prefetch of the band of the row this warp takes next */
+    if (I + nown < nblk) ldr.prefetch(I + nown, lane);
+#endif
     /* the slot's previous tenant (row I-R) was last read by the border warp */
     if (I >= R) spin_ge(S.edone, I - R + 1);
     const uint32_t slot = S.ring + 512u * (uint32_t)((I % R) * NT);
@@ -380,13 +409,35 @@ DS_FN void rows_factor(int tid, int nthr, int nblk, int max_owners, const Loader
   if (lane == 0) {
     unsigned wid;
     asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+#if DS_ROWS_SPLIT_CHAINS
+    wsp[warp] = (int)wid;
+#else
     wsp[warp] = (int)(wid & 3u);
+#endif
   }
   __syncthreads();
   {
+#if DS_ROWS_SPLIT_CHAINS
+    /* experiment: the two CTAs of an SM put their chains on DIFFERENT sub-partitions (0 for the CTA in warp slots
+     * 0-7, 1 for the one in slots 8-15) and both keep their tensor-core work off sub-partitions 0 and 1: two chains
+     * sharing a sub-partition run 1.5x slower each (tools/chainbench.cu: 904 -> 1375 cycles per block) */
+    int minslot = 1 << 30;
+    for (int w = 0; w < nwarp; w++) minslot = wsp[w] < minslot ? wsp[w] : minslot;
+    unsigned nsm;
+    asm volatile("mov.u32 %0, %%nsmid;" : "=r"(nsm));
+    const bool paired = gridDim.x > nsm && nwarp == 8;
+    const int want_sp = paired ? ((minslot >> 3) & 1) : 0;
+    int chain_w = 0;
+    for (int w = nwarp - 1; w >= 0; w--) if ((wsp[w] & 3) == want_sp) chain_w = w;
+    const int chain_sp = wsp[chain_w] & 3;
+    __syncthreads();
+    if (lane == 0) { const int sp = wsp[warp] & 3; wsp[warp] = (paired && sp < 2) ? chain_sp : sp; } /* sub-partitions 0, 1: no workers */
+    __syncthreads();
+#else
     int chain_w = 0;
     for (int w = nwarp - 1; w >= 0; w--) if (wsp[w] == 0) chain_w = w;
     const int chain_sp = wsp[chain_w];
+#endif
     /* the border warp (24 DMMAs per block row, a sixth of an owner's load) shares the chain's sub-partition when a
      * second warp sits there only with DS_ROWS_BORDER_ON_CHAIN_SP (measured: C2 1 % faster, C1/C3/C4 5-9 % slower --
      * the chain loses more than the sixth owner gains; default off); every other warp on that sub-partition idles */

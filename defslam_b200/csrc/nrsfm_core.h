@@ -326,19 +326,40 @@ struct RowBandLoader {
     const int lo = bwE - bw;
     const int i = NB * I + g;
     const double *rowp = Hr + (size_t)i * ld;
+    /* Straight-line for the tiles left of the diagonal: every pair is requested (from a clamped, valid address where
+     * it lies outside the band) before any is used.  With a branch per tile the loads went out one memory round trip
+     * after the other: 4 k cycles per block row of an owner, a quarter of its time, with the chain warp waiting. */
 #pragma unroll
-    for (int t = 0; t < NT; t++) {
+    for (int t = 0; t < NBK; t++) {
+      const int off = NB * (I - NBK + t) + 2 * q - i + bwE; /* even, <= bwE - 2 */
+      /* a row is 16-byte aligned at offsets of its own parity; off = -1 (odd row, its first column the second of the
+       * pair) reads the last slot of the row above with it */
+      const dbl2 w = *(const dbl2 *)(rowp + (off >= -1 ? off : (i & 1)));
+      a0[t] = w.x; a1[t] = w.y;
+    }
+    {
+      /* the diagonal tile: columns up to the diagonal (offset bwE) only */
+      const int off = NB * I + 2 * q - i + bwE;
+      double x0 = 0.0, x1 = 0.0;
+      if (off + 1 <= bwE) { const dbl2 w = *(const dbl2 *)(rowp + off); x0 = w.x; x1 = w.y; }
+      else if (off == bwE) x0 = rowp[off];
+      a0[NBK] = x0; a1[NBK] = x1;
+    }
+#pragma unroll
+    for (int t = 0; t < NBK; t++) {
       const int J = I - NBK + t;
       const int off = NB * J + 2 * q - i + bwE;
-      const bool v0 = J >= 0 && off >= lo && off <= bwE, v1 = J >= 0 && off + 1 >= lo && off + 1 <= bwE;
-      double x0 = 0.0, x1 = 0.0;
-      if (v0 && v1) { const dbl2 v = *(const dbl2 *)(rowp + off); x0 = v.x; x1 = v.y; }
-      else { if (v0) x0 = rowp[off]; if (v1) x1 = rowp[off + 1]; }
-      a0[t] = x0; a1[t] = x1;
+      a0[t] = (J >= 0 && off >= lo) ? a0[t] : 0.0;
+      a1[t] = (J >= 0 && off + 1 >= lo) ? a1[t] : 0.0;
     }
     const double dadd = (add && i < n) ? add[i] : 0.0;
     if (2 * q == g) a0[NT - 1] += dadd;
     if (2 * q + 1 == g) a1[NT - 1] += dadd;
+  }
+  DS_FN void prefetch(int I, int lane) const {
+    const char *seg = (const char *)(Hr + (size_t)(NB * I + (lane >> 2)) * ld + (bwE - bw));
+    const int nline = ((bw + 1) * 8 + 127) / 128 + 1;
+    for (int l = (lane & 3); l < nline; l += 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(seg + 128 * l));
   }
 };
 

@@ -261,7 +261,7 @@ static int batch_wait_kernel(defslam_sft_batch *B) {
     fprintf(stderr, "\n");
     if (h[PF_X_STEPS] == 0 && h[PF_X_WARP + 1]) { /* row-owner factorisation: chain warp and owners, per block row */
       fprintf(stderr, "[defslam profile] row owner path, cycles summed over the launch: chain warp waiting %lld, factoring %lld; "
-                      "owners (everything before the last step, last step):", h[PF_X_WARP], h[PF_X_WARP + 1]);
+                      "owners (reading their band of H / the block-row steps incl. waits):", h[PF_X_WARP], h[PF_X_WARP + 1]);
       for (int w = 0; w < 5; w++) fprintf(stderr, " %lld/%lld", h[PF_X_WARP + 2 + 2 * w], h[PF_X_WARP + 3 + 2 * w]);
       fprintf(stderr, "\n");
     }

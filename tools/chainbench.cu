@@ -169,6 +169,56 @@ __global__ void chain(double *gm, long long *cyc, int n, int busy_warps) {
   }
 }
 
+// two chains on ONE sub-partition (warps 0 and 4 of a 256-thread CTA), as the chain warps of two co-resident CTAs:
+// does predicating the redundant lanes off (only ACT lanes factor the block) shorten the pair?
+template <int ACT>
+__global__ void chain_pair(double *gm, long long *cyc, int n, int second) {
+  __shared__ double D[2][2][64];
+  __shared__ double Y[2][64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  ((double *)D)[threadIdx.x] = gm[threadIdx.x & 63];
+  __syncthreads();
+  if (warp == 0 || (second && warp == 4)) {
+    const int w = warp == 0 ? 0 : 1;
+    double acc = 0.0;
+    long long t0 = clock64();
+    for (int it = 0; it < n; it++) {
+      if (lane < ACT) {
+        double a[36];
+        const volatile double *Dv = D[w][it & 1];
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+          for (int j = 0; j <= i; j++) a[i * (i + 1) / 2 + j] = Dv[i * 8 + j];
+        a[0] += acc;
+        chol8<1>(a);
+        double col[8];
+        invcol8(a, lane & 7, col);
+        if (lane < 8) {
+#pragma unroll
+          for (int m = 0; m < 8; m++) Y[w][m * 8 + lane] = col[m];
+        }
+      }
+      __syncwarp();
+      acc = ((volatile double *)Y[w])[63] * 1e-30;
+    }
+    long long t1 = clock64();
+    if (lane == 0) { cyc[w] = t1 - t0; gm[64 + w] = acc; }
+  }
+}
+template <int ACT> void run_pair(double *gm, long long *cyc) {
+  const int n = 2000;
+  for (int second = 0; second <= 1; second++) {
+    chain_pair<ACT><<<1, 256>>>(gm, cyc, n, second);
+    cudaDeviceSynchronize();
+    chain_pair<ACT><<<1, 256>>>(gm, cyc, n, second);
+    cudaDeviceSynchronize();
+    long long h[2];
+    cudaMemcpy(h, cyc, 16, cudaMemcpyDeviceToHost);
+    printf("chain with %2d active lanes, %s: %7.1f cycles / block\n", ACT, second ? "two chains on the sub-partition" : "alone", (double)h[0] / n);
+  }
+}
+
 template <int RS, int INV, bool LOAD> void run(const char *name, double *gm, long long *cyc, int busy) {
   const int n = 2000;
   chain<RS, INV, LOAD><<<1, 256>>>(gm, cyc, n, busy);
@@ -208,6 +258,9 @@ int main() {
     run<3, 0, true>("2x2 block pivots, no inverse", gm, cyc, busy);
     run<3, 1, true>("2x2 block pivots + inverse (runtime column)", gm, cyc, busy);
   }
+  run_pair<32>(gm, cyc);
+  run_pair<16>(gm, cyc);
+  run_pair<8>(gm, cyc);
   {
     double *out; cudaMalloc(&out, 8);
     cmp_kernel<<<1, 1>>>(gm, out);

@@ -6,6 +6,8 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 
+os.environ["DEFSLAM_NORMALS_CHUNKS"] = "1"  # the normals batch in ONE launch (the call pipelines it in chunks otherwise)
+
 wl = bench.nrsfm_workload()
 api = wl["api"]
 api.schwarp_prepare(wl["pairs"])()
