@@ -77,6 +77,9 @@ DS_FN void spin_ge_relaxed(const int *p, int need) {
 #ifndef DS_ROWS_BORDER_ON_CHAIN_SP
 #define DS_ROWS_BORDER_ON_CHAIN_SP 0
 #endif
+#ifndef DS_ROWS_LOAD_CG
+#define DS_ROWS_LOAD_CG 0
+#endif
 #ifndef DS_ROWS_SPLIT_CHAINS
 #define DS_ROWS_SPLIT_CHAINS 0
 #endif
@@ -230,7 +233,11 @@ struct SftBandLoader {
       const int off = NB * (I - NBK + t) + 2 * q - i + bwE; /* even, <= bwE - 2 */
       /* a row is 16-byte aligned at offsets of its own parity; off = -1 (odd row, its first column the second of the
        * pair) reads the last slot of the row above with it */
+#if DS_ROWS_LOAD_CG
+      const dbl2 w = ldcg_dbl2((const dbl2 *)(rowp + (off >= -1 ? off : (i & 1))));
+#else
       const dbl2 w = *(const dbl2 *)(rowp + (off >= -1 ? off : (i & 1)));
+#endif
       a0[t] = w.x; a1[t] = w.y;
     }
     {
