@@ -303,7 +303,12 @@ def stream_bench(lib, with_cpu: bool):
            "nrsfm_events": r.n_nrsfm, "template_updates": r.n_template_updates,
            "gpu_launches": int(lib.defslam_kernel_launch_count() - l0),
            "node_rmse_vs_ground_truth": {"median": float(np.median(r.rmse)), "max": float(np.max(r.rmse))},
-           "lm_trials_per_frame": float(np.mean(r.trials))}
+           "lm_trials_per_frame": float(np.mean(r.trials)),
+           # where the wall clock goes: the SfT call of every frame, the NRSfM events, and the rest of the host loop
+           # (synthetic observations, NumPy marshalling) -- the like-for-like ratio against the CPU side is tracking_ms
+           "stages": {"tracking_ms_per_frame": 1e3 * r.t_sft / cfg.n_frames,
+                      "nrsfm_ms_per_event": 1e3 * r.t_nrsfm / max(r.n_nrsfm, 1),
+                      "host_loop_ms_per_frame": 1e3 * (dt - r.t_sft - r.t_nrsfm) / cfg.n_frames}}
     if with_cpu:
         from oracle import oracle_py
         try:
@@ -316,6 +321,7 @@ def stream_bench(lib, with_cpu: bool):
         ro = stream.run_stream(ob, stream.StreamConfig(n_frames=n), keep_nodes=True)
         dto = time.perf_counter() - t0
         out["cpu_baseline"] = {"value": n / dto, "unit": "frames/s", "cores": 1, "kind": "port",
+                               "tracking_ms_per_frame": 1e3 * ro.t_sft / n,
                                "sample": f"first {n} frames of the same stream (tracking only: the first NRSfM event "
                                          f"is at frame 50), oracle on one core, {dto:.1f} s"}
         rg = stream.run_stream(be, stream.StreamConfig(n_frames=n), keep_nodes=True)

@@ -19,6 +19,8 @@ from __future__ import annotations
 import ctypes as C
 from dataclasses import dataclass, field
 
+import time
+
 import numpy as np
 
 from . import _capi, nrsfm, synthetic
@@ -155,6 +157,8 @@ class StreamResult:
     n_nrsfm: int = 0
     n_template_updates: int = 0
     template_rmse: list = field(default_factory=list)  # per update: new rest nodes vs ground truth, relative
+    t_sft: float = 0.0    # seconds inside the per-frame SfT solve (the call DefTracking makes)
+    t_nrsfm: float = 0.0  # seconds inside the NRSfM events (Schwarp fits, normals, SfN, registration, template rebuild)
 
 
 def run_stream(be: Backend, cfg: StreamConfig, keep_nodes: bool = True, logs_dir: str | None = None) -> StreamResult:
@@ -203,7 +207,9 @@ def run_stream(be: Backend, cfg: StreamConfig, keep_nodes: bool = True, logs_dir
             match_bary=np.ascontiguousarray(m_bary[sel].astype(np.float64)), match_uv=np.ascontiguousarray(uv32[sel]),
             match_inv_sigma2=np.ascontiguousarray(inv_s2[sel]), T_cw=T_cw.copy(), n_frame_keypoints=cfg.n_points,
             fx=fx, fy=fy, cx=cx, cy=cy, max_iterations=cfg.max_iterations)
+        t_call = time.perf_counter()
         out = be.sft_solve(frame)
+        res.t_sft += time.perf_counter() - t_call
         nodes = np.array(out.nodes, dtype=np.float64)
         T_cw = np.array(out.T_cw, dtype=np.float32).reshape(4, 4)
         Tc = T_cw.astype(np.float64)
@@ -228,7 +234,9 @@ def run_stream(be: Backend, cfg: StreamConfig, keep_nodes: bool = True, logs_dir
             continue
         # ---- NRSfM on the current keyframe against the n_views before it
         res.n_nrsfm += 1
+        t_call = time.perf_counter()
         new = _nrsfm_template(be, cfg, scene, keyframes, octave, tmpl, m_nodes, m_bary, valid, G)
+        res.t_nrsfm += time.perf_counter() - t_call
         if new is None:
             continue
         tmpl, m_nodes, m_bary, valid, node_uv, trel = new

@@ -75,3 +75,14 @@ def test_package_never_imports_the_oracle():
             if f.endswith((".py", ".h", ".cu", ".cpp")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle_py" not in txt and "liboracle" not in txt and "oracle/" not in txt, f
+
+
+def test_host_thread_pool():
+    """the persistent marshalling pool of csrc/ds_host.h (pure C++, compiled for the host)"""
+    import subprocess
+    exe = os.path.join(ROOT, "tests", "_emu", "test_host_pool")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.run(["g++", "-O1", "-std=c++17", "-pthread", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_host_pool.cc")],
+                   check=True, capture_output=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "host pool: ok" in r.stdout, r.stdout + r.stderr
