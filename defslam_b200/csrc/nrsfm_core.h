@@ -1598,6 +1598,129 @@ DS_FN_NOINLINE void packed_solve(const Team team, const double *L, int n, double
   }
 }
 
+/* ---- the same factorisation on the FP64 tensor cores: N as 8x8 tiles of its lower triangle in shared memory, every
+ * tile in operand-fragment order (element (r, c) at (c/4)*32 + r*4 + c%4: one m8n8k4 operand load is 32 consecutive
+ * doubles, an accumulator pair one 16-byte access), right-looking by block columns: diagonal block by one warp (the
+ * 8x8 Cholesky + inverse of ds_rowchol.h), panel X = C inv(L_kk)^T and trailing update C(i,j) -= X_i X_j^T by all
+ * warps with two DMMAs per tile; three barriers per block column instead of two per column.  Yinv: the inverses of the
+ * diagonal blocks (what the substitutions need).  n padded to 8 nt with identity rows. */
+static DS_HD int sfn_tile_doubles(int NC) { const int nt = (NC + 7) / 8; return nt * (nt + 1) / 2 * 64 + nt * 64; }
+DS_FN int tile_id(int i, int j) { return i * (i + 1) / 2 + j; }
+DS_FN int tile_elem(int r, int c) { return (c >> 2) * 32 + r * 4 + (c & 3); }
+#if DS_CUDA
+DS_FN_NOINLINE bool sfn_tile_chol(const Team team, double *T, double *Yinv, int nt, int *flag) {
+  const int warp = team.tid >> 5, lane = team.tid & 31, nwarp = team.nthr >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const uint32_t T32 = smem_u32(T), Y32 = smem_u32(Yinv);
+  const uint32_t pair_off = frag_pair_off(g, q), lane_off = 8u * (uint32_t)lane;
+  if (team.tid == 0) *flag = 0;
+  team.sync();
+  for (int k = 0; k < nt; k++) {
+    if (warp == 0) {
+      const double *D = T + (size_t)tile_id(k, k) * 64;
+      double a[36];
+#pragma unroll
+      for (int i = 0; i < NB; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) a[i * (i + 1) / 2 + j] = D[tile_elem(i, j)];
+      const bool bad = chol8_regs(a);
+      double col[NB];
+      const int j = lane & 7;
+      invcol8_regs(a, j, col);
+      if (lane < NB) {
+        double *Y = Yinv + (size_t)k * 64;
+#pragma unroll
+        for (int m = 0; m < NB; m++) Y[tile_elem(m, j)] = col[m];
+      }
+      if (bad && lane == 0) *flag = 1;
+    }
+    team.sync();
+    if (*flag != 0) return false;
+    const uint32_t yk = Y32 + 512u * (uint32_t)k;
+    for (int i = k + 1 + warp; i < nt; i += nwarp) {
+      const uint32_t tile = T32 + 512u * (uint32_t)tile_id(i, k);
+      const double y0 = lds_f64(yk + lane_off), y1 = lds_f64(yk + 256u + lane_off);
+      const double c0 = lds_f64(tile + lane_off), c1 = lds_f64(tile + 256u + lane_off);
+      double x0 = 0.0, x1 = 0.0;
+      dmma884(x0, x1, c0, y0);
+      dmma884(x0, x1, c1, y1);
+      __syncwarp(); /* every lane has read C before X overwrites it */
+      sts_v2f64(tile + pair_off, x0, x1);
+    }
+    team.sync();
+    const int ntr = nt - 1 - k, total = ntr * (ntr + 1) / 2;
+    for (int e = warp; e < total; e += nwarp) {
+      int ii = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+      while ((ii + 1) * (ii + 2) / 2 <= e) ii++;
+      while (ii * (ii + 1) / 2 > e) ii--;
+      const int jj = e - ii * (ii + 1) / 2;
+      const int i = k + 1 + ii, j = k + 1 + jj;
+      const uint32_t tc = T32 + 512u * (uint32_t)tile_id(i, j) + pair_off;
+      const uint32_t ta = T32 + 512u * (uint32_t)tile_id(i, k), tb = T32 + 512u * (uint32_t)tile_id(j, k);
+      dbl2 acc = lds_v2f64(tc);
+      const double a0 = -lds_f64(ta + lane_off), a1 = -lds_f64(ta + 256u + lane_off);
+      const double b0 = lds_f64(tb + lane_off), b1 = lds_f64(tb + 256u + lane_off);
+      dmma884(acc.x, acc.y, a0, b0);
+      dmma884(acc.x, acc.y, a1, b1);
+      sts_v2f64(tc, acc.x, acc.y);
+    }
+    team.sync();
+  }
+  return true;
+}
+
+/* x <- (L L')^-1 x on the tile-form factor; x: 8 nt doubles of shared memory.  One warp: the block recurrences have no
+ * parallelism across block rows and a CTA-wide barrier per column is what the packed substitution spends its time on. */
+DS_FN_NOINLINE void sfn_tile_solve(const Team team, const double *T, const double *Yinv, int nt, double *x) {
+  const int warp = team.tid >> 5, lane = team.tid & 31;
+  if (warp == 0) {
+    for (int k = 0; k < nt; k++) { /* L y = r */
+      const double *Y = Yinv + (size_t)k * 64;
+      double mine = 0.0;
+      { const int m = lane & 7;
+#pragma unroll
+        for (int j = 0; j < NB; j++) mine += (j <= m ? Y[tile_elem(m, j)] : 0.0) * x[NB * k + j]; }
+      double yk[NB];
+#pragma unroll
+      for (int c = 0; c < NB; c++) yk[c] = __shfl_sync(0xffffffffu, mine, c);
+      __syncwarp();
+      if (lane < NB) x[NB * k + lane] = mine;
+      for (int idx = lane; idx < (nt - 1 - k) * NB; idx += 32) {
+        const int I = k + 1 + (idx >> 3), r = idx & 7;
+        const double *L = T + (size_t)tile_id(I, k) * 64;
+        double s = x[NB * I + r];
+#pragma unroll
+        for (int c = 0; c < NB; c++) s -= L[tile_elem(r, c)] * yk[c];
+        x[NB * I + r] = s;
+      }
+      __syncwarp();
+    }
+    for (int k = nt - 1; k >= 0; k--) { /* L' x = y */
+      const double *Y = Yinv + (size_t)k * 64;
+      double mine = 0.0;
+      { const int j = lane & 7;
+#pragma unroll
+        for (int m = 0; m < NB; m++) mine += (m >= j ? Y[tile_elem(m, j)] : 0.0) * x[NB * k + m]; }
+      double xk[NB];
+#pragma unroll
+      for (int r = 0; r < NB; r++) xk[r] = __shfl_sync(0xffffffffu, mine, r);
+      __syncwarp();
+      if (lane < NB) x[NB * k + lane] = mine;
+      for (int idx = lane; idx < k * NB; idx += 32) {
+        const int J = idx >> 3, c = idx & 7;
+        const double *L = T + (size_t)tile_id(k, J) * 64;
+        double s = x[NB * J + c];
+#pragma unroll
+        for (int r = 0; r < NB; r++) s -= L[tile_elem(r, c)] * xk[r];
+        x[NB * J + c] = s;
+      }
+      __syncwarp();
+    }
+  }
+  team.sync();
+}
+#endif
+
 /* the two M rows of normal i (ShapeFromNormals.cc:234-258) as 16 taps each; false outside the domain */
 DS_FN bool sfn_rows(const BbsView &s, const float *uv, const float *nrm, int i, int &Iu, int &Iv, double *m1,
                     double *m2) {
@@ -1621,14 +1744,21 @@ DS_FN bool sfn_rows(const BbsView &s, const float *uv, const float *nrm, int i, 
   return true;
 }
 
-/* One keyframe.  sh: sfn_smem_fixed(NC) (+ NC(NC+1)/2 if n_in_smem) doubles.
+/* One keyframe.  n_mode 0: packed N in the global workspace, 1: packed N in shared memory, 2 (device only): N as
+ * 8x8 tiles in shared memory, factorised on the tensor cores.  sh: sfn_smem_fixed(NC) (+ NC(NC+1)/2 in mode 1,
+ * + sfn_tile_doubles(NC) in mode 2) doubles.
  * rc: 0 ok, DEFSLAM_EBADARG site outside the domain, DEFSLAM_ENUMERIC not finite / not SPD. */
-DS_FN_NOINLINE void sfn_solve_one(const Team team, const SfnProb &P, const SfnWs &ws, double *sh, bool n_in_smem) {
+DS_FN_NOINLINE void sfn_solve_one(const Team team, const SfnProb &P, const SfnWs &ws, double *sh, int n_mode) {
   const BbsView &s = P.bbs;
   const int nu = s.nptsu, nv = s.nptsv, NC = nu * nv, n = P.n, ncv = nv - 3;
   double *x = sh, *rhs = sh + NC, *col = sh + 2 * NC, *acc = sh + 3 * NC, *ci = sh + 4 * NC, *red = ci + 48;
   float *fl = (float *)(red + 40);
-  double *N = n_in_smem ? (red + 40 + (NC + 1) / 2 + 2) : ws.N;
+  /* (the tiles are accessed 16 bytes at a time: their offset is rounded up to even, the host adds the slack) */
+  double *N = n_mode == 2 ? (red + 40 + (((NC + 1) / 2 + 2 + 1) & ~1)) : (n_mode ? (red + 40 + (NC + 1) / 2 + 2) : ws.N);
+  const bool tiles = n_mode == 2;
+  const int nt = (NC + 7) / 8, Dp = NB * nt;
+  double *Yinv = N + (size_t)nt * (nt + 1) / 2 * 64; /* (mode 2) */
+  (void)Dp; (void)Yinv;
   fill_cell_integrals(team, ci);
   CellSort cs{n, nu - 3, nv - 3, ws.cell, ws.cstart, ws.perm, ws.taps};
   int bad = cell_sort(team, s, P.uv, cs, red);
@@ -1645,6 +1775,11 @@ DS_FN_NOINLINE void sfn_solve_one(const Team team, const SfnProb &P, const SfnWs
   if (bad) {
     if (team.tid == 0 && P.rc_out) *P.rc_out = DEFSLAM_EBADARG;
     return;
+  }
+  if (tiles) { /* padding rows: identity; the upper halves of the diagonal tiles mirror the lower ones */
+    DS_FOR(idx, nt * (nt + 1) / 2 * 64) N[idx] = 0.0;
+    team.sync();
+    DS_FOR(i, Dp - NC) N[(size_t)tile_id(nt - 1, nt - 1) * 64 + tile_elem((NC + i) & 7, (NC + i) & 7)] = 1.0;
   }
   /* N = M'M + B'B + 1 1' (packed lower) */
   DS_FOR(idx, NC * (NC + 1) / 2) {
@@ -1681,13 +1816,39 @@ DS_FN_NOINLINE void sfn_solve_one(const Team team, const SfnProb &P, const SfnWs
         }
       a += bb;
     }
-    N[idx] = a;
+    if (tiles) {
+      N[(size_t)tile_id(p >> 3, q >> 3) * 64 + tile_elem(p & 7, q & 7)] = a;
+      if ((p >> 3) == (q >> 3) && p != q) N[(size_t)tile_id(p >> 3, q >> 3) * 64 + tile_elem(q & 7, p & 7)] = a;
+    } else {
+      N[idx] = a;
+    }
   }
   DS_FOR(p, NC) x[p] = NC * P.mean_depth;
   team.sync();
+  /* (mode 2) the substitutions work on a vector padded to 8 nt entries: col and acc together */
+  double *work = col;
+  int *tflag = (int *)(red + 36);
+  (void)work; (void)tflag;
+#if DS_CUDA
+#define SFN_SOLVE(vec)                                            \
+  do {                                                            \
+    if (tiles) {                                                  \
+      DS_FOR(i_, Dp) work[i_] = i_ < NC ? (vec)[i_] : 0.0;        \
+      team.sync();                                                \
+      sfn_tile_solve(team, N, Yinv, nt, work);                    \
+      DS_FOR(i_, NC)(vec)[i_] = work[i_];                         \
+      team.sync();                                                \
+    } else {                                                      \
+      packed_solve(team, N, NC, (vec));                           \
+    }                                                             \
+  } while (0)
+  bool ok = tiles ? sfn_tile_chol(team, N, Yinv, nt, tflag) : packed_chol(team, N, NC, col);
+#else
+#define SFN_SOLVE(vec) packed_solve(team, N, NC, (vec))
   bool ok = packed_chol(team, N, NC, col);
+#endif
   if (ok) {
-    packed_solve(team, N, NC, x);
+    SFN_SOLVE(x);
     /* two sweeps of corrected semi-normal equations: r = b - A x, x += N^-1 A'r */
     for (int sweep = 0; sweep < 2; sweep++) {
       DS_FOR(i, n) {
@@ -1736,7 +1897,7 @@ DS_FN_NOINLINE void sfn_solve_one(const Team team, const SfnProb &P, const SfnWs
         rhs[p] = a;
       }
       team.sync();
-      packed_solve(team, N, NC, rhs);
+      SFN_SOLVE(rhs);
       DS_FOR(p, NC) x[p] += rhs[p];
       team.sync();
     }

@@ -156,7 +156,7 @@ sfn_solve_kernel(const SfnProb *probs, int nprob, uint8_t *ws_base, size_t ws_st
     __syncthreads();
     const int i = s_next;
     if (i >= nprob) break;
-    sfn_solve_one(team, probs[i], ws, sh, n_in_smem != 0);
+    sfn_solve_one(team, probs[i], ws, sh, n_in_smem);
   }
 }
 
@@ -642,8 +642,12 @@ int defslam_sfn_solve_batched(int32_t nprob, const defslam_sfn_problem *p, int32
   const size_t fixed = sizeof(double) * (size_t)sfn_smem_fixed((int)NCmax);
   const size_t packed = sizeof(double) * NCmax * (NCmax + 1) / 2;
   if (fixed > (size_t)ctx->smem_optin) return DEFSLAM_ETOOLARGE;
-  const int n_in_smem = fixed + packed <= (size_t)ctx->smem_optin;
-  const size_t smem = fixed + (n_in_smem ? packed : 0);
+  /* N: as tiles in shared memory for the tensor-core factorisation (2), else packed in shared memory (1), else packed
+   * in the workspace (0); DEFSLAM_SFN_MODE caps it (A/B runs) */
+  const size_t tiled = sizeof(double) * (size_t)sfn_tile_doubles((int)NCmax) + 16;
+  int n_in_smem = fixed + tiled <= (size_t)ctx->smem_optin ? 2 : (fixed + packed <= (size_t)ctx->smem_optin ? 1 : 0);
+  if (const char *e = getenv("DEFSLAM_SFN_MODE")) { const int v = atoi(e); if (v >= 0 && v < n_in_smem && (v != 1 || fixed + packed <= (size_t)ctx->smem_optin)) n_in_smem = v; }
+  const size_t smem = fixed + (n_in_smem == 2 ? tiled : (n_in_smem ? packed : 0));
   Packer in, outp;
   std::vector<size_t> o_uv(nprob), o_nr(nprob), o_ev(nprob), o_ct(nprob), o_xyz(nprob), o_rc(nprob);
   const size_t o_probs = in.add(sizeof(SfnProb) * nprob), o_counter = in.add(sizeof(int));
