@@ -149,7 +149,7 @@ sfn_solve_kernel(const SfnProb *probs, int nprob, uint8_t *ws_base, size_t ws_st
   SfnWs ws;
   ws.cell = (int *)(b + z.cell); ws.cstart = (int *)(b + z.cstart); ws.perm = (int *)(b + z.perm);
   ws.taps = (double *)(b + z.taps); ws.mrow = (double *)(b + z.mrow); ws.B = (double *)(b + z.B);
-  ws.N = (double *)(b + z.N); ws.res = (double *)(b + z.res);
+  ws.N = (double *)(b + z.N); ws.res = (double *)(b + z.res); ws.G = (double *)(b + z.G);
   for (;;) {
     __syncthreads();
     if (threadIdx.x == 0) s_next = atomicAdd(counter, 1);

@@ -111,7 +111,7 @@ int emu_sfn_solve(const defslam_sfn_problem *p) {
   SfnWs ws;
   ws.cell = (int *)(b + z.cell); ws.cstart = (int *)(b + z.cstart); ws.perm = (int *)(b + z.perm);
   ws.taps = (double *)(b + z.taps); ws.mrow = (double *)(b + z.mrow); ws.B = (double *)(b + z.B);
-  ws.N = (double *)(b + z.N); ws.res = (double *)(b + z.res);
+  ws.N = (double *)(b + z.N); ws.res = (double *)(b + z.res); ws.G = (double *)(b + z.G);
   std::vector<double> sh(sfn_smem_fixed(NC) + (size_t)NC * (NC + 1) / 2 + 8);
   Team team;
   team.tid = 0; team.nthr = 1;
