@@ -516,14 +516,19 @@ DS_FN void fill_cell_integrals(const Team team, double *ci) {
   team.sync();
 }
 
-/* bending matrix entry from the cell-integral table (same sum as bbs_bending_entry) */
-DS_FN double bending_entry_tab(const BbsView &s, const double *ci, int iu, int iv, int ju, int jv) {
+/* bending matrix entry from the cell-integral table (same sum as bbs_bending_entry); the three scale factors of the
+ * grid are formed once per problem (five divisions), not once per entry */
+struct BendCoef { double cxx, cxy, cyy; };
+DS_FN BendCoef bending_coef(const BbsView &s) {
+  const double sy = (s.umax - s.umin) / (s.nptsu - 3);
+  const double sx = (s.vmax - s.vmin) / (s.nptsv - 3);
+  return BendCoef{sy / (sx * sx * sx), 1.0 / (sx * sy), sx / (sy * sy * sy)};
+}
+DS_FN double bending_entry_tab(const BbsView &s, const BendCoef &bc, const double *ci, int iu, int iv, int ju, int jv) {
   const int du = iu > ju ? iu - ju : ju - iu, dv = iv > jv ? iv - jv : jv - iv;
   if (du > 3 || dv > 3) return 0.0;
   const int nx = s.nptsv, ny = s.nptsu;
-  const double sy = (s.umax - s.umin) / (s.nptsu - 3);
-  const double sx = (s.vmax - s.vmin) / (s.nptsv - 3);
-  const double cxx = sy / (sx * sx * sx), cxy = 1.0 / (sx * sy), cyy = sx / (sy * sy * sy);
+  const double cxx = bc.cxx, cxy = bc.cxy, cyy = bc.cyy;
   double acc = 0.0;
   const int b0 = (iu > ju ? iu : ju) - 3, b1 = iu < ju ? iu : ju;
   const int a0 = (iv > jv ? iv : jv) - 3, a1 = iv < jv ? iv : jv;
@@ -535,6 +540,9 @@ DS_FN double bending_entry_tab(const BbsView &s, const double *ci, int iu, int i
       acc += cxx * (u0 * v2) + cxy * (2.0 * u1 * v1) + cyy * (u2 * v0);
     }
   return acc;
+}
+DS_FN double bending_entry_tab(const BbsView &s, const double *ci, int iu, int iv, int ju, int jv) {
+  return bending_entry_tab(s, bending_coef(s), ci, iu, iv, ju, jv);
 }
 
 /* ===================================================================== *
@@ -1037,9 +1045,10 @@ DS_FN_NOINLINE void schwarp_fit_one(const Team team, const SchwarpProb &P, const
   if (P.initialize) {
     /* Warp::initialize (Schwarp.cc:99-160): (C'C + lambda B) x0 = C' q2, two right-hand sides.
      * The system is assembled into Hb (reused later) with bs = nptsv. */
+    const BendCoef bc = bending_coef(s);
     DS_FOR(idx, nu * 4 * nv * nv) {
       const int qv = idx % nv, pv = (idx / nv) % nv, d = (idx / (nv * nv)) & 3, pu = idx / (4 * nv * nv), qu = pu - d;
-      ws.Hb[idx] = qu >= 0 ? ws.CtC[idx] + P.lambda * bending_entry_tab(s, sh + m.ci, pu, pv, qu, qv) : 0.0;
+      ws.Hb[idx] = qu >= 0 ? ws.CtC[idx] + P.lambda * bending_entry_tab(s, bc, sh + m.ci, pu, pv, qu, qv) : 0.0;
     }
     DS_FOR(p, NC) {
       const int pu = p / nv, pv = p - pu * nv;
@@ -1676,47 +1685,56 @@ DS_FN_NOINLINE bool sfn_tile_chol(const Team team, double *T, double *Yinv, int 
 DS_FN_NOINLINE void sfn_tile_solve(const Team team, const double *T, const double *Yinv, int nt, double *x) {
   const int warp = team.tid >> 5, lane = team.tid & 31;
   if (warp == 0) {
-    for (int k = 0; k < nt; k++) { /* L y = r */
-      const double *Y = Yinv + (size_t)k * 64;
-      double mine = 0.0;
-      { const int m = lane & 7;
+    const uint32_t T32 = smem_u32(T), Y32 = smem_u32(Yinv), X32 = smem_u32(x);
+    const int m8 = lane & 7;
+    for (int pass = 0; pass < 2; pass++) { /* 0: L y = r, top down; 1: L' x = y, bottom up */
+      for (int kk = 0; kk < nt; kk++) {
+        const int k = pass ? nt - 1 - kk : kk;
+        /* the block's solution: lane m (mod 8) forms entry m of inv(L_kk) r_k (pass 0) or inv(L_kk)' r_k (pass 1) from
+         * the stored inverse (zeros above its diagonal), two interleaved partial sums */
+        double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-        for (int j = 0; j < NB; j++) mine += (j <= m ? Y[tile_elem(m, j)] : 0.0) * x[NB * k + j]; }
-      double yk[NB];
+        for (int j = 0; j < NB; j += 2) {
+          const double ya = lds_f64(Y32 + 8u * (uint32_t)(k * 64 + (pass ? tile_elem(j, m8) : tile_elem(m8, j))));
+          const double yb = lds_f64(Y32 + 8u * (uint32_t)(k * 64 + (pass ? tile_elem(j + 1, m8) : tile_elem(m8, j + 1))));
+          s0 = fma(ya, lds_f64(X32 + 8u * (uint32_t)(NB * k + j)), s0);
+          s1 = fma(yb, lds_f64(X32 + 8u * (uint32_t)(NB * k + j + 1)), s1);
+        }
+        const double mine = s0 + s1;
+        double v[NB];
 #pragma unroll
-      for (int c = 0; c < NB; c++) yk[c] = __shfl_sync(0xffffffffu, mine, c);
-      __syncwarp();
-      if (lane < NB) x[NB * k + lane] = mine;
-      for (int idx = lane; idx < (nt - 1 - k) * NB; idx += 32) {
-        const int I = k + 1 + (idx >> 3), r = idx & 7;
-        const double *L = T + (size_t)tile_id(I, k) * 64;
-        double s = x[NB * I + r];
+        for (int c = 0; c < NB; c++) v[c] = __shfl_sync(0xffffffffu, mine, c);
+        __syncwarp();
+        if (lane < NB) x[NB * k + lane] = mine;
+        /* the other blocks: pass 0 rows below (tiles (I, k), entry r of block I), pass 1 columns above (tiles (k, J),
+         * entry c of block J); eight entries per lane in flight */
+        const int cnt = (pass ? k : nt - 1 - k) * NB;
+        for (int base = 0; base < cnt; base += 256) {
+          double acc[8];
+          uint32_t xa[8], la[8];
 #pragma unroll
-        for (int c = 0; c < NB; c++) s -= L[tile_elem(r, c)] * yk[c];
-        x[NB * I + r] = s;
+          for (int r = 0; r < 8; r++) {
+            const int idx = base + lane + 32 * r;
+            const int ok = idx < cnt, id = ok ? idx : 0;
+            const int blk = pass ? (id >> 3) : k + 1 + (id >> 3), e = id & 7;
+            xa[r] = ok ? X32 + 8u * (uint32_t)(NB * blk + e) : 0u;
+            /* pass 0: L(blk, k)[e][c], c = 0..7; pass 1: L(k, blk)[r'][e], r' = 0..7 */
+            la[r] = T32 + 512u * (uint32_t)(pass ? tile_id(k, blk) : tile_id(blk, k)) + 8u * (uint32_t)(pass ? tile_elem(0, e) : tile_elem(e, 0));
+            acc[r] = ok ? lds_f64(xa[r]) : 0.0;
+          }
+#pragma unroll
+          for (int c = 0; c < NB; c++) {
+            /* element (e, c) sits at (c/4)*32 + e*4 + c%4, element (c, e) at (e/4)*32 + c*4 + e%4 */
+            const uint32_t step = pass ? 8u * (uint32_t)(c * 4) : 8u * (uint32_t)((c >> 2) * 32 + (c & 3));
+#pragma unroll
+            for (int r = 0; r < 8; r++) acc[r] = fma(-lds_f64(la[r] + step), v[c], acc[r]);
+          }
+#pragma unroll
+          for (int r = 0; r < 8; r++)
+            if (xa[r]) asm volatile("st.shared.f64 [%0], %1;" ::"r"(xa[r]), "d"(acc[r]) : "memory");
+        }
+        __syncwarp();
       }
-      __syncwarp();
-    }
-    for (int k = nt - 1; k >= 0; k--) { /* L' x = y */
-      const double *Y = Yinv + (size_t)k * 64;
-      double mine = 0.0;
-      { const int j = lane & 7;
-#pragma unroll
-        for (int m = 0; m < NB; m++) mine += (m >= j ? Y[tile_elem(m, j)] : 0.0) * x[NB * k + m]; }
-      double xk[NB];
-#pragma unroll
-      for (int r = 0; r < NB; r++) xk[r] = __shfl_sync(0xffffffffu, mine, r);
-      __syncwarp();
-      if (lane < NB) x[NB * k + lane] = mine;
-      for (int idx = lane; idx < k * NB; idx += 32) {
-        const int J = idx >> 3, c = idx & 7;
-        const double *L = T + (size_t)tile_id(k, J) * 64;
-        double s = x[NB * J + c];
-#pragma unroll
-        for (int r = 0; r < NB; r++) s -= L[tile_elem(r, c)] * xk[r];
-        x[NB * J + c] = s;
-      }
-      __syncwarp();
     }
   }
   team.sync();
@@ -1769,9 +1787,10 @@ DS_FN_NOINLINE void sfn_solve_one(const Team team, const SfnProb &P, const SfnWs
     sfn_rows(s, P.uv, P.normals, i, Iu, Iv, ws.mrow + 32 * (size_t)i, ws.mrow + 32 * (size_t)i + 16);
   }
   /* bending * B, dense (rows of the stacked system) */
+  const BendCoef bcoef = bending_coef(s);
   DS_FOR(idx, NC * NC) {
     const int p = idx / NC, q = idx - p * NC;
-    ws.B[idx] = P.bending * bending_entry_tab(s, ci, p / nv, p % nv, q / nv, q % nv);
+    ws.B[idx] = P.bending * bending_entry_tab(s, bcoef, ci, p / nv, p % nv, q / nv, q % nv);
   }
   team.sync();
   if (bad) {
@@ -1823,7 +1842,7 @@ DS_FN_NOINLINE void sfn_solve_one(const Team team, const SfnProb &P, const SfnWs
       for (int ku = ku0; ku <= ku1; ku++)
         for (int kv = kv0; kv <= kv1; kv++) {
           const int k = ku * nv + kv;
-          bb += ws.B[(size_t)k * NC + p] * ws.B[(size_t)k * NC + q];
+          bb += ws.B[(size_t)p * NC + k] * ws.B[(size_t)q * NC + k]; /* B is symmetric: rows instead of columns (contiguous in k) */
         }
       a += bb;
     }
