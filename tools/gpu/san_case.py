@@ -19,6 +19,10 @@ elif which == "nrsfm":
     win = nrsfm.make_window(3, n_keypoints=160, n_views=2)
     fits = api.schwarp_fit_batched(nrsfm.schwarp_cases(win))
     nout = api.normals(nrsfm.normals_case(win, fits))
+    os.environ["DEFSLAM_NORMALS_CHUNKS"] = "3"   # the pipelined path (chunks over two side streams) on the same small case
+    nout3 = api.normals(nrsfm.normals_case(win, fits))
+    del os.environ["DEFSLAM_NORMALS_CHUNKS"]
+    assert (nout3.status == nout.status).all() and (nout3.k == nout.k).all()
     ctrl, xyz = api.sfn_solve(nrsfm.sfn_case(win, nout))
     r = api.sim3_register([nrsfm.sim3_case(2, n=120)])
     print("nrsfm", int((nout.status == 1).sum()), float(ctrl[0]), r[0]["inliers"])
