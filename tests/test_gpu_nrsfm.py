@@ -148,6 +148,31 @@ def test_sfn_batched_and_few_normals(apis):
         assert np.abs(c.xyz - xo).max() <= 1e-6
 
 
+def test_sfn_packed_fallbacks_agree_with_the_tile_path(apis):
+    """N as tiles on the tensor cores (default), packed in shared memory (mode 1), packed in the workspace (mode 0: the
+    path of grids too large for shared memory): all three against the QR oracle, and against each other"""
+    import os
+    api, orc = apis
+    win = nrsfm.make_window(31, n_keypoints=400, n_views=2)
+    fits = [orc.schwarp_fit(c) for c in nrsfm.schwarp_cases(win)]
+    no = orc.normals(nrsfm.normals_case(win, fits))
+    base = nrsfm.sfn_case(win, no)
+    co, xo = orc.sfn_solve(copy.copy(base))
+    co, xo = co.copy(), xo.copy()
+    got = {}
+    for mode in ("2", "1", "0"):
+        os.environ["DEFSLAM_SFN_MODE"] = mode
+        try:
+            c = copy.copy(base)
+            c.ctrl, c.xyz = None, None  # fresh output arrays per mode
+            assert (api.sfn_solve_batched([c]) == 0).all()
+        finally:
+            del os.environ["DEFSLAM_SFN_MODE"]
+        assert np.abs(c.ctrl - co).max() <= ck.CTRL_TOL and np.abs(c.xyz - xo).max() <= 1e-6
+        got[mode] = c.ctrl.copy()
+    assert np.abs(got["2"] - got["1"]).max() <= 1e-9 and np.array_equal(got["1"], got["0"])
+
+
 def test_sfn_nan_normals_fail_loudly(apis):
     api, orc = apis
     win = nrsfm.make_window(4, n_keypoints=200, n_views=1)
