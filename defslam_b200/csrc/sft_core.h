@@ -94,6 +94,7 @@ struct Workspace {
   double *dxg;   /* [Dn_pad+8]    LM step when it does not fit in smem        */
   int *mfac;     /* [M]  facet<<6 | slot0 | slot1<<2 | slot2<<4               */
   int *mperm;    /* [M]  matches grouped by facet                             */
+  double *mrec;  /* [8M] per-match records in facet-grouped order (see match_record) */
   int *fptr;     /* [nf+1] */
   int *fcnt;     /* [nf]   */
 };
@@ -107,7 +108,7 @@ static inline
 __host__ __device__
 #endif
 size_t workspace_bytes(const WorkspaceSizes &z) {
-  size_t b = sizeof(double) * (2 * z.band + z.dinv + 2 * z.cg + z.F + z.S + 3 * z.dp + 8) + sizeof(int) * (2 * z.M + 2 * z.nf + 2);
+  size_t b = sizeof(double) * (2 * z.band + z.dinv + 2 * z.cg + z.F + z.S + 8 * z.M + 2 + 3 * z.dp + 8) + sizeof(int) * (2 * z.M + 2 * z.nf + 2);
   return (b + 255) & ~(size_t)255;
 }
 
@@ -125,6 +126,8 @@ Workspace carve_workspace(uint8_t *base, const WorkspaceSizes &z) {
   w.Eg = d; d += z.cg;
   w.F = d; d += z.F;
   w.S = d; d += z.S;
+  if ((d - (double *)base) & 1) d++; /* 16-byte records */
+  w.mrec = d; d += 8 * z.M;
   w.xb = d; d += z.dp;
   w.xg = d; d += z.dp;
   w.dxg = d; d += z.dp + 8;
@@ -406,6 +409,20 @@ DS_FN_NOINLINE int prologue(const Team team, Ctx &cx) {
     }
   }
   team.sync();
+  /* per-match records in facet-grouped order: the error passes (once per LM iteration and once per trial) then read
+   * one contiguous 64-byte record per match instead of the permutation and, through it, four of the caller's arrays
+   * (two dependent round trips of ~3 k cycles each under this kernel's load) */
+  DS_FOR(sidx, M) {
+    const int m = c.ws.mperm[sidx];
+    double *r = c.ws.mrec + 8 * (size_t)sidx;
+    r[0] = pb.match_bary[3 * m]; r[1] = pb.match_bary[3 * m + 1]; r[2] = pb.match_bary[3 * m + 2];
+    int *ri = (int *)(r + 3);
+    float *rf = (float *)(r + 3);
+    ri[0] = pb.match_nodes[3 * m]; ri[1] = pb.match_nodes[3 * m + 1]; ri[2] = pb.match_nodes[3 * m + 2];
+    rf[3] = pb.match_isig[m]; rf[4] = pb.match_uv[2 * m]; rf[5] = pb.match_uv[2 * m + 1];
+    ri[6] = c.ws.mfac[m]; ri[7] = m;
+  }
+  team.sync();
 
   /* information matrices (DefOptimizer.cc:339-340,376-378,458,499); the context
    * is shared by the CTA: one writer */
@@ -453,6 +470,52 @@ DS_FN void reproj_error(const Ctx &c, const double *x, const Pose &P, int m, dou
 
 DS_FN double match_info(const Ctx &c, int m) {
   return c.info_uniform > 0.0 ? c.info_uniform : (double)c.pb.match_isig[m] / (double)c.pb.n_kp;
+}
+
+/* the same from the facet-grouped record of match slot s (prologue): b[3], v[3], 1/sigma^2, observation, the facet
+ * code of the match (mfac) and its index in the caller's order */
+struct MatchRec {
+  double b[3];
+  int v[3];
+  float isig, u, w;
+  int code, m;
+};
+DS_FN MatchRec match_record(const Ctx &c, int s) {
+  MatchRec r;
+  const double *p = c.ws.mrec + 8 * (size_t)s;
+#if DS_CUDA
+  const dbl2 q0 = *(const dbl2 *)p, q1 = *(const dbl2 *)(p + 2), q2 = *(const dbl2 *)(p + 4), q3 = *(const dbl2 *)(p + 6);
+  r.b[0] = q0.x; r.b[1] = q0.y; r.b[2] = q1.x;
+  r.v[0] = (int)((unsigned long long)__double_as_longlong(q1.y) & 0xffffffffu);
+  r.v[1] = (int)((unsigned long long)__double_as_longlong(q1.y) >> 32);
+  r.v[2] = (int)((unsigned long long)__double_as_longlong(q2.x) & 0xffffffffu);
+  r.isig = __int_as_float((int)((unsigned long long)__double_as_longlong(q2.x) >> 32));
+  r.u = __int_as_float((int)((unsigned long long)__double_as_longlong(q2.y) & 0xffffffffu));
+  r.w = __int_as_float((int)((unsigned long long)__double_as_longlong(q2.y) >> 32));
+  r.code = (int)((unsigned long long)__double_as_longlong(q3.x) & 0xffffffffu);
+  r.m = (int)((unsigned long long)__double_as_longlong(q3.x) >> 32);
+#else
+  const int *pi = (const int *)(p + 3);
+  const float *pf = (const float *)(p + 3);
+  r.b[0] = p[0]; r.b[1] = p[1]; r.b[2] = p[2];
+  r.v[0] = pi[0]; r.v[1] = pi[1]; r.v[2] = pi[2];
+  r.isig = pf[3]; r.u = pf[4]; r.w = pf[5];
+  r.code = pi[6]; r.m = pi[7];
+#endif
+  return r;
+}
+DS_FN void reproj_error_rec(const Ctx &c, const double *x, const Pose &P, const MatchRec &r, double e[2], double Pc[3]) {
+  const ProbView &pb = c.pb;
+  double Pw[3];
+  for (int k = 0; k < 3; k++) Pw[k] = r.b[0] * x[3 * r.v[0] + k] + r.b[1] * x[3 * r.v[1] + k] + r.b[2] * x[3 * r.v[2] + k];
+  pose_map(P, Pw, Pc);
+  const double u = Pc[0] / Pc[2] * pb.fx + pb.cx;
+  const double v = Pc[1] / Pc[2] * pb.fy + pb.cy;
+  e[0] = (double)r.u - u;
+  e[1] = (double)r.w - v;
+}
+DS_FN double match_info_rec(const Ctx &c, const MatchRec &r) {
+  return c.info_uniform > 0.0 ? c.info_uniform : (double)r.isig / (double)c.pb.n_kp;
 }
 
 /* curvature residual of centre i: delta = x_i - sum(w x_j)/W  (sft_types.h:257-291) */
@@ -505,10 +568,10 @@ DS_FN_NOINLINE double eval_state(const Team team, Ctx &cx) {
 
   /* reprojection edges, in facet-grouped order */
   DS_FOR(s, M) {
-    const int m = c.ws.mperm[s];
+    const MatchRec mr = match_record(c, s);
     double e[2], Pc[3];
-    reproj_error(c, x, P, m, e, Pc);
-    const double info = match_info(c, m);
+    reproj_error_rec(c, x, P, mr, e, Pc);
+    const double info = match_info_rec(c, mr);
     const double c2 = e[0] * info * e[0] + e[1] * info * e[1];
     double rho0, rho1; /* RobustKernelHuber::robustify robust_kernel_impl.cpp:78-91 */
     if (c2 <= c.hub_dsqr) { rho0 = c2; rho1 = 1.0; }
@@ -518,8 +581,8 @@ DS_FN_NOINLINE double eval_state(const Team team, Ctx &cx) {
       double *S = c.ws.S;
       /* camera Jacobian at the interpolated point, from the node images like
        * the reference (xyz = sum b_k (R x_k + t))  sft_types.h:151-174 */
-      const int v[3] = {pb.match_nodes[3 * m], pb.match_nodes[3 * m + 1], pb.match_nodes[3 * m + 2]};
-      const double b[3] = {pb.match_bary[3 * m], pb.match_bary[3 * m + 1], pb.match_bary[3 * m + 2]};
+      const int v[3] = {mr.v[0], mr.v[1], mr.v[2]};
+      const double b[3] = {mr.b[0], mr.b[1], mr.b[2]};
       double xk[3][3];
       for (int k = 0; k < 3; k++) pose_map(P, &x[3 * v[k]], xk[k]);
       const double X = xk[0][0] * b[0] + xk[1][0] * b[1] + xk[2][0] * b[2];
@@ -541,7 +604,7 @@ DS_FN_NOINLINE double eval_state(const Team team, Ctx &cx) {
       S[12 * M + s] = 0;
       S[13 * M + s] = -1. / Z * fy;
       S[14 * M + s] = Y / Z2 * fy;
-      const int code = c.ws.mfac[m];
+      const int code = mr.code;
       S[(15 + (code & 3)) * M + s] = b[0];
       S[(15 + ((code >> 2) & 3)) * M + s] = b[1];
       S[(15 + ((code >> 4) & 3)) * M + s] = b[2];
