@@ -226,17 +226,17 @@ def nrsfm_gpu(lib, wl, steps, warmup, flush_fn):
             call()
             wall_s += time.perf_counter() - t0
             dev_ms += lib.defslam_last_kernel_ms()
-        if name == "normals":
-            # the end-to-end call pipelines the batch in chunks of map points (upload / kernel / download of
+        if name in ("normals", "schwarp_fit"):
+            # the end-to-end call pipelines a large batch in chunks (pack / upload / kernel / download / unpack of
             # neighbouring chunks overlap); the kernel-only number is the same batch in one launch
-            os.environ["DEFSLAM_NORMALS_CHUNKS"] = "1"
+            os.environ["DEFSLAM_NO_PIPELINE"] = "1"
             dev_ms = 0.0
             call()
             for _ in range(steps):
                 flush_fn()
                 call()
                 dev_ms += lib.defslam_last_kernel_ms()
-            del os.environ["DEFSLAM_NORMALS_CHUNKS"]
+            del os.environ["DEFSLAM_NO_PIPELINE"]
         res[name] = [units, dev_ms, wall_s]
     return res
 

@@ -233,7 +233,7 @@ int defslam_schwarp_fit_batched(int32_t nprob, const defslam_schwarp_problem *p,
   std::vector<size_t> o_kp1(nprob), o_kp2(nprob), o_sig(nprob), o_x(nprob), o_uv(nprob), o_j12(nprob), o_j21(nprob),
       o_h12(nprob), o_keep(nprob), o_sc(nprob);
   const size_t o_probs = in.add(sizeof(SchwarpProb) * nprob);
-  const size_t o_counter = in.add(sizeof(int));
+  const size_t o_counter = in.add(sizeof(int) * 16); /* one work counter per chunk */
   /* x travels in and comes back: all x first in the output arena, so that the upload is one
    * contiguous span (inputs + x) */
   for (int i = 0; i < nprob; i++) o_x[i] = outp.add(16 * (size_t)p[i].bbs.nptsu * p[i].bbs.nptsv);
@@ -253,41 +253,125 @@ int defslam_schwarp_fit_batched(int32_t nprob, const defslam_schwarp_problem *p,
     return rc;
   uint8_t *h = (uint8_t *)S.host.p, *d_in = (uint8_t *)S.dev.p, *d_out = d_in + in.total, *h_out = h + in.total;
   SchwarpProb *hp = (SchwarpProb *)(h + o_probs);
-  /* (large batches: several host threads, a share of the problems each) */
-  host_parallel_for((size_t)nprob, 32, [&](size_t i_lo, size_t i_hi) {
-  for (size_t i = i_lo; i < i_hi; i++) {
-    const size_t n = p[i].n_matches, NC = (size_t)p[i].bbs.nptsu * p[i].bbs.nptsv;
-    memcpy(h + o_kp1[i], p[i].kp1, 8 * n);
-    memcpy(h + o_kp2[i], p[i].kp2, 8 * n);
-    memcpy(h + o_sig[i], p[i].inv_sigma, 4 * n);
-    memcpy(h_out + o_x[i], p[i].x, 16 * NC);
-    SchwarpProb &P = hp[i];
-    P.bbs = to_view(&p[i].bbs);
-    P.n = p[i].n_matches;
-    P.kp1 = (const float *)(d_in + o_kp1[i]); P.kp2 = (const float *)(d_in + o_kp2[i]);
-    P.isig = (const float *)(d_in + o_sig[i]);
-    P.lambda = p[i].lambda; P.fx = p[i].fx; P.fy = p[i].fy; P.px_fx = p[i].px_fx; P.px_fy = p[i].px_fy;
-    P.max_iterations = p[i].max_iterations; P.initialize = p[i].initialize;
-    P.x = (double *)(d_out + o_x[i]);
-    P.warp_uv = (float *)(d_out + o_uv[i]); P.J12 = (float *)(d_out + o_j12[i]); P.J21 = (float *)(d_out + o_j21[i]);
-    P.H12 = (float *)(d_out + o_h12[i]); P.keep = d_out + o_keep[i]; P.scalars = (double *)(d_out + o_sc[i]);
-  }
-  });
-  *(int *)(h + o_counter) = 0;
-  DS_CUDA_TRY(cudaMemcpyAsync(d_in, h, in.total + x_total, cudaMemcpyHostToDevice, ctx->stream));
+  /* Large batches run as a pipeline of chunks of whole waves (one fit per CTA): the host packs chunk c+1 and unpacks
+   * chunk c-1 (several threads each) while the device works on chunk c; uploads, kernels (one stream: they share the
+   * per-CTA workspace) and downloads on three streams.  Serially the call was 1.7x slower than its kernel. */
+  const int nchunk = (nprob >= 2 * ctx->sm_count && getenv("DEFSLAM_NO_PIPELINE") == nullptr)
+                         ? std::min(16, (nprob + ctx->sm_count - 1) / ctx->sm_count) : 1;
+  if (nchunk > 1 && (rc = S.ensure_side())) return rc;
+  auto chunk_lo = [&](int c) { return (int)((long long)nprob * c / nchunk); };
+  auto pack = [&](int i_lo, int i_hi) {
+    host_parallel_for((size_t)(i_hi - i_lo), 32, [&](size_t a_, size_t b_) {
+      for (size_t i = i_lo + a_; i < i_lo + b_; i++) {
+        const size_t n = p[i].n_matches, NC = (size_t)p[i].bbs.nptsu * p[i].bbs.nptsv;
+        memcpy(h + o_kp1[i], p[i].kp1, 8 * n);
+        memcpy(h + o_kp2[i], p[i].kp2, 8 * n);
+        memcpy(h + o_sig[i], p[i].inv_sigma, 4 * n);
+        memcpy(h_out + o_x[i], p[i].x, 16 * NC);
+        SchwarpProb &P = hp[i];
+        P.bbs = to_view(&p[i].bbs);
+        P.n = p[i].n_matches;
+        P.kp1 = (const float *)(d_in + o_kp1[i]); P.kp2 = (const float *)(d_in + o_kp2[i]);
+        P.isig = (const float *)(d_in + o_sig[i]);
+        P.lambda = p[i].lambda; P.fx = p[i].fx; P.fy = p[i].fy; P.px_fx = p[i].px_fx; P.px_fy = p[i].px_fy;
+        P.max_iterations = p[i].max_iterations; P.initialize = p[i].initialize;
+        P.x = (double *)(d_out + o_x[i]);
+        P.warp_uv = (float *)(d_out + o_uv[i]); P.J12 = (float *)(d_out + o_j12[i]); P.J21 = (float *)(d_out + o_j21[i]);
+        P.H12 = (float *)(d_out + o_h12[i]); P.keep = d_out + o_keep[i]; P.scalars = (double *)(d_out + o_sc[i]);
+      }
+    });
+  };
+  auto unpack = [&](int i_lo, int i_hi) {
+    host_parallel_for((size_t)(i_hi - i_lo), 32, [&](size_t a_, size_t b_) {
+      for (size_t i = i_lo + a_; i < i_lo + b_; i++) {
+        const size_t n = p[i].n_matches, NC = (size_t)p[i].bbs.nptsu * p[i].bbs.nptsv;
+        /* a failed fit leaves its outputs untouched, like the reference keeping its previous estimate */
+        if ((int)((const double *)(h_out + o_sc[i]))[4] != SCHWARP_OK) continue;
+        memcpy(p[i].x, h_out + o_x[i], 16 * NC);
+        if (out[i].warp_uv) memcpy(out[i].warp_uv, h_out + o_uv[i], 8 * n);
+        if (out[i].J12) memcpy(out[i].J12, h_out + o_j12[i], 16 * n);
+        if (out[i].J21) memcpy(out[i].J21, h_out + o_j21[i], 16 * n);
+        if (out[i].H12) memcpy(out[i].H12, h_out + o_h12[i], 24 * n);
+        if (out[i].keep) memcpy(out[i].keep, h_out + o_keep[i], n);
+      }
+    });
+  };
+  memset(h + o_counter, 0, sizeof(int) * 16);
   DS_CUDA_TRY(raise_dynamic_smem((const void *)schwarp_fit_kernel, ctx->device, (int)smem));
-  DS_CUDA_TRY(cudaEventRecord(ctx->e0, ctx->stream));
-  schwarp_fit_kernel<<<grid, NRSFM_THREADS, smem, ctx->stream>>>((const SchwarpProb *)(d_in + o_probs), nprob,
-                                                                 (uint8_t *)S.ws.p, ws_stride, nu, nv, nmax,
-                                                                 (int *)(d_in + o_counter));
-  DS_CUDA_TRY(cudaGetLastError());
-  g_launches.fetch_add(1);
-  DS_CUDA_TRY(cudaEventRecord(ctx->e1, ctx->stream));
-  DS_CUDA_TRY(cudaMemcpyAsync(h_out, d_out, outp.total, cudaMemcpyDeviceToHost, ctx->stream));
-  DS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  float ms = 0.f;
-  cudaEventElapsedTime(&ms, ctx->e0, ctx->e1);
-  g_last_kernel_ms = ms;
+  /* spans of problems [i_lo, i_hi) in the arenas (the per-problem blocks are laid out in problem order) */
+  auto span_in = [&](int i_lo, int i_hi, size_t &off, size_t &len) {
+    off = o_kp1[i_lo];
+    len = (i_hi < nprob ? o_kp1[i_hi] : in.total) - off;
+  };
+  auto span_x = [&](int i_lo, int i_hi, size_t &off, size_t &len) {
+    off = o_x[i_lo];
+    len = (i_hi < nprob ? o_x[i_hi] : x_total) - off;
+  };
+  auto span_out = [&](int i_lo, int i_hi, size_t &off, size_t &len) {
+    off = o_uv[i_lo];
+    len = (i_hi < nprob ? o_uv[i_hi] : outp.total) - off;
+  };
+  float ms_total = 0.f;
+  if (nchunk == 1) {
+    pack(0, nprob);
+    DS_CUDA_TRY(cudaMemcpyAsync(d_in, h, in.total + x_total, cudaMemcpyHostToDevice, ctx->stream));
+    DS_CUDA_TRY(cudaEventRecord(ctx->e0, ctx->stream));
+    schwarp_fit_kernel<<<grid, NRSFM_THREADS, smem, ctx->stream>>>((const SchwarpProb *)(d_in + o_probs), nprob,
+                                                                   (uint8_t *)S.ws.p, ws_stride, nu, nv, nmax,
+                                                                   (int *)(d_in + o_counter));
+    DS_CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1);
+    DS_CUDA_TRY(cudaEventRecord(ctx->e1, ctx->stream));
+    DS_CUDA_TRY(cudaMemcpyAsync(h_out, d_out, outp.total, cudaMemcpyDeviceToHost, ctx->stream));
+    DS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ms_total, ctx->e0, ctx->e1);
+    unpack(0, nprob);
+  } else {
+    cudaStream_t s_up = S.side[0], s_dn = S.side[1], s_k = ctx->stream;
+    /* the problem descriptors and the counters go up once the first chunk is packed; later chunks only rewrite
+     * their own descriptors, so all of them are packed first (cheap: no array copies) -- done inside pack() per
+     * chunk, uploaded per chunk below */
+    for (int c = 0; c < nchunk; c++) {
+      const int i_lo = chunk_lo(c), i_hi = chunk_lo(c + 1);
+      pack(i_lo, i_hi);
+      size_t off, len;
+      if (c == 0) DS_CUDA_TRY(cudaMemcpyAsync(d_in + o_counter, h + o_counter, sizeof(int) * 16, cudaMemcpyHostToDevice, s_up));
+      DS_CUDA_TRY(cudaMemcpyAsync(d_in + o_probs + sizeof(SchwarpProb) * i_lo, h + o_probs + sizeof(SchwarpProb) * i_lo,
+                                  sizeof(SchwarpProb) * (i_hi - i_lo), cudaMemcpyHostToDevice, s_up));
+      span_in(i_lo, i_hi, off, len);
+      DS_CUDA_TRY(cudaMemcpyAsync(d_in + off, h + off, len, cudaMemcpyHostToDevice, s_up));
+      span_x(i_lo, i_hi, off, len);
+      DS_CUDA_TRY(cudaMemcpyAsync(d_out + off, h_out + off, len, cudaMemcpyHostToDevice, s_up));
+      DS_CUDA_TRY(cudaEventRecord(S.ev_done[c], s_up)); /* (reused below for the download of the same chunk) */
+      DS_CUDA_TRY(cudaStreamWaitEvent(s_k, S.ev_done[c], 0));
+      DS_CUDA_TRY(cudaEventRecord(S.ev_k0[c], s_k));
+      const int g = persistent_grid(i_hi - i_lo, ctx->sm_count);
+      schwarp_fit_kernel<<<g, NRSFM_THREADS, smem, s_k>>>((const SchwarpProb *)(d_in + o_probs) + i_lo, i_hi - i_lo,
+                                                          (uint8_t *)S.ws.p, ws_stride, nu, nv, nmax,
+                                                          (int *)(d_in + o_counter) + c);
+      DS_CUDA_TRY(cudaGetLastError());
+      g_launches.fetch_add(1);
+      DS_CUDA_TRY(cudaEventRecord(S.ev_k1[c], s_k));
+      DS_CUDA_TRY(cudaStreamWaitEvent(s_dn, S.ev_k1[c], 0));
+      span_x(i_lo, i_hi, off, len);
+      DS_CUDA_TRY(cudaMemcpyAsync(h_out + off, d_out + off, len, cudaMemcpyDeviceToHost, s_dn));
+      span_out(i_lo, i_hi, off, len);
+      DS_CUDA_TRY(cudaMemcpyAsync(h_out + off, d_out + off, len, cudaMemcpyDeviceToHost, s_dn));
+      if (c >= 1) {
+        DS_CUDA_TRY(cudaEventSynchronize(S.ev_done[c - 1]));
+        unpack(chunk_lo(c - 1), chunk_lo(c));
+      }
+      DS_CUDA_TRY(cudaEventRecord(S.ev_done[c], s_dn));
+    }
+    DS_CUDA_TRY(cudaEventSynchronize(S.ev_done[nchunk - 1]));
+    unpack(chunk_lo(nchunk - 1), nprob);
+    for (int c = 0; c < nchunk; c++) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, S.ev_k0[c], S.ev_k1[c]);
+      ms_total += ms;
+    }
+  }
+  g_last_kernel_ms = ms_total;
   int worst = DEFSLAM_OK;
   for (int i = 0; i < nprob; i++) {
     const double *sc = (const double *)(h_out + o_sc[i]);
@@ -296,19 +380,6 @@ int defslam_schwarp_fit_batched(int32_t nprob, const defslam_schwarp_problem *p,
     out[i].iterations = (int)sc[2]; out[i].accepted = (int)sc[3];
     if (st != SCHWARP_OK && worst == DEFSLAM_OK) worst = st == SCHWARP_OUT_OF_DOMAIN ? DEFSLAM_EBADARG : DEFSLAM_ENUMERIC;
   }
-  host_parallel_for((size_t)nprob, 32, [&](size_t i_lo, size_t i_hi) {
-    for (size_t i = i_lo; i < i_hi; i++) {
-      const size_t n = p[i].n_matches, NC = (size_t)p[i].bbs.nptsu * p[i].bbs.nptsv;
-      /* a failed fit leaves its outputs untouched, like the reference keeping its previous estimate */
-      if ((int)((const double *)(h_out + o_sc[i]))[4] != SCHWARP_OK) continue;
-      memcpy(p[i].x, h_out + o_x[i], 16 * NC);
-      if (out[i].warp_uv) memcpy(out[i].warp_uv, h_out + o_uv[i], 8 * n);
-      if (out[i].J12) memcpy(out[i].J12, h_out + o_j12[i], 16 * n);
-      if (out[i].J21) memcpy(out[i].J21, h_out + o_j21[i], 16 * n);
-      if (out[i].H12) memcpy(out[i].H12, h_out + o_h12[i], 24 * n);
-      if (out[i].keep) memcpy(out[i].keep, h_out + o_keep[i], n);
-    }
-  });
   return worst;
 }
 
@@ -451,6 +522,7 @@ int defslam_normals_batched(const defslam_normals_problem *p, double *k_out, dou
    * upload, 1.5 ms of kernel, download 44 MB, unpack). */
   /* (chunks stay large: a chunk's kernel lasts as long as its slowest point, up to max_iterations trips) */
   size_t nchunk = n >= 65536 ? std::max<size_t>(2, std::min<size_t>(6, n / 98304)) : 1;
+  if (getenv("DEFSLAM_NO_PIPELINE") != nullptr) nchunk = 1;
   if (const char *e = getenv("DEFSLAM_NORMALS_CHUNKS")) { /* 1: one pass (the kernel timed alone), 2..16: forced */
     const int v = atoi(e);
     if (v >= 1) nchunk = std::min<size_t>((size_t)std::min(v, 16), std::max<size_t>(1, n / 128));

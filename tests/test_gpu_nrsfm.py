@@ -52,6 +52,32 @@ def test_schwarp_batched_equals_single(apis):
             assert outs[rep].d.iterations == single.d.iterations
 
 
+def test_schwarp_pipelined_batch_equals_single(apis):
+    """batches of >= 2 waves run as a pipeline of chunks over three streams (upload / kernels / download): same results,
+    fit for fit, as single calls; a fit that fails (site outside the domain) leaves its outputs untouched"""
+    api, orc = apis
+    win = nrsfm.make_window(12, n_keypoints=500, n_views=5, match_frac=0.5)
+    cases = nrsfm.schwarp_cases(win)
+    cases[1] = ck.accepted_steps_case(cases[1])
+    singles = [api.schwarp_fit(c) for c in cases]
+    reps = 70
+    batch = cases * reps  # 350 pairs: three chunks on a 148-SM device
+    bad = copy.copy(batch[177])
+    bad.kp1 = bad.kp1.copy()
+    bad.kp1[3, 0] = bad.bbs.umax + 0.5
+    batch[177] = bad
+    with pytest.raises(nrsfm.DefslamError):
+        api.schwarp_fit_batched(batch)  # the failed fit is reported; the others are complete
+    batch[177] = cases[177 % len(cases)]
+    outs = api.schwarp_fit_batched(batch)
+    for rep in (0, 147, 148, 177, 296, len(batch) - 1):
+        single = singles[rep % len(cases)]
+        assert np.array_equal(outs[rep].x, single.x)
+        assert np.array_equal(outs[rep].J12, single.J12) and np.array_equal(outs[rep].H12, single.H12)
+        assert np.array_equal(outs[rep].keep, single.keep)
+        assert outs[rep].d.iterations == single.d.iterations and outs[rep].d.accepted == single.d.accepted
+
+
 def test_schwarp_out_of_domain_is_rejected(apis):
     api, _ = apis
     win = nrsfm.make_window(2, n_keypoints=200, n_views=1)
