@@ -148,7 +148,7 @@ struct SmemLayout {
 
 /* row-owner factorisation (sft_rows.h): ring slots and sizes */
 constexpr int ROWS_OWNERS_ = 5;
-constexpr int ROWS_LT_STRIDE_ = 72;
+constexpr int ROWS_LT_STRIDE_ = 64;
 #ifndef DS_BWD_BUFS
 #define DS_BWD_BUFS 8
 #endif
